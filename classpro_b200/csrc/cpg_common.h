@@ -1,0 +1,129 @@
+/*******************************************************************************************
+ *  cpg_common.h -- data layouts shared by the CUDA kernels and the C-ABI implementation.
+ *
+ *  The per-read logic in cpg_*.cuh is written in "warp-uniform" style: the 32 lanes of the warp
+ *  that owns a read execute the same scalar control flow on the same values (no divergence),
+ *  split the data-parallel inner loops (profile sweeps, binomial tail terms, the 4x4 transition
+ *  table, interval sorting) by lane, and exchange results through a small per-warp block of
+ *  shared memory.  With CPG_HOSTSIM defined the same sources compile as plain C++ with a warp
+ *  width of 1; that build exists ONLY under tests/ (tests/hostsim) to unit-test the device logic
+ *  on machines without a GPU.  It is never linked into libclasspro_b200.so.
+ *
+ *  file:line citations are relative to /root/reference/.
+ *******************************************************************************************/
+#ifndef CPG_COMMON_H
+#define CPG_COMMON_H
+
+#include <stdint.h>
+#include <math.h>
+
+#ifdef CPG_HOSTSIM
+  #include <string.h>
+  #define CPG_DEV        static inline
+  #define CPG_DEV_NOINL  static
+  #define CPG_WARP       1
+  #define CPG_SYNCWARP() do { } while (0)
+  #define CPG_LDG(p)     (*(p))
+  #define CPG_INF        ((double)INFINITY)
+#else
+  #include <cuda_runtime.h>
+  #define CPG_DEV        __device__ __forceinline__
+  #define CPG_DEV_NOINL  __device__ __noinline__
+  #define CPG_WARP       32
+  #define CPG_SYNCWARP() __syncwarp()
+  #define CPG_LDG(p)     __ldg(p)
+  #define CPG_INF        (__longlong_as_double(0x7ff0000000000000LL))
+#endif
+
+/* enums of src/ClassPro.h:57-60,122 */
+enum { ST_E = 0, ST_R = 1, ST_H = 2, ST_D = 3, ST_N = 4 };
+enum { CT_HP = 0, CT_DS = 1, CT_TS = 2, CT_N = 3 };
+enum { ET_SELF = 0, ET_OTHERS = 1 };
+enum { WT_DROP = 0, WT_GAIN = 1 };
+enum { TH_INIT = 0, TH_FINAL = 1 };
+
+#define CPG_MAX_CNT    32767      /* src/const.c:38 */
+#define CPG_MAX_RLEN   60000      /* src/const.c:57 */
+#define CPG_LROWS      36         /* 20 + 10 + 6 context rows (src/wall.c:123) */
+
+/* constants of src/const.c:56-73 */
+#define CPG_MAX_N_HC        5
+#define CPG_MIN_CNT_CHANGE  3
+#define CPG_MAX_CNT_CHANGE  5
+#define CPG_PE_INIT_SELF    0.001
+#define CPG_PE_INIT_OTHERS  0.05
+#define CPG_PE_FINAL        1e-5          /* PE_THRES[FINAL][SELF] == PE_THRES[FINAL][OTHERS] */
+#define CPG_THRES_DIFF_EO   (-23.025851)
+#define CPG_THRES_DIFF_REL  (-9.210340)
+#define CPG_OFFSET          1000
+#define CPG_R_LOGP          (-10.)
+#define CPG_E_PO_BASE       (-10.)
+#define CPG_PE_MEAN         0.01
+
+/* per-read status bits returned to the host */
+#define CPG_ST_OK             0
+#define CPG_ST_BAD_PROFILE    1    /* decoded length != rlen-K+1 (src/ClassPro.c:234-237: exit(1)) */
+#define CPG_ST_EINTVL_OVF     2    /* "# E-intvls >= plen" (src/wall.c:783-788: exit(1)) */
+#define CPG_ST_NO_PROB        4    /* "No valid probability for interval" (class_unrel.c:221-226) */
+#define CPG_ST_INTERP         8    /* invalid interpolation points (src/util.c:26-31: exit(1)) */
+#define CPG_ST_UNDEF_TRACE   16    /* all DP states impossible at the last interval: the reference
+                                      reads a stale path row (class_rel.c:62-73,606-613) */
+#define CPG_ST_LONG_RUN      32    /* a low-complexity run reached the 127 cap: the reference reads
+                                      never-written right-context cells (context.c:26-27) */
+#define CPG_ST_BINOM         64    /* k > n in a binomial (src/prob.c:51-55: exit(1)) */
+
+/* Device-resident model: host one-shot results (src/ClassPro.c:536-554, src/wall.c:167-244) */
+typedef struct
+  { int32_t  K;
+    int32_t  read_len;
+    int32_t  cmax;
+    int32_t  lmax[3];
+    uint16_t cov[4];
+    double   dr_ratio;
+    double   hc_erate;
+    double   pe[3][21];
+    /* device pointers */
+    const uint8_t *cthres;     /* [CPG_LROWS][256][2(thresT)][2(etype)], row = lrow(t,l) */
+    const double  *logfact;    /* [32768] */
+  } cpg_dmodel;
+
+/* row of context (type t, length l>=1) in the flattened threshold table */
+#define CPG_LROW(t,l) (((t) == 0 ? 0 : ((t) == 1 ? 20 : 30)) + (l) - 1)
+
+typedef struct
+  { int32_t  b, e;
+    uint16_t cb, ce, ccb, cce;
+    uint8_t  is_rel;
+    int8_t   asgn;
+    uint8_t  pad[6];
+    double   pe, peob, peoe;
+  } cpg_intvl;                  /* src/ClassPro.h:159-170 */
+
+typedef struct { int32_t b, e; double pe; } cpg_eintvl;   /* src/ClassPro.h:153-157 */
+
+/* Sequence view: 2-bit packed (A,C,G,T = 0..3, base i in bits 2*(i&3) of byte i>>2) or raw bytes */
+typedef struct { const uint8_t *p; int32_t bits; } cpg_seq;
+
+/* Per-warp scratch in global memory, sized for the longest profile of the batch */
+typedef struct
+  { uint32_t   *mark;     /* [P+2]   flags | (slot+1)<<8 per profile position 0..plen */
+    double     *perr;     /* [(P+2)*4] slot-major: [slot][etype][wtype] */
+    cpg_eintvl *eint;     /* [P+2] */
+    cpg_intvl  *intvl;    /* [P+2] */
+    cpg_intvl  *rint;     /* [MC]  reliable intervals (copy) */
+    cpg_intvl  *wint;     /* [MC]  DP working copy */
+    uint16_t   *bp;       /* [MC]  back pointers: 4 x 3 bits */
+    uint8_t    *asg_f;    /* [MC] */
+    uint8_t    *asg_b;    /* [MC] */
+    uint8_t    *rpos;     /* [MC] */
+    int32_t    *ord;      /* [P+2] */
+    uint8_t    *fixed;    /* [P+2] */
+  } cpg_scratch;
+
+/* Per-warp exchange block (shared memory on the device) */
+typedef struct
+  { double term[CPG_WARP > 16 ? CPG_WARP : 16];
+    int    iv[CPG_WARP > 16 ? CPG_WARP : 16];
+  } cpg_wshared;
+
+#endif

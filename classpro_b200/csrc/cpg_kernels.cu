@@ -1,0 +1,577 @@
+/*******************************************************************************************
+ *  cpg_kernels.cu -- sm_100a kernels and the C ABI of libclasspro_b200.so.
+ *
+ *  Two kernels per batch, both persistent (grid = a multiple of the SM count, warps pull reads
+ *  from an atomic queue ordered longest read first, i.e. length-binned LPT scheduling):
+ *
+ *   k_decode    one warp per read: FastK profile bytes -> uint16 counts (cpg_decode.cuh).
+ *               Streaming, HBM bound: c + 2n bytes per read (c compressed bytes, n k-mers).
+ *   k_classify  one warp per read: candidate sweep over the counts, wall detection, reliable
+ *               interval DP, unreliable intervals, class string (cpg_wall/rel/unrel.cuh).
+ *               Reads 2n + ~r/4 bytes, writes r bytes; bound by FP64 latency (Bessel
+ *               recurrences) and serial control flow, not by bandwidth.
+ *
+ *  No tensor cores: nothing on this path is a dense contraction (integer/byte scans and scalar
+ *  FP64 recurrences).  Compiled with -fmad=false: see cpg_math.cuh.
+ *******************************************************************************************/
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include "../../include/classpro_gpu.h"
+#include "cpg_unrel.cuh"
+#include "cpg_decode.cuh"
+
+#define DECODE_THREADS   256
+#define CLASSIFY_THREADS 128
+#define CLASSIFY_MIN_BLOCKS 4
+
+struct BatchDev
+  { int32_t        n_reads;
+    int32_t        seq_bits;
+    const uint8_t *seq;
+    const int64_t *seq_off;
+    const int32_t *rlen;
+    const uint8_t *prof;
+    const int64_t *prof_off;
+    uint16_t      *cnt;
+    const int64_t *cnt_off;
+    int32_t       *plen;
+    uint8_t       *cls;
+    const int64_t *cls_off;
+    int32_t       *status;
+    const int32_t *order;
+    int32_t       *queue;        /* [2] work counters: decode, classify */
+  };
+
+struct ScratchDev
+  { uint8_t *base;
+    size_t   stride;             /* bytes per warp */
+    int32_t  P;                  /* longest profile the layout is sized for */
+    int32_t  MC;                 /* reliable-interval capacity */
+  };
+
+static inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x+a-1)/a*a; }
+
+/* layout of one warp's scratch; must match scratch_stride() */
+__host__ __device__ static inline size_t scratch_layout(int P, int MC, size_t off[12])
+{ size_t o = 0;
+  off[0]  = o; o = align_up(o+sizeof(uint32_t)*(size_t)(P+2),16);        /* mark  */
+  off[1]  = o; o = align_up(o+sizeof(double)*4*(size_t)(P+2),16);        /* perr  */
+  off[2]  = o; o = align_up(o+sizeof(cpg_eintvl)*(size_t)(P+2),16);      /* eint  */
+  off[3]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)(P+2),16);       /* intvl */
+  off[4]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)MC,16);          /* rint  */
+  off[5]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)MC,16);          /* wint  */
+  off[6]  = o; o = align_up(o+sizeof(uint16_t)*(size_t)MC,16);           /* bp    */
+  off[7]  = o; o = align_up(o+(size_t)MC,16);                            /* asg_f */
+  off[8]  = o; o = align_up(o+(size_t)MC,16);                            /* asg_b */
+  off[9]  = o; o = align_up(o+(size_t)MC,16);                            /* rpos  */
+  off[10] = o; o = align_up(o+sizeof(int32_t)*(size_t)(P+2),16);         /* ord   */
+  off[11] = o; o = align_up(o+(size_t)(P+2),16);                         /* fixed */
+  return align_up(o,256);
+}
+
+__device__ __forceinline__ int next_read(int32_t *counter, int lane)
+{ int r = 0;
+  if (lane == 0) r = atomicAdd(counter,1);
+  return __shfl_sync(0xffffffffu,r,0);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(DECODE_THREADS)
+k_decode(BatchDev B, int K)
+{ __shared__ int s_offs[DECODE_THREADS/32][2*CPG_WARP];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (;;)
+    { int q = next_read(B.queue+0,lane);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      const int64_t po = B.prof_off[r];
+      const int64_t len = B.prof_off[r+1]-po;
+      const int cap = B.rlen[r]-K+1;
+      int n = decode_profile(B.prof+po,len,B.cnt+B.cnt_off[r],cap,lane,s_offs[wib]);
+      if (lane == 0)
+        { B.plen[r] = n;
+          B.status[r] = (n == cap) ? CPG_ST_OK : CPG_ST_BAD_PROFILE;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+struct ClassifyShared
+  { uint8_t     cthres[CPG_LROWS*256*4];
+    cpg_dmodel  model;
+    cpg_wshared ws[CLASSIFY_THREADS/32];
+    RelShared   rel[CLASSIFY_THREADS/32];
+  };
+
+__global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
+k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
+{ extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClassifyShared &sh = *reinterpret_cast<ClassifyShared *>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+
+  for (int i = threadIdx.x; i < CPG_LROWS*256; i += blockDim.x)
+    reinterpret_cast<uint32_t *>(sh.cthres)[i] = reinterpret_cast<const uint32_t *>(M.cthres)[i];
+  if (threadIdx.x == 0) sh.model = M;
+  __syncthreads();
+
+  const size_t gw = (size_t)blockIdx.x*(CLASSIFY_THREADS/32)+wib;
+  uint8_t *sb = SC.base+gw*SC.stride;
+  size_t off[12];
+  scratch_layout(SC.P,SC.MC,off);
+
+  for (;;)
+    { int q = next_read(B.queue+1,lane);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      if (B.status[r] != CPG_ST_OK) continue;          /* undecodable profile: left to the host */
+      const int rlen = B.rlen[r], plen = rlen-M.K+1;
+      uint8_t *cls = B.cls+B.cls_off[r];
+      if (plen > SC.P) { if (lane == 0) B.status[r] = CPG_ST_BAD_PROFILE; continue; }
+
+      WCtx W;
+      W.lane = lane; W.M = &sh.model; W.cthres = sh.cthres; W.ws = &sh.ws[wib]; W.status = 0;
+      ReadCtx R;
+      R.prof = B.cnt+B.cnt_off[r]; R.plen = plen; R.rlen = rlen;
+      R.seq.p = B.seq+B.seq_off[r]; R.seq.bits = B.seq_bits;
+      R.nslots = 0; R.N = 0; R.M = 0;
+      R.S.mark  = reinterpret_cast<uint32_t *>(sb+off[0]);
+      R.S.perr  = reinterpret_cast<double *>(sb+off[1]);
+      R.S.eint  = reinterpret_cast<cpg_eintvl *>(sb+off[2]);
+      R.S.intvl = reinterpret_cast<cpg_intvl *>(sb+off[3]);
+      R.S.rint  = reinterpret_cast<cpg_intvl *>(sb+off[4]);
+      R.S.wint  = reinterpret_cast<cpg_intvl *>(sb+off[5]);
+      R.S.bp    = reinterpret_cast<uint16_t *>(sb+off[6]);
+      R.S.asg_f = sb+off[7];
+      R.S.asg_b = sb+off[8];
+      R.S.rpos  = sb+off[9];
+      R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
+      R.S.fixed = sb+off[11];
+
+      int st = classify_read(R,W,&sh.rel[wib],cls);
+      st = __reduce_or_sync(0xffffffffu,st);
+      if (lane == 0) B.status[r] = st;
+      __syncwarp();
+    }
+}
+
+/* ==========================================================================================
+ *  C ABI
+ * ========================================================================================== */
+struct DevBuf { void *p; size_t cap; };
+
+struct Slot
+  { cudaStream_t stream;
+    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, plen, cls, cls_off, status, order, queue;
+    /* small host-side (pinned) staging for arrays the library computes itself */
+    int64_t *h_cnt_off; int32_t *h_order; size_t h_cap;
+    int32_t *h_status; size_t h_status_cap;
+    int32_t  n_reads; int64_t cls_bytes; int32_t maxP;
+    int      busy;
+    BatchDev B;
+  };
+
+struct cpg_ctx
+  { int        device;
+    cpg_model  model;
+    cpg_dmodel dmodel;
+    void      *d_cthres, *d_logfact;
+    Slot       slot[2];
+    DevBuf     scratch; ScratchDev SC;
+    int        n_sm, decode_blocks, classify_blocks;
+    size_t     classify_smem;
+    cudaEvent_t ev[3];
+    char       err[512];
+  };
+
+static char g_err[512] = "";
+
+static int set_err(cpg_ctx *c, int code, const char *fmt, ...)
+{ va_list ap; va_start(ap,fmt);
+  vsnprintf(c ? c->err : g_err,512,fmt,ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+  return set_err(ctx,CPG_ECUDA,"%s failed: %s (%s:%d)",#call,cudaGetErrorString(e__),__FILE__,__LINE__); } while (0)
+
+static int reserve(cpg_ctx *ctx, DevBuf *b, size_t bytes)
+{ if (bytes <= b->cap) return CPG_OK;
+  if (b->p) { cudaFree(b->p); b->p = NULL; b->cap = 0; }
+  size_t want = bytes+bytes/4+256;
+  cudaError_t e = cudaMalloc(&b->p,want);
+  if (e != cudaSuccess)
+    return set_err(ctx,CPG_ENOMEM,"cudaMalloc(%zu) failed: %s",want,cudaGetErrorString(e));
+  b->cap = want;
+  return CPG_OK;
+}
+
+extern "C" const char *cpg_version(void) { return "classpro_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *cpg_last_error(const cpg_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" int cpg_device_count(void)
+{ int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" const char *cpg_status_string(int32_t st)
+{ if (st == 0) return "ok";
+  if (st & CPG_ST_BAD_PROFILE) return "profile length != read length - K + 1";
+  if (st & CPG_ST_EINTVL_OVF)  return "# E-intvls >= plen";
+  if (st & CPG_ST_NO_PROB)     return "no valid probability for an interval";
+  if (st & CPG_ST_INTERP)      return "invalid points for interpolation";
+  if (st & CPG_ST_BINOM)       return "k > n in a binomial";
+  if (st & CPG_ST_UNDEF_TRACE) return "all DP states impossible (reference behaviour undefined)";
+  if (st & 128)                return "profile[plen] read (reference reads stale memory)";
+  return "unknown";
+}
+
+/* fatal = conditions on which the reference exits */
+#define CPG_ST_FATAL (CPG_ST_BAD_PROFILE|CPG_ST_EINTVL_OVF|CPG_ST_NO_PROB|CPG_ST_INTERP|CPG_ST_BINOM)
+
+extern "C" void cpg_destroy(cpg_ctx *ctx)
+{ if (ctx == NULL) return;
+  cudaSetDevice(ctx->device);
+  for (int s = 0; s < 2; s++)
+    { Slot *S = &ctx->slot[s];
+      DevBuf *bufs[] = { &S->seq,&S->seq_off,&S->rlen,&S->prof,&S->prof_off,&S->cnt,&S->cnt_off,&S->plen,
+                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue };
+      for (unsigned i = 0; i < sizeof(bufs)/sizeof(bufs[0]); i++) if (bufs[i]->p) cudaFree(bufs[i]->p);
+      if (S->h_cnt_off) cudaFreeHost(S->h_cnt_off);
+      if (S->h_order) cudaFreeHost(S->h_order);
+      if (S->h_status) cudaFreeHost(S->h_status);
+      if (S->stream) cudaStreamDestroy(S->stream);
+    }
+  if (ctx->scratch.p) cudaFree(ctx->scratch.p);
+  if (ctx->d_cthres) cudaFree(ctx->d_cthres);
+  if (ctx->d_logfact) cudaFree(ctx->d_logfact);
+  for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  free(ctx);
+}
+
+extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
+                          int64_t max_batch_bases, int32_t max_batch_reads)
+{ (void)max_batch_bases; (void)max_batch_reads;     /* buffers grow on demand */
+  cpg_ctx *ctx = NULL;
+  if (out == NULL || model == NULL) return set_err(NULL,CPG_EINVAL,"cpg_create: NULL argument");
+  *out = NULL;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return set_err(NULL,CPG_ECUDA,"no CUDA device available (%s): this library has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return set_err(NULL,CPG_EINVAL,"device %d out of range [0,%d)",device,ndev);
+  if (model->kmer < 4 || model->kmer > 4096 || model->read_len <= 0 || model->cmax < 1 || model->cmax > 255)
+    return set_err(NULL,CPG_EINVAL,"cpg_create: implausible model (kmer=%d read_len=%d cmax=%d)",
+                   model->kmer,model->read_len,model->cmax);
+  ctx = (cpg_ctx *)calloc(1,sizeof(cpg_ctx));
+  if (ctx == NULL) return set_err(NULL,CPG_ENOMEM,"out of host memory");
+  ctx->device = device;
+  ctx->model = *model;
+#define CU_C(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+    set_err(NULL,CPG_ECUDA,"%s failed: %s",#call,cudaGetErrorString(e__)); cpg_destroy(ctx); return CPG_ECUDA; } } while (0)
+  CU_C(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_C(cudaGetDeviceProperties(&prop,device));
+  ctx->n_sm = prop.multiProcessorCount;
+  CU_C(cudaMalloc(&ctx->d_cthres,sizeof(model->cthres)));
+  CU_C(cudaMalloc(&ctx->d_logfact,sizeof(model->logfact)));
+  CU_C(cudaMemcpy(ctx->d_cthres,model->cthres,sizeof(model->cthres),cudaMemcpyHostToDevice));
+  CU_C(cudaMemcpy(ctx->d_logfact,model->logfact,sizeof(model->logfact),cudaMemcpyHostToDevice));
+  cpg_dmodel &d = ctx->dmodel;
+  d.K = model->kmer; d.read_len = model->read_len; d.cmax = model->cmax;
+  for (int t = 0; t < 3; t++) d.lmax[t] = model->lmax[t];
+  for (int s = 0; s < 4; s++) d.cov[s] = model->cov[s];
+  d.dr_ratio = model->dr_ratio; d.hc_erate = model->hc_erate;
+  memcpy(d.pe,model->pe,sizeof(d.pe));
+  d.cthres = (const uint8_t *)ctx->d_cthres;
+  d.logfact = (const double *)ctx->d_logfact;
+  for (int s = 0; s < 2; s++) CU_C(cudaStreamCreateWithFlags(&ctx->slot[s].stream,cudaStreamNonBlocking));
+  for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->ev[i]));
+
+  ctx->classify_smem = sizeof(ClassifyShared);
+  CU_C(cudaFuncSetAttribute(k_classify,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->classify_smem));
+  int occ = 0;
+  CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,k_classify,CLASSIFY_THREADS,ctx->classify_smem));
+  if (occ < 1) occ = 1;
+  ctx->classify_blocks = ctx->n_sm*occ;
+  CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,k_decode,DECODE_THREADS,0));
+  if (occ < 1) occ = 1;
+  ctx->decode_blocks = ctx->n_sm*occ;
+#undef CU_C
+  *out = ctx;
+  return CPG_OK;
+}
+
+/* scratch arena for the persistent classify warps */
+static int ensure_scratch(cpg_ctx *ctx, int P)
+{ if (ctx->scratch.p && P <= ctx->SC.P) return CPG_OK;
+  size_t off[12];
+  int MC = P/ctx->model.kmer+8;
+  size_t stride = scratch_layout(P,MC,off);
+  size_t warps = (size_t)ctx->classify_blocks*(CLASSIFY_THREADS/32);
+  for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->slot[s].stream);
+  int rc = reserve(ctx,&ctx->scratch,stride*warps);
+  if (rc) return rc;
+  ctx->SC.base = (uint8_t *)ctx->scratch.p; ctx->SC.stride = stride; ctx->SC.P = P; ctx->SC.MC = MC;
+  return CPG_OK;
+}
+
+static int host_reserve(cpg_ctx *ctx, Slot *S, int n)
+{ if ((size_t)n+1 <= S->h_cap) return CPG_OK;
+  if (S->h_cnt_off) cudaFreeHost(S->h_cnt_off);
+  if (S->h_order) cudaFreeHost(S->h_order);
+  if (S->h_status) cudaFreeHost(S->h_status);
+  S->h_cnt_off = NULL; S->h_order = NULL; S->h_status = NULL; S->h_cap = 0;
+  size_t cap = (size_t)n+n/4+64;
+  CU(cudaHostAlloc((void **)&S->h_cnt_off,sizeof(int64_t)*cap,cudaHostAllocDefault));
+  CU(cudaHostAlloc((void **)&S->h_order,sizeof(int32_t)*cap,cudaHostAllocDefault));
+  CU(cudaHostAlloc((void **)&S->h_status,sizeof(int32_t)*cap,cudaHostAllocDefault));
+  S->h_cap = cap;
+  return CPG_OK;
+}
+
+/* Validate a batch, derive count offsets and the longest-first order, upload everything. */
+static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t *cls_off)
+{ const int n = b->n_reads, K = ctx->model.kmer;
+  if (n < 0 || (n > 0 && (!b->seq || !b->seq_off || !b->rlen || !b->prof || !b->prof_off)))
+    return set_err(ctx,CPG_EINVAL,"cpg_batch: NULL array");
+  if (b->seq_bits != 2 && b->seq_bits != 8) return set_err(ctx,CPG_EINVAL,"cpg_batch: seq_bits must be 2 or 8");
+  int rc = host_reserve(ctx,S,n);
+  if (rc) return rc;
+  int64_t co = 0; int maxP = 1; int maxR = 0;
+  for (int i = 0; i < n; i++)
+    { const int rl = b->rlen[i];
+      if (rl < K || rl > CPG_MAX_RLEN)
+        return set_err(ctx,CPG_EINVAL,"read %d of the batch: rlen %d outside [K=%d,%d]",i,rl,K,CPG_MAX_RLEN);
+      const int64_t need = (b->seq_bits == 2) ? (rl+3)/4 : rl;
+      if (b->seq_off[i+1]-b->seq_off[i] < need || b->prof_off[i+1] < b->prof_off[i])
+        return set_err(ctx,CPG_EINVAL,"read %d of the batch: inconsistent offsets",i);
+      S->h_cnt_off[i] = co;
+      co += (rl-K+1+7) & ~7;
+      if (rl-K+1 > maxP) maxP = rl-K+1;
+      if (rl > maxR) maxR = rl;
+    }
+  S->h_cnt_off[n] = co;
+  /* counting sort by length, longest first */
+  { int *bucket = (int *)calloc((size_t)maxR+2,sizeof(int));
+    if (bucket == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
+    for (int i = 0; i < n; i++) bucket[maxR-b->rlen[i]+1]++;
+    for (int l = 1; l <= maxR+1; l++) bucket[l] += bucket[l-1];
+    for (int i = 0; i < n; i++) S->h_order[bucket[maxR-b->rlen[i]]++] = i;
+    free(bucket);
+  }
+  rc = ensure_scratch(ctx,maxP);
+  if (rc) return rc;
+
+  const size_t seq_bytes = n ? (size_t)b->seq_off[n] : 0, prof_bytes = n ? (size_t)b->prof_off[n] : 0;
+  const size_t cls_bytes = n ? (size_t)cls_off[n] : 0;
+  if ((rc = reserve(ctx,&S->seq,seq_bytes+16)) || (rc = reserve(ctx,&S->seq_off,sizeof(int64_t)*(n+1)))
+      || (rc = reserve(ctx,&S->rlen,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->prof,prof_bytes+16))
+      || (rc = reserve(ctx,&S->prof_off,sizeof(int64_t)*(n+1))) || (rc = reserve(ctx,&S->cnt,sizeof(uint16_t)*(size_t)co+16))
+      || (rc = reserve(ctx,&S->cnt_off,sizeof(int64_t)*(n+1))) || (rc = reserve(ctx,&S->plen,sizeof(int32_t)*(n+1)))
+      || (rc = reserve(ctx,&S->cls,cls_bytes+16)) || (rc = reserve(ctx,&S->cls_off,sizeof(int64_t)*(n+1)))
+      || (rc = reserve(ctx,&S->status,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->order,sizeof(int32_t)*(n+1)))
+      || (rc = reserve(ctx,&S->queue,sizeof(int32_t)*4)))
+    return rc;
+  cudaStream_t st = S->stream;
+  if (n > 0)
+    { CU(cudaMemcpyAsync(S->seq.p,b->seq,seq_bytes,cudaMemcpyHostToDevice,st));
+      CU(cudaMemcpyAsync(S->seq_off.p,b->seq_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+      CU(cudaMemcpyAsync(S->rlen.p,b->rlen,sizeof(int32_t)*n,cudaMemcpyHostToDevice,st));
+      CU(cudaMemcpyAsync(S->prof.p,b->prof,prof_bytes,cudaMemcpyHostToDevice,st));
+      CU(cudaMemcpyAsync(S->prof_off.p,b->prof_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+      CU(cudaMemcpyAsync(S->cnt_off.p,S->h_cnt_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+      CU(cudaMemcpyAsync(S->cls_off.p,cls_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+      CU(cudaMemcpyAsync(S->order.p,S->h_order,sizeof(int32_t)*n,cudaMemcpyHostToDevice,st));
+    }
+  S->n_reads = n; S->cls_bytes = (int64_t)cls_bytes; S->maxP = maxP;
+  BatchDev &B = S->B;
+  B.n_reads = n; B.seq_bits = b->seq_bits;
+  B.seq = (const uint8_t *)S->seq.p; B.seq_off = (const int64_t *)S->seq_off.p;
+  B.rlen = (const int32_t *)S->rlen.p; B.prof = (const uint8_t *)S->prof.p;
+  B.prof_off = (const int64_t *)S->prof_off.p; B.cnt = (uint16_t *)S->cnt.p;
+  B.cnt_off = (const int64_t *)S->cnt_off.p; B.plen = (int32_t *)S->plen.p;
+  B.cls = (uint8_t *)S->cls.p; B.cls_off = (const int64_t *)S->cls_off.p;
+  B.status = (int32_t *)S->status.p; B.order = (const int32_t *)S->order.p;
+  B.queue = (int32_t *)S->queue.p;
+  return CPG_OK;
+}
+
+static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
+{ cudaStream_t st = S->stream;
+  if (S->n_reads == 0) return CPG_OK;
+  CU(cudaMemsetAsync(S->queue.p,0,sizeof(int32_t)*4,st));
+  if (timed) CU(cudaEventRecord(ctx->ev[0],st));
+  k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(S->B,ctx->model.kmer);
+  if (timed) CU(cudaEventRecord(ctx->ev[1],st));
+  k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+  if (timed) CU(cudaEventRecord(ctx->ev[2],st));
+  CU(cudaGetLastError());
+  return CPG_OK;
+}
+
+static int fetch_result(cpg_ctx *ctx, Slot *S, cpg_result *res)
+{ cudaStream_t st = S->stream;
+  const int n = S->n_reads;
+  if (n > 0)
+    { CU(cudaMemcpyAsync(res->cls,S->cls.p,(size_t)S->cls_bytes,cudaMemcpyDeviceToHost,st));
+      CU(cudaMemcpyAsync(S->h_status,S->status.p,sizeof(int32_t)*n,cudaMemcpyDeviceToHost,st));
+    }
+  CU(cudaStreamSynchronize(st));
+  int bad = 0;
+  for (int i = 0; i < n; i++)
+    { if (res->status) res->status[i] = S->h_status[i];
+      if (S->h_status[i] & CPG_ST_FATAL)
+        { if (!bad) set_err(ctx,CPG_EREAD,"read %d of the batch: %s",i,cpg_status_string(S->h_status[i]));
+          bad = 1;
+        }
+    }
+  return bad ? CPG_EREAD : CPG_OK;
+}
+
+extern "C" int cpg_submit(cpg_ctx *ctx, int slot, const cpg_batch *batch)
+{ if (ctx == NULL || batch == NULL || slot < 0 || slot > 1) return set_err(ctx,CPG_EINVAL,"cpg_submit: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  Slot *S = &ctx->slot[slot];
+  if (S->busy) return set_err(ctx,CPG_EINVAL,"cpg_submit: slot %d not collected",slot);
+  /* class offsets default to the prefix sums of rlen; the caller's cpg_result must match */
+  int rc = host_reserve(ctx,S,batch->n_reads);
+  if (rc) return rc;
+  static thread_local int64_t *tmp = NULL; static thread_local size_t tmp_cap = 0;
+  if ((size_t)batch->n_reads+1 > tmp_cap)
+    { free(tmp); tmp_cap = (size_t)batch->n_reads+1024; tmp = (int64_t *)malloc(sizeof(int64_t)*tmp_cap);
+      if (tmp == NULL) { tmp_cap = 0; return set_err(ctx,CPG_ENOMEM,"out of host memory"); }
+    }
+  tmp[0] = 0;
+  for (int i = 0; i < batch->n_reads; i++) tmp[i+1] = tmp[i]+batch->rlen[i];
+  rc = stage_batch(ctx,S,batch,tmp);
+  if (rc) return rc;
+  /* the offsets buffer is consumed by an async copy from pageable memory, which CUDA stages
+     before returning, so reusing tmp on the next call is safe */
+  rc = launch_kernels(ctx,S,0);
+  if (rc) return rc;
+  S->busy = 1;
+  return CPG_OK;
+}
+
+extern "C" int cpg_collect(cpg_ctx *ctx, int slot, cpg_result *res)
+{ if (ctx == NULL || res == NULL || slot < 0 || slot > 1) return set_err(ctx,CPG_EINVAL,"cpg_collect: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  Slot *S = &ctx->slot[slot];
+  if (!S->busy) return set_err(ctx,CPG_EINVAL,"cpg_collect: slot %d has no batch in flight",slot);
+  S->busy = 0;
+  if (res->cls == NULL && S->cls_bytes > 0) return set_err(ctx,CPG_EINVAL,"cpg_result.cls is NULL");
+  if (res->cls_off && (res->cls_off[0] != 0 || res->cls_off[S->n_reads] != S->cls_bytes))
+    return set_err(ctx,CPG_EINVAL,"cpg_result.cls_off must be the prefix sums of rlen");
+  return fetch_result(ctx,S,res);
+}
+
+extern "C" int cpg_classify(cpg_ctx *ctx, const cpg_batch *batch, cpg_result *res)
+{ int rc = cpg_submit(ctx,0,batch);
+  if (rc) return rc;
+  return cpg_collect(ctx,0,res);
+}
+
+extern "C" int cpg_upload(cpg_ctx *ctx, const cpg_batch *batch)
+{ if (ctx == NULL || batch == NULL) return set_err(ctx,CPG_EINVAL,"cpg_upload: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  Slot *S = &ctx->slot[0];
+  int64_t *tmp = (int64_t *)malloc(sizeof(int64_t)*((size_t)batch->n_reads+1));
+  if (tmp == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
+  tmp[0] = 0;
+  for (int i = 0; i < batch->n_reads; i++) tmp[i+1] = tmp[i]+batch->rlen[i];
+  int rc = stage_batch(ctx,S,batch,tmp);
+  if (rc == CPG_OK && cudaStreamSynchronize(S->stream) != cudaSuccess)
+    rc = set_err(ctx,CPG_ECUDA,"upload failed: %s",cudaGetErrorString(cudaGetLastError()));
+  free(tmp);
+  return rc;
+}
+
+extern "C" int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float *ms_classify, int *launches)
+{ if (ctx == NULL || iters < 1) return set_err(ctx,CPG_EINVAL,"cpg_run_resident: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  Slot *S = &ctx->slot[0];
+  double td = 0., tc = 0.;
+  for (int it = 0; it < iters; it++)
+    { int rc = launch_kernels(ctx,S,1);
+      if (rc) return rc;
+      CU(cudaStreamSynchronize(S->stream));
+      float a = 0.f, b = 0.f;
+      if (S->n_reads > 0)
+        { CU(cudaEventElapsedTime(&a,ctx->ev[0],ctx->ev[1]));
+          CU(cudaEventElapsedTime(&b,ctx->ev[1],ctx->ev[2]));
+        }
+      td += a; tc += b;
+    }
+  if (ms_decode) *ms_decode = (float)(td/iters);
+  if (ms_classify) *ms_classify = (float)(tc/iters);
+  if (launches) *launches = 2*iters;
+  return CPG_OK;
+}
+
+extern "C" int cpg_download(cpg_ctx *ctx, cpg_result *res)
+{ if (ctx == NULL || res == NULL) return set_err(ctx,CPG_EINVAL,"cpg_download: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  return fetch_result(ctx,&ctx->slot[0],res);
+}
+
+extern "C" int cpg_decode_profiles(cpg_ctx *ctx, int32_t n, const uint8_t *prof, const int64_t *prof_off,
+                                   const int64_t *cnt_off, uint16_t *counts, int32_t *plen)
+{ if (ctx == NULL || n < 0 || (n > 0 && (!prof || !prof_off || !cnt_off || !counts || !plen)))
+    return set_err(ctx,CPG_EINVAL,"cpg_decode_profiles: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) return CPG_OK;
+  Slot *S = &ctx->slot[0];
+  if (S->busy) return set_err(ctx,CPG_EINVAL,"cpg_decode_profiles: slot 0 busy");
+  const int K = ctx->model.kmer;
+  int rc = host_reserve(ctx,S,n);
+  if (rc) return rc;
+  const size_t prof_bytes = (size_t)prof_off[n], cnt_n = (size_t)cnt_off[n];
+  int32_t *rl = (int32_t *)malloc(sizeof(int32_t)*(size_t)n);
+  if (rl == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
+  for (int i = 0; i < n; i++) { rl[i] = (int32_t)(cnt_off[i+1]-cnt_off[i])+K-1; S->h_order[i] = i; }
+  if ((rc = reserve(ctx,&S->prof,prof_bytes+16)) || (rc = reserve(ctx,&S->prof_off,sizeof(int64_t)*(n+1)))
+      || (rc = reserve(ctx,&S->cnt,sizeof(uint16_t)*cnt_n+16)) || (rc = reserve(ctx,&S->cnt_off,sizeof(int64_t)*(n+1)))
+      || (rc = reserve(ctx,&S->rlen,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->plen,sizeof(int32_t)*(n+1)))
+      || (rc = reserve(ctx,&S->status,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->order,sizeof(int32_t)*(n+1)))
+      || (rc = reserve(ctx,&S->queue,sizeof(int32_t)*4)))
+    { free(rl); return rc; }
+  cudaStream_t st = S->stream;
+  BatchDev B; memset(&B,0,sizeof(B));
+  B.n_reads = n; B.prof = (const uint8_t *)S->prof.p; B.prof_off = (const int64_t *)S->prof_off.p;
+  B.cnt = (uint16_t *)S->cnt.p; B.cnt_off = (const int64_t *)S->cnt_off.p; B.rlen = (const int32_t *)S->rlen.p;
+  B.plen = (int32_t *)S->plen.p; B.status = (int32_t *)S->status.p; B.order = (const int32_t *)S->order.p;
+  B.queue = (int32_t *)S->queue.p;
+  cudaError_t e = cudaSuccess;
+#define TRY(x) if (e == cudaSuccess) e = (x)
+  TRY(cudaMemcpyAsync(S->prof.p,prof,prof_bytes,cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->prof_off.p,prof_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->cnt_off.p,cnt_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->rlen.p,rl,sizeof(int32_t)*n,cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->order.p,S->h_order,sizeof(int32_t)*n,cudaMemcpyHostToDevice,st));
+  TRY(cudaMemsetAsync(S->queue.p,0,sizeof(int32_t)*4,st));
+  TRY(cudaMemsetAsync(S->cnt.p,0,sizeof(uint16_t)*cnt_n,st));
+  if (e == cudaSuccess) k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(B,K);
+  TRY(cudaGetLastError());
+  TRY(cudaMemcpyAsync(counts,S->cnt.p,sizeof(uint16_t)*cnt_n,cudaMemcpyDeviceToHost,st));
+  TRY(cudaMemcpyAsync(plen,S->plen.p,sizeof(int32_t)*n,cudaMemcpyDeviceToHost,st));
+  TRY(cudaStreamSynchronize(st));
+#undef TRY
+  free(rl);
+  if (e != cudaSuccess) return set_err(ctx,CPG_ECUDA,"cpg_decode_profiles: %s",cudaGetErrorString(e));
+  return CPG_OK;
+}
+
+/* pinned host memory for callers that want true asynchronous copies */
+extern "C" void *cpg_host_alloc(size_t bytes)
+{ void *p = NULL;
+  if (cudaHostAlloc(&p,bytes ? bytes : 1,cudaHostAllocDefault) != cudaSuccess) return NULL;
+  return p;
+}
+extern "C" void cpg_host_free(void *p) { if (p) cudaFreeHost(p); }

@@ -1,0 +1,172 @@
+/*******************************************************************************************
+ *  cpg_math.cuh -- FP64 primitives of the classification path, device side.
+ *
+ *  Replaces src/bessel.c:390-521 (bessi0/bessi1/bessi), src/prob.c:22-112 and src/util.c:9-55.
+ *  Every expression keeps the reference's operation order; the translation unit is compiled with
+ *  -fmad=false so that no multiply-add is contracted (gcc emits none for baseline x86-64), and
+ *  +,-,*,/,sqrt are IEEE-754 correctly rounded on both sides.  exp/log come from the CUDA math
+ *  library (<= 1 ulp) where the reference uses glibc; DESIGN.md "Floating-point parity" covers the
+ *  consequences.
+ *******************************************************************************************/
+#ifndef CPG_MATH_CUH
+#define CPG_MATH_CUH
+#include "cpg_common.h"
+
+/* Warp context: the same values in every lane except `lane` */
+struct WCtx
+  { int               lane;
+    const cpg_dmodel *M;
+    const uint8_t    *cthres;    /* shared-memory copy of M->cthres (or M->cthres itself) */
+    cpg_wshared      *ws;
+    int               status;
+  };
+
+CPG_DEV double cpg_exp(double x) { return exp(x); }
+CPG_DEV double cpg_log(double x) { return log(x); }
+
+CPG_DEV int imin(int a, int b) { return a < b ? a : b; }
+CPG_DEV int imax(int a, int b) { return a > b ? a : b; }
+/* the reference's MAX macro on doubles: (x) > (y) ? (x) : (y) */
+CPG_DEV double dmax_ref(double x, double y) { return x > y ? x : y; }
+
+/* src/bessel.c:390-411 */
+CPG_DEV double cpg_bessi0(double x)
+{ double ax = fabs(x), y, ans;
+  if (ax < 3.75)
+    { y = x/3.75; y = y*y;
+      ans = 1.0+y*(3.5156229+y*(3.0899424+y*(1.2067492+y*(0.2659732+y*(0.360768e-1+y*0.45813e-2)))));
+    }
+  else
+    { y = 3.75/ax;
+      ans = (cpg_exp(ax)/sqrt(ax))*(0.39894228+y*(0.1328592e-1+y*(0.225319e-2+y*(-0.157565e-2
+            +y*(0.916281e-2+y*(-0.2057706e-1+y*(0.2635537e-1+y*(-0.1647633e-1+y*0.392377e-2))))))));
+    }
+  return ans;
+}
+
+/* src/bessel.c:416-439 */
+CPG_DEV double cpg_bessi1(double x)
+{ double ax = fabs(x), y, ans;
+  if (ax < 3.75)
+    { y = x/3.75; y = y*y;
+      ans = ax*(0.5+y*(0.87890594+y*(0.51498869+y*(0.15084934+y*(0.2658733e-1+y*(0.301532e-2
+            +y*0.32411e-3))))));
+    }
+  else
+    { y = 3.75/ax;
+      ans = 0.2282967e-1+y*(-0.2895312e-1+y*(0.1787654e-1-y*0.420059e-2));
+      ans = 0.39894228+y*(-0.3988024e-1+y*(-0.362018e-2+y*(0.163801e-2+y*(-0.1031555e-1+y*ans))));
+      ans *= (cpg_exp(ax)/sqrt(ax));
+    }
+  return x < 0.0 ? -ans : ans;
+}
+
+/* src/bessel.c:482-521: Miller downward recurrence started at 2*(n+floor(sqrt(40 n))), rescaled by
+ * 1e-10 whenever |bi| passes 1e10, normalised with I0 */
+CPG_DEV_NOINL double cpg_bessi(int n, double x)
+{ if (n == 0) return cpg_bessi0(x);
+  if (n == 1) return cpg_bessi1(x);
+  if (x == 0.0) return 0.0;
+  double tox = 2.0/fabs(x), bip = 0.0, ans = 0.0, bi = 1.0, bim;
+  for (int j = 2*(n+(int)sqrt(40.0*n)); j > 0; j--)
+    { bim = bip+j*tox*bi;
+      bip = bi;
+      bi = bim;
+      if (fabs(bi) > 1.0e10)
+        { ans *= 1.0e-10; bi *= 1.0e-10; bip *= 1.0e-10; }
+      if (j == n) ans = bip;
+    }
+  ans *= cpg_bessi0(x)/bi;
+  return (x < 0.0 && (n%2) == 1) ? -ans : ans;
+}
+
+/* src/prob.c:22-31: counts above 32767 are clamped (the reference also prints a note) */
+CPG_DEV int cpg_clamp_cnt(int n) { return n > CPG_MAX_CNT ? CPG_MAX_CNT : n; }
+
+/* src/prob.c:33-39 */
+CPG_DEV double cpg_lp_poisson(const WCtx &W, uint16_t k16, int lambda)
+{ int k = cpg_clamp_cnt(k16);
+  return k*cpg_log((double)lambda)-lambda-CPG_LDG(W.M->logfact+k);
+}
+
+/* src/prob.c:41-44 */
+CPG_DEV double cpg_lp_skellam(int k, double lambda)
+{ return -2.*lambda+cpg_log(cpg_bessi(k < 0 ? -k : k,2.*lambda)); }
+
+/* src/util.c:35-44; `cov` is a 16-bit count in the reference's signature */
+CPG_DEV double cpg_lp_trans(const WCtx &W, int b, int e, int cb, int ce, uint16_t cov)
+{ int d = e-b; if (d < 0) d = -d;
+  return cpg_lp_skellam(ce-cb,(double)cov*d/W.M->read_len);
+}
+
+/* src/prob.c:59-65 */
+CPG_DEV double cpg_lp_binom(WCtx &W, uint16_t k16, uint16_t n16, double p)
+{ int k = cpg_clamp_cnt(k16), n = cpg_clamp_cnt(n16);
+  if (k > n) { W.status |= CPG_ST_BINOM; return -CPG_INF; }
+  const double *lf = W.M->logfact;
+  return CPG_LDG(lf+n)-CPG_LDG(lf+k)-CPG_LDG(lf+(n-k))+k*cpg_log(p)+(n-k)*cpg_log(1-p);
+}
+
+/* src/prob.c:76-112 with exact = false: one-sided binomial tail summed in the reference's order
+ * and cut after the first term below a tenth of the first one.  The lanes evaluate CPG_WARP
+ * consecutive terms at a time (the exp() calls); the running sum is then formed serially in the
+ * reference's order from the shared term buffer, so the rounding sequence is unchanged. */
+CPG_DEV_NOINL double cpg_binom_tail(WCtx &W, int k, int n, double pe)
+{ k = cpg_clamp_cnt(k & 0xffff); n = cpg_clamp_cnt(n & 0xffff);
+  if (k > n) { W.status |= CPG_ST_BINOM; return 0.; }
+  const double *lf = W.M->logfact;
+  const double lpe = cpg_log(pe), l1mpe = cpg_log(1-pe), mean = n*pe;
+  const double lfn = CPG_LDG(lf+n);
+  double *term = W.ws->term;
+  double p, p_first;
+#define CPG_LBP(x) (lfn-CPG_LDG(lf+(x))-CPG_LDG(lf+(n-(x)))+(x)*lpe+(n-(x))*l1mpe)
+  if ((double)k >= mean)
+    { p = p_first = cpg_exp(CPG_LBP(k));
+      for (int x0 = k+1; x0 <= n; x0 += CPG_WARP)
+        { int x = x0+W.lane;
+          if (x <= n) term[W.lane] = cpg_exp(CPG_LBP(x));
+          CPG_SYNCWARP();
+          int cnt = imin(CPG_WARP,n-x0+1), stop = 0;
+          for (int l = 0; l < cnt; l++)
+            { double t = term[l];
+              p += t;
+              if (10*t < p_first) { stop = 1; break; }
+            }
+          CPG_SYNCWARP();
+          if (stop) break;
+        }
+    }
+  else
+    { p = p_first = (k == 0) ? 0. : cpg_exp(CPG_LBP(k-1));
+      for (int x0 = k-2; x0 >= 0; x0 -= CPG_WARP)
+        { int x = x0-W.lane;
+          if (x >= 0) term[W.lane] = cpg_exp(CPG_LBP(x));
+          CPG_SYNCWARP();
+          int cnt = imin(CPG_WARP,x0+1), stop = 0;
+          for (int l = 0; l < cnt; l++)
+            { double t = term[l];
+              p += t;
+              if (10*t < p_first) { stop = 1; break; }
+            }
+          CPG_SYNCWARP();
+          if (stop) break;
+        }
+      p = 1-p;
+    }
+#undef CPG_LBP
+  return p;
+}
+
+/* src/util.c:46-55 */
+CPG_DEV double cpg_p_errorin(WCtx &W, int etype, double erate, uint16_t cout, uint16_t cin)
+{ if (!(cin <= cout)) { W.status |= CPG_ST_BINOM; return 0.; }
+  return cpg_binom_tail(W,(etype == ET_SELF) ? cin : (uint16_t)(cout-cin),cout,erate);
+}
+
+/* src/util.c:24-33 */
+CPG_DEV double cpg_lin_interp(WCtx &W, int x, int p1, uint16_t c1, int p2, uint16_t c2)
+{ if (!(p1 < x && x < p2)) W.status |= CPG_ST_INTERP;
+  return (double)c1+((double)c2-c1)*(x-p1)/(p2-p1);
+}
+
+#endif

@@ -1,0 +1,163 @@
+/*******************************************************************************************
+ *  cpg_unrel.cuh -- classification of the remaining (unreliable) intervals of one read and the
+ *  whole per-read pipeline, one warp.
+ *
+ *  Replaces classify_unrel and everything under it (src/class_unrel.c:11-300) and the loop body
+ *  src/ClassPro.c:229-271 (context is evaluated on demand, see cpg_context.cuh).
+ *
+ *  The two sweeps are order dependent (an interval's new state is visible to the ones handled
+ *  after it, src/class_unrel.c:260-274) and stay serial; the stable sort by min(cb,ce) becomes a
+ *  lane-parallel rank computation with the interval index as tie break, which is the order
+ *  glibc's merge-sort qsort produces for the single-key comparator (src/class_unrel.c:244-246).
+ *******************************************************************************************/
+#ifndef CPG_UNREL_CUH
+#define CPG_UNREL_CUH
+#include "cpg_rel.cuh"
+
+/* src/class_unrel.c:11-25 */
+CPG_DEV void un_nn(int idx, int s, const cpg_intvl *v, int N, int &l, int &r)
+{ l = idx-1;
+  while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--;
+  if (l < 0) l = -1;
+  r = idx+1;
+  while (r < N && !(v[r].asgn == s && v[r].is_rel)) r++;
+  if (r >= N) r = -1;
+}
+
+/* src/class_unrel.c:27-51 */
+CPG_DEV uint16_t un_est_cov(WCtx &W, int x, int idx, const cpg_intvl *v, int N, int s)
+{ int l, r;
+  un_nn(idx,s,v,N,l,r);
+  if (l != -1 && r != -1) return (uint16_t)cpg_lin_interp(W,x,v[l].e-1,v[l].cce,v[r].b,v[r].ccb);
+  if (l != -1) return v[l].cce;
+  if (r != -1) return v[r].ccb;
+  /* nothing of state s around: fall back on the other state, once */
+  const int o = (s == ST_H) ? ST_D : ST_H;
+  uint16_t c;
+  un_nn(idx,o,v,N,l,r);
+  if (l != -1 && r != -1) c = (uint16_t)cpg_lin_interp(W,x,v[l].e-1,v[l].cce,v[r].b,v[r].ccb);
+  else if (l != -1) c = v[l].cce;
+  else if (r != -1) c = v[r].ccb;
+  else c = 0;
+  if (c > 0) return (uint16_t)((s == ST_H) ? c/2 : c*2);
+  return W.M->cov[s];
+}
+
+/* src/class_unrel.c:53-65 */
+CPG_DEV double un_lp_e(const WCtx &W, const cpg_intvl &I)
+{ const int ce = W.M->cov[ST_E];
+  double po = cpg_lp_poisson(W,I.cb,ce)+cpg_lp_poisson(W,I.ce,ce)+CPG_E_PO_BASE;
+  return dmax_ref(I.pe,po);
+}
+
+/* src/class_unrel.c:67-113 */
+CPG_DEV double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
+{ const cpg_intvl &I = v[idx];
+  const cpg_dmodel *M = W.M;
+  if (imax(I.cb,I.ce) >= M->cov[ST_R]) return 0.;
+  int l, r;
+  un_nn(idx,ST_D,v,N,l,r);
+  uint16_t dl, dr;
+  if (l == -1 && r == -1) dl = dr = M->cov[ST_D];
+  else if (l == -1) dl = dr = v[r].cb;
+  else if (r == -1) dl = dr = v[l].ce;
+  else { dl = v[l].ce; dr = v[r].cb; }
+  uint16_t rl = (uint16_t)(M->dr_ratio*dl), rr = (uint16_t)(M->dr_ratio*dr);
+  if (I.cb >= rl || I.ce >= rr) return CPG_R_LOGP;
+  double a = cpg_lp_binom(W,I.cb,rl,1-CPG_PE_MEAN);
+  double b = cpg_lp_binom(W,I.ce,rr,1-CPG_PE_MEAN);
+  return a+b;
+}
+
+/* src/class_unrel.c:115-175 */
+CPG_DEV_NOINL double un_lp_hd(WCtx &W, int s, int idx, const cpg_intvl *v, int N)
+{ const cpg_intvl I = v[idx];
+  int lrel, rrel;
+  un_nn(idx,s,v,N,lrel,rrel);
+  double lpl, lpr;
+  { double er = -CPG_INF, sf = -CPG_INF, sfer = -CPG_INF;
+    int l = idx-1;
+    if (l >= 0 && v[l].asgn == s) er = I.peob;
+    if (lrel != -1) sf = cpg_lp_trans(W,v[lrel].e-1,I.b,v[lrel].cce,I.cb,v[lrel].cce);
+    uint16_t est = un_est_cov(W,I.b,idx,v,N,s);
+    if (est >= I.cb) sfer = cpg_log(cpg_p_errorin(W,ET_OTHERS,0.1,est,I.cb));
+    lpl = dmax_ref(dmax_ref(er,sf),sfer);
+  }
+  { double er = -CPG_INF, sf = -CPG_INF, sfer = -CPG_INF;
+    int r = idx+1;
+    if (r < N && v[r].asgn == s) er = I.peoe;
+    if (rrel != -1) sf = cpg_lp_trans(W,I.e-1,v[rrel].b,I.ce,v[rrel].ccb,v[rrel].ccb);
+    uint16_t est = un_est_cov(W,I.e-1,idx,v,N,s);
+    if (est >= I.ce) sfer = cpg_log(cpg_p_errorin(W,ET_OTHERS,0.1,est,I.ce));
+    lpr = dmax_ref(dmax_ref(er,sf),sfer);
+  }
+  if (lpl == -CPG_INF && lpr == -CPG_INF)
+    { lpl = cpg_lp_poisson(W,I.cb,W.M->cov[s]); lpr = cpg_lp_poisson(W,I.ce,W.M->cov[s]); }
+  else if (lpl == -CPG_INF) lpl = lpr;
+  else if (lpr == -CPG_INF) lpr = lpl;
+  return lpl+lpr;
+}
+
+/* src/class_unrel.c:192-237 */
+CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N)
+{ const cpg_intvl I = v[idx];
+  int ns;
+  if (imax(I.cb,I.ce) >= W.M->cov[ST_R]) ns = ST_R;
+  else
+    { double mx = -CPG_INF; int ms = -1;
+      for (int s = ST_E; s <= ST_D; s++)
+        { double lp = (s == ST_E) ? un_lp_e(W,I)
+                    : (s == ST_R) ? un_lp_r(W,idx,v,N) : un_lp_hd(W,s,idx,v,N);
+          if (mx < lp) { mx = lp; ms = s; }
+        }
+      if (ms == -1) { W.status |= CPG_ST_NO_PROB; ms = ST_E; }
+      ns = ms;
+    }
+  CPG_SYNCWARP();
+  if (W.lane == 0 && I.asgn != ns) v[idx].asgn = (int8_t)ns;
+  CPG_SYNCWARP();
+}
+
+/* src/class_unrel.c:248-275 */
+CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
+{ cpg_intvl *v = R.S.intvl;
+  const int N = R.N;
+  int32_t *ord = R.S.ord;
+  uint8_t *fixed = R.S.fixed;
+  for (int i = W.lane; i < N; i += CPG_WARP)
+    { const int key = imin(v[i].cb,v[i].ce);
+      int rank = 0;
+      for (int j = 0; j < N; j++)
+        { int kj = imin(v[j].cb,v[j].ce);
+          rank += (kj < key) || (kj == key && j < i);
+        }
+      ord[rank] = i;
+      fixed[i] = (uint8_t)(v[i].is_rel && (v[i].asgn == ST_H || v[i].asgn == ST_D));
+    }
+  CPG_SYNCWARP();
+  for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
+  for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
+}
+
+/* ---- the whole read: src/ClassPro.c:229-271 ---- */
+CPG_DEV_NOINL int classify_read(ReadCtx &R, WCtx &W, RelShared *sh, uint8_t *cls)
+{ const int K = W.M->K;
+  find_walls_and_reliable(R,W);
+  if (!(W.status & CPG_ST_EINTVL_OVF))
+    { classify_reliable(R,W,sh);
+      classify_unreliable(R,W);
+    }
+  /* emit: 'N' x (K-1), then one class character per k-mer */
+  for (int j = W.lane; j < K-1; j += CPG_WARP) cls[j] = 'N';
+  const cpg_intvl *v = R.S.intvl;
+  for (int i = 0; i < R.N; i++)
+    { const int a = v[i].asgn;
+      const char c = (a == ST_E) ? 'E' : (a == ST_R) ? 'R' : (a == ST_H) ? 'H' : (a == ST_D) ? 'D' : '?';
+      const int b = v[i].b, e = v[i].e;
+      for (int j = b+W.lane; j < e; j += CPG_WARP) cls[K-1+j] = (uint8_t)c;
+    }
+  CPG_SYNCWARP();
+  return W.status;
+}
+
+#endif

@@ -1,0 +1,528 @@
+/*******************************************************************************************
+ *  cpg_wall.cuh -- wall detection and reliable-interval selection for one read, one warp.
+ *
+ *  Replaces find_wall (+ find_gain/find_drop/find_pair, update_perror, remove_duplicates,
+ *  bs_eintvl) src/wall.c:264-958 and find_rel_intvl/correct_wall_cnt src/wall.c:960-1051.
+ *
+ *  Layout differences from the reference (results identical):
+ *   - one 32-bit word per profile position holds the wall flags and the index of a lazily
+ *     allocated slot of four error probabilities; the reference keeps a flag byte plus four
+ *     doubles for every position (33 B/position reset per read, here 4 B/position);
+ *   - candidates, lone O-walls and interval boundaries are found by lane-parallel sweeps + ballot
+ *     and then handled in position order, because pairing, the first-writer-wins probability
+ *     cache and the paired flags are order dependent (src/wall.c:310-315,639-640);
+ *   - pairs explained by errors in others are not stored: their only use in the reference is to
+ *     clear the O-wall flag of both ends (src/wall.c:722-726), which commutes with the rest of
+ *     pass A and is done at pairing time;
+ *   - index plen of the scratch is reset with the rest (the reference leaves stale state there,
+ *     SURVEY A.5), and profile[plen], which src/wall.c:977-978 can read one past the end when a
+ *     low-complexity run reaches the end of the read, is defined as profile[plen-1].
+ *******************************************************************************************/
+#ifndef CPG_WALL_CUH
+#define CPG_WALL_CUH
+#include "cpg_math.cuh"
+#include "cpg_context.cuh"
+
+/* ---- warp primitives (width 1 in the host-side unit-test build) ---- */
+#ifdef CPG_HOSTSIM
+CPG_DEV unsigned cpg_ballot(int pred) { return pred ? 1u : 0u; }
+CPG_DEV int      cpg_warp_sum(int v)  { return v; }
+CPG_DEV int      cpg_ffs(unsigned m)  { return __builtin_ffs((int)m); }
+#else
+CPG_DEV unsigned cpg_ballot(int pred) { return __ballot_sync(0xffffffffu,pred); }
+CPG_DEV int      cpg_warp_sum(int v)  { return __reduce_add_sync(0xffffffffu,v); }
+CPG_DEV int      cpg_ffs(unsigned m)  { return __ffs((int)m); }
+#endif
+
+/* flag bits (src/wall.c:264-269) in the low byte of a mark word */
+#define MK_BY_S       0x01u
+#define MK_PAIR_S     0x02u
+#define MK_BY_O       0x10u
+#define MK_PAIR_O     0x20u
+#define MK_PAIR_MULT  0x40u
+#define MK_ERROR      0x80u
+#define MK_STALE_PROF 128     /* status bit: profile[plen] was read (reference reads stale memory) */
+
+struct ReadCtx
+  { const uint16_t *prof;
+    int             plen, rlen;
+    cpg_seq         seq;
+    cpg_scratch     S;
+    int             nslots;
+    int             N, M;
+  };
+
+CPG_DEV uint16_t rc_prof(const ReadCtx &R, WCtx &W, int p)
+{ if (p >= R.plen) { W.status |= MK_STALE_PROF; p = R.plen-1; }
+  return R.prof[p];
+}
+
+CPG_DEV unsigned mk_by(int e)   { return e == ET_SELF ? MK_BY_S : MK_BY_O; }
+CPG_DEV unsigned mk_pair(int e) { return e == ET_SELF ? MK_PAIR_S : MK_PAIR_O; }
+
+CPG_DEV void mark_or(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
+{ if (W.lane == 0) R.S.mark[pos] |= bits;
+  CPG_SYNCWARP();
+}
+CPG_DEV void mark_clear(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
+{ if (W.lane == 0) R.S.mark[pos] &= ~bits;
+  CPG_SYNCWARP();
+}
+
+CPG_DEV double perr_get(const ReadCtx &R, int pos, int e, int w)
+{ unsigned s = R.S.mark[pos] >> 8;
+  return s ? R.S.perr[(size_t)(s-1)*4+e*2+w] : -CPG_INF;
+}
+
+/* src/wall.c:310-315: first writer wins, with the caller's error rate */
+CPG_DEV_NOINL void perr_once(ReadCtx &R, WCtx &W, int pos, int e, int w,
+                             uint16_t cout, uint16_t cin, double erate)
+{ if (perr_get(R,pos,e,w) != -CPG_INF) return;
+  double v = cpg_p_errorin(W,e,erate,cout,cin);
+  unsigned m = R.S.mark[pos];
+  unsigned s = m >> 8;
+  if (s == 0)
+    { s = (unsigned)(++R.nslots);
+      if (W.lane == 0)
+        { R.S.mark[pos] = m | (s << 8);
+          double *q = R.S.perr+(size_t)(s-1)*4;
+          q[0] = q[1] = q[2] = q[3] = -CPG_INF;
+        }
+      CPG_SYNCWARP();
+    }
+  if (W.lane == 0) R.S.perr[(size_t)(s-1)*4+e*2+w] = v;
+  CPG_SYNCWARP();
+}
+
+/* src/wall.c:317-322 */
+CPG_DEV double lp_diff_pair(const ReadCtx &R, const WCtx &W, int i, int j)
+{ const uint16_t *p = R.prof;
+  int n_drop = (int)p[i-1]-p[i], n_gain = (int)p[j]-p[j-1];
+  uint16_t cov = (uint16_t)imax(p[i-1],p[j]);
+  return cpg_lp_trans(W,i,j,n_drop,n_gain,cov);
+}
+
+CPG_DEV int cthres_at(const WCtx &W, int t, int l, int cout, int s, int e)
+{ return W.cthres[((CPG_LROW(t,l)*256+cout)*2+s)*2+e]; }
+
+/* src/wall.c:324-329 (cin travels through an 8-bit parameter in the reference) */
+CPG_DEV int thres_ng(int e, int cin, int ct)
+{ cin &= 0xff; return (e == ET_SELF) ? (cin >= ct) : (cin < ct); }
+
+/* src/wall.c:331-507.  fwd = 1: a DROP at i looks for its GAIN about K-1 positions ahead
+ * (find_gain); fwd = 0: a GAIN at i looks for its DROP behind (find_drop). */
+CPG_DEV_NOINL int find_pair(ReadCtx &R, WCtx &W, int fwd, int i, uint16_t cout, uint16_t cin,
+                            int e, int t, int l, double erate, cpg_eintvl *out)
+{ const cpg_dmodel *M = W.M;
+  const uint16_t *prof = R.prof;
+  const int plen = R.plen, K = M->K, ulen = t+1, cmax = M->cmax;
+  const int wi = fwd ? WT_DROP : WT_GAIN, wj = fwd ? WT_GAIN : WT_DROP;
+  int max_j = -1; double max_pe = -CPG_INF, pe;
+
+  /* low-complexity partner: walk the context run by whole units */
+  int m = ulen*l, n = 0, j;
+  for (;;)
+    { int idx = fwd ? i+ulen*(n+1) : i-ulen*(n+1);
+      if (fwd) { if (idx >= plen) break; }
+      else     { if (idx <= 0) break; }
+      if (cpg_ctx_at(R.seq,R.rlen,K,wi,idx,t) != m+n+1) break;
+      n++;
+    }
+  j = fwd ? i+K-1+n-m : i-K+1-n+m;
+  if (fwd ? (j <= i) : (j >= i)) return 0;
+  if (fwd ? (j >= plen) : (j <= 0))
+    { j = fwd ? plen : 0;
+      double pi = perr_get(R,i,e,wi);
+      pe = pi*pi;
+    }
+  else
+    { uint16_t cin_j  = fwd ? prof[j-1] : prof[j];
+      uint16_t cout_j = fwd ? prof[j]   : prof[j-1];
+      pe = -CPG_INF;
+      if (cin_j <= cout_j
+          && !(cout_j < cmax && thres_ng(e,cin_j,cthres_at(W,t,l,cout_j,TH_FINAL,e)))
+          && (e == ET_SELF || (fwd ? lp_diff_pair(R,W,i,j) : lp_diff_pair(R,W,j,i)) >= CPG_THRES_DIFF_EO))
+        { perr_once(R,W,j,e,wj,cout_j,cin_j,erate);
+          pe = fwd ? perr_get(R,i,e,WT_DROP)*perr_get(R,j,e,WT_GAIN)
+                   : perr_get(R,j,e,WT_DROP)*perr_get(R,i,e,WT_GAIN);
+        }
+    }
+  if (max_pe < pe) { max_j = j; max_pe = pe; }
+
+  /* high-complexity partner: up to MAX_N_HC extra bases */
+  double pe_i = 0.; int have_pe_i = 0;
+  for (n = 0; n <= CPG_MAX_N_HC; n++)
+    { j = fwd ? i+K-1+n : i-K+1-n;
+      if (fwd ? (j >= plen) : (j <= 0)) break;
+      uint16_t cin_j  = fwd ? prof[j-1] : prof[j];
+      uint16_t cout_j = fwd ? prof[j]   : prof[j-1];
+      if (!(cin_j <= cout_j)) continue;
+      if ((cout < cmax && thres_ng(e,cin,cthres_at(W,CT_HP,1,cout,TH_FINAL,e)))
+          || (cout_j < cmax && thres_ng(e,cin_j,cthres_at(W,CT_HP,1,cout_j,TH_FINAL,e))))
+        continue;
+      if (e == ET_OTHERS && (fwd ? lp_diff_pair(R,W,i,j) : lp_diff_pair(R,W,j,i)) < CPG_THRES_DIFF_EO)
+        continue;
+      if (!have_pe_i) { pe_i = cpg_p_errorin(W,e,M->hc_erate,cout,cin); have_pe_i = 1; }
+      double pe_j = cpg_p_errorin(W,e,M->hc_erate,cout_j,cin_j);
+      pe = pe_i*pe_j;
+      if (max_pe < pe) { max_j = j; max_pe = pe; }
+    }
+  if (max_j == -1) return 0;
+  if (fwd) { out->b = i; out->e = max_j; }
+  else     { out->b = max_j; out->e = i; }
+  out->pe = max_pe;
+  return 1;
+}
+
+/* ---- E-interval list helpers: order of src/wall.c:519-528 under a stable sort is (b,e) then
+ *      input order, since the (int) cast of a probability difference is 0 ---- */
+CPG_DEV int ei_before(const cpg_eintvl &x, const cpg_eintvl &y)
+{ if (x.b == y.b)
+    { if (x.e == y.e) return ((int)(y.pe-x.pe)) < 0;
+      return x.e < y.e;
+    }
+  return x.b < y.b;
+}
+
+/* stable insertion sort; the lists are produced almost in order */
+CPG_DEV_NOINL void ei_sort(cpg_eintvl *a, int n, const WCtx &W)
+{ if (W.lane == 0)
+    for (int i = 1; i < n; i++)
+      { cpg_eintvl v = a[i];
+        int j = i-1;
+        while (j >= 0 && ei_before(v,a[j])) { a[j+1] = a[j]; j--; }
+        a[j+1] = v;
+      }
+  CPG_SYNCWARP();
+}
+
+/* src/wall.c:548-568 */
+CPG_DEV int ei_unique(cpg_eintvl *a, int n, const WCtx &W)
+{ ei_sort(a,n,W);
+  if (n >= 2)
+    { int i = 1;
+      while (i < n && !(a[i-1].b == a[i].b && a[i-1].e == a[i].e)) i++;
+      /* every lane needs the new length: count first (read only), then lane 0 compacts */
+      int keep_b = (i < n) ? a[i-1].b : 0, keep_e = (i < n) ? a[i-1].e : 0;
+      int cnt = i;
+      for (int j = i+1; j < n; j++)
+        if (!(keep_b == a[j].b && keep_e == a[j].e))
+          { keep_b = a[j].b; keep_e = a[j].e; cnt++; }
+      CPG_SYNCWARP();
+      if (W.lane == 0)
+        { int w = i;
+          for (int j = i+1; j < n; j++)
+            if (!(a[w-1].b == a[j].b && a[w-1].e == a[j].e))
+              a[w++] = a[j];
+        }
+      CPG_SYNCWARP();
+      n = cnt;
+    }
+  return n;
+}
+
+/* src/wall.c:530-546 */
+CPG_DEV int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
+{ while (l <= r)
+    { int m = (l+r)/2;
+      if (a[m].b == b)
+        { if (a[m].e == e) return m;
+          if (e > a[m].e) l = m+1; else r = m-1;
+        }
+      else if (b > a[m].b) l = m+1;
+      else r = m-1;
+    }
+  return -1;
+}
+
+CPG_DEV void ei_put(ReadCtx &R, const WCtx &W, int k, int b, int e, double pe)
+{ if (W.lane == 0) { R.S.eint[k].b = b; R.S.eint[k].e = e; R.S.eint[k].pe = pe; }
+  CPG_SYNCWARP();
+}
+
+/* clear bits on the open range (b,e), lanes striding */
+CPG_DEV void mark_clear_range(ReadCtx &R, const WCtx &W, int b, int e, unsigned bits)
+{ for (int j = b+1+W.lane; j < e; j += CPG_WARP) R.S.mark[j] &= ~bits;
+  CPG_SYNCWARP();
+}
+
+/* ---- pass A for one candidate position (src/wall.c:606-692) ---- */
+CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
+{ const cpg_dmodel *M = W.M;
+  const uint16_t cim1 = R.prof[i-1], ci = R.prof[i];
+  const int cng = (cim1 > ci) ? cim1-ci : ci-cim1;
+  int wtype; uint16_t cin, cout;
+  if (cim1 > ci) { wtype = WT_DROP; cin = ci;   cout = cim1; }
+  else           { wtype = WT_GAIN; cin = cim1; cout = ci;   }
+
+  int maxt = -1, maxl = -1; double maxpe = -CPG_INF;
+  for (int t = 0; t < CT_N; t++)
+    { int l = imin(cpg_ctx_at(R.seq,R.rlen,M->K,wtype,i,t),M->lmax[t]);
+      double pe = M->pe[t][l];
+      if (maxpe < pe) { maxpe = pe; maxt = t; maxl = l; }
+    }
+
+  int ct_init = 0, ct_final = 0;
+  for (int e = ET_SELF; e <= ET_OTHERS; e++)
+    { if (R.S.mark[i] & mk_pair(e)) continue;
+      if (cout < M->cmax)
+        { ct_init  = cthres_at(W,maxt,maxl,cout,TH_INIT,e);
+          ct_final = cthres_at(W,maxt,maxl,cout,TH_FINAL,e);
+          if (!(cng > CPG_MAX_CNT_CHANGE || cin < imax(ct_init,3))) continue;
+        }
+      cpg_eintvl I;
+      if (e == ET_SELF)
+        { if (cout < M->cmax && cin >= ct_final) continue;
+          perr_once(R,W,i,e,wtype,cout,cin,maxpe);
+          if (perr_get(R,i,e,wtype) < CPG_PE_FINAL) continue;
+          if (find_pair(R,W,wtype == WT_DROP,i,cout,cin,e,maxt,maxl,maxpe,&I) && I.pe >= CPG_PE_FINAL)
+            { mark_or(R,W,I.b,MK_BY_S|MK_PAIR_S);
+              mark_or(R,W,I.e,MK_BY_S|MK_PAIR_S);
+              ei_put(R,W,eidx,I.b,I.e,I.pe);
+              eidx++;
+            }
+        }
+      else
+        { if (cng >= M->cov[ST_H] || (cout < M->cmax && cin < ct_final))
+            { mark_or(R,W,i,MK_BY_O); continue; }
+          perr_once(R,W,i,e,wtype,cout,cin,maxpe);
+          if (perr_get(R,i,e,wtype) < CPG_PE_FINAL)
+            { mark_or(R,W,i,MK_BY_O); continue; }
+          if (find_pair(R,W,wtype == WT_DROP,i,cout,cin,e,maxt,maxl,maxpe,&I) && I.pe >= CPG_PE_FINAL)
+            { /* paired O-walls stop being walls (src/wall.c:722-726), see header note */
+              if (W.lane == 0)
+                { R.S.mark[I.b] = (R.S.mark[I.b] | MK_PAIR_O) & ~MK_BY_O;
+                  R.S.mark[I.e] = (R.S.mark[I.e] | MK_PAIR_O) & ~MK_BY_O;
+                }
+              CPG_SYNCWARP();
+              continue;
+            }
+          mark_or(R,W,i,MK_BY_O);
+        }
+    }
+}
+
+/* ---- pass C for one lone O-wall (src/wall.c:763-860) ---- */
+CPG_DEV_NOINL int wall_multi(ReadCtx &R, WCtx &W, int i, int NS, int midx)
+{ const int plen = R.plen;
+  cpg_eintvl *eint = R.S.eint;
+  for (int w = WT_DROP; w <= WT_GAIN; w++)
+    { double pe_i = perr_get(R,i,ET_SELF,w), pe;
+      if (pe_i < CPG_PE_FINAL) continue;
+      const int jend = (w == WT_DROP) ? imin(i+200,plen+1) : imax(i-200,0);   /* DROP: j < jend; GAIN: j >= jend */
+      int done = 0;
+      for (int jb = (w == WT_DROP) ? i+1 : i-1; !done && ((w == WT_DROP) ? (jb < jend) : (jb >= jend));
+           jb += (w == WT_DROP) ? CPG_WARP : -CPG_WARP)
+        { int j = (w == WT_DROP) ? jb+W.lane : jb-W.lane;
+          int in = (w == WT_DROP) ? (j < jend) : (j >= jend);
+          int edge = in && (j == ((w == WT_DROP) ? plen : 0));
+          unsigned f = in ? (R.S.mark[j] & (MK_BY_S|MK_BY_O)) : 0u;
+          unsigned mask = cpg_ballot(f != 0 || edge);
+          while (mask)
+            { int l = cpg_ffs(mask)-1; mask &= mask-1;
+              j = (w == WT_DROP) ? jb+l : jb-l;
+              if (j == ((w == WT_DROP) ? plen : 0))          /* boundary E-interval */
+                { if ((pe = pe_i*pe_i) < CPG_PE_FINAL) continue;
+                  if (w == WT_DROP) ei_put(R,W,midx,i,plen,pe); else ei_put(R,W,midx,0,i,pe);
+                  mark_or(R,W,i,MK_PAIR_MULT);
+                  midx++;
+                  if (midx >= plen) { W.status |= CPG_ST_EINTVL_OVF; return midx; }
+                }
+              unsigned mj = R.S.mark[j];
+              if (!(mj & (MK_BY_S|MK_BY_O))) continue;
+              int b = (w == WT_DROP) ? i : j, e = (w == WT_DROP) ? j : i;
+              if (ei_find(eint,0,NS-1,b,e) == -1)
+                { double pe_j = perr_get(R,j,ET_SELF,(w == WT_DROP) ? WT_GAIN : WT_DROP);
+                  if ((pe = pe_i*pe_j) >= CPG_PE_FINAL)
+                    { ei_put(R,W,midx,b,e,pe);
+                      mark_or(R,W,i,MK_PAIR_MULT);
+                      mark_or(R,W,j,MK_PAIR_MULT);
+                      midx++;
+                      if (midx >= plen) { W.status |= CPG_ST_EINTVL_OVF; return midx; }
+                    }
+                }
+              if (mj & MK_BY_O) { done = 1; break; }
+            }
+        }
+    }
+  return midx;
+}
+
+/* ---- src/wall.c:960-1014 ---- */
+CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
+{ const int K = W.M->K;
+  const cpg_intvl I = R.S.intvl[idx];
+  const uint16_t *prof = R.prof;
+  int n_gain = 0, n_drop = 0, last, first, lmax;
+
+  last = imin(I.b+K-1,I.e-1);
+  { int s = 0;
+    for (int p = I.b+W.lane; p < last; p += CPG_WARP) s += imax((int)prof[p+1]-prof[p],0);
+    n_gain += cpg_warp_sum(s);
+  }
+  if (I.b+K-1 < I.e)
+    { lmax = 0;
+      for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_rctx(R.seq,R.rlen,I.b+K-1,t)*(t+1));
+      last = I.b+lmax;
+      int s = 0;
+      for (int p = I.b+W.lane; p < last; p += CPG_WARP) s += imax((int)prof[p]-rc_prof(R,W,p+1),0);
+      n_gain -= cpg_warp_sum(s);
+    }
+  first = imax(I.e-K+1,I.b);
+  { int s = 0;
+    for (int p = first+W.lane; p < I.e-1; p += CPG_WARP) s += imax((int)prof[p]-prof[p+1],0);
+    n_drop += cpg_warp_sum(s);
+  }
+  if (I.b < I.e-K+1)
+    { lmax = 0;
+      for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_lctx(R.seq,R.rlen,I.e-K+1+K-2,t)*(t+1));
+      first = I.e-lmax;
+      int s = 0;
+      for (int p = first+W.lane; p < I.e-1; p += CPG_WARP) s += imax((int)prof[p+1]-prof[p],0);
+      n_drop -= cpg_warp_sum(s);
+    }
+  uint16_t ccb = (uint16_t)imin(I.cb+imax(n_gain,0),CPG_MAX_CNT);
+  uint16_t cce = (uint16_t)imin(I.ce+imax(n_drop,0),CPG_MAX_CNT);
+  /* src/wall.c:999-1006 index intvl[] with a POSITION that hides the interval index; the only
+     write that can land on this interval is the one at position I.b, when I.b == idx:
+     ccb = max(ccb,profile[I.b]) is a no-op, cce = max(cce,profile[I.b]) happens iff the scan
+     [max(I.e-2K,I.b),I.e) starts at I.b.  Writes to higher slots hit intervals that are either
+     recomputed from scratch later or never read. */
+  if (I.b == idx && I.e-2*K <= I.b && cce < I.cb) cce = I.cb;
+  if (W.lane == 0) { R.S.intvl[idx].ccb = ccb; R.S.intvl[idx].cce = cce; }
+  CPG_SYNCWARP();
+}
+
+/* ---- whole wall stage: fills R.S.intvl[0..N) and R.S.rint[0..M) ---- */
+CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
+{ const cpg_dmodel *M = W.M;
+  const int plen = R.plen, K = M->K;
+  const uint16_t *prof = R.prof;
+  uint32_t *mark = R.S.mark;
+  cpg_eintvl *eint = R.S.eint;
+
+  for (int i = W.lane; i <= plen; i += CPG_WARP) mark[i] = 0;
+  R.nslots = 0;
+  CPG_SYNCWARP();
+
+  /* pass A: candidates in position order */
+  int eidx = 0;
+  const int rcov = M->cov[ST_R];
+  for (int base = 1; base < plen; base += CPG_WARP)
+    { int i = base+W.lane, cand = 0;
+      if (i < plen)
+        { int a = prof[i-1], b = prof[i];
+          int d = (a > b) ? a-b : b-a;
+          cand = (imin(a,b) < rcov) && (d >= CPG_MIN_CNT_CHANGE);
+        }
+      unsigned mask = cpg_ballot(cand);
+      while (mask)
+        { int l = cpg_ffs(mask)-1; mask &= mask-1;
+          wall_candidate(R,W,base+l,eidx);
+        }
+    }
+  int NS = eidx;
+
+  /* pass B (src/wall.c:727-735) */
+  for (int k = 0; k < NS; k++) mark_clear_range(R,W,eint[k].b,eint[k].e,MK_BY_O);
+  NS = ei_unique(eint,eidx,W);
+
+  /* pass C */
+  int midx = NS;
+  for (int base = 1; base < plen && !(W.status & CPG_ST_EINTVL_OVF); base += CPG_WARP)
+    { int i = base+W.lane;
+      unsigned f = (i < plen) ? mark[i] : 0u;
+      unsigned mask = cpg_ballot((f & MK_BY_O) && !(f & MK_BY_S));
+      while (mask)
+        { int l = cpg_ffs(mask)-1; mask &= mask-1;
+          if (mark[base+l] & MK_PAIR_MULT) continue;
+          midx = wall_multi(R,W,base+l,NS,midx);
+          if (W.status & CPG_ST_EINTVL_OVF) break;
+        }
+    }
+  if (W.status & CPG_ST_EINTVL_OVF) { R.N = 0; R.M = 0; return; }
+  for (int k = NS; k < midx; k++) mark_clear_range(R,W,eint[k].b,eint[k].e,MK_BY_O);
+  if (NS < midx) { NS = midx; ei_sort(eint,NS,W); }
+
+  /* pass D (src/wall.c:877-909): hulls of chains of overlapping E-intervals are appended while
+     the list is being walked, and the loop bound is re-read */
+  { int i = 0;
+    while (i < NS-1)
+      { int max_e = eint[i].e; double max_pe = eint[i].pe;
+        int j = i;
+        while (j < NS-1 && eint[j+1].b <= eint[j].e)
+          { max_e = imax(max_e,eint[j+1].e);
+            max_pe = dmax_ref(max_pe,eint[j+1].pe);
+            j++;
+          }
+        if (i < j)
+          { ei_put(R,W,NS,eint[i].b,max_e,max_pe);
+            NS++;
+            if (NS >= plen) { W.status |= CPG_ST_EINTVL_OVF; R.N = 0; R.M = 0; return; }
+          }
+        i = j+1;
+      }
+  }
+  ei_sort(eint,NS,W);
+  for (int k = 0; k < NS; k++)
+    { for (int j = eint[k].b+W.lane; j < eint[k].e; j += CPG_WARP) mark[j] |= MK_ERROR;
+      CPG_SYNCWARP();
+    }
+
+  /* pass E (src/wall.c:921-948) */
+  int N = 0, b = 0;
+  cpg_intvl *intvl = R.S.intvl;
+  for (int base = 1; base <= plen; base += CPG_WARP)
+    { int i = base+W.lane, cut = 0;
+      if (i <= plen)
+        { unsigned m1 = mark[i-1], m0 = mark[i];
+          cut = (i == plen) || (((m1 & MK_ERROR) != 0) != ((m0 & MK_ERROR) != 0))
+                || (!(m0 & MK_ERROR) && (m0 & MK_BY_O));
+        }
+      unsigned mask = cpg_ballot(cut);
+      while (mask)
+        { int l = cpg_ffs(mask)-1; mask &= mask-1;
+          int e = base+l;
+          int k = ei_find(eint,0,NS-1,b,e);
+          double pe  = (k != -1) ? cpg_log(eint[k].pe) : -CPG_INF;
+          double pob = dmax_ref(perr_get(R,b,ET_OTHERS,WT_DROP),perr_get(R,b,ET_OTHERS,WT_GAIN));
+          double poe = dmax_ref(perr_get(R,e,ET_OTHERS,WT_DROP),perr_get(R,e,ET_OTHERS,WT_GAIN));
+          double lpob = (pob != -CPG_INF) ? cpg_log(pob) : -CPG_INF;
+          double lpoe = (poe != -CPG_INF) ? cpg_log(poe) : -CPG_INF;
+          if (W.lane == 0)
+            { cpg_intvl *I = intvl+N;
+              I->b = b; I->e = e; I->cb = prof[b]; I->ce = prof[e-1];
+              I->ccb = 0; I->cce = 0; I->is_rel = 0; I->asgn = ST_N;
+              I->pe = pe; I->peob = lpob; I->peoe = lpoe;
+            }
+          N++;
+          b = e;
+        }
+    }
+  CPG_SYNCWARP();
+  R.N = N;
+
+  /* reliable intervals (src/wall.c:1016-1037) */
+  int Mrel = 0;
+  const double logpthres = cpg_log(CPG_PE_FINAL);
+  for (int i = 0; i < N; i++)
+    { const cpg_intvl I = intvl[i];
+      if (I.e-I.b < K) continue;
+      if (imax(I.cb,I.ce) >= rcov) continue;
+      if (I.pe >= logpthres) continue;
+      correct_wall_cnt(R,W,i);
+      const int ccb = intvl[i].ccb, cce = intvl[i].cce;
+      if (cpg_lp_trans(W,I.b,I.e,ccb,cce,(uint16_t)((ccb+cce)/2)) < CPG_THRES_DIFF_REL) continue;
+      if (imax(ccb,cce) == CPG_MAX_CNT) continue;
+      if (W.lane == 0)
+        { intvl[i].is_rel = 1;
+          R.S.rint[Mrel] = intvl[i];
+          R.S.rint[Mrel].is_rel = 1;
+        }
+      CPG_SYNCWARP();
+      Mrel++;
+    }
+  R.M = Mrel;
+}
+
+#endif

@@ -1,0 +1,648 @@
+/*******************************************************************************************
+ *  classpro_main.c -- the ClassPro command line on top of libclasspro_b200.so.
+ *
+ *      ClassPro [-vs] [-T<int(4)>] [-c<int>] [-r<int(20000)>] [-P<tmp_dir(./)>] [-N<fastk_root>]
+ *               [-M<model_path>] [-G<int>] [-B<int>] <source>[.f[ast][aq][.gz]]
+ *
+ *  Same options, inputs and output bytes as the reference program (src/ClassPro.c:348-631,
+ *  usage string src/const.c:14-17): reads <source> plus the FastK <root>.hist / <root>.prof
+ *  (+ hidden .pidx.N / .prof.N parts) and writes <dir of source>/<root>.class with one
+ *  fastq-like record per read (src/ClassPro.c:289).
+ *
+ *  What changed is how the work is organised (the host stays C, the per-read path is CUDA):
+ *    reader thread   parses the FASTX stream once (the reference re-parses it from byte 0 in every
+ *                    thread, src/ClassPro.c:104-110), 2-bit packs the reads, reads the compressed
+ *                    profiles of a whole batch with one pread per part file (the reference does
+ *                    one lseek + >= 2 read(4096) per read, src/libfastk.c:1444-1462);
+ *    GPU workers     one host thread per GPU, each with its own cpg_ctx; batches are contiguous
+ *                    read ranges handed out in order, no data ever moves between GPUs;
+ *    writer thread   emits the records of finished batches in read order (the reference writes
+ *                    per-thread part files and concatenates them, src/io.c:70-112).
+ *  -T is accepted for compatibility (it no longer selects the degree of parallelism), -P is
+ *  accepted and unused (no part files), -G<n> limits the number of GPUs (default: all),
+ *  -B<n> sets the batch size in megabases (default 256).
+ *  Not supported, with a clear error: .db/.dam inputs (DAZZ_DB is out of scope), -M (needs GSL).
+ *  -s is accepted and ignored with a note: in the reference it never changes .class bytes and
+ *  crashes on FASTX input (src/ClassPro.c:281-282, src/seed.c:548-572).
+ *******************************************************************************************/
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <ctype.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <pthread.h>
+#include <time.h>
+#include <sys/resource.h>
+#include <zlib.h>
+#include <stdarg.h>
+#include <strings.h>
+#include "classpro_gpu.h"
+
+static const char *PROG = "ClassPro";
+static const char *USAGE = "[-vs] [-T<int(4)>] [-c<int>] [-r<int(20000)>] [-P<tmp_dir(./)>] [-N<fastk_root>] "
+                           "[-M<model_path>] [-G<int>] [-B<int>] <source>[.f[ast][aq][.gz]]";
+#define MAX_READ_LEN 60000       /* src/const.c:57 */
+
+static void die(const char *fmt, ...)
+{ va_list ap; va_start(ap,fmt); vfprintf(stderr,fmt,ap); va_end(ap); fputc('\n',stderr); exit(1); }
+
+static void *xmalloc(size_t n)
+{ void *p = malloc(n ? n : 1);
+  if (p == NULL) die("%s: Out of memory",PROG);
+  return p;
+}
+static void *xrealloc(void *p, size_t n)
+{ p = realloc(p,n ? n : 1);
+  if (p == NULL) die("%s: Out of memory",PROG);
+  return p;
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  FASTA/FASTQ(.gz) stream with the record semantics of src/kseq.h:177-218
+ * --------------------------------------------------------------------------------------- */
+typedef struct { char *s; size_t l, m; } str_t;
+
+typedef struct
+  { gzFile  f;
+    uint8_t *buf;
+    int      beg, end, eof;
+    int      last_char;
+    str_t    name, comment, seq;
+    int      have_comment;          /* comment.s non-NULL in kseq terms */
+  } fastx_t;
+
+#define FX_BUF (1<<20)
+
+static int fx_getc(fastx_t *x)
+{ if (x->beg >= x->end)
+    { if (x->eof) return -1;
+      x->beg = 0;
+      x->end = gzread(x->f,x->buf,FX_BUF);
+      if (x->end <= 0) { x->eof = 1; x->end = 0; return -1; }
+    }
+  return x->buf[x->beg++];
+}
+
+static void str_reserve(str_t *s, size_t extra)
+{ if (s->l+extra+1 > s->m)
+    { s->m = (s->l+extra+1)*2;
+      s->s = xrealloc(s->s,s->m);
+    }
+}
+
+/* mode 0: stop at any isspace(); mode 1: stop at '\n'.  Returns -1 at EOF with nothing read. */
+static int fx_getuntil(fastx_t *x, int line_mode, str_t *s, int *dret, int append)
+{ int got = 0;
+  if (dret) *dret = 0;
+  if (!append) s->l = 0;
+  for (;;)
+    { if (x->beg >= x->end)
+        { if (x->eof) break;
+          x->beg = 0;
+          x->end = gzread(x->f,x->buf,FX_BUF);
+          if (x->end <= 0) { x->eof = 1; x->end = 0; break; }
+        }
+      int i = x->beg;
+      if (line_mode) { uint8_t *q = memchr(x->buf+i,'\n',(size_t)(x->end-i)); i = q ? (int)(q-x->buf) : x->end; }
+      else while (i < x->end && !isspace(x->buf[i])) i++;
+      str_reserve(s,(size_t)(i-x->beg));
+      got = 1;
+      memcpy(s->s+s->l,x->buf+x->beg,(size_t)(i-x->beg));
+      s->l += (size_t)(i-x->beg);
+      x->beg = i+1;
+      if (i < x->end) { if (dret) *dret = x->buf[i]; break; }
+    }
+  if (!got && x->eof) return -1;
+  str_reserve(s,0);
+  if (line_mode && s->l > 1 && s->s[s->l-1] == '\r') s->l--;
+  s->s[s->l] = 0;
+  return (int)s->l;
+}
+
+/* >= 0 sequence length, -1 end of file */
+static int fx_read(fastx_t *x)
+{ int c;
+  if (x->last_char == 0)
+    { while ((c = fx_getc(x)) >= 0 && c != '>' && c != '@');
+      if (c < 0) return -1;
+      x->last_char = c;
+    }
+  x->seq.l = 0;
+  if (fx_getuntil(x,0,&x->name,&c,0) < 0) return -1;
+  if (c != '\n') { fx_getuntil(x,1,&x->comment,NULL,0); x->have_comment = 1; }
+  str_reserve(&x->seq,256);
+  while ((c = fx_getc(x)) >= 0 && c != '>' && c != '+' && c != '@')
+    { if (c == '\n') continue;
+      str_reserve(&x->seq,1);
+      x->seq.s[x->seq.l++] = (char)c;
+      fx_getuntil(x,1,&x->seq,NULL,1);
+    }
+  if (c == '>' || c == '@') x->last_char = c;
+  str_reserve(&x->seq,0);
+  x->seq.s[x->seq.l] = 0;
+  if (c != '+') return (int)x->seq.l;
+  while ((c = fx_getc(x)) >= 0 && c != '\n');          /* rest of the '+' line */
+  if (c < 0) return -2;
+  { static __thread str_t qual;
+    qual.l = 0;
+    while (fx_getuntil(x,1,&qual,NULL,1) >= 0 && qual.l < x->seq.l);
+    x->last_char = 0;
+    if (qual.l != x->seq.l) return -2;
+  }
+  return (int)x->seq.l;
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  FastK profile index (format of src/libfastk.c:1267-1361)
+ * --------------------------------------------------------------------------------------- */
+typedef struct
+  { int      kmer, nparts;
+    int64_t  nreads;
+    int64_t *index;         /* [nreads+1]: index[i+1] = end offset of read i inside its part */
+    int64_t *nbase;         /* [nparts]: reads before the end of part p */
+    int     *fd;            /* [nparts] */
+  } profidx_t;
+
+static void split_path(const char *name, char *dir, size_t dn, char *base, size_t bn)
+{ const char *sl = strrchr(name,'/');
+  if (sl) { snprintf(dir,dn,"%.*s",(int)(sl-name),name); snprintf(base,bn,"%s",sl+1); }
+  else    { snprintf(dir,dn,"."); snprintf(base,bn,"%s",name); }
+}
+
+static int profidx_open(profidx_t *P, const char *fk_root)
+{ char dir[4096], root[1024], path[8192];
+  split_path(fk_root,dir,sizeof(dir),root,sizeof(root));
+  size_t rl = strlen(root);
+  if (rl > 5 && strcasecmp(root+rl-5,".prof") == 0) root[rl-5] = 0;
+  snprintf(path,sizeof(path),"%s/%s.prof",dir,root);
+  int f = open(path,O_RDONLY);
+  if (f < 0) return 1;
+  int32_t smer, nthreads;
+  if (read(f,&smer,4) != 4 || read(f,&nthreads,4) != 4) { close(f); return 1; }
+  close(f);
+  P->kmer = smer; P->nparts = nthreads;
+  P->nbase = xmalloc(sizeof(int64_t)*(size_t)nthreads);
+  P->fd = xmalloc(sizeof(int)*(size_t)nthreads);
+  int64_t total = 0;
+  for (int p = 0; p < nthreads; p++)
+    { snprintf(path,sizeof(path),"%s/.%s.pidx.%d",dir,root,p+1);
+      f = open(path,O_RDONLY);
+      if (f < 0) die("Profile part %s is misssing ?",path);
+      int32_t k; int64_t n;
+      if (read(f,&k,4) != 4 || read(f,&n,8) != 8 || read(f,&n,8) != 8) die("Profile part %s is truncated",path);
+      if (k != smer) die("Profile part %s does not have k-mer length matching stub ?",path);
+      close(f);
+      total += n;
+    }
+  P->index = xmalloc(sizeof(int64_t)*(size_t)(total+1));
+  P->index[0] = 0;
+  int64_t nr = 0;
+  for (int p = 0; p < nthreads; p++)
+    { snprintf(path,sizeof(path),"%s/.%s.pidx.%d",dir,root,p+1);
+      f = open(path,O_RDONLY);
+      int32_t k; int64_t n;
+      if (read(f,&k,4) != 4 || read(f,&n,8) != 8 || read(f,&n,8) != 8) die("Profile part %s is truncated",path);
+      size_t want = sizeof(int64_t)*(size_t)n, got = 0;
+      while (got < want)
+        { ssize_t r = read(f,(char *)(P->index+nr+1)+got,want-got);
+          if (r <= 0) die("Profile part %s is truncated",path);
+          got += (size_t)r;
+        }
+      close(f);
+      nr += n;
+      P->nbase[p] = nr;
+      snprintf(path,sizeof(path),"%s/.%s.prof.%d",dir,root,p+1);
+      P->fd[p] = open(path,O_RDONLY);
+      if (P->fd[p] < 0) die("Profile part %s is misssing ?",path);
+    }
+  P->nreads = nr;
+  return 0;
+}
+
+/* byte range of read id inside its part (src/libfastk.c:1444-1454) */
+static void prof_range(const profidx_t *P, int64_t id, int *part, int64_t *off, int64_t *len)
+{ int w = 0;
+  while (w < P->nparts && id >= P->nbase[w]) w++;
+  if (w >= P->nparts) die("Id %lld is out of range [1,%lld]",(long long)id,(long long)P->nbase[P->nparts-1]);
+  *part = w;
+  *off = (id == 0 || (w > 0 && id == P->nbase[w-1])) ? 0 : P->index[id];
+  *len = P->index[id+1]-*off;
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  Batches and the three-stage pipeline
+ * --------------------------------------------------------------------------------------- */
+typedef struct batch
+  { int64_t   first_id;
+    int       n_all;             /* records in the batch, including reads shorter than K */
+    int       n;                 /* reads sent to the GPU */
+    /* per record */
+    char    **header; char **seq; int32_t *rlen_all; int32_t *slot_of;   /* slot_of[i] = index among the n, or -1 */
+    /* device-side inputs / outputs (pinned) */
+    uint8_t  *pseq; int64_t *seq_off; int32_t *rlen; uint8_t *prof; int64_t *prof_off;
+    uint8_t  *cls;  int64_t *cls_off; int32_t *status;
+    size_t    pseq_cap, prof_cap, cls_cap; int rec_cap, n_cap;
+    int       seq_bits;
+    int64_t   kmers;
+    struct batch *next;
+  } batch_t;
+
+typedef struct
+  { pthread_mutex_t mu; pthread_cond_t cv;
+    batch_t *head, *tail; int closed;
+  } queue_t;
+
+static void q_init(queue_t *q) { pthread_mutex_init(&q->mu,NULL); pthread_cond_init(&q->cv,NULL); q->head = q->tail = NULL; q->closed = 0; }
+static void q_push(queue_t *q, batch_t *b)
+{ pthread_mutex_lock(&q->mu);
+  b->next = NULL;
+  if (q->tail) q->tail->next = b; else q->head = b;
+  q->tail = b;
+  pthread_cond_broadcast(&q->cv);
+  pthread_mutex_unlock(&q->mu);
+}
+static void q_close(queue_t *q)
+{ pthread_mutex_lock(&q->mu); q->closed = 1; pthread_cond_broadcast(&q->cv); pthread_mutex_unlock(&q->mu); }
+static batch_t *q_pop(queue_t *q)
+{ pthread_mutex_lock(&q->mu);
+  while (q->head == NULL && !q->closed) pthread_cond_wait(&q->cv,&q->mu);
+  batch_t *b = q->head;
+  if (b) { q->head = b->next; if (q->head == NULL) q->tail = NULL; }
+  pthread_mutex_unlock(&q->mu);
+  return b;
+}
+
+typedef struct
+  { /* options */
+    int verbose, find_seeds, nthreads, cov, read_len, ngpus; int64_t batch_bases;
+    char *fk_root, *model_path, *src_path, *out_path;
+    /* shared state */
+    profidx_t  P;
+    cpg_model *model;
+    queue_t    q_free, q_ready;
+    /* finished batches, handed to the writer in id order */
+    pthread_mutex_t mu; pthread_cond_t cv;
+    batch_t   *done;              /* unordered list */
+    int64_t    next_id;           /* first_id the writer waits for */
+    int        reader_done; int64_t total_reads;
+    int64_t    kmers;
+  } app_t;
+
+static void *pinned(size_t n)
+{ void *p = cpg_host_alloc(n);
+  if (p == NULL) die("%s: cannot allocate %zu bytes of pinned memory",PROG,n);
+  return p;
+}
+
+static void batch_reserve(batch_t *b, int nrec, size_t pseq, size_t prof, size_t cls)
+{ if (nrec > b->rec_cap)
+    { int cap = nrec+nrec/2+64;
+      b->header = xrealloc(b->header,sizeof(char *)*(size_t)cap);
+      b->seq = xrealloc(b->seq,sizeof(char *)*(size_t)cap);
+      for (int i = b->rec_cap; i < cap; i++) { b->header[i] = NULL; b->seq[i] = NULL; }
+      b->rlen_all = xrealloc(b->rlen_all,sizeof(int32_t)*(size_t)cap);
+      b->slot_of = xrealloc(b->slot_of,sizeof(int32_t)*(size_t)cap);
+      b->rec_cap = cap;
+    }
+  if (nrec > b->n_cap)
+    { int cap = nrec+nrec/2+64;
+      int64_t *so = pinned(sizeof(int64_t)*(size_t)(cap+1)), *po = pinned(sizeof(int64_t)*(size_t)(cap+1)),
+              *co = pinned(sizeof(int64_t)*(size_t)(cap+1));
+      int32_t *rl = pinned(sizeof(int32_t)*(size_t)(cap+1)), *st = pinned(sizeof(int32_t)*(size_t)(cap+1));
+      if (b->n_cap)
+        { memcpy(so,b->seq_off,sizeof(int64_t)*(size_t)(b->n_cap+1)); memcpy(po,b->prof_off,sizeof(int64_t)*(size_t)(b->n_cap+1));
+          memcpy(co,b->cls_off,sizeof(int64_t)*(size_t)(b->n_cap+1)); memcpy(rl,b->rlen,sizeof(int32_t)*(size_t)(b->n_cap+1));
+          cpg_host_free(b->seq_off); cpg_host_free(b->prof_off); cpg_host_free(b->cls_off); cpg_host_free(b->rlen); cpg_host_free(b->status);
+        }
+      b->seq_off = so; b->prof_off = po; b->cls_off = co; b->rlen = rl; b->status = st;
+      b->n_cap = cap;
+    }
+  if (pseq > b->pseq_cap)
+    { size_t cap = pseq+pseq/2+4096; uint8_t *p = pinned(cap);
+      if (b->pseq_cap) { memcpy(p,b->pseq,b->pseq_cap); cpg_host_free(b->pseq); }
+      b->pseq = p; b->pseq_cap = cap;
+    }
+  if (prof > b->prof_cap)
+    { size_t cap = prof+prof/2+4096; uint8_t *p = pinned(cap);
+      if (b->prof_cap) { memcpy(p,b->prof,b->prof_cap); cpg_host_free(b->prof); }
+      b->prof = p; b->prof_cap = cap;
+    }
+  if (cls > b->cls_cap)
+    { size_t cap = cls+cls/2+4096; uint8_t *p = pinned(cap);
+      if (b->cls_cap) cpg_host_free(b->cls);
+      b->cls = p; b->cls_cap = cap;
+    }
+}
+
+/* reader: FASTX -> batches */
+static void *reader_main(void *arg)
+{ app_t *A = arg;
+  const int K = A->P.kmer;
+  fastx_t X; memset(&X,0,sizeof(X));
+  X.f = gzopen(A->src_path,"r");
+  if (X.f == NULL) die("%s: Cannot open %s",PROG,A->src_path);
+  gzbuffer(X.f,1<<20);
+  X.buf = xmalloc(FX_BUF);
+  int64_t id = 0;
+  int eof = 0;
+  while (!eof && id < A->P.nreads)
+    { batch_t *b = q_pop(&A->q_free);
+      if (b == NULL) break;
+      b->first_id = id; b->n_all = 0; b->n = 0; b->kmers = 0; b->seq_bits = 2;
+      int64_t bases = 0; size_t pseq = 0, prof = 0, cls = 0;
+      /* pass 1: parse records, keep header + sequence text */
+      while (bases < A->batch_bases && id < A->P.nreads)
+        { int rlen = fx_read(&X);
+          if (rlen < 0)
+            { if (rlen == -1) { eof = 1; break; }
+              die("%s: truncated quality string in %s",PROG,A->src_path);
+            }
+          if (rlen > MAX_READ_LEN)
+            die("rlen (%d) > MAX_READ_LEN for FASTX inputs (%d)",rlen,MAX_READ_LEN);
+          batch_reserve(b,b->n_all+1,0,0,0);
+          const int i = b->n_all++;
+          const char *cm = X.have_comment ? X.comment.s : "(null)";      /* src/ClassPro.c:188 */
+          size_t hl = strlen(X.name.s)+strlen(cm)+3;
+          b->header[i] = xrealloc(b->header[i],hl);
+          snprintf(b->header[i],hl,"@%s %s",X.name.s,cm);
+          b->seq[i] = xrealloc(b->seq[i],(size_t)rlen+1);
+          memcpy(b->seq[i],X.seq.s,(size_t)rlen+1);
+          b->rlen_all[i] = rlen;
+          if (rlen >= K)
+            { int part; int64_t off, len;
+              prof_range(&A->P,id,&part,&off,&len);
+              b->slot_of[i] = b->n++;
+              pseq += (size_t)(rlen+3)/4; prof += (size_t)len; cls += (size_t)rlen;
+              b->kmers += rlen-K+1;
+            }
+          else b->slot_of[i] = -1;
+          bases += rlen;
+          id++;
+        }
+      /* pass 2: pack + fetch profiles into pinned memory */
+      batch_reserve(b,b->n_all,pseq+16,prof+16,cls+16);
+      int64_t so = 0, po = 0, co = 0;
+      int k = 0, bad = 0;
+      for (int i = 0; i < b->n_all; i++)
+        { if (b->slot_of[i] < 0) continue;
+          const int rlen = b->rlen_all[i];
+          b->seq_off[k] = so; b->prof_off[k] = po; b->cls_off[k] = co; b->rlen[k] = rlen;
+          bad |= cpg_pack_seq(b->seq[i],rlen,b->pseq+so);
+          so += (rlen+3)/4; co += rlen;
+          int part; int64_t off, len;
+          prof_range(&A->P,b->first_id+i,&part,&off,&len);
+          int64_t got = 0;
+          while (got < len)
+            { ssize_t r = pread(A->P.fd[part],b->prof+po+got,(size_t)(len-got),off+got);
+              if (r <= 0) die("%s: cannot read profile of read %lld",PROG,(long long)(b->first_id+i+1));
+              got += r;
+            }
+          po += len;
+          k++;
+        }
+      b->seq_off[k] = so; b->prof_off[k] = po; b->cls_off[k] = co;
+      if (bad)
+        { /* a character outside ACGT: ship the raw bytes, compared as the reference compares them */
+          size_t raw = 0;
+          for (int i = 0; i < b->n_all; i++) if (b->slot_of[i] >= 0) raw += (size_t)b->rlen_all[i];
+          batch_reserve(b,b->n_all,raw+16,0,0);
+          so = 0; k = 0;
+          for (int i = 0; i < b->n_all; i++)
+            { if (b->slot_of[i] < 0) continue;
+              b->seq_off[k++] = so;
+              memcpy(b->pseq+so,b->seq[i],(size_t)b->rlen_all[i]);
+              so += b->rlen_all[i];
+            }
+          b->seq_off[k] = so;
+          b->seq_bits = 8;
+        }
+      if (b->n_all == 0) { q_push(&A->q_free,b); break; }
+      q_push(&A->q_ready,b);
+    }
+  pthread_mutex_lock(&A->mu);
+  A->reader_done = 1; A->total_reads = id;
+  pthread_cond_broadcast(&A->cv);
+  pthread_mutex_unlock(&A->mu);
+  q_close(&A->q_ready);
+  gzclose(X.f);
+  return NULL;
+}
+
+typedef struct { app_t *A; int device; } gpu_arg_t;
+
+static void *gpu_main(void *arg)
+{ gpu_arg_t *G = arg; app_t *A = G->A;
+  cpg_ctx *ctx = NULL;
+  if (cpg_create(&ctx,G->device,A->model,0,0) != CPG_OK)
+    die("%s: %s",PROG,cpg_last_error(NULL));
+  batch_t *b;
+  while ((b = q_pop(&A->q_ready)) != NULL)
+    { if (b->n > 0)
+        { cpg_batch in = { b->n, b->seq_bits, b->pseq, b->seq_off, b->rlen, b->prof, b->prof_off };
+          cpg_result out = { b->cls, b->cls_off, b->status };
+          int rc = cpg_classify(ctx,&in,&out);
+          if (rc == CPG_EREAD)
+            { for (int i = 0; i < b->n_all; i++)
+                { int k = b->slot_of[i];
+                  if (k >= 0 && (b->status[k] & (1|2|4|8|64)))
+                    { if (b->status[k] & 1)
+                        die("Read %lld: rlen (%d) != plen+Km1",(long long)(b->first_id+i+1),b->rlen_all[i]);
+                      die("Read %lld: %s",(long long)(b->first_id+i+1),cpg_status_string(b->status[k]));
+                    }
+                }
+            }
+          else if (rc != CPG_OK) die("%s: %s",PROG,cpg_last_error(ctx));
+        }
+      pthread_mutex_lock(&A->mu);
+      b->next = A->done; A->done = b;
+      pthread_cond_broadcast(&A->cv);
+      pthread_mutex_unlock(&A->mu);
+    }
+  cpg_destroy(ctx);
+  return NULL;
+}
+
+static void *writer_main(void *arg)
+{ app_t *A = arg;
+  const int K = A->P.kmer;
+  FILE *out = fopen(A->out_path,"wb");
+  if (out == NULL) die("Cannot open %s",A->out_path);
+  setvbuf(out,NULL,_IOFBF,1<<22);
+  /* the class string of the last classified read: printed again, whole, for reads shorter than K
+     ("%*s" is a minimum width, src/ClassPro.c:215) */
+  char *rasgn = xmalloc(MAX_READ_LEN+2);
+  memset(rasgn,0,MAX_READ_LEN+2);
+  for (int i = 0; i < K-1; i++) rasgn[i] = 'N';
+  for (;;)
+    { pthread_mutex_lock(&A->mu);
+      batch_t *b = NULL;
+      for (;;)
+        { batch_t **pp = &A->done;
+          while (*pp && (*pp)->first_id != A->next_id) pp = &(*pp)->next;
+          if (*pp) { b = *pp; *pp = b->next; break; }
+          if (A->reader_done && A->next_id >= A->total_reads) break;
+          pthread_cond_wait(&A->cv,&A->mu);
+        }
+      pthread_mutex_unlock(&A->mu);
+      if (b == NULL) break;
+      for (int i = 0; i < b->n_all; i++)
+        { const int rlen = b->rlen_all[i], k = b->slot_of[i];
+          fputs(b->header[i],out); fputc('\n',out);
+          fwrite(b->seq[i],1,(size_t)rlen,out);
+          fputs("\n+\n",out);
+          if (k >= 0)
+            { const uint8_t *c = b->cls+b->cls_off[k];
+              fwrite(c,1,(size_t)rlen,out);
+              memcpy(rasgn,c,(size_t)rlen); rasgn[rlen] = 0;
+            }
+          else fprintf(out,"%*s",rlen,rasgn);
+          fputc('\n',out);
+        }
+      pthread_mutex_lock(&A->mu);
+      A->next_id = b->first_id+b->n_all;
+      A->kmers += b->kmers;
+      pthread_mutex_unlock(&A->mu);
+      q_push(&A->q_free,b);
+    }
+  q_close(&A->q_free);
+  if (fclose(out) != 0) die("Cannot write %s",A->out_path);
+  free(rasgn);
+  return NULL;
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  Command line (src/ClassPro.c:348-501) and timing lines (src/benchmark.c:12-96)
+ * --------------------------------------------------------------------------------------- */
+static struct timespec T0;
+static struct rusage   R0;
+
+static void time_line(FILE *f, const char *what)
+{ struct timespec t; struct rusage r;
+  clock_gettime(CLOCK_MONOTONIC,&t); getrusage(RUSAGE_SELF,&r);
+  double wall = (t.tv_sec-T0.tv_sec)+(t.tv_nsec-T0.tv_nsec)*1e-9;
+  double user = (r.ru_utime.tv_sec-R0.ru_utime.tv_sec)+(r.ru_utime.tv_usec-R0.ru_utime.tv_usec)*1e-6;
+  double sys  = (r.ru_stime.tv_sec-R0.ru_stime.tv_sec)+(r.ru_stime.tv_usec-R0.ru_stime.tv_usec)*1e-6;
+  fprintf(f,"%s  %.3f (s.ms) user  %.3f (s.ms) sys  %.3f (s.ms) wall  %.1f%%  %ld MB max rss\n",
+          what,user,sys,wall,wall > 0 ? 100.*(user+sys)/wall : 0.,r.ru_maxrss/1024);
+}
+
+static const char *EXT[10] = { ".db",".dam",".fastq",".fasta",".fq",".fa",".fastq.gz",".fasta.gz",".fq.gz",".fa.gz" };
+
+int main(int argc, char **argv)
+{ clock_gettime(CLOCK_MONOTONIC,&T0); getrusage(RUSAGE_SELF,&R0);
+  app_t *A = calloc(1,sizeof(app_t));
+  A->nthreads = 4; A->read_len = 20000; A->ngpus = 0; A->batch_bases = 256000000;
+  int npos = 0; char *pos = NULL;
+  for (int i = 1; i < argc; i++)
+    { char *a = argv[i];
+      if (a[0] != '-') { pos = a; npos++; continue; }
+      char *e = NULL;
+      switch (a[1])
+        { case 'T': A->nthreads = (int)strtol(a+2,&e,10);
+                    if (*e || a[2] == 0) die("%s: -T '%s' argument is not an integer",PROG,a+2);
+                    if (A->nthreads <= 0) die("%s: Number of threads must be positive (%d)",PROG,A->nthreads);
+                    break;
+          case 'c': A->cov = (int)strtol(a+2,&e,10);
+                    if (*e || a[2] == 0) die("%s: -c '%s' argument is not an integer",PROG,a+2);
+                    if (A->cov < 0) die("%s: Estimated k-mer coverage must be non-negative (%d)",PROG,A->cov);
+                    break;
+          case 'r': A->read_len = (int)strtol(a+2,&e,10);
+                    if (*e || a[2] == 0) die("%s: -r '%s' argument is not an integer",PROG,a+2);
+                    if (A->read_len <= 0) die("%s: Average read length must be positive (%d)",PROG,A->read_len);
+                    break;
+          case 'G': A->ngpus = (int)strtol(a+2,&e,10);
+                    if (*e || a[2] == 0 || A->ngpus <= 0) die("%s: -G needs a positive integer",PROG);
+                    break;
+          case 'B': { long mb = strtol(a+2,&e,10);
+                      if (*e || a[2] == 0 || mb <= 0) die("%s: -B needs a positive integer (megabases)",PROG);
+                      A->batch_bases = mb*1000000L;
+                    }
+                    break;
+          case 'N': A->fk_root = a+2; break;
+          case 'P': break;                                   /* no part files any more */
+          case 'M': A->model_path = a+2; break;
+          default:
+            for (char *p = a+1; *p; p++)
+              { if (*p == 'v') A->verbose = 1;
+                else if (*p == 's') A->find_seeds = 1;
+                else die("%s: -%c is an illegal option",PROG,*p);
+              }
+        }
+    }
+  if (npos < 1) { fprintf(stderr,"Usage: %s %s\n",PROG,USAGE); return 1; }
+  if (npos != 1) die("Currently only single file is accepted for FASTX input");
+  if (A->model_path) die("%s: -M <model_path> is not supported (the polynomial fit needs GSL, absent from the reference tree)",PROG);
+  if (A->find_seeds)
+    fprintf(stderr,"%s: -s has no effect on the .class output and is not implemented for FASTX inputs; ignored\n",PROG);
+
+  if (A->verbose) fprintf(stderr,"Info about inputs:\n");
+  /* resolve <source> by trying the extensions in the reference's order (src/ClassPro.c:411-430) */
+  char dir[4096], base[1024], root[1024], path[8192];
+  split_path(pos,dir,sizeof(dir),base,sizeof(base));
+  int idx;
+  for (idx = 0; idx < 10; idx++)
+    { size_t bl = strlen(base), el = strlen(EXT[idx]);
+      snprintf(root,sizeof(root),"%s",base);
+      if (bl > el && strcasecmp(base+bl-el,EXT[idx]) == 0) root[bl-el] = 0;
+      snprintf(path,sizeof(path),"%s/%s%s",dir,root,EXT[idx]);
+      int f = open(path,O_RDONLY);
+      if (f >= 0) { close(f); break; }
+    }
+  if (idx == 10) die("Cannot open %s as a .db|.dam or .f{ast}[aq][.gz] file",pos);
+  if (idx <= 1) die("%s: .db/.dam inputs are not supported by this build (DAZZ_DB is out of scope)",PROG);
+  A->src_path = strdup(path);
+  char fk[8192], outp[8192];
+  if (A->fk_root == NULL) { snprintf(fk,sizeof(fk),"%s/%s",dir,root); A->fk_root = fk; }
+  snprintf(outp,sizeof(outp),"%s/%s.class",dir,root);
+  A->out_path = outp;
+  if (A->verbose)
+    { fprintf(stderr,"    # of sequence files   = %d\n",1);
+      fprintf(stderr,"    First (path,root,ext) = (%s, %s, %s)\n",dir,root,EXT[idx]);
+      fprintf(stderr,"    FASTK outputs' root   = %s\n",A->fk_root);
+      fprintf(stderr,"    Output .class file    = %s/%s.class\n",dir,root);
+    }
+
+  if (profidx_open(&A->P,A->fk_root)) die("%s: Cannot open %s.prof",PROG,A->fk_root);
+  if (A->verbose) fprintf(stderr,"    Total # of reads      = %lld\n",(long long)A->P.nreads);
+
+  A->model = xmalloc(sizeof(cpg_model));
+  int rc = cpg_model_load(A->model,A->fk_root,A->cov,A->read_len,A->verbose);
+  if (rc == CPG_EIO) die("%s: Cannot open %s.hist",PROG,A->fk_root);
+  if (rc != CPG_OK) exit(1);
+  A->model->kmer = A->P.kmer;
+  if (A->verbose) fprintf(stderr,"Error model not specified. Using the default error model.\n");
+
+  int ndev = cpg_device_count();
+  if (ndev <= 0) die("%s: no CUDA device found: this program has no CPU fallback",PROG);
+  const char *env = getenv("CLASSPRO_GPUS");
+  if (A->ngpus == 0 && env && atoi(env) > 0) A->ngpus = atoi(env);
+  if (A->ngpus == 0 || A->ngpus > ndev) A->ngpus = ndev;
+  if (A->verbose)
+    fprintf(stderr,"Classifying %d-mers on %d GPU%s...\n",A->P.kmer,A->ngpus,A->ngpus > 1 ? "s" : "");
+
+  q_init(&A->q_free); q_init(&A->q_ready);
+  pthread_mutex_init(&A->mu,NULL); pthread_cond_init(&A->cv,NULL);
+  const int nbatch = 2*A->ngpus+2;
+  for (int i = 0; i < nbatch; i++) q_push(&A->q_free,calloc(1,sizeof(batch_t)));
+
+  pthread_t rd, wr, *gp = xmalloc(sizeof(pthread_t)*(size_t)A->ngpus);
+  gpu_arg_t *ga = xmalloc(sizeof(gpu_arg_t)*(size_t)A->ngpus);
+  pthread_create(&wr,NULL,writer_main,A);
+  for (int g = 0; g < A->ngpus; g++) { ga[g].A = A; ga[g].device = g; pthread_create(&gp[g],NULL,gpu_main,&ga[g]); }
+  pthread_create(&rd,NULL,reader_main,A);
+  pthread_join(rd,NULL);
+  for (int g = 0; g < A->ngpus; g++) pthread_join(gp[g],NULL);
+  pthread_mutex_lock(&A->mu); pthread_cond_broadcast(&A->cv); pthread_mutex_unlock(&A->mu);
+  pthread_join(wr,NULL);
+
+  if (A->verbose)
+    { time_line(stderr,"Resources for phase:");
+      fprintf(stderr,"Classified %lld k-mers of %lld reads\n",(long long)A->kmers,(long long)A->total_reads);
+      time_line(stderr,"Total Resources:");
+    }
+  return 0;
+}

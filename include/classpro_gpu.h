@@ -1,0 +1,143 @@
+/*******************************************************************************************
+ *  classpro_gpu.h -- C ABI of libclasspro_b200.so: ClassPro's per-read classification path
+ *  (profile decode -> sequence context -> wall detection -> reliable-interval DP ->
+ *  unreliable-interval assignment -> per-k-mer E/H/D/R string) on a B200.
+ *
+ *  Plain C: pointers and sizes only, no CUDA or torch types.  The reference has no library
+ *  boundary for this path (one translation unit, src/ClassPro.c:16-25); every entry point below
+ *  names the reference code it stands in for.  file:line are relative to the reference tree.
+ *
+ *  Threading: a cpg_ctx is bound to one GPU and must be driven by one host thread at a time; use
+ *  one context per GPU (reads are independent, src/io.c:353-354, so GPUs never talk to each other).
+ *  Errors: every call returns 0 on success or a CPG_E* code; cpg_last_error() gives the text.
+ *  There is NO CPU fallback: without a usable CUDA device cpg_create fails.
+ *******************************************************************************************/
+#ifndef CLASSPRO_GPU_H
+#define CLASSPRO_GPU_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPG_OK          0
+#define CPG_EINVAL      1      /* bad argument                                           */
+#define CPG_ECUDA       2      /* CUDA runtime error (text in cpg_last_error)            */
+#define CPG_ENOMEM      3      /* host or device allocation failed                       */
+#define CPG_EMODEL      4      /* histogram/model error (hist.c:65-68, wall.c:174-177)   */
+#define CPG_EREAD       5      /* at least one read failed; see cpg_result.status        */
+#define CPG_EIO         6
+
+/* ---- host one-shot model ---------------------------------------------------------------
+ * Replaces process_global_hist (src/hist.c:28-143), the derived globals of
+ * src/ClassPro.c:543-548, calc_init_thres/load_emodel (src/wall.c:120-244, default error model)
+ * and precompute_logfact (src/prob.c:14-19).  Computed on the host with the host libm exactly as
+ * the reference does (north-star item 3), uploaded once by cpg_create. */
+typedef struct
+  { int32_t  kmer;              /* K                                      */
+    int32_t  read_len;          /* -r, READ_LEN (src/ClassPro.c:516)      */
+    uint16_t cov[4];            /* GLOBAL_COV[E,R,H,D]                    */
+    double   dr_ratio;          /* DR_RATIO                               */
+    int32_t  cmax;              /* CMAX (src/wall.c:178)                  */
+    double   hc_erate;          /* HC_ERATE (src/wall.c:180)              */
+    int32_t  lmax[3];           /* per context type (src/wall.c:123)      */
+    double   pe[3][21];         /* error rate by context type and length  */
+    uint8_t  cthres[36*256*4];  /* [row(t,l)][cout][INIT|FINAL][SELF|OTHERS], rows 20+10+6 */
+    double   logfact[32768];
+  } cpg_model;
+
+/* hist = the (high-low+1) int64 bins as stored in <root>.hist after the 28-byte header
+ * (src/libfastk.c:72-83).  cov_opt = the -c value (0 = estimate from the histogram). */
+int cpg_model_from_hist(cpg_model *m, int kmer, int low, int high, int64_t ilowcnt, int64_t ihighcnt,
+                        const int64_t *hist, int cov_opt, int read_len, int verbose);
+/* Same, reading <fk_root>.hist (src/libfastk.c:51-96). */
+int cpg_model_load(cpg_model *m, const char *fk_root, int cov_opt, int read_len, int verbose);
+/* Model for given (H,D) coverages (what -c<D> gives with h = 0 -> D>>1, src/hist.c:44-49). */
+int cpg_model_from_cov(cpg_model *m, int kmer, int h, int d, int read_len);
+
+/* ---- context ------------------------------------------------------------------------------ */
+typedef struct cpg_ctx cpg_ctx;
+
+int  cpg_device_count(void);
+/* max_batch_bases / max_batch_reads size the device and pinned staging buffers (0 = defaults). */
+int  cpg_create(cpg_ctx **ctx, int device, const cpg_model *model,
+                int64_t max_batch_bases, int32_t max_batch_reads);
+void cpg_destroy(cpg_ctx *ctx);
+const char *cpg_last_error(const cpg_ctx *ctx);   /* ctx may be NULL: last creation error */
+
+/* ---- batches ------------------------------------------------------------------------------
+ * A batch is n_reads consecutive reads, every one with rlen >= K (shorter reads never reach the
+ * stage functions in the reference either, src/ClassPro.c:209-226; the caller prints them).
+ *   seq      : read sequences. seq_bits = 8: the raw characters (compared as bytes, exactly as
+ *              src/context.c does); seq_bits = 2: bases packed 4 per byte, base i of a read in
+ *              bits 2*(i&3) of byte i>>2, A,C,G,T = 0..3 (cpg_pack_seq), every read starting at
+ *              a byte boundary.
+ *   seq_off  : [n_reads+1] byte offsets of each read inside seq
+ *   rlen     : [n_reads]   read lengths in bases
+ *   prof     : FastK-compressed profiles (src/libfastk.c:1467-1535), read after read
+ *   prof_off : [n_reads+1] byte offsets inside prof  (= the .pidx index of the part, rebased)
+ * The arrays may live in pageable or pinned host memory. */
+typedef struct
+  { int32_t        n_reads;
+    int32_t        seq_bits;
+    const uint8_t *seq;
+    const int64_t *seq_off;
+    const int32_t *rlen;
+    const uint8_t *prof;
+    const int64_t *prof_off;
+  } cpg_batch;
+
+/* Result of a batch, owned by the caller.
+ *   cls      : class strings, read after read: rlen characters per read, 'N' x (K-1) followed by
+ *              one of E/H/D/R per k-mer -- the 4th line of the read's .class record without the
+ *              newline (src/ClassPro.c:114-117,265-271,289)
+ *   cls_off  : [n_reads+1] byte offsets inside cls; the caller fills it (normally the prefix sums
+ *              of rlen) and must provide cls_off[n_reads] bytes
+ *   status   : [n_reads] 0 = classified; otherwise CPG_ST_* bits (cpg_status_string) for the
+ *              conditions on which the reference prints a message and exits */
+typedef struct
+  { uint8_t       *cls;
+    const int64_t *cls_off;
+    int32_t       *status;
+  } cpg_result;
+
+/* Pack an ASCII read into 2-bit codes.  Returns 0, or 1 if a character outside "ACGT" is met
+ * (then ship the batch with seq_bits = 8). */
+int cpg_pack_seq(const char *seq, int32_t rlen, uint8_t *out);
+
+/* Host buffers in, host buffers out: H2D copies, kernels, D2H copy, synchronous.
+ * Stands in for steps 2-6 of the per-read loop, src/ClassPro.c:229-271, for a whole batch. */
+int cpg_classify(cpg_ctx *ctx, const cpg_batch *batch, cpg_result *result);
+
+/* Asynchronous pair on one of two slots (double buffering: slot 0/1): cpg_submit stages the
+ * batch into pinned memory and enqueues copies + kernels; cpg_collect waits for that slot and
+ * copies the classes out.  A slot must be collected before it is submitted again. */
+int cpg_submit(cpg_ctx *ctx, int slot, const cpg_batch *batch);
+int cpg_collect(cpg_ctx *ctx, int slot, cpg_result *result);
+
+/* ---- stage access (tests, benchmarks) ------------------------------------------------------
+ * cpg_decode_profiles: the Fetch_Profile replacement alone (src/libfastk.c:1414-1562): counts of
+ * read r are written to counts[cnt_off[r] .. ) with capacity cnt_off[r+1]-cnt_off[r]; plen[r]
+ * receives the decoded length (which may exceed the capacity, as Fetch_Profile's return does). */
+int cpg_decode_profiles(cpg_ctx *ctx, int32_t n_reads, const uint8_t *prof, const int64_t *prof_off,
+                        const int64_t *cnt_off, uint16_t *counts, int32_t *plen);
+
+/* Device-resident timing: upload once, run the kernels `iters` times on data already in HBM,
+ * report the mean device time of each kernel in milliseconds (CUDA events on the context's
+ * stream), then fetch the result of the last run. */
+int cpg_upload(cpg_ctx *ctx, const cpg_batch *batch);
+int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float *ms_classify, int *launches);
+int cpg_download(cpg_ctx *ctx, cpg_result *result);
+
+/* Pinned (page-locked) host memory, so that the copies of cpg_submit/cpg_collect are truly
+ * asynchronous DMA transfers; pageable buffers work too but are staged by the driver. */
+void *cpg_host_alloc(size_t bytes);
+void  cpg_host_free(void *p);
+
+const char *cpg_status_string(int32_t status);
+const char *cpg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

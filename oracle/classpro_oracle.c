@@ -1413,7 +1413,14 @@ int cpo_classify_read(const cpo_model *M, cpo_work *W, const char *seq, int rlen
 { const int K = M->K;
   if (rlen > CPO_MAX_RLEN || rlen != plen+K-1 || plen < 1) return -1;
   if (W->clean)
-    { memset(W->rctx,0,(size_t)(rlen+8)*3); }
+    { /* device definition of the reference's stale reads: right-context cells that
+         the sweep never writes are 0, and profile[plen] (read by wall.c:977-978 when a
+         low-complexity run reaches the end of the read) equals profile[plen-1] */
+      memset(W->rctx,0,(size_t)(rlen+8)*3);
+      if (prof != W->profile) memcpy(W->profile,prof,sizeof(uint16_t)*(size_t)plen);
+      W->profile[plen] = W->profile[plen-1];
+      prof = W->profile;
+    }
   cpo_seq_context(W->lctx_base,W->rctx,seq,rlen);
   int N = find_walls(M,W,prof,plen);
   int Mrel = find_reliable(M,W,N,prof);
