@@ -1,0 +1,148 @@
+"""C-ABI surface (loads, exports everything include/classpro_gpu.h declares, fails loudly without
+a GPU), host model parity, packing, and the multi-rank sharding logic under gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "classpro_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cpg_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import classpro_b200 as cp
+    L = cp.lib()
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), "libclasspro_b200.so does not export %s" % n
+
+
+def test_library_does_not_link_the_oracle():
+    """The product must not route through oracle/: no cpo_* symbol, no liboracle dependency."""
+    import classpro_b200 as cp
+    out = subprocess.run(["nm", "-D", cp.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "cpo_" not in out
+    ldd = subprocess.run(["ldd", cp.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "oracle" not in ldd and "hostsim" not in ldd
+
+
+def test_no_gpu_means_loud_failure():
+    import classpro_b200 as cp
+    if cp.lib().cpg_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    m = cp.Model.from_cov(40, 0, 30)
+    with pytest.raises(cp.CpgError) as e:
+        cp.Context(m)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_host_model_matches_oracle(kit):
+    import classpro_b200 as cp
+    sim = kit.simulate(seed=51, genome_len=40000, cov=30., het=0.01)
+    for cov_opt, rl in ((0, 20000), (41, 15000)):
+        om = kit.oracle_model(sim, cov_opt, rl)
+        gm = cp.Model.from_hist(sim.kmer, sim.hist[1:32768], sim.hist[32768], sim.hist[32769], cov_opt=cov_opt, read_len=rl)
+        assert gm.cov == list(om.cov)
+        assert gm.c.dr_ratio == om.dr_ratio and gm.c.cmax == om.cmax
+        assert np.array_equal(np.frombuffer(gm.c.logfact, dtype=np.float64), np.frombuffer(om.logfact, dtype=np.float64))
+    with pytest.raises(cp.CpgError):      # D-coverage too high for the 8-bit threshold table (wall.c:174-177)
+        cp.Model.from_cov(40, 0, 250)
+
+
+def test_model_errors(kit):
+    import classpro_b200 as cp
+    flat = np.ones(32767, dtype=np.int64)      # no peak >= 10 (hist.c:65-68)
+    with pytest.raises(cp.CpgError):
+        cp.Model.from_hist(40, flat, 1, 1)
+
+
+def test_pack_seq():
+    import classpro_b200 as cp
+    L = cp.lib()
+    s = b"ACGTTGCAAC"
+    out = np.zeros(4, dtype=np.uint8)
+    assert L.cpg_pack_seq(s, len(s), out.ctypes.data) == 0
+    codes = [(out[i >> 2] >> ((i & 3) * 2)) & 3 for i in range(len(s))]
+    assert codes == ["ACGT".index(chr(c)) for c in s]
+    assert L.cpg_pack_seq(b"ACGNT", 5, out.ctypes.data) == 1
+    assert L.cpg_pack_seq(b"acgt", 4, out.ctypes.data) == 1      # the reference compares raw bytes
+    from classpro_b200.abi import pack_codes
+    rng = np.random.default_rng(3)
+    rl = np.array([5, 8, 13, 40], dtype=np.int32)
+    so = np.concatenate([[0], np.cumsum(rl)]).astype(np.int64)
+    codes = rng.integers(0, 4, size=int(so[-1])).astype(np.uint8)
+    pk, po = pack_codes(codes, so, rl)
+    for r in range(len(rl)):
+        asc = bytes(b"ACGT"[c] for c in codes[so[r]:so[r + 1]])
+        ref = np.zeros((rl[r] + 3) // 4, dtype=np.uint8)
+        L.cpg_pack_seq(asc, int(rl[r]), ref.ctypes.data)
+        assert np.array_equal(ref, pk[po[r]:po[r + 1]])
+
+
+def test_shard_ranges_properties():
+    from classpro_b200.shard import shard_ranges, reference_thread_ranges
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 1000):
+        w = rng.integers(1, 5000, size=n)
+        for ranks in (1, 2, 3, 8):
+            rs = shard_ranges(w, ranks)
+            assert len(rs) == ranks and rs[0][0] == 0 and rs[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+            if n >= 100:
+                tot = [int(w[a:b].sum()) for a, b in rs]
+                assert max(tot) - min(tot) <= 2 * int(w.max())
+    assert reference_thread_ranges(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import cpkit
+from classpro_b200.shard import shard_ranges
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sim = cpkit.simulate(seed=61, genome_len=30000, cov=20., het=0.01)
+w = np.diff(sim.prof_off)
+beg, end = shard_ranges(w, world)[rank]
+# each rank classifies ONLY its own contiguous range (host-sim of the device logic stands in for
+# the GPU here); no data-path collective is needed
+gm = cpkit.gpu_model_from_sim(cpkit.hostsim_lib(), sim)
+mine = [cpkit.hostsim_classify(gm, sim.read_ascii(i).tobytes(), sim.read_counts(i), 2)[1] for i in range(beg, end)]
+kmers = sum(len(x) - 39 for x in mine)
+# the only cross-rank steps: ordered gather of the outputs on rank 0, max of the timings
+gathered = [None] * world
+dist.all_gather_object(gathered, (beg, end, mine))
+t = torch.tensor([float(rank + 1)]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+tot = torch.tensor([float(kmers)]); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+if rank == 0:
+    om = cpkit.oracle_model(sim); ow = cpkit.OracleWork(clean=True)
+    full = [ow.classify(om, sim.read_ascii(i).tobytes(), sim.read_counts(i)) for i in range(sim.nreads)]
+    got = []
+    for b, e, part in sorted(gathered):
+        got.extend(part)
+    assert got == full, "sharded result differs"
+    assert int(tot.item()) == sim.total_kmers and t.item() == world
+    print("SHARD_OK", world, sim.nreads)
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_gloo(kit, hostsim, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:]
+    assert "SHARD_OK 2" in p.stdout

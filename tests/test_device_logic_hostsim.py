@@ -1,0 +1,183 @@
+"""The device-side per-read logic (classpro_b200/csrc/*.cuh) compiled for the host with a warp
+width of 1 (tests/hostsim), against the oracle.  This is how the CUDA sources are unit-tested on a
+machine without a GPU; it is a test build only, the product has no CPU path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def compare_dataset(kit, sim, cov_opt=0, read_len=20000, seq_bits=2, intervals=True):
+    om = kit.oracle_model(sim, cov_opt, read_len)
+    gm = kit.gpu_model_from_sim(kit.hostsim_lib(), sim, cov_opt, read_len)
+    ow = kit.OracleWork(clean=True)
+    status = 0
+    for i in range(sim.nreads):
+        if sim.rlen[i] < sim.kmer:
+            continue
+        s, c = sim.read_ascii(i).tobytes(), sim.read_counts(i)
+        if intervals:
+            a, ia, ma = ow.classify(om, s, c, True)
+            st, b, ib, mb = kit.hostsim_classify(gm, s, c, seq_bits, True)
+            assert ma == mb and ia == ib, "read %d: interval tables differ" % i
+        else:
+            a = ow.classify(om, s, c)
+            st, b = kit.hostsim_classify(gm, s, c, seq_bits)
+        assert a == b, "read %d: class strings differ" % i
+        status |= st
+    return status
+
+
+def test_model_matches_oracle(kit, hostsim):
+    sim = kit.simulate(seed=41, genome_len=40000, cov=30., het=0.01)
+    for cov_opt, rl in ((0, 20000), (33, 12000)):
+        om = kit.oracle_model(sim, cov_opt, rl)
+        gm = kit.gpu_model_from_sim(hostsim, sim, cov_opt, rl)
+        assert list(om.cov) == list(gm.cov) and om.cmax == gm.cmax
+        assert om.dr_ratio == gm.dr_ratio and om.hc_erate == gm.hc_erate
+        assert np.array_equal(np.frombuffer(om.logfact, dtype=np.float64), np.frombuffer(gm.logfact, dtype=np.float64))
+        oc = np.frombuffer(om.cthres, dtype=np.uint8).reshape(3, 21, 256, 2, 2)
+        gc = np.frombuffer(gm.cthres, dtype=np.uint8).reshape(36, 256, 2, 2)
+        row = 0
+        for t, lmax in enumerate((20, 10, 6)):
+            for l in range(1, lmax + 1):
+                assert np.array_equal(oc[t, l], gc[row]), (t, l)
+                row += 1
+            assert np.array_equal(np.array(om.pe[t][:lmax + 1]), np.array(gm.pe[t][:lmax + 1]))
+
+
+def test_plain_dataset(kit, hostsim):
+    sim = kit.simulate(seed=42, genome_len=50000, cov=30., het=0.006)
+    assert compare_dataset(kit, sim) == 0
+
+
+def test_repeat_rich_dataset(kit, hostsim):
+    sim = kit.simulate(seed=43, genome_len=60000, cov=40., het=0.01, repeat_frac=0.6, seg_dups=2)
+    compare_dataset(kit, sim)
+
+
+def test_options_and_raw_bytes(kit, hostsim):
+    sim = kit.simulate(seed=44, genome_len=40000, cov=50., het=0.02, len_mean=9000, short_reads=1)
+    compare_dataset(kit, sim, cov_opt=47, read_len=9000, seq_bits=8, intervals=False)
+
+
+def test_noisy_low_complexity(kit, hostsim):
+    sim = kit.simulate(seed=45, genome_len=40000, cov=35., het=0.001, err_indel_hp=0.003, err_sub=0.002,
+                       repeat_frac=0.8)
+    compare_dataset(kit, sim)
+
+
+def test_minimal_reads(kit, hostsim):
+    """Reads of length K, K+1 (profiles of 1 and 2 counts) and constant profiles."""
+    sim = kit.simulate(seed=46, genome_len=30000, cov=20., het=0.01)
+    om = kit.oracle_model(sim)
+    gm = kit.gpu_model_from_sim(hostsim, sim)
+    ow = kit.OracleWork(clean=True)
+    s = sim.read_ascii(0).tobytes()
+    c = sim.read_counts(0)
+    for n in (1, 2, 3, 39, 40, 41, 80, 81):
+        a = ow.classify(om, s[:n + 39], c[:n])
+        st, b = kit.hostsim_classify(gm, s[:n + 39], c[:n], 2)
+        assert a == b, n
+    flat = np.full(500, 30, dtype=np.uint16)
+    a = ow.classify(om, s[:539], flat)
+    st, b = kit.hostsim_classify(gm, s[:539], flat, 2)
+    assert a == b
+    high = np.full(500, 3000, dtype=np.uint16)
+    a = ow.classify(om, s[:539], high)
+    st, b = kit.hostsim_classify(gm, s[:539], high, 2)
+    assert a == b and set(a[39:]) == {ord("R")}
+
+
+def test_context_closed_form_exhaustive(kit, hostsim):
+    """cpg_context.cuh's on-demand run lengths equal the reference sweep (src/context.c) at every
+    base, for every sequence of length <= 7 over ACGT and <= 12 over a two-letter alphabet."""
+    L = kit.oracle_lib()
+
+    def check(seq):
+        n = len(seq)
+        lc = np.zeros((n + 4, 3), dtype=np.uint8)
+        rc = np.full((n + 4, 3), 0xEE, dtype=np.uint8)
+        lc[0] = (1, 0, 0)
+        L.cpo_seq_context(lc.ctypes.data, rc.ctypes.data, seq, n)
+        for p in range(n):
+            for t in range(3):
+                assert hostsim.hs_ctx(seq, n, p, 0, t) == lc[p, t], (seq, p, t, "left")
+                assert hostsim.hs_ctx(seq, n, p, 1, t) == rc[p, t], (seq, p, t, "right")
+
+    import itertools
+    for n in range(2, 7):
+        for tup in itertools.product(b"ACGT", repeat=n):
+            check(bytes(tup))
+    for n in range(7, 12):
+        for tup in itertools.product(b"AC", repeat=n):
+            check(bytes(tup))
+
+
+def test_context_random_low_complexity(kit, hostsim):
+    L = kit.oracle_lib()
+    rng = np.random.default_rng(7)
+    for _ in range(60):
+        parts = []
+        while sum(map(len, parts)) < 600:
+            kind = rng.integers(0, 4)
+            if kind == 0:
+                parts.append(bytes(rng.choice(list(b"ACGT"), size=rng.integers(1, 30)).tolist()))
+            else:
+                u = bytes(rng.choice(list(b"ACGT"), size=kind).tolist())
+                parts.append((u * 40)[:int(rng.integers(kind, kind * 30))])
+        seq = b"".join(parts)
+        n = len(seq)
+        lc = np.zeros((n + 4, 3), dtype=np.uint8)
+        rc = np.full((n + 4, 3), 0xEE, dtype=np.uint8)
+        lc[0] = (1, 0, 0)
+        L.cpo_seq_context(lc.ctypes.data, rc.ctypes.data, seq, n)
+        if lc[:n].max() >= 127:
+            continue   # beyond the cap the reference reads cells it never wrote
+        for p in range(0, n, 3):
+            for t in range(3):
+                assert hostsim.hs_ctx(seq, n, p, 0, t) == lc[p, t]
+                assert hostsim.hs_ctx(seq, n, p, 1, t) == rc[p, t]
+
+
+def random_stream(rng, n_tokens, adversarial):
+    """A FastK token stream; adversarial = arbitrary bytes (wrap-around and mask corner cases)."""
+    first = int(rng.integers(0, 32768))
+    out = bytearray()
+    if first >= 128 or rng.random() < 0.2:
+        out += bytes([0x80 | (first >> 8), first & 0xff])
+    else:
+        out.append(first)
+    for _ in range(n_tokens):
+        k = rng.random()
+        if adversarial:
+            b = int(rng.integers(0, 256))
+            out.append(b)
+            if b & 0x80:
+                out.append(int(rng.integers(0, 256)))
+        elif k < 0.5:
+            out.append(int(rng.integers(0, 64)))
+        elif k < 0.9:
+            out.append(0x40 | int(rng.integers(0, 64)))
+        else:
+            out += bytes([0x80 | int(rng.integers(0, 128)), int(rng.integers(0, 256))])
+    return bytes(out)
+
+
+@pytest.mark.parametrize("adversarial", [False, True])
+def test_decode_streams(kit, hostsim, adversarial):
+    """The scan-based decoder equals the byte-serial one on well-formed and on arbitrary streams
+    (16-bit wrap of short deltas, 15-bit mask of long ones, zero-length runs, cap truncation)."""
+    rng = np.random.default_rng(11 + adversarial)
+    for it in range(300):
+        s = random_stream(rng, int(rng.integers(0, 400)), adversarial)
+        n1, o1 = kit.oracle_decode(np.frombuffer(s, dtype=np.uint8), 100000)
+        for cap in (100000, max(1, n1 // 2)):
+            n2, o2 = kit.hostsim_decode(np.frombuffer(s, dtype=np.uint8), cap)
+            assert n2 == n1
+            assert np.array_equal(o2, o1[:min(cap, n1)])
+
+
+def test_decode_empty_profile(kit, hostsim):
+    n, o = kit.hostsim_decode(np.zeros(0, dtype=np.uint8), 10)
+    assert n == 0
