@@ -77,7 +77,8 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
         }
       if (c == lane) c += (int)carry;
       const int second = valid && (c & 1);
-      const unsigned prev = (lane == 0) ? carry_hi : dc_shfl_up(x,1,lane);
+      const unsigned up = dc_shfl_up(x,1,lane);          /* every lane takes part in the shuffle */
+      const unsigned prev = (lane == 0) ? carry_hi : up;
 
       unsigned a = 0, cnt = 0; int masked = 0;
       if (valid)

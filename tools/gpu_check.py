@@ -13,6 +13,7 @@ def run(name, cov_opt=0, read_len=20000, **kw):
     om = cpkit.oracle_model(sim, cov_opt, read_len)
     gm = cp.Model.from_hist(sim.kmer, sim.hist[1:32768], sim.hist[32768], sim.hist[32769], cov_opt=cov_opt, read_len=read_len)
     assert list(om.cov) == gm.cov, (list(om.cov), gm.cov)
+    print("[%s] ctx..." % name, flush=True)
     ctx = cp.Context(gm)
     rl = sim.rlen[keep]
     seq_parts = [sim.seq[sim.seq_off[i]:sim.seq_off[i+1]] for i in keep]
@@ -22,12 +23,16 @@ def run(name, cov_opt=0, read_len=20000, **kw):
     prof = np.concatenate(prof_parts); pro = np.zeros(len(keep)+1, np.int64); np.cumsum([len(p) for p in prof_parts], out=pro[1:])
     # decode parity
     caps = rl.astype(np.int64) - sim.kmer + 1
+    print("[%s] decode..." % name, flush=True)
     counts, cnt_off, plen = ctx.decode_profiles(prof, pro, caps)
+    print("[%s] decode done" % name, flush=True)
     dec_bad = 0
     for k, i in enumerate(keep):
         if plen[k] != caps[k] or not np.array_equal(counts[cnt_off[k]:cnt_off[k+1]], sim.read_counts(i)): dec_bad += 1
     batch = cp.Batch(packed, poff, rl, prof, pro, 2)
+    print("[%s] classify %d reads..." % (name, len(keep)), flush=True)
     t0 = time.time(); cls, status = ctx.classify(batch); t1 = time.time()
+    print("[%s] classify done %.3fs" % (name, t1-t0), flush=True)
     ow = cpkit.OracleWork(clean=True)
     flips = 0; bad_reads = 0; nk = 0
     t2 = time.time()
@@ -54,6 +59,7 @@ def run(name, cov_opt=0, read_len=20000, **kw):
 
 if __name__ == "__main__":
     out = []
+    out.append(run("tiny", seed=1, genome_len=20000, cov=10., het=0.005, len_mean=5000, len_sd=500))
     out.append(run("basic", seed=1, genome_len=100000, cov=30., het=0.005))
     out.append(run("repeat", seed=2, genome_len=200000, cov=40., het=0.01, repeat_frac=0.5, seg_dups=3))
     out.append(run("hicov", seed=6, genome_len=120000, cov=100., het=0.01, repeat_frac=0.3, len_mean=25000, len_sd=3000))
