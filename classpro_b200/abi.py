@@ -3,7 +3,7 @@ import ctypes as C
 import os
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libclasspro_b200.so")
+LIB_PATH = os.environ.get("CLASSPRO_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libclasspro_b200.so")
 
 ST_FATAL = 1 | 2 | 4 | 8 | 64   # conditions on which the reference exits (cpg_common.h)
 

@@ -21,10 +21,23 @@
   #include <string.h>
   #define CPG_DEV        static inline
   #define CPG_DEV_NOINL  static
-  #define CPG_WARP       1
-  #define CPG_SYNCWARP() do { } while (0)
   #define CPG_LDG(p)     (*(p))
   #define CPG_INF        ((double)INFINITY)
+  #if CPG_HOSTSIM == 32
+    /* 32 host threads play the lanes of one warp; every warp primitive is a rendezvous, so a
+       collective reached by only some lanes, or a missing __syncwarp, shows up as a hang or as
+       nondeterministic output in the CPU test-suite (tests/hostsim/hostsim.cpp) */
+    #define CPG_WARP       32
+    void     cpg_sim_barrier(void);
+    unsigned cpg_sim_ballot(int pred);
+    unsigned cpg_sim_shfl(unsigned v, int src);
+    unsigned cpg_sim_shfl_up(unsigned v, int d);
+    int      cpg_sim_sum(int v);
+    #define CPG_SYNCWARP() cpg_sim_barrier()
+  #else
+    #define CPG_WARP       1
+    #define CPG_SYNCWARP() do { } while (0)
+  #endif
 #else
   #include <cuda_runtime.h>
   #define CPG_DEV        __device__ __forceinline__
@@ -122,8 +135,8 @@ typedef struct
 
 /* Per-warp exchange block (shared memory on the device) */
 typedef struct
-  { double term[CPG_WARP > 16 ? CPG_WARP : 16];
-    int    iv[CPG_WARP > 16 ? CPG_WARP : 16];
+  { double term[32];
+    int    iv[32];
   } cpg_wshared;
 
 #endif

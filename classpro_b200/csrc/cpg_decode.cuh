@@ -23,7 +23,20 @@
 #define CPG_DECODE_CUH
 #include "cpg_common.h"
 
-#ifdef CPG_HOSTSIM
+#if defined(CPG_HOSTSIM) && CPG_HOSTSIM == 32
+CPG_DEV unsigned dc_ballot(int p) { return cpg_sim_ballot(p); }
+CPG_DEV unsigned dc_shfl(unsigned v, int src) { return cpg_sim_shfl(v,src); }
+CPG_DEV unsigned dc_shfl_up(unsigned v, int d, int lane) { unsigned r = cpg_sim_shfl_up(v,d); return lane >= d ? r : 0u; }
+CPG_DEV unsigned dc_scan_add(unsigned v, int lane)
+{ for (int d = 1; d < 32; d <<= 1) { unsigned t = cpg_sim_shfl_up(v,d); if (lane >= d) v += t; }
+  return v;
+}
+CPG_DEV int dc_scan_max(int v, int lane)
+{ for (int d = 1; d < 32; d <<= 1) { int t = (int)cpg_sim_shfl_up((unsigned)v,d); if (lane >= d && t > v) v = t; }
+  return v;
+}
+CPG_DEV int dc_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+#elif defined(CPG_HOSTSIM)
 CPG_DEV unsigned dc_ballot(int p) { return p ? 1u : 0u; }
 CPG_DEV unsigned dc_shfl(unsigned v, int src) { (void)src; return v; }
 CPG_DEV unsigned dc_shfl_up(unsigned v, int d, int lane) { (void)d; (void)lane; return v; }

@@ -24,8 +24,12 @@
 #include "cpg_decode.cuh"
 
 #define DECODE_THREADS   256
+#ifndef CLASSIFY_THREADS
 #define CLASSIFY_THREADS 128
+#endif
+#ifndef CLASSIFY_MIN_BLOCKS
 #define CLASSIFY_MIN_BLOCKS 4
+#endif
 
 struct BatchDev
   { int32_t        n_reads;
@@ -170,6 +174,8 @@ struct Slot
     int32_t *h_status; size_t h_status_cap;
     int32_t  n_reads; int64_t cls_bytes; int32_t maxP;
     int      busy;
+    cudaEvent_t kdone;           /* recorded after this slot's kernels */
+    int      kdone_valid;
     BatchDev B;
   };
 
@@ -245,6 +251,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
       if (S->h_cnt_off) cudaFreeHost(S->h_cnt_off);
       if (S->h_order) cudaFreeHost(S->h_order);
       if (S->h_status) cudaFreeHost(S->h_status);
+      if (S->kdone) cudaEventDestroy(S->kdone);
       if (S->stream) cudaStreamDestroy(S->stream);
     }
   if (ctx->scratch.p) cudaFree(ctx->scratch.p);
@@ -291,7 +298,10 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
   memcpy(d.pe,model->pe,sizeof(d.pe));
   d.cthres = (const uint8_t *)ctx->d_cthres;
   d.logfact = (const double *)ctx->d_logfact;
-  for (int s = 0; s < 2; s++) CU_C(cudaStreamCreateWithFlags(&ctx->slot[s].stream,cudaStreamNonBlocking));
+  for (int s = 0; s < 2; s++)
+    { CU_C(cudaStreamCreateWithFlags(&ctx->slot[s].stream,cudaStreamNonBlocking));
+      CU_C(cudaEventCreateWithFlags(&ctx->slot[s].kdone,cudaEventDisableTiming));
+    }
   for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->ev[i]));
 
   ctx->classify_smem = sizeof(ClassifyShared);
@@ -406,12 +416,19 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
 static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
 { cudaStream_t st = S->stream;
   if (S->n_reads == 0) return CPG_OK;
+  /* The two slots overlap their copies with each other's kernels, but the kernels themselves are
+     serialised: k_classify is a persistent grid that fills the GPU, and both slots share the
+     per-warp scratch arena. */
+  Slot *other = &ctx->slot[S == &ctx->slot[0] ? 1 : 0];
+  if (other->kdone_valid) CU(cudaStreamWaitEvent(st,other->kdone,0));
   CU(cudaMemsetAsync(S->queue.p,0,sizeof(int32_t)*4,st));
   if (timed) CU(cudaEventRecord(ctx->ev[0],st));
   k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(S->B,ctx->model.kmer);
   if (timed) CU(cudaEventRecord(ctx->ev[1],st));
   k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
   if (timed) CU(cudaEventRecord(ctx->ev[2],st));
+  CU(cudaEventRecord(S->kdone,st));
+  S->kdone_valid = 1;
   CU(cudaGetLastError());
   return CPG_OK;
 }

@@ -68,8 +68,13 @@ CPG_DEV_NOINL double cpg_bessi(int n, double x)
   if (n == 1) return cpg_bessi1(x);
   if (x == 0.0) return 0.0;
   double tox = 2.0/fabs(x), bip = 0.0, ans = 0.0, bi = 1.0, bim;
-  for (int j = 2*(n+(int)sqrt(40.0*n)); j > 0; j--)
-    { bim = bip+j*tox*bi;
+  int j = 2*(n+(int)sqrt(40.0*n));
+  double jd = (double)j;                 /* (double)j kept as a double: exact, saves an I2F per step */
+#ifndef CPG_HOSTSIM
+#pragma unroll 1
+#endif
+  for (; j > 0; j--, jd -= 1.0)
+    { bim = bip+jd*tox*bi;
       bip = bi;
       bi = bim;
       if (fabs(bi) > 1.0e10)
@@ -156,6 +161,39 @@ CPG_DEV_NOINL double cpg_binom_tail(WCtx &W, int k, int n, double pe)
 #undef CPG_LBP
   return p;
 }
+
+/* The same tail evaluated by ONE lane, term after term exactly as the reference loops
+ * (src/prob.c:76-112).  Used where several independent tails are wanted at once: each lane takes
+ * one, instead of the whole warp sharing the terms of a single tail. */
+CPG_DEV_NOINL double cpg_binom_tail_lane(const double *lf, int k, int n, double pe, int *bad)
+{ k = cpg_clamp_cnt(k & 0xffff); n = cpg_clamp_cnt(n & 0xffff);
+  if (k > n) { *bad = 1; return 0.; }
+  const double lpe = cpg_log(pe), l1mpe = cpg_log(1-pe), mean = n*pe;
+  const double lfn = CPG_LDG(lf+n);
+  double p, p_first, t;
+#define CPG_LBP(x) (lfn-CPG_LDG(lf+(x))-CPG_LDG(lf+(n-(x)))+(x)*lpe+(n-(x))*l1mpe)
+  if ((double)k >= mean)
+    { p = p_first = cpg_exp(CPG_LBP(k));
+      for (int x = k+1; x <= n; x++)
+        { p += t = cpg_exp(CPG_LBP(x));
+          if (10*t < p_first) break;
+        }
+    }
+  else
+    { p = p_first = (k == 0) ? 0. : cpg_exp(CPG_LBP(k-1));
+      for (int x = k-2; x >= 0; x--)
+        { p += t = cpg_exp(CPG_LBP(x));
+          if (10*t < p_first) break;
+        }
+      p = 1-p;
+    }
+#undef CPG_LBP
+  return p;
+}
+
+/* p_errorin (src/util.c:46-55) for one lane; the caller guarantees cin <= cout */
+CPG_DEV double cpg_p_errorin_lane(const double *lf, int etype, double erate, int cout, int cin, int *bad)
+{ return cpg_binom_tail_lane(lf,(etype == ET_SELF) ? cin : cout-cin,cout,erate,bad); }
 
 /* src/util.c:46-55 */
 CPG_DEV double cpg_p_errorin(WCtx &W, int etype, double erate, uint16_t cout, uint16_t cin)

@@ -65,22 +65,24 @@ CPG_DEV double rl_lp_r(WCtx &W, const cpg_intvl &I, uint16_t pr_cnt, int F, cons
   return lp;
 }
 
-/* src/class_rel.c:213-270.  H: the H-track transition is replaced by the D-track one scaled by the
- * predecessor's D/H ratio whenever that ratio exists.  D: always the plain D-track transition
- * (the ratio-scaled H-track value is computed and dropped by the reference). */
-CPG_DEV double rl_lp_hd(const WCtx &W, int t, const cpg_intvl &I, const RelState &P, int F)
+/* src/class_rel.c:213-270, argument side.  H: the H-track transition is replaced by the D-track
+ * one scaled by the predecessor's D/H ratio whenever that ratio exists.  D: always the plain
+ * D-track transition (the ratio-scaled H-track value is computed and dropped by the reference).
+ * Only the Skellam arguments are formed here: the evaluation itself (a Bessel recurrence) happens
+ * at ONE call site for all lanes, so lanes on different branches do not serialise it. */
+CPG_DEV void rl_hd_args(const WCtx &W, int t, const cpg_intvl &I, const RelState &P, int F,
+                        int &k, double &lambda)
 { int bp = rl_begpos(I,F); uint16_t bc = rl_begcnt(I,F);
-  double sf;
-  if (t == ST_H)
-    { double r = P.dhr;
-      if (r != -CPG_INF)
-        sf = cpg_lp_trans(W,rl_pred(P.pos[ST_D],F),bp,P.cnt[ST_D],(int)(r*bc),P.cnt[ST_D]);
-      else
-        sf = cpg_lp_trans(W,rl_pred(P.pos[ST_H],F),bp,P.cnt[ST_H],bc,P.cnt[ST_H]);
-    }
+  int b, cb, ce; uint16_t cov;
+  if (t == ST_H && P.dhr != -CPG_INF)
+    { b = rl_pred(P.pos[ST_D],F); cb = P.cnt[ST_D]; ce = (int)(P.dhr*bc); cov = P.cnt[ST_D]; }
+  else if (t == ST_H)
+    { b = rl_pred(P.pos[ST_H],F); cb = P.cnt[ST_H]; ce = bc; cov = P.cnt[ST_H]; }
   else
-    sf = cpg_lp_trans(W,rl_pred(P.pos[ST_D],F),bp,P.cnt[ST_D],bc,P.cnt[ST_D]);
-  return sf+0.;
+    { b = rl_pred(P.pos[ST_D],F); cb = P.cnt[ST_D]; ce = bc; cov = P.cnt[ST_D]; }
+  int d = bp-b; if (d < 0) d = -d;
+  k = ce-cb;
+  lambda = (double)cov*d/W.M->read_len;          /* src/util.c:43 */
 }
 
 /* src/class_rel.c:80-96 with s (or t) as the wildcard */
@@ -135,15 +137,14 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
 
   for (int q = W.lane; q < 16; q += CPG_WARP)
     { int s = q >> 2, t = q & 3;
-      double v;
-      if (prv[s].dp == -CPG_INF) v = 0.;
-      else
-        { double lp;
-          if (t == ST_E)      lp = rl_lp_e(W,I,U.COV);
-          else if (t == ST_R) lp = rl_lp_r(W,I,prv[s].cnt[ST_R],F,U.COV);
-          else                lp = rl_lp_hd(W,t,I,prv[s],F);
-          v = cpg_exp(lp);
+      double v = 0.;
+      int need = 0, k = 0; double lambda = 0.;
+      if (prv[s].dp != -CPG_INF)
+        { if (t == ST_E)      v = cpg_exp(rl_lp_e(W,I,U.COV));
+          else if (t == ST_R) v = cpg_exp(rl_lp_r(W,I,prv[s].cnt[ST_R],F,U.COV));
+          else { rl_hd_args(W,t,I,prv[s],F,k,lambda); need = 1; }
         }
+      if (need) v = cpg_exp(cpg_lp_skellam(k,lambda)+0.);
       tr[q] = v;
     }
   CPG_SYNCWARP();

@@ -24,7 +24,11 @@
 #include "cpg_context.cuh"
 
 /* ---- warp primitives (width 1 in the host-side unit-test build) ---- */
-#ifdef CPG_HOSTSIM
+#if defined(CPG_HOSTSIM) && CPG_HOSTSIM == 32
+CPG_DEV unsigned cpg_ballot(int pred) { return cpg_sim_ballot(pred); }
+CPG_DEV int      cpg_warp_sum(int v)  { return cpg_sim_sum(v); }
+CPG_DEV int      cpg_ffs(unsigned m)  { return __builtin_ffs((int)m); }
+#elif defined(CPG_HOSTSIM)
 CPG_DEV unsigned cpg_ballot(int pred) { return pred ? 1u : 0u; }
 CPG_DEV int      cpg_warp_sum(int v)  { return v; }
 CPG_DEV int      cpg_ffs(unsigned m)  { return __builtin_ffs((int)m); }
@@ -60,12 +64,17 @@ CPG_DEV uint16_t rc_prof(const ReadCtx &R, WCtx &W, int p)
 CPG_DEV unsigned mk_by(int e)   { return e == ET_SELF ? MK_BY_S : MK_BY_O; }
 CPG_DEV unsigned mk_pair(int e) { return e == ET_SELF ? MK_PAIR_S : MK_PAIR_O; }
 
+/* Lane 0 is the only writer of the scratch words below.  Each helper synchronises the warp BEFORE
+ * the write (the other lanes may still be reading the old value: the CUDA memory model does not
+ * promise lock-step execution) and AFTER it (so that every lane sees the new one). */
 CPG_DEV void mark_or(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
-{ if (W.lane == 0) R.S.mark[pos] |= bits;
+{ CPG_SYNCWARP();
+  if (W.lane == 0) R.S.mark[pos] |= bits;
   CPG_SYNCWARP();
 }
 CPG_DEV void mark_clear(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
-{ if (W.lane == 0) R.S.mark[pos] &= ~bits;
+{ CPG_SYNCWARP();
+  if (W.lane == 0) R.S.mark[pos] &= ~bits;
   CPG_SYNCWARP();
 }
 
@@ -81,6 +90,7 @@ CPG_DEV_NOINL void perr_once(ReadCtx &R, WCtx &W, int pos, int e, int w,
   double v = cpg_p_errorin(W,e,erate,cout,cin);
   unsigned m = R.S.mark[pos];
   unsigned s = m >> 8;
+  CPG_SYNCWARP();
   if (s == 0)
     { s = (unsigned)(++R.nslots);
       if (W.lane == 0)
@@ -109,67 +119,99 @@ CPG_DEV int cthres_at(const WCtx &W, int t, int l, int cout, int s, int e)
 CPG_DEV int thres_ng(int e, int cin, int ct)
 { cin &= 0xff; return (e == ET_SELF) ? (cin >= ct) : (cin < ct); }
 
-/* src/wall.c:331-507.  fwd = 1: a DROP at i looks for its GAIN about K-1 positions ahead
- * (find_gain); fwd = 0: a GAIN at i looks for its DROP behind (find_drop). */
-CPG_DEV_NOINL int find_pair(ReadCtx &R, WCtx &W, int fwd, int i, uint16_t cout, uint16_t cin,
-                            int e, int t, int l, double erate, cpg_eintvl *out)
-{ const cpg_dmodel *M = W.M;
-  const uint16_t *prof = R.prof;
-  const int plen = R.plen, K = M->K, ulen = t+1, cmax = M->cmax;
-  const int wi = fwd ? WT_DROP : WT_GAIN, wj = fwd ? WT_GAIN : WT_DROP;
-  int max_j = -1; double max_pe = -CPG_INF, pe;
-
-  /* low-complexity partner: walk the context run by whole units */
-  int m = ulen*l, n = 0, j;
-  for (;;)
-    { int idx = fwd ? i+ulen*(n+1) : i-ulen*(n+1);
-      if (fwd) { if (idx >= plen) break; }
-      else     { if (idx <= 0) break; }
-      if (cpg_ctx_at(R.seq,R.rlen,K,wi,idx,t) != m+n+1) break;
-      n++;
+/* store a freshly computed probability in the first-writer-wins cache (src/wall.c:310-315) */
+CPG_DEV_NOINL void perr_store(ReadCtx &R, WCtx &W, int pos, int e, int w, double v)
+{ unsigned m = R.S.mark[pos];
+  unsigned s = m >> 8;
+  CPG_SYNCWARP();
+  if (s == 0)
+    { s = (unsigned)(++R.nslots);
+      if (W.lane == 0)
+        { R.S.mark[pos] = m | (s << 8);
+          double *q = R.S.perr+(size_t)(s-1)*4;
+          q[0] = q[1] = q[2] = q[3] = -CPG_INF;
+        }
+      CPG_SYNCWARP();
     }
-  j = fwd ? i+K-1+n-m : i-K+1-n+m;
-  if (fwd ? (j <= i) : (j >= i)) return 0;
-  if (fwd ? (j >= plen) : (j <= 0))
-    { j = fwd ? plen : 0;
-      double pi = perr_get(R,i,e,wi);
+  if (W.lane == 0) R.S.perr[(size_t)(s-1)*4+e*2+w] = v;
+  CPG_SYNCWARP();
+}
+
+/* Everything find_gain/find_drop (src/wall.c:331-507) need to know about one candidate.
+ * fwd = 1: a DROP at i looks for its GAIN about K-1 positions ahead; fwd = 0: a GAIN at i looks
+ * for its DROP behind.  Partner slot 0 is the low-complexity partner (context run walked by whole
+ * units), slots 1..6 the high-complexity partners at 0..MAX_N_HC extra bases. */
+struct PairGeom
+  { int      fwd, i, t, l, lc_kind;       /* lc_kind: 0 = no partner (find_* returns false), 1 = read boundary, 2 = regular */
+    int      lc_j;
+    uint16_t cout, cin;
+    double   erate;
+  };
+
+CPG_DEV int pg_hc_j(const PairGeom &G, int K, int n) { return G.fwd ? G.i+K-1+n : G.i-K+1-n; }
+CPG_DEV int pg_in_range(const PairGeom &G, int plen, int j) { return G.fwd ? (j < plen) : (j > 0); }
+CPG_DEV void pg_counts(const PairGeom &G, const uint16_t *prof, int j, uint16_t &cin_j, uint16_t &cout_j)
+{ cin_j  = G.fwd ? prof[j-1] : prof[j];
+  cout_j = G.fwd ? prof[j]   : prof[j-1];
+}
+/* count tests of the low-complexity partner (src/wall.c:364-365,455-456) */
+CPG_DEV int pg_lc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e)
+{ uint16_t cin_j, cout_j;
+  pg_counts(G,prof,G.lc_j,cin_j,cout_j);
+  return cin_j <= cout_j
+         && !(cout_j < W.M->cmax && thres_ng(e,cin_j,cthres_at(W,G.t,G.l,cout_j,TH_FINAL,e)));
+}
+/* count tests of a high-complexity partner (src/wall.c:384-389,475-480) */
+CPG_DEV int pg_hc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e, int j)
+{ uint16_t cin_j, cout_j;
+  pg_counts(G,prof,j,cin_j,cout_j);
+  const int cmax = W.M->cmax;
+  if (!(cin_j <= cout_j)) return 0;
+  if ((G.cout < cmax && thres_ng(e,G.cin,cthres_at(W,CT_HP,1,G.cout,TH_FINAL,e)))
+      || (cout_j < cmax && thres_ng(e,cin_j,cthres_at(W,CT_HP,1,cout_j,TH_FINAL,e))))
+    return 0;
+  return 1;
+}
+
+/* Layout of the per-candidate task results in the warp's exchange block:
+ *   [e*8+0]      p_errorin of the low-complexity partner under this candidate's error rate
+ *   [e*8+1+n]    p_errorin of high-complexity partner n under HC_ERATE
+ *   [e*8+7]      p_errorin of the candidate itself under HC_ERATE
+ *   [16+p]       log Skellam probability that candidate and partner p belong together (OTHERS) */
+
+/* The decision part of find_gain/find_drop, replayed serially on the precomputed values. */
+CPG_DEV_NOINL int pair_replay(ReadCtx &R, WCtx &W, const PairGeom &G, int e, cpg_eintvl *out)
+{ const uint16_t *prof = R.prof;
+  const int plen = R.plen, K = W.M->K;
+  const int wi = G.fwd ? WT_DROP : WT_GAIN, wj = G.fwd ? WT_GAIN : WT_DROP;
+  const double *term = W.ws->term;
+  int max_j = -1; double max_pe = -CPG_INF, pe;
+  if (G.lc_kind == 0) return 0;
+  int j = G.lc_j;
+  if (G.lc_kind == 1)
+    { double pi = perr_get(R,G.i,e,wi);
       pe = pi*pi;
     }
   else
-    { uint16_t cin_j  = fwd ? prof[j-1] : prof[j];
-      uint16_t cout_j = fwd ? prof[j]   : prof[j-1];
-      pe = -CPG_INF;
-      if (cin_j <= cout_j
-          && !(cout_j < cmax && thres_ng(e,cin_j,cthres_at(W,t,l,cout_j,TH_FINAL,e)))
-          && (e == ET_SELF || (fwd ? lp_diff_pair(R,W,i,j) : lp_diff_pair(R,W,j,i)) >= CPG_THRES_DIFF_EO))
-        { perr_once(R,W,j,e,wj,cout_j,cin_j,erate);
-          pe = fwd ? perr_get(R,i,e,WT_DROP)*perr_get(R,j,e,WT_GAIN)
-                   : perr_get(R,j,e,WT_DROP)*perr_get(R,i,e,WT_GAIN);
+    { pe = -CPG_INF;
+      if (pg_lc_ok(G,W,prof,e) && (e == ET_SELF || term[16] >= CPG_THRES_DIFF_EO))
+        { if (perr_get(R,j,e,wj) == -CPG_INF) perr_store(R,W,j,e,wj,term[e*8]);
+          pe = G.fwd ? perr_get(R,G.i,e,WT_DROP)*perr_get(R,j,e,WT_GAIN)
+                     : perr_get(R,j,e,WT_DROP)*perr_get(R,G.i,e,WT_GAIN);
         }
     }
   if (max_pe < pe) { max_j = j; max_pe = pe; }
-
-  /* high-complexity partner: up to MAX_N_HC extra bases */
-  double pe_i = 0.; int have_pe_i = 0;
-  for (n = 0; n <= CPG_MAX_N_HC; n++)
-    { j = fwd ? i+K-1+n : i-K+1-n;
-      if (fwd ? (j >= plen) : (j <= 0)) break;
-      uint16_t cin_j  = fwd ? prof[j-1] : prof[j];
-      uint16_t cout_j = fwd ? prof[j]   : prof[j-1];
-      if (!(cin_j <= cout_j)) continue;
-      if ((cout < cmax && thres_ng(e,cin,cthres_at(W,CT_HP,1,cout,TH_FINAL,e)))
-          || (cout_j < cmax && thres_ng(e,cin_j,cthres_at(W,CT_HP,1,cout_j,TH_FINAL,e))))
-        continue;
-      if (e == ET_OTHERS && (fwd ? lp_diff_pair(R,W,i,j) : lp_diff_pair(R,W,j,i)) < CPG_THRES_DIFF_EO)
-        continue;
-      if (!have_pe_i) { pe_i = cpg_p_errorin(W,e,M->hc_erate,cout,cin); have_pe_i = 1; }
-      double pe_j = cpg_p_errorin(W,e,M->hc_erate,cout_j,cin_j);
-      pe = pe_i*pe_j;
+  for (int n = 0; n <= CPG_MAX_N_HC; n++)
+    { j = pg_hc_j(G,K,n);
+      if (!pg_in_range(G,plen,j)) break;
+      if (!pg_hc_ok(G,W,prof,e,j)) continue;
+      if (e == ET_OTHERS && term[17+n] < CPG_THRES_DIFF_EO) continue;
+      pe = term[e*8+7]*term[e*8+1+n];
       if (max_pe < pe) { max_j = j; max_pe = pe; }
     }
   if (max_j == -1) return 0;
-  if (fwd) { out->b = i; out->e = max_j; }
-  else     { out->b = max_j; out->e = i; }
+  if (G.fwd) { out->b = G.i; out->e = max_j; }
+  else       { out->b = max_j; out->e = G.i; }
   out->pe = max_pe;
   return 1;
 }
@@ -186,7 +228,8 @@ CPG_DEV int ei_before(const cpg_eintvl &x, const cpg_eintvl &y)
 
 /* stable insertion sort; the lists are produced almost in order */
 CPG_DEV_NOINL void ei_sort(cpg_eintvl *a, int n, const WCtx &W)
-{ if (W.lane == 0)
+{ CPG_SYNCWARP();
+  if (W.lane == 0)
     for (int i = 1; i < n; i++)
       { cpg_eintvl v = a[i];
         int j = i-1;
@@ -236,20 +279,31 @@ CPG_DEV int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
 }
 
 CPG_DEV void ei_put(ReadCtx &R, const WCtx &W, int k, int b, int e, double pe)
-{ if (W.lane == 0) { R.S.eint[k].b = b; R.S.eint[k].e = e; R.S.eint[k].pe = pe; }
+{ CPG_SYNCWARP();
+  if (W.lane == 0) { R.S.eint[k].b = b; R.S.eint[k].e = e; R.S.eint[k].pe = pe; }
   CPG_SYNCWARP();
 }
 
 /* clear bits on the open range (b,e), lanes striding */
 CPG_DEV void mark_clear_range(ReadCtx &R, const WCtx &W, int b, int e, unsigned bits)
-{ for (int j = b+1+W.lane; j < e; j += CPG_WARP) R.S.mark[j] &= ~bits;
+{ CPG_SYNCWARP();
+  for (int j = b+1+W.lane; j < e; j += CPG_WARP) R.S.mark[j] &= ~bits;
   CPG_SYNCWARP();
 }
 
-/* ---- pass A for one candidate position (src/wall.c:606-692) ---- */
+/* ---- pass A for one candidate position (src/wall.c:606-692) ----
+ * The reference evaluates, one after the other, up to 18 binomial tails and 7 Skellam
+ * probabilities per candidate.  They are pure functions of the profile, so here they are formed as
+ * independent tasks, one per lane, and evaluated together (stage 1: the candidate's own
+ * probabilities; stage 2: every partner of both error types); the order-dependent part -- the
+ * first-writer-wins probability cache, the paired flags, the E-interval list -- is then replayed
+ * serially on the results, in the reference's order. */
 CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
 { const cpg_dmodel *M = W.M;
-  const uint16_t cim1 = R.prof[i-1], ci = R.prof[i];
+  const uint16_t *prof = R.prof;
+  const double *lf = M->logfact;
+  const int plen = R.plen, K = M->K, cmax = M->cmax;
+  const uint16_t cim1 = prof[i-1], ci = prof[i];
   const int cng = (cim1 > ci) ? cim1-ci : ci-cim1;
   int wtype; uint16_t cin, cout;
   if (cim1 > ci) { wtype = WT_DROP; cin = ci;   cout = cim1; }
@@ -257,49 +311,126 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
 
   int maxt = -1, maxl = -1; double maxpe = -CPG_INF;
   for (int t = 0; t < CT_N; t++)
-    { int l = imin(cpg_ctx_at(R.seq,R.rlen,M->K,wtype,i,t),M->lmax[t]);
+    { int l = imin(cpg_ctx_at(R.seq,R.rlen,K,wtype,i,t),M->lmax[t]);
       double pe = M->pe[t][l];
       if (maxpe < pe) { maxpe = pe; maxt = t; maxl = l; }
     }
 
-  int ct_init = 0, ct_final = 0;
+  /* stage 0: how far does each error type get before any probability is needed */
+  int reach[2] = {0,0}, o_wall_now = 0;
+  const unsigned mi = R.S.mark[i];
   for (int e = ET_SELF; e <= ET_OTHERS; e++)
-    { if (R.S.mark[i] & mk_pair(e)) continue;
-      if (cout < M->cmax)
-        { ct_init  = cthres_at(W,maxt,maxl,cout,TH_INIT,e);
+    { if (mi & mk_pair(e)) continue;
+      int ct_final = 0;
+      if (cout < cmax)
+        { int ct_init = cthres_at(W,maxt,maxl,cout,TH_INIT,e);
           ct_final = cthres_at(W,maxt,maxl,cout,TH_FINAL,e);
           if (!(cng > CPG_MAX_CNT_CHANGE || cin < imax(ct_init,3))) continue;
         }
-      cpg_eintvl I;
       if (e == ET_SELF)
-        { if (cout < M->cmax && cin >= ct_final) continue;
-          perr_once(R,W,i,e,wtype,cout,cin,maxpe);
-          if (perr_get(R,i,e,wtype) < CPG_PE_FINAL) continue;
-          if (find_pair(R,W,wtype == WT_DROP,i,cout,cin,e,maxt,maxl,maxpe,&I) && I.pe >= CPG_PE_FINAL)
-            { mark_or(R,W,I.b,MK_BY_S|MK_PAIR_S);
-              mark_or(R,W,I.e,MK_BY_S|MK_PAIR_S);
-              ei_put(R,W,eidx,I.b,I.e,I.pe);
-              eidx++;
-            }
+        { if (cout < cmax && cin >= ct_final) continue;
+          reach[e] = 1;
         }
       else
-        { if (cng >= M->cov[ST_H] || (cout < M->cmax && cin < ct_final))
-            { mark_or(R,W,i,MK_BY_O); continue; }
-          perr_once(R,W,i,e,wtype,cout,cin,maxpe);
-          if (perr_get(R,i,e,wtype) < CPG_PE_FINAL)
-            { mark_or(R,W,i,MK_BY_O); continue; }
-          if (find_pair(R,W,wtype == WT_DROP,i,cout,cin,e,maxt,maxl,maxpe,&I) && I.pe >= CPG_PE_FINAL)
-            { /* paired O-walls stop being walls (src/wall.c:722-726), see header note */
-              if (W.lane == 0)
-                { R.S.mark[I.b] = (R.S.mark[I.b] | MK_PAIR_O) & ~MK_BY_O;
-                  R.S.mark[I.e] = (R.S.mark[I.e] | MK_PAIR_O) & ~MK_BY_O;
-                }
-              CPG_SYNCWARP();
-              continue;
-            }
-          mark_or(R,W,i,MK_BY_O);
+        { if (cng >= M->cov[ST_H] || (cout < cmax && cin < ct_final)) { o_wall_now = 1; continue; }
+          reach[e] = 1;
         }
     }
+  if (!reach[0] && !reach[1])
+    { if (o_wall_now) mark_or(R,W,i,MK_BY_O);
+      return;
+    }
+
+  /* stage 1: the candidate's own probabilities, lanes 0 and 1 */
+  double *term = W.ws->term;
+  int bad = 0;
+  int fresh[2];
+  for (int e = 0; e < 2; e++) fresh[e] = reach[e] && perr_get(R,i,e,wtype) == -CPG_INF;
+  CPG_SYNCWARP();
+  for (int q = W.lane; q < 2; q += CPG_WARP)
+    if (fresh[q]) term[q] = cpg_p_errorin_lane(lf,q,maxpe,cout,cin,&bad);
+  CPG_SYNCWARP();
+  int go[2];
+  for (int e = 0; e < 2; e++)
+    { if (fresh[e]) perr_store(R,W,i,e,wtype,term[e]);
+      go[e] = reach[e] && !(perr_get(R,i,e,wtype) < CPG_PE_FINAL);
+    }
+
+  cpg_eintvl I;
+  if (go[0] || go[1])
+    { /* stage 2: partner geometry (src/wall.c:344-357,432-450), shared by both error types */
+      PairGeom G;
+      G.fwd = (wtype == WT_DROP); G.i = i; G.t = maxt; G.l = maxl; G.cout = cout; G.cin = cin; G.erate = maxpe;
+      { const int ulen = maxt+1, m = ulen*maxl;
+        int n = 0;
+        for (;;)
+          { int idx = G.fwd ? i+ulen*(n+1) : i-ulen*(n+1);
+            if (G.fwd) { if (idx >= plen) break; }
+            else       { if (idx <= 0) break; }
+            if (cpg_ctx_at(R.seq,R.rlen,K,wtype,idx,maxt) != m+n+1) break;
+            n++;
+          }
+        int j = G.fwd ? i+K-1+n-m : i-K+1-n+m;
+        if (G.fwd ? (j <= i) : (j >= i)) { G.lc_kind = 0; G.lc_j = j; }
+        else if (G.fwd ? (j >= plen) : (j <= 0)) { G.lc_kind = 1; G.lc_j = G.fwd ? plen : 0; }
+        else { G.lc_kind = 2; G.lc_j = j; }
+      }
+      const int wj = G.fwd ? WT_GAIN : WT_DROP;
+      CPG_SYNCWARP();
+      for (int q = W.lane; q < 23; q += CPG_WARP)
+        { double val = 0.;
+          int need_b = 0, need_s = 0, be = 0, bco = 0, bci = 0, sj = 0; double ber = 0.;
+          if (G.lc_kind != 0)
+            { if (q < 16)
+                { const int e = q >> 3, p = q & 7;
+                  if (go[e])
+                    { if (p == 7) { need_b = 1; be = e; ber = M->hc_erate; bco = cout; bci = cin; }
+                      else
+                        { int j = (p == 0) ? G.lc_j : pg_hc_j(G,K,p-1);
+                          int ok = (p == 0) ? (G.lc_kind == 2 && pg_lc_ok(G,W,prof,e) && perr_get(R,j,e,wj) == -CPG_INF)
+                                            : (pg_in_range(G,plen,j) && pg_hc_ok(G,W,prof,e,j));
+                          if (ok)
+                            { uint16_t cin_j, cout_j;
+                              pg_counts(G,prof,j,cin_j,cout_j);
+                              need_b = 1; be = e; ber = (p == 0) ? maxpe : M->hc_erate; bco = cout_j; bci = cin_j;
+                            }
+                        }
+                    }
+                }
+              else if (go[ET_OTHERS])
+                { const int p = q-16;
+                  int j = (p == 0) ? G.lc_j : pg_hc_j(G,K,p-1);
+                  int ok = (p == 0) ? (G.lc_kind == 2 && pg_lc_ok(G,W,prof,ET_OTHERS))
+                                    : (pg_in_range(G,plen,j) && pg_hc_ok(G,W,prof,ET_OTHERS,j));
+                  if (ok) { need_s = 1; sj = j; }
+                }
+            }
+          if (need_b) val = cpg_p_errorin_lane(lf,be,ber,bco,bci,&bad);
+          if (need_s) val = G.fwd ? lp_diff_pair(R,W,i,sj) : lp_diff_pair(R,W,sj,i);
+          term[q] = val;
+        }
+      CPG_SYNCWARP();
+
+      if (go[ET_SELF] && pair_replay(R,W,G,ET_SELF,&I) && I.pe >= CPG_PE_FINAL)
+        { mark_or(R,W,I.b,MK_BY_S|MK_PAIR_S);
+          mark_or(R,W,I.e,MK_BY_S|MK_PAIR_S);
+          ei_put(R,W,eidx,I.b,I.e,I.pe);
+          eidx++;
+        }
+      if (go[ET_OTHERS] && pair_replay(R,W,G,ET_OTHERS,&I) && I.pe >= CPG_PE_FINAL)
+        { /* paired O-walls stop being walls (src/wall.c:722-726), see header note */
+          CPG_SYNCWARP();
+          if (W.lane == 0)
+            { R.S.mark[I.b] = (R.S.mark[I.b] | MK_PAIR_O) & ~MK_BY_O;
+              R.S.mark[I.e] = (R.S.mark[I.e] | MK_PAIR_O) & ~MK_BY_O;
+            }
+          CPG_SYNCWARP();
+          reach[ET_OTHERS] = 0;          /* explained by a pair: not a wall */
+        }
+    }
+  if (bad) W.status |= CPG_ST_BINOM;
+  /* OTHERS: whatever is not explained by a pair is a wall (src/wall.c:672-690) */
+  if (o_wall_now || reach[ET_OTHERS]) mark_or(R,W,i,MK_BY_O);
 }
 
 /* ---- pass C for one lone O-wall (src/wall.c:763-860) ---- */
@@ -389,6 +520,7 @@ CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
      [max(I.e-2K,I.b),I.e) starts at I.b.  Writes to higher slots hit intervals that are either
      recomputed from scratch later or never read. */
   if (I.b == idx && I.e-2*K <= I.b && cce < I.cb) cce = I.cb;
+  CPG_SYNCWARP();
   if (W.lane == 0) { R.S.intvl[idx].ccb = ccb; R.S.intvl[idx].cce = cce; }
   CPG_SYNCWARP();
 }
@@ -464,6 +596,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
       }
   }
   ei_sort(eint,NS,W);
+  CPG_SYNCWARP();
   for (int k = 0; k < NS; k++)
     { for (int j = eint[k].b+W.lane; j < eint[k].e; j += CPG_WARP) mark[j] |= MK_ERROR;
       CPG_SYNCWARP();
@@ -514,6 +647,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
       const int ccb = intvl[i].ccb, cce = intvl[i].cce;
       if (cpg_lp_trans(W,I.b,I.e,ccb,cce,(uint16_t)((ccb+cce)/2)) < CPG_THRES_DIFF_REL) continue;
       if (imax(ccb,cce) == CPG_MAX_CNT) continue;
+      CPG_SYNCWARP();
       if (W.lane == 0)
         { intvl[i].is_rel = 1;
           R.S.rint[Mrel] = intvl[i];

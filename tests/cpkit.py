@@ -262,6 +262,30 @@ class GpuIntvl(C.Structure):
 
 
 _hostsim = None
+_hostsim32 = None
+
+
+def _bind_hostsim(L):
+    L.cpg_model_from_hist.argtypes = [C.POINTER(GpuModel), C.c_int, C.c_int, C.c_int, C.c_int64,
+                                      C.c_int64, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int]
+    L.cpg_model_from_cov.argtypes = [C.POINTER(GpuModel), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.hs_classify_read.argtypes = [C.POINTER(GpuModel), C.c_char_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int, C.c_char_p, C.POINTER(GpuIntvl), C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int)]
+    L.hs_decode_profile.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    L.hs_ctx.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    assert L.hs_sizeof_intvl() == C.sizeof(GpuIntvl)
+    return L
+
+
+def hostsim32_lib():
+    """The 32-host-threads-per-warp emulation (slow; small inputs only)."""
+    global _hostsim32
+    if _hostsim32 is None:
+        build_hostsim()
+        _hostsim32 = _bind_hostsim(C.CDLL(os.path.join(HOSTSIM_DIR, "_build", "libhostsim32.so")))
+        assert _hostsim32.hs_warp_width() == 32
+    return _hostsim32
 
 
 def hostsim_lib():
@@ -292,8 +316,8 @@ def gpu_model_from_sim(lib, sim, cov_opt=0, read_len=20000):
     return m
 
 
-def hostsim_classify(model, seq_ascii, counts, seq_bits=2, want_intervals=False):
-    L = hostsim_lib()
+def hostsim_classify(model, seq_ascii, counts, seq_bits=2, want_intervals=False, lib=None):
+    L = lib or hostsim_lib()
     rlen, plen = int(len(seq_ascii)), int(len(counts))
     cls = C.create_string_buffer(rlen + 1)
     counts = np.ascontiguousarray(counts, dtype=np.uint16)
@@ -310,10 +334,10 @@ def hostsim_classify(model, seq_ascii, counts, seq_bits=2, want_intervals=False)
     return st, cls.raw[:rlen], out, M.value
 
 
-def hostsim_decode(prof_bytes, cap):
+def hostsim_decode(prof_bytes, cap, lib=None):
     prof_bytes = np.ascontiguousarray(prof_bytes, dtype=np.uint8)
     out = np.zeros(max(cap, 1), dtype=np.uint16)
-    n = hostsim_lib().hs_decode_profile(prof_bytes.ctypes.data, len(prof_bytes), out.ctypes.data, cap)
+    n = (lib or hostsim_lib()).hs_decode_profile(prof_bytes.ctypes.data, len(prof_bytes), out.ctypes.data, cap)
     return n, out[:min(n, cap)]
 
 

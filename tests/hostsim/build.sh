@@ -1,5 +1,6 @@
 #!/bin/bash
-# Builds the TEST-ONLY host simulation of the device logic (see hostsim.cpp) into _build/.
+# Builds the TEST-ONLY host simulations of the device logic (see hostsim.cpp) into _build/:
+# libhostsim.so (warp width 1) and libhostsim32.so (32 host threads per warp).
 set -e
 here="$(cd "$(dirname "$0")" && pwd)"
 root="$(cd "$here/../.." && pwd)"
@@ -7,5 +8,7 @@ mkdir -p "$here/_build"
 CF="-O2 -Wall -Wextra -ffp-contract=off -fPIC -I$root/include"
 gcc $CF -c "$root/classpro_b200/host/cpg_model.c" -o "$here/_build/cpg_model.o"
 gcc $CF -c "$root/classpro_b200/host/cpg_pack.c"  -o "$here/_build/cpg_pack.o"
-g++ $CF -c "$here/hostsim.cpp" -o "$here/_build/hostsim.o"
+g++ $CF -DCPG_HOSTSIM=1 -c "$here/hostsim.cpp" -o "$here/_build/hostsim.o"
 g++ -shared -o "$here/_build/libhostsim.so" "$here/_build/hostsim.o" "$here/_build/cpg_model.o" "$here/_build/cpg_pack.o" -lm
+g++ $CF -DCPG_HOSTSIM=32 -c "$here/hostsim.cpp" -o "$here/_build/hostsim32.o"
+g++ -shared -o "$here/_build/libhostsim32.so" "$here/_build/hostsim32.o" "$here/_build/cpg_model.o" "$here/_build/cpg_pack.o" -lm -lpthread

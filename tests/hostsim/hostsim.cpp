@@ -1,19 +1,66 @@
 /*******************************************************************************************
- *  hostsim.cpp -- TEST-ONLY build of the device-side per-read logic for machines without a GPU.
+ *  hostsim.cpp -- TEST-ONLY builds of the device-side per-read logic for machines without a GPU.
  *
- *  The CUDA sources classpro_b200/csrc/cpg_*.cuh are written so that, with CPG_HOSTSIM defined,
- *  they compile as plain C++ with a warp width of 1.  This file wraps them behind a tiny C
- *  interface so that the CPU test-suite (`pytest -m "not gpu"`) can compare the device logic with
- *  the oracle read by read.  It is built by tests/ into tests/hostsim/_build/, is never linked
- *  into or loaded by libclasspro_b200.so, and is not a fallback: the product path has none.
+ *  The CUDA sources classpro_b200/csrc/cpg_*.cuh compile as plain C++ when CPG_HOSTSIM is defined:
+ *    CPG_HOSTSIM=1   warp width 1: one host thread runs the per-read logic serially
+ *                    (libhostsim.so, fast, used for dataset-level parity with the oracle);
+ *    CPG_HOSTSIM=32  warp width 32: 32 host threads play the lanes of one warp and meet at a
+ *                    barrier for every __syncwarp/ballot/shuffle/reduction (libhostsim32.so).
+ *                    Lanes run truly asynchronously between rendezvous, so a collective executed
+ *                    by only some lanes deadlocks (test timeout) and a missing __syncwarp shows up
+ *                    as wrong or unstable output -- stricter than the hardware.
+ *  Built by tests/ into tests/hostsim/_build/, never linked into or loaded by
+ *  libclasspro_b200.so; not a fallback: the product path has none.
  *******************************************************************************************/
+#ifndef CPG_HOSTSIM
 #define CPG_HOSTSIM 1
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
+#if CPG_HOSTSIM == 32
+#include <pthread.h>
+#endif
 #include "../../classpro_b200/csrc/cpg_unrel.cuh"
 #include "../../classpro_b200/csrc/cpg_decode.cuh"
 #include "../../include/classpro_gpu.h"
+
+#if CPG_HOSTSIM == 32
+static pthread_barrier_t g_bar;
+static unsigned g_slot[32];
+static thread_local int t_lane = 0;
+void cpg_sim_barrier(void) { pthread_barrier_wait(&g_bar); }
+unsigned cpg_sim_ballot(int pred)
+{ g_slot[t_lane] = pred ? 1u : 0u;
+  pthread_barrier_wait(&g_bar);
+  unsigned m = 0;
+  for (int l = 0; l < 32; l++) m |= g_slot[l] << l;
+  pthread_barrier_wait(&g_bar);
+  return m;
+}
+unsigned cpg_sim_shfl(unsigned v, int src)
+{ g_slot[t_lane] = v;
+  pthread_barrier_wait(&g_bar);
+  unsigned r = g_slot[src & 31];
+  pthread_barrier_wait(&g_bar);
+  return r;
+}
+unsigned cpg_sim_shfl_up(unsigned v, int d)
+{ g_slot[t_lane] = v;
+  pthread_barrier_wait(&g_bar);
+  unsigned r = (t_lane >= d) ? g_slot[t_lane-d] : v;
+  pthread_barrier_wait(&g_bar);
+  return r;
+}
+int cpg_sim_sum(int v)
+{ g_slot[t_lane] = (unsigned)v;
+  pthread_barrier_wait(&g_bar);
+  int s = 0;
+  for (int l = 0; l < 32; l++) s += (int)g_slot[l];
+  pthread_barrier_wait(&g_bar);
+  return s;
+}
+#endif
 
 struct HsWork
   { std::vector<uint32_t> mark; std::vector<double> perr; std::vector<cpg_eintvl> eint;
@@ -27,10 +74,53 @@ struct HsWork
       }
   };
 
+struct LaneJob
+  { int lane; const cpg_dmodel *dm; cpg_wshared *ws; RelShared *sh; ReadCtx R; uint8_t *cls; int status;
+    int N, M;
+    /* decode job */
+    const uint8_t *src; int64_t len; uint16_t *out; int cap; int *offs; int n;
+  };
+
+static void *lane_classify(void *arg)
+{ LaneJob *J = (LaneJob *)arg;
+#if CPG_HOSTSIM == 32
+  t_lane = J->lane;
+#endif
+  WCtx W; W.lane = J->lane; W.M = J->dm; W.cthres = J->dm->cthres; W.ws = J->ws; W.status = 0;
+  ReadCtx R = J->R;
+  J->status = classify_read(R,W,J->sh,J->cls);
+  J->N = R.N; J->M = R.M;
+  return NULL;
+}
+
+static void *lane_decode(void *arg)
+{ LaneJob *J = (LaneJob *)arg;
+#if CPG_HOSTSIM == 32
+  t_lane = J->lane;
+#endif
+  J->n = decode_profile(J->src,J->len,J->out,J->cap,J->lane,J->offs);
+  return NULL;
+}
+
+static void run_lanes(void *(*fn)(void *), LaneJob *jobs)
+{
+#if CPG_HOSTSIM == 32
+  pthread_t th[32];
+  pthread_barrier_init(&g_bar,NULL,32);
+  for (int l = 0; l < 32; l++) pthread_create(&th[l],NULL,fn,&jobs[l]);
+  for (int l = 0; l < 32; l++) pthread_join(th[l],NULL);
+  pthread_barrier_destroy(&g_bar);
+#else
+  fn(&jobs[0]);
+#endif
+}
+
 extern "C" {
 
-/* classify one read; seq = rlen raw characters (seq_bits 8) ; returns status bits, fills cls[rlen],
- * and (optionally) the interval table */
+int hs_warp_width(void) { return CPG_WARP; }
+
+/* classify one read; seq = rlen raw characters; returns the OR of the lanes' status bits, fills
+ * cls[rlen] and (optionally) the interval table */
 int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits,
                      const uint16_t *prof, int plen, char *cls,
                      cpg_intvl *ivl_out, int *N_out, int *M_out)
@@ -53,24 +143,40 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
 
   static HsWork Wk; static int sized = 0;
   if (sized < plen) { Wk.size(plen+64); sized = plen+64; }
-  cpg_wshared ws; RelShared sh;
-  WCtx W; W.lane = 0; W.M = &dm; W.cthres = dm.cthres; W.ws = &ws; W.status = 0;
-  ReadCtx R;
-  R.prof = prof; R.plen = plen; R.rlen = rlen; R.seq = S; R.nslots = 0; R.N = R.M = 0;
-  R.S.mark = Wk.mark.data(); R.S.perr = Wk.perr.data(); R.S.eint = Wk.eint.data();
-  R.S.intvl = Wk.intvl.data(); R.S.rint = Wk.rint.data(); R.S.wint = Wk.wint.data();
-  R.S.bp = Wk.bp.data(); R.S.asg_f = Wk.af.data(); R.S.asg_b = Wk.ab.data();
-  R.S.rpos = Wk.rpos.data(); R.S.ord = Wk.ord.data(); R.S.fixed = Wk.fixed.data();
-  int st = classify_read(R,W,&sh,(uint8_t *)cls);
-  if (ivl_out) for (int i = 0; i < R.N; i++) ivl_out[i] = R.S.intvl[i];
-  if (N_out) *N_out = R.N;
-  if (M_out) *M_out = R.M;
+  static cpg_wshared ws; static RelShared sh;
+  LaneJob jobs[CPG_WARP];
+  for (int l = 0; l < CPG_WARP; l++)
+    { LaneJob &J = jobs[l];
+      J.lane = l; J.dm = &dm; J.ws = &ws; J.sh = &sh; J.cls = (uint8_t *)cls; J.status = 0;
+      ReadCtx &R = J.R;
+      R.prof = prof; R.plen = plen; R.rlen = rlen; R.seq = S; R.nslots = 0; R.N = R.M = 0;
+      R.S.mark = Wk.mark.data(); R.S.perr = Wk.perr.data(); R.S.eint = Wk.eint.data();
+      R.S.intvl = Wk.intvl.data(); R.S.rint = Wk.rint.data(); R.S.wint = Wk.wint.data();
+      R.S.bp = Wk.bp.data(); R.S.asg_f = Wk.af.data(); R.S.asg_b = Wk.ab.data();
+      R.S.rpos = Wk.rpos.data(); R.S.ord = Wk.ord.data(); R.S.fixed = Wk.fixed.data();
+    }
+  run_lanes(lane_classify,jobs);
+  int st = 0;
+  for (int l = 0; l < CPG_WARP; l++)
+    { st |= jobs[l].status;
+      if (jobs[l].N != jobs[0].N || jobs[l].M != jobs[0].M) st |= 1<<30;      /* lanes disagree */
+    }
+  if (ivl_out) for (int i = 0; i < jobs[0].N; i++) ivl_out[i] = Wk.intvl[i];
+  if (N_out) *N_out = jobs[0].N;
+  if (M_out) *M_out = jobs[0].M;
   return st;
 }
 
 int hs_decode_profile(const uint8_t *src, int64_t len, uint16_t *out, int cap)
-{ int offs[2*CPG_WARP];
-  return decode_profile(src,len,out,cap,0,offs);
+{ static int offs[2*CPG_WARP];
+  LaneJob jobs[CPG_WARP];
+  for (int l = 0; l < CPG_WARP; l++)
+    { jobs[l].lane = l; jobs[l].src = src; jobs[l].len = len; jobs[l].out = out; jobs[l].cap = cap;
+      jobs[l].offs = offs; jobs[l].n = 0;
+    }
+  run_lanes(lane_decode,jobs);
+  for (int l = 1; l < CPG_WARP; l++) if (jobs[l].n != jobs[0].n) return -1000000;
+  return jobs[0].n;
 }
 
 int hs_ctx(const char *seq, int rlen, int p, int right, int t)

@@ -172,11 +172,17 @@ def test_edge_batches(kit, cp):
     assert compare_with_oracle(kit, sim, ba, ka, ca, om)[1] == 0
     assert compare_with_oracle(kit, sim, bb, kb, cb, om)[1] == 0
     # a profile that does not match its read length is reported, not classified (ClassPro.c:234-237)
-    bad, keep1 = make_batch(cp, sim, keep=np.array([0, 1]))
-    bad.rlen[1] += 5
-    bad2 = cp.Batch(np.concatenate([bad.seq, np.zeros(8, np.uint8)]), bad.seq_off, bad.rlen, bad.prof, bad.prof_off, 2)
-    cls, st = ctx.classify(bad2)
-    assert st[0] == 0 and (st[1] & 1)
+    i0, i1 = 0, 1
+    while sim.rlen[i1] == sim.rlen[i0]:
+        i1 += 1
+    ok, _ = make_batch(cp, sim, keep=np.array([i0, i1]))
+    swapped = np.concatenate([sim.read_prof(i1), sim.read_prof(i0)])
+    po = np.array([0, len(sim.read_prof(i1)), len(swapped)], dtype=np.int64)
+    bad = cp.Batch(ok.seq, ok.seq_off, ok.rlen, swapped, po, 2)
+    cls, st = ctx.classify(bad)
+    assert (st[0] & 1) and (st[1] & 1)
+    with pytest.raises(cp.CpgError):
+        ctx.classify(bad, allow_read_errors=False)
     ctx.close()
 
 
