@@ -69,45 +69,71 @@ CPG_DEV double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
   return a+b;
 }
 
-/* src/class_unrel.c:115-175 */
-CPG_DEV_NOINL double un_lp_hd(WCtx &W, int s, int idx, const cpg_intvl *v, int N)
-{ const cpg_intvl I = v[idx];
-  int lrel, rrel;
-  un_nn(idx,s,v,N,lrel,rrel);
-  double lpl, lpr;
-  { double er = -CPG_INF, sf = -CPG_INF, sfer = -CPG_INF;
-    int l = idx-1;
-    if (l >= 0 && v[l].asgn == s) er = I.peob;
-    if (lrel != -1) sf = cpg_lp_trans(W,v[lrel].e-1,I.b,v[lrel].cce,I.cb,v[lrel].cce);
-    uint16_t est = un_est_cov(W,I.b,idx,v,N,s);
-    if (est >= I.cb) sfer = cpg_log(cpg_p_errorin(W,ET_OTHERS,0.1,est,I.cb));
-    lpl = dmax_ref(dmax_ref(er,sf),sfer);
-  }
-  { double er = -CPG_INF, sf = -CPG_INF, sfer = -CPG_INF;
-    int r = idx+1;
-    if (r < N && v[r].asgn == s) er = I.peoe;
-    if (rrel != -1) sf = cpg_lp_trans(W,I.e-1,v[rrel].b,I.ce,v[rrel].ccb,v[rrel].ccb);
-    uint16_t est = un_est_cov(W,I.e-1,idx,v,N,s);
-    if (est >= I.ce) sfer = cpg_log(cpg_p_errorin(W,ET_OTHERS,0.1,est,I.ce));
-    lpr = dmax_ref(dmax_ref(er,sf),sfer);
-  }
-  if (lpl == -CPG_INF && lpr == -CPG_INF)
-    { lpl = cpg_lp_poisson(W,I.cb,W.M->cov[s]); lpr = cpg_lp_poisson(W,I.ce,W.M->cov[s]); }
-  else if (lpl == -CPG_INF) lpl = lpr;
-  else if (lpr == -CPG_INF) lpr = lpl;
-  return lpl+lpr;
-}
-
-/* src/class_unrel.c:192-237 */
+/* src/class_unrel.c:115-237.  The ten independent pieces of an update -- the E and R
+ * log-probabilities and, for H and D, the Skellam transition and the error-in-others tail on
+ * either side -- are evaluated by ten lanes at once; the arg-max (first maximum wins, order
+ * E,R,H,D) is formed uniformly afterwards.
+ *   task 0: E     task 1: R     task 2+4*h+2*side+kind (h: 0=H,1=D; side: 0=left,1=right;
+ *   kind 0 = Skellam transition from/to the nearest fixed interval of that state,
+ *   kind 1 = log binomial tail of the count against the interpolated coverage) */
 CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N)
 { const cpg_intvl I = v[idx];
   int ns;
   if (imax(I.cb,I.ce) >= W.M->cov[ST_R]) ns = ST_R;
   else
-    { double mx = -CPG_INF; int ms = -1;
+    { double *term = W.ws->term;
+      const double *lf = W.M->logfact;
+      int bad = 0;
+      CPG_SYNCWARP();
+      for (int q = W.lane; q < 10; q += CPG_WARP)
+        { double val = -CPG_INF;
+          int need_s = 0, need_b = 0, k = 0, bn = 0, bc = 0; double lambda = 0.;
+          if (q == 0) val = un_lp_e(W,I);
+          else if (q == 1) val = un_lp_r(W,idx,v,N);
+          else
+            { const int t = q-2, s = (t & 4) ? ST_D : ST_H, right = (t >> 1) & 1, kind = t & 1;
+              if (kind == 0)
+                { int l, r;
+                  un_nn(idx,s,v,N,l,r);
+                  if (!right && l != -1)
+                    { int d = I.b-(v[l].e-1); if (d < 0) d = -d;
+                      k = (int)I.cb-(int)v[l].cce; lambda = (double)v[l].cce*d/W.M->read_len; need_s = 1;
+                    }
+                  if (right && r != -1)
+                    { int d = v[r].b-(I.e-1); if (d < 0) d = -d;
+                      k = (int)v[r].ccb-(int)I.ce; lambda = (double)v[r].ccb*d/W.M->read_len; need_s = 1;
+                    }
+                }
+              else
+                { uint16_t est = un_est_cov(W,right ? I.e-1 : I.b,idx,v,N,s);
+                  uint16_t c = right ? I.ce : I.cb;
+                  if (est >= c) { need_b = 1; bn = est; bc = c; }
+                }
+            }
+          if (need_s) val = cpg_lp_skellam(k,lambda);
+          if (need_b) val = cpg_log(cpg_p_errorin_lane(lf,ET_OTHERS,0.1,bn,bc,&bad));
+          term[q] = val;
+        }
+      CPG_SYNCWARP();
+      if (bad) W.status |= CPG_ST_BINOM;
+      double mx = -CPG_INF; int ms = -1;
       for (int s = ST_E; s <= ST_D; s++)
-        { double lp = (s == ST_E) ? un_lp_e(W,I)
-                    : (s == ST_R) ? un_lp_r(W,idx,v,N) : un_lp_hd(W,s,idx,v,N);
+        { double lp;
+          if (s == ST_E) lp = term[0];
+          else if (s == ST_R) lp = term[1];
+          else
+            { const double *t = term+2+(s == ST_D ? 4 : 0);
+              double er_l = -CPG_INF, er_r = -CPG_INF;
+              if (idx-1 >= 0 && v[idx-1].asgn == s) er_l = I.peob;
+              if (idx+1 < N && v[idx+1].asgn == s) er_r = I.peoe;
+              double lpl = dmax_ref(dmax_ref(er_l,t[0]),t[1]);
+              double lpr = dmax_ref(dmax_ref(er_r,t[2]),t[3]);
+              if (lpl == -CPG_INF && lpr == -CPG_INF)
+                { lpl = cpg_lp_poisson(W,I.cb,W.M->cov[s]); lpr = cpg_lp_poisson(W,I.ce,W.M->cov[s]); }
+              else if (lpl == -CPG_INF) lpl = lpr;
+              else if (lpr == -CPG_INF) lpr = lpl;
+              lp = lpl+lpr;
+            }
           if (mx < lp) { mx = lp; ms = s; }
         }
       if (ms == -1) { W.status |= CPG_ST_NO_PROB; ms = ST_E; }

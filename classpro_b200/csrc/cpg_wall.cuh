@@ -635,27 +635,43 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
   CPG_SYNCWARP();
   R.N = N;
 
-  /* reliable intervals (src/wall.c:1016-1037) */
-  int Mrel = 0;
+  /* reliable intervals (src/wall.c:1016-1037).  Three phases: corrected end counts of every
+     interval that passes the cheap filters (warp-cooperative sums), then the Skellam plausibility
+     test of all of them at once (one interval per lane), then the copies in interval order. */
+  int ncand = 0;
   const double logpthres = cpg_log(CPG_PE_FINAL);
+  int32_t *cand = R.S.ord;
+  uint8_t *keep = R.S.fixed;
   for (int i = 0; i < N; i++)
     { const cpg_intvl I = intvl[i];
       if (I.e-I.b < K) continue;
       if (imax(I.cb,I.ce) >= rcov) continue;
       if (I.pe >= logpthres) continue;
       correct_wall_cnt(R,W,i);
-      const int ccb = intvl[i].ccb, cce = intvl[i].cce;
-      if (cpg_lp_trans(W,I.b,I.e,ccb,cce,(uint16_t)((ccb+cce)/2)) < CPG_THRES_DIFF_REL) continue;
-      if (imax(ccb,cce) == CPG_MAX_CNT) continue;
-      CPG_SYNCWARP();
-      if (W.lane == 0)
-        { intvl[i].is_rel = 1;
-          R.S.rint[Mrel] = intvl[i];
-          R.S.rint[Mrel].is_rel = 1;
-        }
-      CPG_SYNCWARP();
-      Mrel++;
+      if (W.lane == 0) cand[ncand] = i;
+      ncand++;
     }
+  CPG_SYNCWARP();
+  for (int q = W.lane; q < ncand; q += CPG_WARP)
+    { const cpg_intvl I = intvl[cand[q]];
+      const int ccb = I.ccb, cce = I.cce;
+      int ok = !(cpg_lp_trans(W,I.b,I.e,ccb,cce,(uint16_t)((ccb+cce)/2)) < CPG_THRES_DIFF_REL);
+      if (imax(ccb,cce) == CPG_MAX_CNT) ok = 0;
+      keep[q] = (uint8_t)ok;
+    }
+  CPG_SYNCWARP();
+  int Mrel = 0;
+  for (int q = 0; q < ncand; q++) if (keep[q]) Mrel++;
+  if (W.lane == 0)
+    { int m = 0;
+      for (int q = 0; q < ncand; q++)
+        if (keep[q])
+          { const int i = cand[q];
+            intvl[i].is_rel = 1;
+            R.S.rint[m++] = intvl[i];
+          }
+    }
+  CPG_SYNCWARP();
   R.M = Mrel;
 }
 

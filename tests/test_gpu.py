@@ -209,7 +209,7 @@ def test_minimal_and_maximal_reads(kit, cp):
         enc = [int(c[0])] if c[0] < 128 else [0x80 | (int(c[0]) >> 8), int(c[0]) & 0xff]
         for j in range(1, n):
             d = int(c[j]) - int(c[j - 1])
-            enc += [0x40 | (d & 0x3f)] if -32 <= d <= 31 and d != 0 else ([0] if d == 0 else [0x80 | ((d & 0x7fff) >> 8), d & 0xff])
+            enc += [0x40 | (d & 0x3f)] if -32 <= d <= 31 and d != 0 else ([1] if d == 0 else [0x80 | ((d & 0x7fff) >> 8), d & 0xff])
         profs.append(bytes(enc))
     pk, po = pack_reads(reads)
     pr = np.frombuffer(b"".join(profs), dtype=np.uint8)
