@@ -20,12 +20,13 @@
 #define CPG_CONTEXT_CUH
 #include "cpg_common.h"
 
-CPG_DEV int cpg_base(const cpg_seq &S, int i)
+/* the view is taken by value: it lives in registers for the duration of a query */
+CPG_DEV int cpg_base(const cpg_seq S, int i)
 { return (S.bits == 8) ? (int)S.p[i] : (int)((S.p[i >> 2] >> ((i & 3)*2)) & 3); }
 
 CPG_DEV int cpg_cap127(int x) { return x > 127 ? 127 : x; }
 
-CPG_DEV int cpg_lctx(const cpg_seq &S, int rlen, int p, int t)
+CPG_DEV int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
 { (void)rlen;
   if (t == CT_HP)
     { int c = cpg_base(S,p), n = 1;
@@ -49,7 +50,7 @@ CPG_DEV int cpg_lctx(const cpg_seq &S, int rlen, int p, int t)
   return u;
 }
 
-CPG_DEV int cpg_rctx(const cpg_seq &S, int rlen, int p, int t)
+CPG_DEV int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
 { if (t == CT_HP)
     { int c = cpg_base(S,p), n = 1;
       while (n < 127 && p+n < rlen && cpg_base(S,p+n) == c) n++;
@@ -73,7 +74,7 @@ CPG_DEV int cpg_rctx(const cpg_seq &S, int rlen, int p, int t)
 }
 
 /* ctx[wtype][i][t] of the reference, i a profile position */
-CPG_DEV int cpg_ctx_at(const cpg_seq &S, int rlen, int K, int wtype, int i, int t)
+CPG_DEV int cpg_ctx_at(const cpg_seq S, int rlen, int K, int wtype, int i, int t)
 { return (wtype == WT_DROP) ? cpg_lctx(S,rlen,i+K-2,t) : cpg_rctx(S,rlen,i,t); }
 
 #endif

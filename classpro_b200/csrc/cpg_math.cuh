@@ -61,27 +61,50 @@ CPG_DEV double cpg_bessi1(double x)
   return x < 0.0 ? -ans : ans;
 }
 
-/* src/bessel.c:482-521: Miller downward recurrence started at 2*(n+floor(sqrt(40 n))), rescaled by
- * 1e-10 whenever |bi| passes 1e10, normalised with I0 */
+/* keeps the compiler from turning the (rare, three-multiply) rescale into always-executed
+ * predicated code inside the recurrence */
+#ifdef CPG_HOSTSIM
+#define CPG_NO_IFCVT() do { } while (0)
+#else
+#define CPG_NO_IFCVT() asm volatile("")
+#endif
+
+/* src/bessel.c:482-521: Miller downward recurrence started at j = 2*(n+floor(sqrt(40 n))),
+ * rescaled by 1e-10 whenever |bi| passes 1e10, normalised with I0.  The loop is split at j == n:
+ * before that point `ans` is still 0 (its rescale multiplies are no-ops and are skipped), at
+ * j == n it takes the value of bip, afterwards it is rescaled with the others.  j is kept as a
+ * double (exact) so no integer->double conversion sits in the dependent chain, and the steps are
+ * written in pairs so that bi/bip swap roles instead of being copied.
+ * Same operations on the same values, in the same order, as the reference. */
 CPG_DEV_NOINL double cpg_bessi(int n, double x)
 { if (n == 0) return cpg_bessi0(x);
   if (n == 1) return cpg_bessi1(x);
   if (x == 0.0) return 0.0;
-  double tox = 2.0/fabs(x), bip = 0.0, ans = 0.0, bi = 1.0, bim;
-  int j = 2*(n+(int)sqrt(40.0*n));
-  double jd = (double)j;                 /* (double)j kept as a double: exact, saves an I2F per step */
+  const double tox = 2.0/fabs(x), big = 1.0e10, small = 1.0e-10;
+  const int start = 2*(n+(int)sqrt(40.0*n));
+  double jd = (double)start;
+  /* One step of the recurrence without register shuffling: X holds bip and becomes the new bi,
+     Y holds bi and becomes the new bip.  Two steps bring the roles back. */
+#define CPG_BSTEP(X,Y,RESCALE_ANS) \
+    { X = X+jd*tox*Y; \
+      if (fabs(X) > big) { CPG_NO_IFCVT(); RESCALE_ANS X *= small; Y *= small; } \
+      jd -= 1.0; }
+  double P = 0.0, Q = 1.0, ans;                     /* bip = P, bi = Q */
+  int c = start-n+1;                                /* steps j = start .. n: ans is still 0 */
 #ifndef CPG_HOSTSIM
 #pragma unroll 1
 #endif
-  for (; j > 0; j--, jd -= 1.0)
-    { bim = bip+jd*tox*bi;
-      bip = bi;
-      bi = bim;
-      if (fabs(bi) > 1.0e10)
-        { ans *= 1.0e-10; bi *= 1.0e-10; bip *= 1.0e-10; }
-      if (j == n) ans = bip;
-    }
-  ans *= cpg_bessi0(x)/bi;
+  for (; c >= 2; c -= 2) { CPG_BSTEP(P,Q,) CPG_BSTEP(Q,P,) }
+  if (c) { CPG_BSTEP(P,Q,) double t = P; P = Q; Q = t; }
+  ans = P;                                          /* if (j == n) ans = bip */
+  c = n-1;                                          /* steps j = n-1 .. 1 */
+#ifndef CPG_HOSTSIM
+#pragma unroll 1
+#endif
+  for (; c >= 2; c -= 2) { CPG_BSTEP(P,Q,ans *= small;) CPG_BSTEP(Q,P,ans *= small;) }
+  if (c) { CPG_BSTEP(P,Q,ans *= small;) Q = P; }
+#undef CPG_BSTEP
+  ans *= cpg_bessi0(x)/Q;
   return (x < 0.0 && (n%2) == 1) ? -ans : ans;
 }
 

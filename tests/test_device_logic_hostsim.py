@@ -181,3 +181,30 @@ def test_decode_streams(kit, hostsim, adversarial):
 def test_decode_empty_profile(kit, hostsim):
     n, o = kit.hostsim_decode(np.zeros(0, dtype=np.uint8), 10)
     assert n == 0
+
+
+def test_warp32_emulation_classify(kit):
+    """The same device sources with 32 host threads playing the lanes of one warp: every ballot,
+    shuffle, reduction and __syncwarp is a rendezvous, lanes run asynchronously in between.
+    Catches collectives reached by only some lanes (hang) and missing synchronisation (mismatch)."""
+    L32 = kit.hostsim32_lib()
+    sim = kit.simulate(seed=47, genome_len=20000, cov=14., het=0.01, repeat_frac=0.4, len_mean=2200, len_sd=400,
+                       len_min=500)
+    om = kit.oracle_model(sim)
+    gm = kit.gpu_model_from_sim(L32, sim)
+    ow = kit.OracleWork(clean=True)
+    for i in range(min(sim.nreads, 10)):
+        s, c = sim.read_ascii(i).tobytes(), sim.read_counts(i)
+        a, ia, ma = ow.classify(om, s, c, True)
+        st, b, ib, mb = kit.hostsim_classify(gm, s, c, 2, True, lib=L32)
+        assert st == 0 and a == b and ia == ib and ma == mb, i
+
+
+def test_warp32_emulation_decode(kit):
+    L32 = kit.hostsim32_lib()
+    rng = np.random.default_rng(13)
+    for it in range(40):
+        s = random_stream(rng, int(rng.integers(0, 300)), bool(it & 1))
+        n1, o1 = kit.oracle_decode(np.frombuffer(s, dtype=np.uint8), 100000)
+        n2, o2 = kit.hostsim_decode(np.frombuffer(s, dtype=np.uint8), 100000, lib=L32)
+        assert n2 == n1 and np.array_equal(o2, o1)
