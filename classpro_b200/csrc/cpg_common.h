@@ -23,6 +23,7 @@
   #define CPG_DEV_NOINL  static
   #define CPG_LDG(p)     (*(p))
   #define CPG_INF        ((double)INFINITY)
+  #define CPG_LOOP
   #if CPG_HOSTSIM == 32
     /* 32 host threads play the lanes of one warp; every warp primitive is a rendezvous, so a
        collective reached by only some lanes, or a missing __syncwarp, shows up as a hang or as
@@ -45,6 +46,9 @@
   #define CPG_WARP       32
   #define CPG_SYNCWARP() __syncwarp()
   #define CPG_LDG(p)     __ldg(p)
+  /* loops of the per-read logic are not unrolled: with ~30 warps per SM in different phases of a
+     large kernel, the instruction-cache footprint matters more than loop overhead */
+  #define CPG_LOOP       _Pragma("unroll 1")
   #define CPG_INF        (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 

@@ -26,11 +26,11 @@ CPG_DEV int cpg_base(const cpg_seq S, int i)
 
 CPG_DEV int cpg_cap127(int x) { return x > 127 ? 127 : x; }
 
-CPG_DEV int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
+CPG_DEV_NOINL int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
 { (void)rlen;
   if (t == CT_HP)
     { int c = cpg_base(S,p), n = 1;
-      while (n < 127 && p-n >= 0 && cpg_base(S,p-n) == c) n++;
+      CPG_LOOP while (n < 127 && p-n >= 0 && cpg_base(S,p-n) == c) n++;
       return n;
     }
   if (t == CT_DS)
@@ -38,22 +38,22 @@ CPG_DEV int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
       int a = cpg_base(S,p-1), b = cpg_base(S,p);
       if (a == b) return 0;
       int u = 1, q = p;
-      while (u < 127 && q >= 3 && cpg_base(S,q-3) == a && cpg_base(S,q-2) == b) { u++; q -= 2; }
+      CPG_LOOP while (u < 127 && q >= 3 && cpg_base(S,q-3) == a && cpg_base(S,q-2) == b) { u++; q -= 2; }
       return u;
     }
   if (p < 2) return 0;
   int a = cpg_base(S,p-2), b = cpg_base(S,p-1), c = cpg_base(S,p);
   if (a == b && b == c) return 0;
   int u = 1, q = p;
-  while (u < 127 && q >= 5 && cpg_base(S,q-5) == a && cpg_base(S,q-4) == b && cpg_base(S,q-3) == c)
+  CPG_LOOP while (u < 127 && q >= 5 && cpg_base(S,q-5) == a && cpg_base(S,q-4) == b && cpg_base(S,q-3) == c)
     { u++; q -= 3; }
   return u;
 }
 
-CPG_DEV int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
+CPG_DEV_NOINL int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
 { if (t == CT_HP)
     { int c = cpg_base(S,p), n = 1;
-      while (n < 127 && p+n < rlen && cpg_base(S,p+n) == c) n++;
+      CPG_LOOP while (n < 127 && p+n < rlen && cpg_base(S,p+n) == c) n++;
       return n;
     }
   if (t == CT_DS)
@@ -61,14 +61,14 @@ CPG_DEV int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
       int a = cpg_base(S,p), b = cpg_base(S,p+1);
       if (a == b) return 0;
       int u = 1, q = p;
-      while (u < 127 && q+3 <= rlen-1 && cpg_base(S,q+2) == a && cpg_base(S,q+3) == b) { u++; q += 2; }
+      CPG_LOOP while (u < 127 && q+3 <= rlen-1 && cpg_base(S,q+2) == a && cpg_base(S,q+3) == b) { u++; q += 2; }
       return u;
     }
   if (p > rlen-3) return 0;
   int a = cpg_base(S,p), b = cpg_base(S,p+1), c = cpg_base(S,p+2);
   if (a == b && b == c) return 0;
   int u = 1, q = p;
-  while (u < 127 && q+5 <= rlen-1 && cpg_base(S,q+3) == a && cpg_base(S,q+4) == b && cpg_base(S,q+5) == c)
+  CPG_LOOP while (u < 127 && q+5 <= rlen-1 && cpg_base(S,q+3) == a && cpg_base(S,q+4) == b && cpg_base(S,q+5) == c)
     { u++; q += 3; }
   return u;
 }

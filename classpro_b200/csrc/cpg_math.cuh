@@ -21,8 +21,10 @@ struct WCtx
     int               status;
   };
 
-CPG_DEV double cpg_exp(double x) { return exp(x); }
-CPG_DEV double cpg_log(double x) { return log(x); }
+/* one copy of each in the kernel: the per-read code is executed by up to 32 warps per SM that sit in
+   different phases, so instruction-cache footprint matters more than call overhead */
+CPG_DEV_NOINL double cpg_exp(double x) { return exp(x); }
+CPG_DEV_NOINL double cpg_log(double x) { return log(x); }
 
 CPG_DEV int imin(int a, int b) { return a < b ? a : b; }
 CPG_DEV int imax(int a, int b) { return a > b ? a : b; }
@@ -30,7 +32,7 @@ CPG_DEV int imax(int a, int b) { return a > b ? a : b; }
 CPG_DEV double dmax_ref(double x, double y) { return x > y ? x : y; }
 
 /* src/bessel.c:390-411 */
-CPG_DEV double cpg_bessi0(double x)
+CPG_DEV_NOINL double cpg_bessi0(double x)
 { double ax = fabs(x), y, ans;
   if (ax < 3.75)
     { y = x/3.75; y = y*y;
@@ -45,7 +47,7 @@ CPG_DEV double cpg_bessi0(double x)
 }
 
 /* src/bessel.c:416-439 */
-CPG_DEV double cpg_bessi1(double x)
+CPG_DEV_NOINL double cpg_bessi1(double x)
 { double ax = fabs(x), y, ans;
   if (ax < 3.75)
     { y = x/3.75; y = y*y;
@@ -112,13 +114,13 @@ CPG_DEV_NOINL double cpg_bessi(int n, double x)
 CPG_DEV int cpg_clamp_cnt(int n) { return n > CPG_MAX_CNT ? CPG_MAX_CNT : n; }
 
 /* src/prob.c:33-39 */
-CPG_DEV double cpg_lp_poisson(const WCtx &W, uint16_t k16, int lambda)
+CPG_DEV_NOINL double cpg_lp_poisson(const WCtx &W, uint16_t k16, int lambda)
 { int k = cpg_clamp_cnt(k16);
   return k*cpg_log((double)lambda)-lambda-CPG_LDG(W.M->logfact+k);
 }
 
 /* src/prob.c:41-44 */
-CPG_DEV double cpg_lp_skellam(int k, double lambda)
+CPG_DEV_NOINL double cpg_lp_skellam(int k, double lambda)
 { return -2.*lambda+cpg_log(cpg_bessi(k < 0 ? -k : k,2.*lambda)); }
 
 /* src/util.c:35-44; `cov` is a 16-bit count in the reference's signature */
@@ -128,7 +130,7 @@ CPG_DEV double cpg_lp_trans(const WCtx &W, int b, int e, int cb, int ce, uint16_
 }
 
 /* src/prob.c:59-65 */
-CPG_DEV double cpg_lp_binom(WCtx &W, uint16_t k16, uint16_t n16, double p)
+CPG_DEV_NOINL double cpg_lp_binom(WCtx &W, uint16_t k16, uint16_t n16, double p)
 { int k = cpg_clamp_cnt(k16), n = cpg_clamp_cnt(n16);
   if (k > n) { W.status |= CPG_ST_BINOM; return -CPG_INF; }
   const double *lf = W.M->logfact;
@@ -150,12 +152,12 @@ CPG_DEV_NOINL double cpg_binom_tail(WCtx &W, int k, int n, double pe)
 #define CPG_LBP(x) (lfn-CPG_LDG(lf+(x))-CPG_LDG(lf+(n-(x)))+(x)*lpe+(n-(x))*l1mpe)
   if ((double)k >= mean)
     { p = p_first = cpg_exp(CPG_LBP(k));
-      for (int x0 = k+1; x0 <= n; x0 += CPG_WARP)
+      CPG_LOOP for (int x0 = k+1; x0 <= n; x0 += CPG_WARP)
         { int x = x0+W.lane;
           if (x <= n) term[W.lane] = cpg_exp(CPG_LBP(x));
           CPG_SYNCWARP();
           int cnt = imin(CPG_WARP,n-x0+1), stop = 0;
-          for (int l = 0; l < cnt; l++)
+          CPG_LOOP for (int l = 0; l < cnt; l++)
             { double t = term[l];
               p += t;
               if (10*t < p_first) { stop = 1; break; }
@@ -166,12 +168,12 @@ CPG_DEV_NOINL double cpg_binom_tail(WCtx &W, int k, int n, double pe)
     }
   else
     { p = p_first = (k == 0) ? 0. : cpg_exp(CPG_LBP(k-1));
-      for (int x0 = k-2; x0 >= 0; x0 -= CPG_WARP)
+      CPG_LOOP for (int x0 = k-2; x0 >= 0; x0 -= CPG_WARP)
         { int x = x0-W.lane;
           if (x >= 0) term[W.lane] = cpg_exp(CPG_LBP(x));
           CPG_SYNCWARP();
           int cnt = imin(CPG_WARP,x0+1), stop = 0;
-          for (int l = 0; l < cnt; l++)
+          CPG_LOOP for (int l = 0; l < cnt; l++)
             { double t = term[l];
               p += t;
               if (10*t < p_first) { stop = 1; break; }
@@ -197,14 +199,14 @@ CPG_DEV_NOINL double cpg_binom_tail_lane(const double *lf, int k, int n, double 
 #define CPG_LBP(x) (lfn-CPG_LDG(lf+(x))-CPG_LDG(lf+(n-(x)))+(x)*lpe+(n-(x))*l1mpe)
   if ((double)k >= mean)
     { p = p_first = cpg_exp(CPG_LBP(k));
-      for (int x = k+1; x <= n; x++)
+      CPG_LOOP for (int x = k+1; x <= n; x++)
         { p += t = cpg_exp(CPG_LBP(x));
           if (10*t < p_first) break;
         }
     }
   else
     { p = p_first = (k == 0) ? 0. : cpg_exp(CPG_LBP(k-1));
-      for (int x = k-2; x >= 0; x--)
+      CPG_LOOP for (int x = k-2; x >= 0; x--)
         { p += t = cpg_exp(CPG_LBP(x));
           if (10*t < p_first) break;
         }

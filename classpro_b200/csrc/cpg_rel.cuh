@@ -47,13 +47,13 @@ CPG_DEV uint16_t rl_begcnt(const cpg_intvl &I, int F) { return F ? I.ccb : I.cce
 CPG_DEV uint16_t rl_endcnt(const cpg_intvl &I, int F) { return F ? I.cce : I.ccb; }
 
 /* src/class_rel.c:158-170 */
-CPG_DEV double rl_lp_e(const WCtx &W, const cpg_intvl &I, const uint16_t *COV)
+CPG_DEV_NOINL double rl_lp_e(const WCtx &W, const cpg_intvl &I, const uint16_t *COV)
 { double po = cpg_lp_poisson(W,I.ccb,COV[ST_E])+cpg_lp_poisson(W,I.cce,COV[ST_E])+CPG_E_PO_BASE;
   return dmax_ref(po,I.pe);
 }
 
 /* src/class_rel.c:172-211 */
-CPG_DEV double rl_lp_r(WCtx &W, const cpg_intvl &I, uint16_t pr_cnt, int F, const uint16_t *COV)
+CPG_DEV_NOINL double rl_lp_r(WCtx &W, const cpg_intvl &I, uint16_t pr_cnt, int F, const uint16_t *COV)
 { uint16_t bc = rl_begcnt(I,F);
   double sf = -CPG_INF;
   double er = (bc < pr_cnt) ? cpg_lp_binom(W,bc,pr_cnt,1-CPG_PE_MEAN) : -CPG_INF;
@@ -88,7 +88,7 @@ CPG_DEV void rl_hd_args(const WCtx &W, int t, const cpg_intvl &I, const RelState
 /* src/class_rel.c:80-96 with s (or t) as the wildcard */
 CPG_DEV int rl_best_from(const RelState *prv, const double *tr, int t, double *out)   /* wildcard s */
 { double mx = -CPG_INF; int ms = ST_N;
-  for (int x = 0; x < 4; x++)
+  CPG_LOOP for (int x = 0; x < 4; x++)
     { double lp = prv[x].dp+tr[x*4+t];
       if (mx < lp) { mx = lp; ms = x; }
     }
@@ -97,7 +97,7 @@ CPG_DEV int rl_best_from(const RelState *prv, const double *tr, int t, double *o
 }
 CPG_DEV int rl_best_to(const RelState *prv, const double *tr, int s)                  /* wildcard t */
 { double mx = -CPG_INF; int mt = ST_N;
-  for (int x = 0; x < 4; x++)
+  CPG_LOOP for (int x = 0; x < 4; x++)
     { double lp = prv[s].dp+tr[s*4+x];
       if (mx < lp) { mx = lp; mt = x; }
     }
@@ -105,7 +105,7 @@ CPG_DEV int rl_best_to(const RelState *prv, const double *tr, int s)            
 }
 
 /* src/class_rel.c:113-156 on the path summary of predecessor P extended by state t at interval i */
-CPG_DEV double rl_dh_ratio(WCtx &W, const ReadCtx &R, int t, int i, const RelState &P, int F)
+CPG_DEV_NOINL double rl_dh_ratio(WCtx &W, const ReadCtx &R, int t, int i, const RelState &P, int F)
 { int i2 = (t == ST_H) ? P.lastD : P.lastH;
   if (i2 < 0) return -CPG_INF;
   int i3 = (t == ST_H) ? P.hbd : P.dbh;
@@ -135,7 +135,7 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
   const int ip = rl_pred(i,F);
   double *tr = U.sh->tr;
 
-  for (int q = W.lane; q < 16; q += CPG_WARP)
+  CPG_LOOP for (int q = W.lane; q < 16; q += CPG_WARP)
     { int s = q >> 2, t = q & 3;
       double v = 0.;
       int need = 0, k = 0; double lambda = 0.;
@@ -149,10 +149,10 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
     }
   CPG_SYNCWARP();
   double psum = 0.;
-  for (int q = 0; q < 16; q++) psum += tr[q];
+  CPG_LOOP for (int q = 0; q < 16; q++) psum += tr[q];
   int fix = (psum == 0.);
   CPG_SYNCWARP();
-  for (int q = W.lane; q < 16; q += CPG_WARP)
+  CPG_LOOP for (int q = W.lane; q < 16; q += CPG_WARP)
     { double v = tr[q];
       if (fix) v = ((q & 3) == ST_E) ? 1. : v;
       tr[q] = cpg_log(v/(fix ? 4. : psum));
@@ -161,7 +161,7 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
 
   /* every live predecessor prefers R: freeze this interval (src/class_rel.c:348-380) */
   int only_r = 1;
-  for (int s = 0; s < 4; s++)
+  CPG_LOOP for (int s = 0; s < 4; s++)
     { int mt = rl_best_to(prv,tr,s);
       if (mt != ST_N && mt != ST_R) { only_r = 0; break; }
     }
@@ -170,12 +170,12 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
         { R.S.rpos[i] = 1;
           wint[i] = wint[ip];
           uint16_t bp = 0;
-          for (int s = 0; s < 4; s++)
+          CPG_LOOP for (int s = 0; s < 4; s++)
             { cur[s].dp = prv[s].dp;
               cur[s].dhr = -CPG_INF;
               bp |= (uint16_t)(((prv[s].dp == -CPG_INF) ? ST_N : s) << (3*s));
               if (prv[s].dp == -CPG_INF) continue;
-              for (int t = 0; t < 4; t++) { cur[s].pos[t] = prv[s].pos[t]; cur[s].cnt[t] = prv[s].cnt[t]; }
+              CPG_LOOP for (int t = 0; t < 4; t++) { cur[s].pos[t] = prv[s].pos[t]; cur[s].cnt[t] = prv[s].cnt[t]; }
               rl_extend_path(cur[s],prv[s],s,i);
             }
           R.S.bp[i] = bp;
@@ -194,21 +194,21 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
     }
 
   uint16_t bpw = 0;
-  for (int t = 0; t < 4; t++)
+  CPG_LOOP for (int t = 0; t < 4; t++)
     { double mlp;
       int ms = rl_best_from(prv,tr,t,&mlp);
       bpw |= (uint16_t)(ms << (3*t));
       RelState ns;
       ns.dp = mlp; ns.dhr = -CPG_INF;
-      for (int k = 0; k < 4; k++) { ns.pos[k] = 0; ns.cnt[k] = 0; }
+      CPG_LOOP for (int k = 0; k < 4; k++) { ns.pos[k] = 0; ns.cnt[k] = 0; }
       ns.lastH = ns.lastD = ns.hbd = ns.dbh = -1;
       if (ms != ST_N)
         { const RelState P = prv[ms];
           rl_extend_path(ns,P,t,i);
           if (t == ST_E)
-            { for (int s = ST_R; s <= ST_D; s++) { ns.pos[s] = P.pos[s]; ns.cnt[s] = P.cnt[s]; } }
+            { CPG_LOOP for (int s = ST_R; s <= ST_D; s++) { ns.pos[s] = P.pos[s]; ns.cnt[s] = P.cnt[s]; } }
           else if (t == ST_R)
-            { for (int s = ST_H; s <= ST_D; s++) { ns.pos[s] = rl_off(ep,F); ns.cnt[s] = P.cnt[s]; }
+            { CPG_LOOP for (int s = ST_H; s <= ST_D; s++) { ns.pos[s] = rl_off(ep,F); ns.cnt[s] = P.cnt[s]; }
               uint16_t rc = (uint16_t)imin(ec,U.COV[ST_R]);
               if (P.cnt[ST_R] < rc) { ns.pos[ST_R] = P.pos[ST_R]; ns.cnt[ST_R] = P.cnt[ST_R]; }
               else                  { ns.pos[ST_R] = rl_off(ep,F); ns.cnt[ST_R] = rc; }
@@ -243,7 +243,7 @@ CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
 { const int F = U.F, Mrel = U.M;
   const uint16_t *COV = U.COV;
   cpg_intvl *wint = R.S.wint;
-  for (int i = W.lane; i < Mrel; i += CPG_WARP) { wint[i] = R.S.rint[i]; R.S.rpos[i] = 0; R.S.bp[i] = 0; }
+  CPG_LOOP for (int i = W.lane; i < Mrel; i += CPG_WARP) { wint[i] = R.S.rint[i]; R.S.rpos[i] = 0; R.S.bp[i] = 0; }
   CPG_SYNCWARP();
 
   const int POS_INIT = rl_off(F ? 0 : U.plen,F);
@@ -257,13 +257,13 @@ CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
     d[ST_H] = cpg_lp_poisson(W,bc,COV[ST_H]);
     d[ST_D] = cpg_lp_poisson(W,bc,COV[ST_D]);
     double psum = 0.;
-    for (int s = 0; s < 4; s++) psum += cpg_exp(d[s]);
-    for (int s = 0; s < 4; s++) d[s] = cpg_log(cpg_exp(d[s])/psum);
+    CPG_LOOP for (int s = 0; s < 4; s++) psum += cpg_exp(d[s]);
+    CPG_LOOP for (int s = 0; s < 4; s++) d[s] = cpg_log(cpg_exp(d[s])/psum);
     if (W.lane == 0)
-      { for (int s = 0; s < 4; s++)
+      { CPG_LOOP for (int s = 0; s < 4; s++)
           { RelState &X = c0[s];
             X.dp = d[s]; X.dhr = -CPG_INF;
-            for (int t = ST_R; t <= ST_D; t++) { X.pos[t] = POS_INIT; X.cnt[t] = COV[t]; }
+            CPG_LOOP for (int t = ST_R; t <= ST_D; t++) { X.pos[t] = POS_INIT; X.cnt[t] = COV[t]; }
             X.pos[0] = 0; X.cnt[0] = 0;
             X.lastH = X.lastD = X.hbd = X.dbh = -1;
           }
@@ -279,7 +279,7 @@ CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
   }
 
   RelState *prv = c0, *cur = c1;
-  for (;;)
+  CPG_LOOP for (;;)
     { i = F ? i+1 : i-1;
       if ((F && i >= Mrel) || (!F && i < 0)) break;
       rl_update(R,W,U,i,prv,cur);
@@ -293,7 +293,7 @@ CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
   CPG_SYNCWARP();
   if (W.lane == 0)
     { const int first = F ? 0 : Mrel-1;
-      for (;;)
+      CPG_LOOP for (;;)
         { asgn[i] = (uint8_t)(R.S.rpos[i] ? ST_R : s);
           if (i == first) break;
           int p = (R.S.bp[i] >> (3*s)) & 7;
@@ -305,9 +305,9 @@ CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
 }
 
 /* integer accumulation of src/class_rel.c:634-664 */
-CPG_DEV double rl_mean_cov(const cpg_intvl *r, const uint8_t *asgn, int Mrel, int want)
+CPG_DEV_NOINL double rl_mean_cov(const cpg_intvl *r, const uint8_t *asgn, int Mrel, int want)
 { int lsum = 0, csum = 0;
-  for (int i = 0; i < Mrel; i++)
+  CPG_LOOP for (int i = 0; i < Mrel; i++)
     if (want < 0 || asgn[i] == want)
       { int l = r[i].e-r[i].b;
         lsum += l;
@@ -317,13 +317,13 @@ CPG_DEV double rl_mean_cov(const cpg_intvl *r, const uint8_t *asgn, int Mrel, in
 }
 
 CPG_DEV int rl_has(const uint8_t *asgn, int Mrel, int s)
-{ for (int i = 0; i < Mrel; i++) if (asgn[i] == s) return 1;
+{ CPG_LOOP for (int i = 0; i < Mrel; i++) if (asgn[i] == s) return 1;
   return 0;
 }
 
-CPG_DEV void rl_relabel(uint8_t *asgn, int Mrel, int from1, int to1, int from2, int to2, const WCtx &W)
+CPG_DEV_NOINL void rl_relabel(uint8_t *asgn, int Mrel, int from1, int to1, int from2, int to2, const WCtx &W)
 { CPG_SYNCWARP();
-  for (int i = W.lane; i < Mrel; i += CPG_WARP)
+  CPG_LOOP for (int i = W.lane; i < Mrel; i += CPG_WARP)
     { uint8_t a = asgn[i];
       if (from1 < 0 || a == from1) asgn[i] = (uint8_t)to1;
       else if (a == from2) asgn[i] = (uint8_t)to2;
@@ -337,11 +337,11 @@ CPG_DEV_NOINL double rl_direction(ReadCtx &R, WCtx &W, RelShared *sh, int F, int
   const uint16_t *G = W.M->cov;
   RelRun U;
   U.F = F; U.M = Mrel; U.plen = plen; U.sh = sh;
-  for (int s = 0; s < 4; s++) U.COV[s] = G[s];
+  CPG_LOOP for (int s = 0; s < 4; s++) U.COV[s] = G[s];
   rl_pass(R,W,U,asgn);
   if (!rl_has(asgn,Mrel,ST_H))
     { int anchor = -1;
-      for (int i = 0; i < Mrel; i++)
+      CPG_LOOP for (int i = 0; i < Mrel; i++)
         if (asgn[i] == ST_D) { if (F) { if (anchor == -1) anchor = i; } else anchor = i; }
       if (anchor >= 0)
         { double mean_d = rl_mean_cov(r,asgn,Mrel,ST_D);
@@ -358,7 +358,7 @@ CPG_DEV_NOINL double rl_direction(ReadCtx &R, WCtx &W, RelShared *sh, int F, int
         }
     }
   { int all_h = 1;
-    for (int i = 0; i < Mrel; i++) if (asgn[i] != ST_H) all_h = 0;
+    CPG_LOOP for (int i = 0; i < Mrel; i++) if (asgn[i] != ST_H) all_h = 0;
     if (all_h)
       { double mean_h = rl_mean_cov(r,asgn,Mrel,-1);
         if (fabs(mean_h-G[ST_H]) >= fabs(mean_h-G[ST_D]))
@@ -366,7 +366,7 @@ CPG_DEV_NOINL double rl_direction(ReadCtx &R, WCtx &W, RelShared *sh, int F, int
       }
   }
   { int n = 0;
-    for (int i = 0; i < Mrel; i++) if (asgn[i] == ST_H) n++;
+    CPG_LOOP for (int i = 0; i < Mrel; i++) if (asgn[i] == ST_H) n++;
     if (n >= Mrel*0.7)
       { double mean_h = rl_mean_cov(r,asgn,Mrel,ST_H);
         if (fabs(mean_h-G[ST_H]) >= fabs(mean_h-G[ST_D]))
@@ -374,7 +374,7 @@ CPG_DEV_NOINL double rl_direction(ReadCtx &R, WCtx &W, RelShared *sh, int F, int
       }
   }
   int fd = -1, ld = -1, fh = -1, lh = -1;
-  for (int i = 0; i < Mrel; i++)
+  CPG_LOOP for (int i = 0; i < Mrel; i++)
     { if (asgn[i] == ST_D) { if (fd == -1) fd = i; ld = i; }
       else if (asgn[i] == ST_H) { if (fh == -1) fh = i; lh = i; }
     }
@@ -385,15 +385,15 @@ CPG_DEV_NOINL double rl_direction(ReadCtx &R, WCtx &W, RelShared *sh, int F, int
 CPG_DEV int rl_eq_prefix(const uint8_t *a, int Mrel)
 { if (a[0] != 1) return 0;
   int i = 0;
-  while (i < Mrel && a[i]) i++;
-  for (; i < Mrel; i++) if (a[i]) return 0;
+  CPG_LOOP while (i < Mrel && a[i]) i++;
+  CPG_LOOP for (; i < Mrel; i++) if (a[i]) return 0;
   return 1;
 }
 CPG_DEV int rl_eq_suffix(const uint8_t *a, int Mrel)
 { if (a[Mrel-1] != 1) return 0;
   int i = Mrel-2;
-  while (i >= 0 && a[i]) i--;
-  for (; i >= 0; i--) if (a[i]) return 0;
+  CPG_LOOP while (i >= 0 && a[i]) i--;
+  CPG_LOOP for (; i >= 0; i--) if (a[i]) return 0;
   return 1;
 }
 
@@ -405,7 +405,7 @@ CPG_DEV_NOINL void classify_reliable(ReadCtx &R, WCtx &W, RelShared *sh)
   double hf = rl_direction(R,W,sh,1,Mrel,R.plen,af);
   double hb = rl_direction(R,W,sh,0,Mrel,R.plen,ab);
   int eq = 1;
-  for (int i = 0; i < Mrel; i++) if (af[i] != ab[i]) { eq = 0; break; }
+  CPG_LOOP for (int i = 0; i < Mrel; i++) if (af[i] != ab[i]) { eq = 0; break; }
   int use_b = 0;
   if (!eq)
     { if (rl_eq_prefix(af,Mrel)) use_b = 0;
@@ -416,8 +416,8 @@ CPG_DEV_NOINL void classify_reliable(ReadCtx &R, WCtx &W, RelShared *sh)
   CPG_SYNCWARP();
   if (W.lane == 0)
     { cpg_intvl *v = R.S.intvl;
-      for (int ri = 0, ii = 0; ri < Mrel; ri++, ii++)
-        { while (ii < N && !v[ii].is_rel) ii++;
+      CPG_LOOP for (int ri = 0, ii = 0; ri < Mrel; ri++, ii++)
+        { CPG_LOOP while (ii < N && !v[ii].is_rel) ii++;
           if (ii >= N) break;
           v[ii].asgn = (int8_t)fin[ri];
         }

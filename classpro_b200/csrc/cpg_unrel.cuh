@@ -15,17 +15,17 @@
 #include "cpg_rel.cuh"
 
 /* src/class_unrel.c:11-25 */
-CPG_DEV void un_nn(int idx, int s, const cpg_intvl *v, int N, int &l, int &r)
+CPG_DEV_NOINL void un_nn(int idx, int s, const cpg_intvl *v, int N, int &l, int &r)
 { l = idx-1;
-  while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--;
+  CPG_LOOP while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--;
   if (l < 0) l = -1;
   r = idx+1;
-  while (r < N && !(v[r].asgn == s && v[r].is_rel)) r++;
+  CPG_LOOP while (r < N && !(v[r].asgn == s && v[r].is_rel)) r++;
   if (r >= N) r = -1;
 }
 
 /* src/class_unrel.c:27-51 */
-CPG_DEV uint16_t un_est_cov(WCtx &W, int x, int idx, const cpg_intvl *v, int N, int s)
+CPG_DEV_NOINL uint16_t un_est_cov(WCtx &W, int x, int idx, const cpg_intvl *v, int N, int s)
 { int l, r;
   un_nn(idx,s,v,N,l,r);
   if (l != -1 && r != -1) return (uint16_t)cpg_lin_interp(W,x,v[l].e-1,v[l].cce,v[r].b,v[r].ccb);
@@ -44,14 +44,14 @@ CPG_DEV uint16_t un_est_cov(WCtx &W, int x, int idx, const cpg_intvl *v, int N, 
 }
 
 /* src/class_unrel.c:53-65 */
-CPG_DEV double un_lp_e(const WCtx &W, const cpg_intvl &I)
+CPG_DEV_NOINL double un_lp_e(const WCtx &W, const cpg_intvl &I)
 { const int ce = W.M->cov[ST_E];
   double po = cpg_lp_poisson(W,I.cb,ce)+cpg_lp_poisson(W,I.ce,ce)+CPG_E_PO_BASE;
   return dmax_ref(I.pe,po);
 }
 
 /* src/class_unrel.c:67-113 */
-CPG_DEV double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
+CPG_DEV_NOINL double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
 { const cpg_intvl &I = v[idx];
   const cpg_dmodel *M = W.M;
   if (imax(I.cb,I.ce) >= M->cov[ST_R]) return 0.;
@@ -85,7 +85,7 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N)
       const double *lf = W.M->logfact;
       int bad = 0;
       CPG_SYNCWARP();
-      for (int q = W.lane; q < 10; q += CPG_WARP)
+      CPG_LOOP for (int q = W.lane; q < 10; q += CPG_WARP)
         { double val = -CPG_INF;
           int need_s = 0, need_b = 0, k = 0, bn = 0, bc = 0; double lambda = 0.;
           if (q == 0) val = un_lp_e(W,I);
@@ -117,7 +117,7 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N)
       CPG_SYNCWARP();
       if (bad) W.status |= CPG_ST_BINOM;
       double mx = -CPG_INF; int ms = -1;
-      for (int s = ST_E; s <= ST_D; s++)
+      CPG_LOOP for (int s = ST_E; s <= ST_D; s++)
         { double lp;
           if (s == ST_E) lp = term[0];
           else if (s == ST_R) lp = term[1];
@@ -150,10 +150,10 @@ CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
   const int N = R.N;
   int32_t *ord = R.S.ord;
   uint8_t *fixed = R.S.fixed;
-  for (int i = W.lane; i < N; i += CPG_WARP)
+  CPG_LOOP for (int i = W.lane; i < N; i += CPG_WARP)
     { const int key = imin(v[i].cb,v[i].ce);
       int rank = 0;
-      for (int j = 0; j < N; j++)
+      CPG_LOOP for (int j = 0; j < N; j++)
         { int kj = imin(v[j].cb,v[j].ce);
           rank += (kj < key) || (kj == key && j < i);
         }
@@ -161,8 +161,8 @@ CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
       fixed[i] = (uint8_t)(v[i].is_rel && (v[i].asgn == ST_H || v[i].asgn == ST_D));
     }
   CPG_SYNCWARP();
-  for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
-  for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
+  CPG_LOOP for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
+  CPG_LOOP for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
 }
 
 /* ---- the whole read: src/ClassPro.c:229-271 ---- */
@@ -174,13 +174,13 @@ CPG_DEV_NOINL int classify_read(ReadCtx &R, WCtx &W, RelShared *sh, uint8_t *cls
       classify_unreliable(R,W);
     }
   /* emit: 'N' x (K-1), then one class character per k-mer */
-  for (int j = W.lane; j < K-1; j += CPG_WARP) cls[j] = 'N';
+  CPG_LOOP for (int j = W.lane; j < K-1; j += CPG_WARP) cls[j] = 'N';
   const cpg_intvl *v = R.S.intvl;
-  for (int i = 0; i < R.N; i++)
+  CPG_LOOP for (int i = 0; i < R.N; i++)
     { const int a = v[i].asgn;
       const char c = (a == ST_E) ? 'E' : (a == ST_R) ? 'R' : (a == ST_H) ? 'H' : (a == ST_D) ? 'D' : '?';
       const int b = v[i].b, e = v[i].e;
-      for (int j = b+W.lane; j < e; j += CPG_WARP) cls[K-1+j] = (uint8_t)c;
+      CPG_LOOP for (int j = b+W.lane; j < e; j += CPG_WARP) cls[K-1+j] = (uint8_t)c;
     }
   CPG_SYNCWARP();
   return W.status;

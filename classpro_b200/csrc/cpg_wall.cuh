@@ -67,18 +67,18 @@ CPG_DEV unsigned mk_pair(int e) { return e == ET_SELF ? MK_PAIR_S : MK_PAIR_O; }
 /* Lane 0 is the only writer of the scratch words below.  Each helper synchronises the warp BEFORE
  * the write (the other lanes may still be reading the old value: the CUDA memory model does not
  * promise lock-step execution) and AFTER it (so that every lane sees the new one). */
-CPG_DEV void mark_or(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
+CPG_DEV_NOINL void mark_or(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
 { CPG_SYNCWARP();
   if (W.lane == 0) R.S.mark[pos] |= bits;
   CPG_SYNCWARP();
 }
-CPG_DEV void mark_clear(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
+CPG_DEV_NOINL void mark_clear(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
 { CPG_SYNCWARP();
   if (W.lane == 0) R.S.mark[pos] &= ~bits;
   CPG_SYNCWARP();
 }
 
-CPG_DEV double perr_get(const ReadCtx &R, int pos, int e, int w)
+CPG_DEV_NOINL double perr_get(const ReadCtx &R, int pos, int e, int w)
 { unsigned s = R.S.mark[pos] >> 8;
   return s ? R.S.perr[(size_t)(s-1)*4+e*2+w] : -CPG_INF;
 }
@@ -105,7 +105,7 @@ CPG_DEV_NOINL void perr_once(ReadCtx &R, WCtx &W, int pos, int e, int w,
 }
 
 /* src/wall.c:317-322 */
-CPG_DEV double lp_diff_pair(const ReadCtx &R, const WCtx &W, int i, int j)
+CPG_DEV_NOINL double lp_diff_pair(const ReadCtx &R, const WCtx &W, int i, int j)
 { const uint16_t *p = R.prof;
   int n_drop = (int)p[i-1]-p[i], n_gain = (int)p[j]-p[j-1];
   uint16_t cov = (uint16_t)imax(p[i-1],p[j]);
@@ -155,14 +155,14 @@ CPG_DEV void pg_counts(const PairGeom &G, const uint16_t *prof, int j, uint16_t 
   cout_j = G.fwd ? prof[j]   : prof[j-1];
 }
 /* count tests of the low-complexity partner (src/wall.c:364-365,455-456) */
-CPG_DEV int pg_lc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e)
+CPG_DEV_NOINL int pg_lc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e)
 { uint16_t cin_j, cout_j;
   pg_counts(G,prof,G.lc_j,cin_j,cout_j);
   return cin_j <= cout_j
          && !(cout_j < W.M->cmax && thres_ng(e,cin_j,cthres_at(W,G.t,G.l,cout_j,TH_FINAL,e)));
 }
 /* count tests of a high-complexity partner (src/wall.c:384-389,475-480) */
-CPG_DEV int pg_hc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e, int j)
+CPG_DEV_NOINL int pg_hc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e, int j)
 { uint16_t cin_j, cout_j;
   pg_counts(G,prof,j,cin_j,cout_j);
   const int cmax = W.M->cmax;
@@ -201,7 +201,7 @@ CPG_DEV_NOINL int pair_replay(ReadCtx &R, WCtx &W, const PairGeom &G, int e, cpg
         }
     }
   if (max_pe < pe) { max_j = j; max_pe = pe; }
-  for (int n = 0; n <= CPG_MAX_N_HC; n++)
+  CPG_LOOP for (int n = 0; n <= CPG_MAX_N_HC; n++)
     { j = pg_hc_j(G,K,n);
       if (!pg_in_range(G,plen,j)) break;
       if (!pg_hc_ok(G,W,prof,e,j)) continue;
@@ -230,31 +230,31 @@ CPG_DEV int ei_before(const cpg_eintvl &x, const cpg_eintvl &y)
 CPG_DEV_NOINL void ei_sort(cpg_eintvl *a, int n, const WCtx &W)
 { CPG_SYNCWARP();
   if (W.lane == 0)
-    for (int i = 1; i < n; i++)
+    CPG_LOOP for (int i = 1; i < n; i++)
       { cpg_eintvl v = a[i];
         int j = i-1;
-        while (j >= 0 && ei_before(v,a[j])) { a[j+1] = a[j]; j--; }
+        CPG_LOOP while (j >= 0 && ei_before(v,a[j])) { a[j+1] = a[j]; j--; }
         a[j+1] = v;
       }
   CPG_SYNCWARP();
 }
 
 /* src/wall.c:548-568 */
-CPG_DEV int ei_unique(cpg_eintvl *a, int n, const WCtx &W)
+CPG_DEV_NOINL int ei_unique(cpg_eintvl *a, int n, const WCtx &W)
 { ei_sort(a,n,W);
   if (n >= 2)
     { int i = 1;
-      while (i < n && !(a[i-1].b == a[i].b && a[i-1].e == a[i].e)) i++;
+      CPG_LOOP while (i < n && !(a[i-1].b == a[i].b && a[i-1].e == a[i].e)) i++;
       /* every lane needs the new length: count first (read only), then lane 0 compacts */
       int keep_b = (i < n) ? a[i-1].b : 0, keep_e = (i < n) ? a[i-1].e : 0;
       int cnt = i;
-      for (int j = i+1; j < n; j++)
+      CPG_LOOP for (int j = i+1; j < n; j++)
         if (!(keep_b == a[j].b && keep_e == a[j].e))
           { keep_b = a[j].b; keep_e = a[j].e; cnt++; }
       CPG_SYNCWARP();
       if (W.lane == 0)
         { int w = i;
-          for (int j = i+1; j < n; j++)
+          CPG_LOOP for (int j = i+1; j < n; j++)
             if (!(a[w-1].b == a[j].b && a[w-1].e == a[j].e))
               a[w++] = a[j];
         }
@@ -265,8 +265,8 @@ CPG_DEV int ei_unique(cpg_eintvl *a, int n, const WCtx &W)
 }
 
 /* src/wall.c:530-546 */
-CPG_DEV int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
-{ while (l <= r)
+CPG_DEV_NOINL int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
+{ CPG_LOOP while (l <= r)
     { int m = (l+r)/2;
       if (a[m].b == b)
         { if (a[m].e == e) return m;
@@ -278,16 +278,16 @@ CPG_DEV int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
   return -1;
 }
 
-CPG_DEV void ei_put(ReadCtx &R, const WCtx &W, int k, int b, int e, double pe)
+CPG_DEV_NOINL void ei_put(ReadCtx &R, const WCtx &W, int k, int b, int e, double pe)
 { CPG_SYNCWARP();
   if (W.lane == 0) { R.S.eint[k].b = b; R.S.eint[k].e = e; R.S.eint[k].pe = pe; }
   CPG_SYNCWARP();
 }
 
 /* clear bits on the open range (b,e), lanes striding */
-CPG_DEV void mark_clear_range(ReadCtx &R, const WCtx &W, int b, int e, unsigned bits)
+CPG_DEV_NOINL void mark_clear_range(ReadCtx &R, const WCtx &W, int b, int e, unsigned bits)
 { CPG_SYNCWARP();
-  for (int j = b+1+W.lane; j < e; j += CPG_WARP) R.S.mark[j] &= ~bits;
+  CPG_LOOP for (int j = b+1+W.lane; j < e; j += CPG_WARP) R.S.mark[j] &= ~bits;
   CPG_SYNCWARP();
 }
 
@@ -310,7 +310,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
   else           { wtype = WT_GAIN; cin = cim1; cout = ci;   }
 
   int maxt = -1, maxl = -1; double maxpe = -CPG_INF;
-  for (int t = 0; t < CT_N; t++)
+  CPG_LOOP for (int t = 0; t < CT_N; t++)
     { int l = imin(cpg_ctx_at(R.seq,R.rlen,K,wtype,i,t),M->lmax[t]);
       double pe = M->pe[t][l];
       if (maxpe < pe) { maxpe = pe; maxt = t; maxl = l; }
@@ -319,7 +319,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
   /* stage 0: how far does each error type get before any probability is needed */
   int reach[2] = {0,0}, o_wall_now = 0;
   const unsigned mi = R.S.mark[i];
-  for (int e = ET_SELF; e <= ET_OTHERS; e++)
+  CPG_LOOP for (int e = ET_SELF; e <= ET_OTHERS; e++)
     { if (mi & mk_pair(e)) continue;
       int ct_final = 0;
       if (cout < cmax)
@@ -345,13 +345,13 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
   double *term = W.ws->term;
   int bad = 0;
   int fresh[2];
-  for (int e = 0; e < 2; e++) fresh[e] = reach[e] && perr_get(R,i,e,wtype) == -CPG_INF;
+  CPG_LOOP for (int e = 0; e < 2; e++) fresh[e] = reach[e] && perr_get(R,i,e,wtype) == -CPG_INF;
   CPG_SYNCWARP();
-  for (int q = W.lane; q < 2; q += CPG_WARP)
+  CPG_LOOP for (int q = W.lane; q < 2; q += CPG_WARP)
     if (fresh[q]) term[q] = cpg_p_errorin_lane(lf,q,maxpe,cout,cin,&bad);
   CPG_SYNCWARP();
   int go[2];
-  for (int e = 0; e < 2; e++)
+  CPG_LOOP for (int e = 0; e < 2; e++)
     { if (fresh[e]) perr_store(R,W,i,e,wtype,term[e]);
       go[e] = reach[e] && !(perr_get(R,i,e,wtype) < CPG_PE_FINAL);
     }
@@ -363,7 +363,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
       G.fwd = (wtype == WT_DROP); G.i = i; G.t = maxt; G.l = maxl; G.cout = cout; G.cin = cin; G.erate = maxpe;
       { const int ulen = maxt+1, m = ulen*maxl;
         int n = 0;
-        for (;;)
+        CPG_LOOP for (;;)
           { int idx = G.fwd ? i+ulen*(n+1) : i-ulen*(n+1);
             if (G.fwd) { if (idx >= plen) break; }
             else       { if (idx <= 0) break; }
@@ -377,7 +377,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
       }
       const int wj = G.fwd ? WT_GAIN : WT_DROP;
       CPG_SYNCWARP();
-      for (int q = W.lane; q < 23; q += CPG_WARP)
+      CPG_LOOP for (int q = W.lane; q < 23; q += CPG_WARP)
         { double val = 0.;
           int need_b = 0, need_s = 0, be = 0, bco = 0, bci = 0, sj = 0; double ber = 0.;
           if (G.lc_kind != 0)
@@ -437,19 +437,19 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
 CPG_DEV_NOINL int wall_multi(ReadCtx &R, WCtx &W, int i, int NS, int midx)
 { const int plen = R.plen;
   cpg_eintvl *eint = R.S.eint;
-  for (int w = WT_DROP; w <= WT_GAIN; w++)
+  CPG_LOOP for (int w = WT_DROP; w <= WT_GAIN; w++)
     { double pe_i = perr_get(R,i,ET_SELF,w), pe;
       if (pe_i < CPG_PE_FINAL) continue;
       const int jend = (w == WT_DROP) ? imin(i+200,plen+1) : imax(i-200,0);   /* DROP: j < jend; GAIN: j >= jend */
       int done = 0;
-      for (int jb = (w == WT_DROP) ? i+1 : i-1; !done && ((w == WT_DROP) ? (jb < jend) : (jb >= jend));
+      CPG_LOOP for (int jb = (w == WT_DROP) ? i+1 : i-1; !done && ((w == WT_DROP) ? (jb < jend) : (jb >= jend));
            jb += (w == WT_DROP) ? CPG_WARP : -CPG_WARP)
         { int j = (w == WT_DROP) ? jb+W.lane : jb-W.lane;
           int in = (w == WT_DROP) ? (j < jend) : (j >= jend);
           int edge = in && (j == ((w == WT_DROP) ? plen : 0));
           unsigned f = in ? (R.S.mark[j] & (MK_BY_S|MK_BY_O)) : 0u;
           unsigned mask = cpg_ballot(f != 0 || edge);
-          while (mask)
+          CPG_LOOP while (mask)
             { int l = cpg_ffs(mask)-1; mask &= mask-1;
               j = (w == WT_DROP) ? jb+l : jb-l;
               if (j == ((w == WT_DROP) ? plen : 0))          /* boundary E-interval */
@@ -488,28 +488,28 @@ CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
 
   last = imin(I.b+K-1,I.e-1);
   { int s = 0;
-    for (int p = I.b+W.lane; p < last; p += CPG_WARP) s += imax((int)prof[p+1]-prof[p],0);
+    CPG_LOOP for (int p = I.b+W.lane; p < last; p += CPG_WARP) s += imax((int)prof[p+1]-prof[p],0);
     n_gain += cpg_warp_sum(s);
   }
   if (I.b+K-1 < I.e)
     { lmax = 0;
-      for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_rctx(R.seq,R.rlen,I.b+K-1,t)*(t+1));
+      CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_rctx(R.seq,R.rlen,I.b+K-1,t)*(t+1));
       last = I.b+lmax;
       int s = 0;
-      for (int p = I.b+W.lane; p < last; p += CPG_WARP) s += imax((int)prof[p]-rc_prof(R,W,p+1),0);
+      CPG_LOOP for (int p = I.b+W.lane; p < last; p += CPG_WARP) s += imax((int)prof[p]-rc_prof(R,W,p+1),0);
       n_gain -= cpg_warp_sum(s);
     }
   first = imax(I.e-K+1,I.b);
   { int s = 0;
-    for (int p = first+W.lane; p < I.e-1; p += CPG_WARP) s += imax((int)prof[p]-prof[p+1],0);
+    CPG_LOOP for (int p = first+W.lane; p < I.e-1; p += CPG_WARP) s += imax((int)prof[p]-prof[p+1],0);
     n_drop += cpg_warp_sum(s);
   }
   if (I.b < I.e-K+1)
     { lmax = 0;
-      for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_lctx(R.seq,R.rlen,I.e-K+1+K-2,t)*(t+1));
+      CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_lctx(R.seq,R.rlen,I.e-K+1+K-2,t)*(t+1));
       first = I.e-lmax;
       int s = 0;
-      for (int p = first+W.lane; p < I.e-1; p += CPG_WARP) s += imax((int)prof[p+1]-prof[p],0);
+      CPG_LOOP for (int p = first+W.lane; p < I.e-1; p += CPG_WARP) s += imax((int)prof[p+1]-prof[p],0);
       n_drop -= cpg_warp_sum(s);
     }
   uint16_t ccb = (uint16_t)imin(I.cb+imax(n_gain,0),CPG_MAX_CNT);
@@ -533,14 +533,14 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
   uint32_t *mark = R.S.mark;
   cpg_eintvl *eint = R.S.eint;
 
-  for (int i = W.lane; i <= plen; i += CPG_WARP) mark[i] = 0;
+  CPG_LOOP for (int i = W.lane; i <= plen; i += CPG_WARP) mark[i] = 0;
   R.nslots = 0;
   CPG_SYNCWARP();
 
   /* pass A: candidates in position order */
   int eidx = 0;
   const int rcov = M->cov[ST_R];
-  for (int base = 1; base < plen; base += CPG_WARP)
+  CPG_LOOP for (int base = 1; base < plen; base += CPG_WARP)
     { int i = base+W.lane, cand = 0;
       if (i < plen)
         { int a = prof[i-1], b = prof[i];
@@ -548,7 +548,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
           cand = (imin(a,b) < rcov) && (d >= CPG_MIN_CNT_CHANGE);
         }
       unsigned mask = cpg_ballot(cand);
-      while (mask)
+      CPG_LOOP while (mask)
         { int l = cpg_ffs(mask)-1; mask &= mask-1;
           wall_candidate(R,W,base+l,eidx);
         }
@@ -556,16 +556,16 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
   int NS = eidx;
 
   /* pass B (src/wall.c:727-735) */
-  for (int k = 0; k < NS; k++) mark_clear_range(R,W,eint[k].b,eint[k].e,MK_BY_O);
+  CPG_LOOP for (int k = 0; k < NS; k++) mark_clear_range(R,W,eint[k].b,eint[k].e,MK_BY_O);
   NS = ei_unique(eint,eidx,W);
 
   /* pass C */
   int midx = NS;
-  for (int base = 1; base < plen && !(W.status & CPG_ST_EINTVL_OVF); base += CPG_WARP)
+  CPG_LOOP for (int base = 1; base < plen && !(W.status & CPG_ST_EINTVL_OVF); base += CPG_WARP)
     { int i = base+W.lane;
       unsigned f = (i < plen) ? mark[i] : 0u;
       unsigned mask = cpg_ballot((f & MK_BY_O) && !(f & MK_BY_S));
-      while (mask)
+      CPG_LOOP while (mask)
         { int l = cpg_ffs(mask)-1; mask &= mask-1;
           if (mark[base+l] & MK_PAIR_MULT) continue;
           midx = wall_multi(R,W,base+l,NS,midx);
@@ -573,16 +573,16 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
         }
     }
   if (W.status & CPG_ST_EINTVL_OVF) { R.N = 0; R.M = 0; return; }
-  for (int k = NS; k < midx; k++) mark_clear_range(R,W,eint[k].b,eint[k].e,MK_BY_O);
+  CPG_LOOP for (int k = NS; k < midx; k++) mark_clear_range(R,W,eint[k].b,eint[k].e,MK_BY_O);
   if (NS < midx) { NS = midx; ei_sort(eint,NS,W); }
 
   /* pass D (src/wall.c:877-909): hulls of chains of overlapping E-intervals are appended while
      the list is being walked, and the loop bound is re-read */
   { int i = 0;
-    while (i < NS-1)
+    CPG_LOOP while (i < NS-1)
       { int max_e = eint[i].e; double max_pe = eint[i].pe;
         int j = i;
-        while (j < NS-1 && eint[j+1].b <= eint[j].e)
+        CPG_LOOP while (j < NS-1 && eint[j+1].b <= eint[j].e)
           { max_e = imax(max_e,eint[j+1].e);
             max_pe = dmax_ref(max_pe,eint[j+1].pe);
             j++;
@@ -597,15 +597,15 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
   }
   ei_sort(eint,NS,W);
   CPG_SYNCWARP();
-  for (int k = 0; k < NS; k++)
-    { for (int j = eint[k].b+W.lane; j < eint[k].e; j += CPG_WARP) mark[j] |= MK_ERROR;
+  CPG_LOOP for (int k = 0; k < NS; k++)
+    { CPG_LOOP for (int j = eint[k].b+W.lane; j < eint[k].e; j += CPG_WARP) mark[j] |= MK_ERROR;
       CPG_SYNCWARP();
     }
 
   /* pass E (src/wall.c:921-948) */
   int N = 0, b = 0;
   cpg_intvl *intvl = R.S.intvl;
-  for (int base = 1; base <= plen; base += CPG_WARP)
+  CPG_LOOP for (int base = 1; base <= plen; base += CPG_WARP)
     { int i = base+W.lane, cut = 0;
       if (i <= plen)
         { unsigned m1 = mark[i-1], m0 = mark[i];
@@ -613,7 +613,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
                 || (!(m0 & MK_ERROR) && (m0 & MK_BY_O));
         }
       unsigned mask = cpg_ballot(cut);
-      while (mask)
+      CPG_LOOP while (mask)
         { int l = cpg_ffs(mask)-1; mask &= mask-1;
           int e = base+l;
           int k = ei_find(eint,0,NS-1,b,e);
@@ -642,7 +642,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
   const double logpthres = cpg_log(CPG_PE_FINAL);
   int32_t *cand = R.S.ord;
   uint8_t *keep = R.S.fixed;
-  for (int i = 0; i < N; i++)
+  CPG_LOOP for (int i = 0; i < N; i++)
     { const cpg_intvl I = intvl[i];
       if (I.e-I.b < K) continue;
       if (imax(I.cb,I.ce) >= rcov) continue;
@@ -652,7 +652,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
       ncand++;
     }
   CPG_SYNCWARP();
-  for (int q = W.lane; q < ncand; q += CPG_WARP)
+  CPG_LOOP for (int q = W.lane; q < ncand; q += CPG_WARP)
     { const cpg_intvl I = intvl[cand[q]];
       const int ccb = I.ccb, cce = I.cce;
       int ok = !(cpg_lp_trans(W,I.b,I.e,ccb,cce,(uint16_t)((ccb+cce)/2)) < CPG_THRES_DIFF_REL);
@@ -661,10 +661,10 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
     }
   CPG_SYNCWARP();
   int Mrel = 0;
-  for (int q = 0; q < ncand; q++) if (keep[q]) Mrel++;
+  CPG_LOOP for (int q = 0; q < ncand; q++) if (keep[q]) Mrel++;
   if (W.lane == 0)
     { int m = 0;
-      for (int q = 0; q < ncand; q++)
+      CPG_LOOP for (int q = 0; q < ncand; q++)
         if (keep[q])
           { const int i = cand[q];
             intvl[i].is_rel = 1;
