@@ -326,6 +326,7 @@ def main():
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
+    phase = ctx.phase_cycles()
     cls_res, status = ctx.download(data.whole)
     n_bad = int((status & cp.ST_FATAL != 0).sum())
     step_ms = max_over_ranks(ms_dec + ms_cls)
@@ -383,7 +384,9 @@ def main():
                              "frac": bytes_dec / (ms_dec * 1e-3) / 1e9 / peak},
                 "k_classify": {"ms": ms_cls, "bytes": bytes_cls, "GBps": bytes_cls / (ms_cls * 1e-3) / 1e9,
                                "frac": bytes_cls / (ms_cls * 1e-3) / 1e9 / peak,
-                               "note": "FP64-latency / control-flow bound, not a streaming kernel"}}}
+                               "note": "FP64-latency / control-flow bound, not a streaming kernel",
+                               "phase_share": dict(zip(("wall", "reliable_dp", "unreliable_emit", "barrier_wait"),
+                                                       [round(x / max(1, sum(phase)), 3) for x in phase]))}}}
 
     ctx.close()
     if rank == 0:

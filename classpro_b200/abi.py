@@ -61,6 +61,7 @@ def lib():
         L.cpg_run_resident.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                        C.POINTER(C.c_int)]
         L.cpg_download.argtypes = [C.c_void_p, C.POINTER(CResult)]
+        L.cpg_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.cpg_host_alloc.argtypes = [C.c_size_t]
         L.cpg_host_alloc.restype = C.c_void_p
         L.cpg_host_free.argtypes = [C.c_void_p]
@@ -236,6 +237,13 @@ class Context:
         if rc:
             raise self._err("cpg_run_resident", rc)
         return a.value, b.value, n.value
+
+    def phase_cycles(self):
+        out = (C.c_uint64 * 4)()
+        rc = self.L.cpg_phase_cycles(self.h, out)
+        if rc:
+            raise self._err("cpg_phase_cycles", rc)
+        return list(out)
 
     def download(self, batch, allow_read_errors=True):
         res, cls, status = self._result(batch)

@@ -21,6 +21,8 @@
   #include <string.h>
   #define CPG_DEV        static inline
   #define CPG_DEV_NOINL  static
+  #define CPG_DEV_HELPER static inline
+  #define CPG_DEV_MATHFN static inline
   #define CPG_LDG(p)     (*(p))
   #define CPG_INF        ((double)INFINITY)
   #define CPG_LOOP
@@ -35,20 +37,41 @@
     unsigned cpg_sim_shfl_up(unsigned v, int d);
     int      cpg_sim_sum(int v);
     #define CPG_SYNCWARP() cpg_sim_barrier()
+    void     cpg_sim_group_barrier(unsigned mask);
+    #define CPG_SYNCGROUP(W) cpg_sim_group_barrier((W).gmask)
   #else
     #define CPG_WARP       1
     #define CPG_SYNCWARP() do { } while (0)
+    #define CPG_SYNCGROUP(W) do { } while (0)
   #endif
 #else
   #include <cuda_runtime.h>
   #define CPG_DEV        __device__ __forceinline__
   #define CPG_DEV_NOINL  __device__ __noinline__
+  /* small helpers: inlined at every use (measured faster than one out-of-line copy each:
+     107 ms vs 118 ms for k_classify on the 10 Mb bench); -DCPG_NOINLINE_HELPERS flips it */
+  #ifndef CPG_NOINLINE_HELPERS
+    #define CPG_DEV_HELPER __device__ __forceinline__
+  #else
+    #define CPG_DEV_HELPER __device__ __noinline__
+  #endif
+  /* exp/log: inlined (default) or one shared copy (-DCPG_NOINLINE_MATH) */
+  #ifdef CPG_NOINLINE_MATH
+    #define CPG_DEV_MATHFN __device__ __noinline__
+  #else
+    #define CPG_DEV_MATHFN __device__ __forceinline__
+  #endif
   #define CPG_WARP       32
   #define CPG_SYNCWARP() __syncwarp()
+  #define CPG_SYNCGROUP(W) __syncwarp((W).gmask)
   #define CPG_LDG(p)     __ldg(p)
   /* loops of the per-read logic are not unrolled: with ~30 warps per SM in different phases of a
      large kernel, the instruction-cache footprint matters more than loop overhead */
-  #define CPG_LOOP       _Pragma("unroll 1")
+  #ifdef CPG_UNROLL_LOOPS
+    #define CPG_LOOP
+  #else
+    #define CPG_LOOP     _Pragma("unroll 1")
+  #endif
   #define CPG_INF        (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 
@@ -128,11 +151,12 @@ typedef struct
     cpg_eintvl *eint;     /* [P+2] */
     cpg_intvl  *intvl;    /* [P+2] */
     cpg_intvl  *rint;     /* [MC]  reliable intervals (copy) */
-    cpg_intvl  *wint;     /* [MC]  DP working copy */
-    uint16_t   *bp;       /* [MC]  back pointers: 4 x 3 bits */
+    cpg_intvl  *wint;     /* [2*MC] DP working copies (forward, backward) */
+    uint16_t   *bp;       /* [2*MC] back pointers: 4 x 3 bits */
     uint8_t    *asg_f;    /* [MC] */
     uint8_t    *asg_b;    /* [MC] */
-    uint8_t    *rpos;     /* [MC] */
+    uint8_t    *rpos;     /* [2*MC] */
+    int32_t     MC;
     int32_t    *ord;      /* [P+2] */
     uint8_t    *fixed;    /* [P+2] */
   } cpg_scratch;

@@ -26,7 +26,7 @@ CPG_DEV int cpg_base(const cpg_seq S, int i)
 
 CPG_DEV int cpg_cap127(int x) { return x > 127 ? 127 : x; }
 
-CPG_DEV_NOINL int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
+CPG_DEV_HELPER int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
 { (void)rlen;
   if (t == CT_HP)
     { int c = cpg_base(S,p), n = 1;
@@ -50,7 +50,7 @@ CPG_DEV_NOINL int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
   return u;
 }
 
-CPG_DEV_NOINL int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
+CPG_DEV_HELPER int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
 { if (t == CT_HP)
     { int c = cpg_base(S,p), n = 1;
       CPG_LOOP while (n < 127 && p+n < rlen && cpg_base(S,p+n) == c) n++;

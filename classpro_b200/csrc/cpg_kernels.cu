@@ -46,7 +46,8 @@ struct BatchDev
     const int64_t *cls_off;
     int32_t       *status;
     const int32_t *order;
-    int32_t       *queue;        /* [2] work counters: decode, classify */
+    int32_t       *queue;        /* [2] work counters: decode, classify; [2..3] spare */
+    unsigned long long *phase_cycles;   /* [4] summed per-warp cycles of the three phases (+ idle at the CTA barriers) */
   };
 
 struct ScratchDev
@@ -66,11 +67,11 @@ __host__ __device__ static inline size_t scratch_layout(int P, int MC, size_t of
   off[2]  = o; o = align_up(o+sizeof(cpg_eintvl)*(size_t)(P+2),16);      /* eint  */
   off[3]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)(P+2),16);       /* intvl */
   off[4]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)MC,16);          /* rint  */
-  off[5]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)MC,16);          /* wint  */
-  off[6]  = o; o = align_up(o+sizeof(uint16_t)*(size_t)MC,16);           /* bp    */
+  off[5]  = o; o = align_up(o+sizeof(cpg_intvl)*2*(size_t)MC,16);        /* wint (fw, bw) */
+  off[6]  = o; o = align_up(o+sizeof(uint16_t)*2*(size_t)MC,16);         /* bp   (fw, bw) */
   off[7]  = o; o = align_up(o+(size_t)MC,16);                            /* asg_f */
   off[8]  = o; o = align_up(o+(size_t)MC,16);                            /* asg_b */
-  off[9]  = o; o = align_up(o+(size_t)MC,16);                            /* rpos  */
+  off[9]  = o; o = align_up(o+2*(size_t)MC,16);                          /* rpos (fw, bw) */
   off[10] = o; o = align_up(o+sizeof(int32_t)*(size_t)(P+2),16);         /* ord   */
   off[11] = o; o = align_up(o+(size_t)(P+2),16);                         /* fixed */
   return align_up(o,256);
@@ -107,7 +108,7 @@ struct ClassifyShared
   { uint8_t     cthres[CPG_LROWS*256*4];
     cpg_dmodel  model;
     cpg_wshared ws[CLASSIFY_THREADS/32];
-    RelShared   rel[CLASSIFY_THREADS/32];
+    RelShared   rel[CLASSIFY_THREADS/32][2];
   };
 
 __global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
@@ -126,20 +127,32 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
   size_t off[12];
   scratch_layout(SC.P,SC.MC,off);
 
+  /* One read per warp, eight/sixteen/thirty-two reads per CTA at a time, taken from the
+     longest-first queue (neighbouring reads have similar lengths, so the phases of a CTA finish
+     close together). */
+  __shared__ int s_base;
+  const int wpc = CLASSIFY_THREADS/32;
   for (;;)
-    { int q = next_read(B.queue+1,lane);
-      if (q >= B.n_reads) break;
-      const int r = B.order[q];
-      if (B.status[r] != CPG_ST_OK) continue;          /* undecodable profile: left to the host */
-      const int rlen = B.rlen[r], plen = rlen-M.K+1;
-      uint8_t *cls = B.cls+B.cls_off[r];
-      if (plen > SC.P) { if (lane == 0) B.status[r] = CPG_ST_BAD_PROFILE; continue; }
-
+    { __syncthreads();
+      if (threadIdx.x == 0) s_base = atomicAdd(B.queue+1,wpc);
+      __syncthreads();
+      const int base = s_base;
+      if (base >= B.n_reads) break;
+      const int q = base+wib;
+      int active = (q < B.n_reads);
+      int r = 0, rlen = 0, plen = 0;
+      if (active)
+        { r = B.order[q];
+          rlen = B.rlen[r]; plen = rlen-M.K+1;
+          if (B.status[r] != CPG_ST_OK) active = 0;          /* undecodable profile: left to the host */
+          else if (plen > SC.P) { if (lane == 0) B.status[r] = CPG_ST_BAD_PROFILE; active = 0; }
+        }
       WCtx W;
       W.lane = lane; W.M = &sh.model; W.cthres = sh.cthres; W.ws = &sh.ws[wib]; W.status = 0;
+      W.glane = lane; W.gsize = 32; W.gmask = 0xffffffffu;
       ReadCtx R;
-      R.prof = B.cnt+B.cnt_off[r]; R.plen = plen; R.rlen = rlen;
-      R.seq.p = B.seq+B.seq_off[r]; R.seq.bits = B.seq_bits;
+      R.prof = B.cnt+(active ? B.cnt_off[r] : 0); R.plen = plen; R.rlen = rlen;
+      R.seq.p = B.seq+(active ? B.seq_off[r] : 0); R.seq.bits = B.seq_bits;
       R.nslots = 0; R.N = 0; R.M = 0;
       R.S.mark  = reinterpret_cast<uint32_t *>(sb+off[0]);
       R.S.perr  = reinterpret_cast<double *>(sb+off[1]);
@@ -153,11 +166,29 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
       R.S.rpos  = sb+off[9];
       R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
       R.S.fixed = sb+off[11];
+      R.S.MC = SC.MC;
 
-      int st = classify_read(R,W,&sh.rel[wib],cls);
-      st = __reduce_or_sync(0xffffffffu,st);
-      if (lane == 0) B.status[r] = st;
-      __syncwarp();
+      long long t0 = clock64();
+      if (active) classify_phase1(R,W);
+      long long t1 = clock64();
+      __syncthreads();
+      long long t2 = clock64();
+      if (active) classify_phase2(R,W,sh.rel[wib]);
+      long long t3 = clock64();
+      __syncthreads();
+      long long t4 = clock64();
+      if (active)
+        { int st = classify_phase3(R,W,B.cls+B.cls_off[r]);
+          st = __reduce_or_sync(0xffffffffu,st);
+          if (lane == 0) B.status[r] = st;
+        }
+      long long t5 = clock64();
+      if (lane == 0 && B.phase_cycles)
+        { atomicAdd(B.phase_cycles+0,(unsigned long long)(t1-t0));
+          atomicAdd(B.phase_cycles+1,(unsigned long long)(t3-t2));
+          atomicAdd(B.phase_cycles+2,(unsigned long long)(t5-t4));
+          atomicAdd(B.phase_cycles+3,(unsigned long long)((t2-t1)+(t4-t3)));
+        }
     }
 }
 
@@ -387,7 +418,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
       || (rc = reserve(ctx,&S->cnt_off,sizeof(int64_t)*(n+1))) || (rc = reserve(ctx,&S->plen,sizeof(int32_t)*(n+1)))
       || (rc = reserve(ctx,&S->cls,cls_bytes+16)) || (rc = reserve(ctx,&S->cls_off,sizeof(int64_t)*(n+1)))
       || (rc = reserve(ctx,&S->status,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->order,sizeof(int32_t)*(n+1)))
-      || (rc = reserve(ctx,&S->queue,sizeof(int32_t)*4)))
+      || (rc = reserve(ctx,&S->queue,64)))
     return rc;
   cudaStream_t st = S->stream;
   if (n > 0)
@@ -410,6 +441,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   B.cls = (uint8_t *)S->cls.p; B.cls_off = (const int64_t *)S->cls_off.p;
   B.status = (int32_t *)S->status.p; B.order = (const int32_t *)S->order.p;
   B.queue = (int32_t *)S->queue.p;
+  B.phase_cycles = (unsigned long long *)((char *)S->queue.p+16);
   return CPG_OK;
 }
 
@@ -421,7 +453,7 @@ static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
      per-warp scratch arena. */
   Slot *other = &ctx->slot[S == &ctx->slot[0] ? 1 : 0];
   if (other->kdone_valid) CU(cudaStreamWaitEvent(st,other->kdone,0));
-  CU(cudaMemsetAsync(S->queue.p,0,sizeof(int32_t)*4,st));
+  CU(cudaMemsetAsync(S->queue.p,0,64,st));
   if (timed) CU(cudaEventRecord(ctx->ev[0],st));
   k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(S->B,ctx->model.kmer);
   if (timed) CU(cudaEventRecord(ctx->ev[1],st));
@@ -529,6 +561,16 @@ extern "C" int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float
   if (ms_decode) *ms_decode = (float)(td/iters);
   if (ms_classify) *ms_classify = (float)(tc/iters);
   if (launches) *launches = 2*iters;
+  return CPG_OK;
+}
+
+extern "C" int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4])
+{ if (ctx == NULL || out == NULL) return set_err(ctx,CPG_EINVAL,"cpg_phase_cycles: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  Slot *S = &ctx->slot[0];
+  if (S->queue.p == NULL) { out[0] = out[1] = out[2] = out[3] = 0; return CPG_OK; }
+  CU(cudaStreamSynchronize(S->stream));
+  CU(cudaMemcpy(out,(char *)S->queue.p+16,32,cudaMemcpyDeviceToHost));
   return CPG_OK;
 }
 

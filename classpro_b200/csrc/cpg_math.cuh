@@ -19,12 +19,16 @@ struct WCtx
     const uint8_t    *cthres;    /* shared-memory copy of M->cthres (or M->cthres itself) */
     cpg_wshared      *ws;
     int               status;
+    /* lane group: the whole warp, except in the reliable-interval DP where the two half-warps run
+       the forward and the backward pass at the same time */
+    int               glane, gsize;
+    unsigned          gmask;
   };
 
 /* one copy of each in the kernel: the per-read code is executed by up to 32 warps per SM that sit in
    different phases, so instruction-cache footprint matters more than call overhead */
-CPG_DEV_NOINL double cpg_exp(double x) { return exp(x); }
-CPG_DEV_NOINL double cpg_log(double x) { return log(x); }
+CPG_DEV_MATHFN double cpg_exp(double x) { return exp(x); }
+CPG_DEV_MATHFN double cpg_log(double x) { return log(x); }
 
 CPG_DEV int imin(int a, int b) { return a < b ? a : b; }
 CPG_DEV int imax(int a, int b) { return a > b ? a : b; }
@@ -32,7 +36,7 @@ CPG_DEV int imax(int a, int b) { return a > b ? a : b; }
 CPG_DEV double dmax_ref(double x, double y) { return x > y ? x : y; }
 
 /* src/bessel.c:390-411 */
-CPG_DEV_NOINL double cpg_bessi0(double x)
+CPG_DEV_HELPER double cpg_bessi0(double x)
 { double ax = fabs(x), y, ans;
   if (ax < 3.75)
     { y = x/3.75; y = y*y;
@@ -47,7 +51,7 @@ CPG_DEV_NOINL double cpg_bessi0(double x)
 }
 
 /* src/bessel.c:416-439 */
-CPG_DEV_NOINL double cpg_bessi1(double x)
+CPG_DEV_HELPER double cpg_bessi1(double x)
 { double ax = fabs(x), y, ans;
   if (ax < 3.75)
     { y = x/3.75; y = y*y;
@@ -114,13 +118,13 @@ CPG_DEV_NOINL double cpg_bessi(int n, double x)
 CPG_DEV int cpg_clamp_cnt(int n) { return n > CPG_MAX_CNT ? CPG_MAX_CNT : n; }
 
 /* src/prob.c:33-39 */
-CPG_DEV_NOINL double cpg_lp_poisson(const WCtx &W, uint16_t k16, int lambda)
+CPG_DEV_HELPER double cpg_lp_poisson(const WCtx &W, uint16_t k16, int lambda)
 { int k = cpg_clamp_cnt(k16);
   return k*cpg_log((double)lambda)-lambda-CPG_LDG(W.M->logfact+k);
 }
 
 /* src/prob.c:41-44 */
-CPG_DEV_NOINL double cpg_lp_skellam(int k, double lambda)
+CPG_DEV_HELPER double cpg_lp_skellam(int k, double lambda)
 { return -2.*lambda+cpg_log(cpg_bessi(k < 0 ? -k : k,2.*lambda)); }
 
 /* src/util.c:35-44; `cov` is a 16-bit count in the reference's signature */
@@ -130,7 +134,7 @@ CPG_DEV double cpg_lp_trans(const WCtx &W, int b, int e, int cb, int ce, uint16_
 }
 
 /* src/prob.c:59-65 */
-CPG_DEV_NOINL double cpg_lp_binom(WCtx &W, uint16_t k16, uint16_t n16, double p)
+CPG_DEV_HELPER double cpg_lp_binom(WCtx &W, uint16_t k16, uint16_t n16, double p)
 { int k = cpg_clamp_cnt(k16), n = cpg_clamp_cnt(n16);
   if (k > n) { W.status |= CPG_ST_BINOM; return -CPG_INF; }
   const double *lf = W.M->logfact;

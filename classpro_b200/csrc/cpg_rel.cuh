@@ -37,6 +37,9 @@ struct RelRun
     uint16_t  COV[4];
     int       M, plen;
     RelShared *sh;
+    cpg_intvl *wint;          /* this direction's working copy, back pointers and freeze flags */
+    uint16_t  *bp;
+    uint8_t   *rpos;
   };
 
 CPG_DEV int rl_pred(int x, int F) { return F ? x-1 : x+1; }
@@ -47,13 +50,13 @@ CPG_DEV uint16_t rl_begcnt(const cpg_intvl &I, int F) { return F ? I.ccb : I.cce
 CPG_DEV uint16_t rl_endcnt(const cpg_intvl &I, int F) { return F ? I.cce : I.ccb; }
 
 /* src/class_rel.c:158-170 */
-CPG_DEV_NOINL double rl_lp_e(const WCtx &W, const cpg_intvl &I, const uint16_t *COV)
+CPG_DEV_HELPER double rl_lp_e(const WCtx &W, const cpg_intvl &I, const uint16_t *COV)
 { double po = cpg_lp_poisson(W,I.ccb,COV[ST_E])+cpg_lp_poisson(W,I.cce,COV[ST_E])+CPG_E_PO_BASE;
   return dmax_ref(po,I.pe);
 }
 
 /* src/class_rel.c:172-211 */
-CPG_DEV_NOINL double rl_lp_r(WCtx &W, const cpg_intvl &I, uint16_t pr_cnt, int F, const uint16_t *COV)
+CPG_DEV_HELPER double rl_lp_r(WCtx &W, const cpg_intvl &I, uint16_t pr_cnt, int F, const uint16_t *COV)
 { uint16_t bc = rl_begcnt(I,F);
   double sf = -CPG_INF;
   double er = (bc < pr_cnt) ? cpg_lp_binom(W,bc,pr_cnt,1-CPG_PE_MEAN) : -CPG_INF;
@@ -105,12 +108,11 @@ CPG_DEV int rl_best_to(const RelState *prv, const double *tr, int s)            
 }
 
 /* src/class_rel.c:113-156 on the path summary of predecessor P extended by state t at interval i */
-CPG_DEV_NOINL double rl_dh_ratio(WCtx &W, const ReadCtx &R, int t, int i, const RelState &P, int F)
+CPG_DEV_HELPER double rl_dh_ratio(WCtx &W, const cpg_intvl *v, int t, int i, const RelState &P, int F)
 { int i2 = (t == ST_H) ? P.lastD : P.lastH;
   if (i2 < 0) return -CPG_INF;
   int i3 = (t == ST_H) ? P.hbd : P.dbh;
   if (i3 < 0) return -CPG_INF;
-  const cpg_intvl *v = R.S.wint;
   int s1p = rl_begpos(v[i],F);  uint16_t s1c = rl_begcnt(v[i],F);
   int tp  = rl_endpos(v[i2],F); uint16_t tc  = rl_endcnt(v[i2],F);
   int s2p = rl_endpos(v[i3],F); uint16_t s2c = rl_endcnt(v[i3],F);
@@ -129,13 +131,13 @@ CPG_DEV void rl_extend_path(RelState &dst, const RelState &P, int t, int i)
 CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelState *prv, RelState *cur)
 { const int F = U.F;
   const cpg_dmodel *M = W.M;
-  cpg_intvl *wint = R.S.wint;
+  cpg_intvl *wint = U.wint;
   const cpg_intvl I = wint[i];
   const int ep = rl_endpos(I,F); const uint16_t ec = rl_endcnt(I,F);
   const int ip = rl_pred(i,F);
   double *tr = U.sh->tr;
 
-  CPG_LOOP for (int q = W.lane; q < 16; q += CPG_WARP)
+  CPG_LOOP for (int q = W.glane; q < 16; q += W.gsize)
     { int s = q >> 2, t = q & 3;
       double v = 0.;
       int need = 0, k = 0; double lambda = 0.;
@@ -147,17 +149,17 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
       if (need) v = cpg_exp(cpg_lp_skellam(k,lambda)+0.);
       tr[q] = v;
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
   double psum = 0.;
   CPG_LOOP for (int q = 0; q < 16; q++) psum += tr[q];
   int fix = (psum == 0.);
-  CPG_SYNCWARP();
-  CPG_LOOP for (int q = W.lane; q < 16; q += CPG_WARP)
+  CPG_SYNCGROUP(W);
+  CPG_LOOP for (int q = W.glane; q < 16; q += W.gsize)
     { double v = tr[q];
       if (fix) v = ((q & 3) == ST_E) ? 1. : v;
       tr[q] = cpg_log(v/(fix ? 4. : psum));
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
 
   /* every live predecessor prefers R: freeze this interval (src/class_rel.c:348-380) */
   int only_r = 1;
@@ -166,8 +168,8 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
       if (mt != ST_N && mt != ST_R) { only_r = 0; break; }
     }
   if (only_r)
-    { if (W.lane == 0)
-        { R.S.rpos[i] = 1;
+    { if (W.glane == 0)
+        { U.rpos[i] = 1;
           wint[i] = wint[ip];
           uint16_t bp = 0;
           CPG_LOOP for (int s = 0; s < 4; s++)
@@ -178,9 +180,9 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
               CPG_LOOP for (int t = 0; t < 4; t++) { cur[s].pos[t] = prv[s].pos[t]; cur[s].cnt[t] = prv[s].cnt[t]; }
               rl_extend_path(cur[s],prv[s],s,i);
             }
-          R.S.bp[i] = bp;
+          U.bp[i] = bp;
         }
-      CPG_SYNCWARP();
+      CPG_SYNCGROUP(W);
       return;
     }
 
@@ -188,9 +190,9 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
   if (mh == ST_H && md == ST_D)
     { double a = tr[ST_H*4+ST_H], b = tr[ST_D*4+ST_D];
       double m = (a < b) ? a : b;
-      CPG_SYNCWARP();
-      if (W.lane == 0) { tr[ST_H*4+ST_H] = m; tr[ST_D*4+ST_D] = m; }
-      CPG_SYNCWARP();
+      CPG_SYNCGROUP(W);
+      if (W.glane == 0) { tr[ST_H*4+ST_H] = m; tr[ST_D*4+ST_D] = m; }
+      CPG_SYNCGROUP(W);
     }
 
   uint16_t bpw = 0;
@@ -215,7 +217,7 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
             }
           else
             { int ch, cd, cr;
-              double r = rl_dh_ratio(W,R,t,i,P,F);
+              double r = rl_dh_ratio(W,U.wint,t,i,P,F);
               if (t == ST_H)
                 { ch = ec;
                   if (r == -CPG_INF) cd = (P.lastD >= 0) ? P.cnt[ST_D] : ch+U.COV[ST_H];
@@ -232,19 +234,19 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
             }
           if (!(ns.cnt[ST_H] < ns.cnt[ST_D] && ns.cnt[ST_D] < ns.cnt[ST_R])) ns.dp = -CPG_INF;
         }
-      if (W.lane == 0) cur[t] = ns;
+      if (W.glane == 0) cur[t] = ns;
     }
-  if (W.lane == 0) R.S.bp[i] = bpw;
-  CPG_SYNCWARP();
+  if (W.glane == 0) U.bp[i] = bpw;
+  CPG_SYNCGROUP(W);
 }
 
 /* src/class_rel.c:515-614; the state path is written to `asgn` */
 CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
 { const int F = U.F, Mrel = U.M;
   const uint16_t *COV = U.COV;
-  cpg_intvl *wint = R.S.wint;
-  CPG_LOOP for (int i = W.lane; i < Mrel; i += CPG_WARP) { wint[i] = R.S.rint[i]; R.S.rpos[i] = 0; R.S.bp[i] = 0; }
-  CPG_SYNCWARP();
+  cpg_intvl *wint = U.wint;
+  CPG_LOOP for (int i = W.glane; i < Mrel; i += W.gsize) { wint[i] = R.S.rint[i]; U.rpos[i] = 0; U.bp[i] = 0; }
+  CPG_SYNCGROUP(W);
 
   const int POS_INIT = rl_off(F ? 0 : U.plen,F);
   int i = F ? 0 : Mrel-1;
@@ -259,7 +261,7 @@ CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
     double psum = 0.;
     CPG_LOOP for (int s = 0; s < 4; s++) psum += cpg_exp(d[s]);
     CPG_LOOP for (int s = 0; s < 4; s++) d[s] = cpg_log(cpg_exp(d[s])/psum);
-    if (W.lane == 0)
+    if (W.glane == 0)
       { CPG_LOOP for (int s = 0; s < 4; s++)
           { RelState &X = c0[s];
             X.dp = d[s]; X.dhr = -CPG_INF;
@@ -275,7 +277,7 @@ CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
         c0[ST_D].pos[ST_D] = ep; c0[ST_D].cnt[ST_D] = ec;
         c0[ST_D].lastD = i;
       }
-    CPG_SYNCWARP();
+    CPG_SYNCGROUP(W);
   }
 
   RelState *prv = c0, *cur = c1;
@@ -290,22 +292,22 @@ CPG_DEV_NOINL void rl_pass(ReadCtx &R, WCtx &W, const RelRun &U, uint8_t *asgn)
   i = F ? Mrel-1 : 0;
   int s = ST_N; { double mx = -CPG_INF; for (int x = 0; x < 4; x++) if (mx < prv[x].dp) { mx = prv[x].dp; s = x; } }
   if (s == ST_N) { W.status |= CPG_ST_UNDEF_TRACE; s = ST_E; }
-  CPG_SYNCWARP();
-  if (W.lane == 0)
+  CPG_SYNCGROUP(W);
+  if (W.glane == 0)
     { const int first = F ? 0 : Mrel-1;
       CPG_LOOP for (;;)
-        { asgn[i] = (uint8_t)(R.S.rpos[i] ? ST_R : s);
+        { asgn[i] = (uint8_t)(U.rpos[i] ? ST_R : s);
           if (i == first) break;
-          int p = (R.S.bp[i] >> (3*s)) & 7;
+          int p = (U.bp[i] >> (3*s)) & 7;
           s = (p == ST_N) ? ST_E : p;
           i = F ? i-1 : i+1;
         }
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
 }
 
 /* integer accumulation of src/class_rel.c:634-664 */
-CPG_DEV_NOINL double rl_mean_cov(const cpg_intvl *r, const uint8_t *asgn, int Mrel, int want)
+CPG_DEV_HELPER double rl_mean_cov(const cpg_intvl *r, const uint8_t *asgn, int Mrel, int want)
 { int lsum = 0, csum = 0;
   CPG_LOOP for (int i = 0; i < Mrel; i++)
     if (want < 0 || asgn[i] == want)
@@ -321,14 +323,14 @@ CPG_DEV int rl_has(const uint8_t *asgn, int Mrel, int s)
   return 0;
 }
 
-CPG_DEV_NOINL void rl_relabel(uint8_t *asgn, int Mrel, int from1, int to1, int from2, int to2, const WCtx &W)
-{ CPG_SYNCWARP();
-  CPG_LOOP for (int i = W.lane; i < Mrel; i += CPG_WARP)
+CPG_DEV_HELPER void rl_relabel(uint8_t *asgn, int Mrel, int from1, int to1, int from2, int to2, const WCtx &W)
+{ CPG_SYNCGROUP(W);
+  CPG_LOOP for (int i = W.glane; i < Mrel; i += W.gsize)
     { uint8_t a = asgn[i];
       if (from1 < 0 || a == from1) asgn[i] = (uint8_t)to1;
       else if (a == from2) asgn[i] = (uint8_t)to2;
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
 }
 
 /* src/class_rel.c:623-845: one direction with its optional re-run and relabel heuristics */
@@ -337,6 +339,7 @@ CPG_DEV_NOINL double rl_direction(ReadCtx &R, WCtx &W, RelShared *sh, int F, int
   const uint16_t *G = W.M->cov;
   RelRun U;
   U.F = F; U.M = Mrel; U.plen = plen; U.sh = sh;
+  U.wint = R.S.wint+(F ? 0 : R.S.MC); U.bp = R.S.bp+(F ? 0 : R.S.MC); U.rpos = R.S.rpos+(F ? 0 : R.S.MC);
   CPG_LOOP for (int s = 0; s < 4; s++) U.COV[s] = G[s];
   rl_pass(R,W,U,asgn);
   if (!rl_has(asgn,Mrel,ST_H))
@@ -397,13 +400,29 @@ CPG_DEV int rl_eq_suffix(const uint8_t *a, int Mrel)
   return 1;
 }
 
-/* src/class_rel.c:871-963 */
+/* src/class_rel.c:871-963.  The forward and the backward pass are independent (the reference runs
+ * them one after the other): with a full warp the two half-warps run them at the same time, each
+ * with its own lane group, DP columns, working copy and back pointers. */
 CPG_DEV_NOINL void classify_reliable(ReadCtx &R, WCtx &W, RelShared *sh)
 { const int Mrel = R.M, N = R.N;
   if (Mrel == 0) return;
   uint8_t *af = R.S.asg_f, *ab = R.S.asg_b;
-  double hf = rl_direction(R,W,sh,1,Mrel,R.plen,af);
-  double hb = rl_direction(R,W,sh,0,Mrel,R.plen,ab);
+  double hf, hb;
+  CPG_SYNCWARP();
+  if (CPG_WARP >= 32)
+    { const int h = W.lane >> 4;
+      WCtx G = W;
+      G.glane = W.lane & 15; G.gsize = 16; G.gmask = h ? 0xffff0000u : 0x0000ffffu; G.status = 0;
+      double hd = rl_direction(R,G,sh+h,h == 0,Mrel,R.plen,h ? ab : af);
+      W.status |= G.status;
+      if (G.glane == 0) W.ws->term[h] = hd;
+      CPG_SYNCWARP();
+      hf = W.ws->term[0]; hb = W.ws->term[1];
+    }
+  else
+    { hf = rl_direction(R,W,sh,1,Mrel,R.plen,af);
+      hb = rl_direction(R,W,sh+1,0,Mrel,R.plen,ab);
+    }
   int eq = 1;
   CPG_LOOP for (int i = 0; i < Mrel; i++) if (af[i] != ab[i]) { eq = 0; break; }
   int use_b = 0;

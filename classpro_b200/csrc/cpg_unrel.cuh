@@ -15,7 +15,7 @@
 #include "cpg_rel.cuh"
 
 /* src/class_unrel.c:11-25 */
-CPG_DEV_NOINL void un_nn(int idx, int s, const cpg_intvl *v, int N, int &l, int &r)
+CPG_DEV_HELPER void un_nn(int idx, int s, const cpg_intvl *v, int N, int &l, int &r)
 { l = idx-1;
   CPG_LOOP while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--;
   if (l < 0) l = -1;
@@ -25,7 +25,7 @@ CPG_DEV_NOINL void un_nn(int idx, int s, const cpg_intvl *v, int N, int &l, int 
 }
 
 /* src/class_unrel.c:27-51 */
-CPG_DEV_NOINL uint16_t un_est_cov(WCtx &W, int x, int idx, const cpg_intvl *v, int N, int s)
+CPG_DEV_HELPER uint16_t un_est_cov(WCtx &W, int x, int idx, const cpg_intvl *v, int N, int s)
 { int l, r;
   un_nn(idx,s,v,N,l,r);
   if (l != -1 && r != -1) return (uint16_t)cpg_lin_interp(W,x,v[l].e-1,v[l].cce,v[r].b,v[r].ccb);
@@ -44,14 +44,14 @@ CPG_DEV_NOINL uint16_t un_est_cov(WCtx &W, int x, int idx, const cpg_intvl *v, i
 }
 
 /* src/class_unrel.c:53-65 */
-CPG_DEV_NOINL double un_lp_e(const WCtx &W, const cpg_intvl &I)
+CPG_DEV_HELPER double un_lp_e(const WCtx &W, const cpg_intvl &I)
 { const int ce = W.M->cov[ST_E];
   double po = cpg_lp_poisson(W,I.cb,ce)+cpg_lp_poisson(W,I.ce,ce)+CPG_E_PO_BASE;
   return dmax_ref(I.pe,po);
 }
 
 /* src/class_unrel.c:67-113 */
-CPG_DEV_NOINL double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
+CPG_DEV_HELPER double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
 { const cpg_intvl &I = v[idx];
   const cpg_dmodel *M = W.M;
   if (imax(I.cb,I.ce) >= M->cov[ST_R]) return 0.;
@@ -165,14 +165,19 @@ CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
   CPG_LOOP for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
 }
 
-/* ---- the whole read: src/ClassPro.c:229-271 ---- */
-CPG_DEV_NOINL int classify_read(ReadCtx &R, WCtx &W, RelShared *sh, uint8_t *cls)
+/* ---- the whole read: src/ClassPro.c:229-271, in three phases.
+ * The kernel runs the phases CTA-synchronously (all warps of a CTA do phase 1 on their reads, then
+ * phase 2, then phase 3): the per-read code is large and branchy, and warps that sit in the same
+ * phase share their instruction-cache lines instead of evicting each other's. ---- */
+CPG_DEV_NOINL void classify_phase1(ReadCtx &R, WCtx &W)
+{ find_walls_and_reliable(R,W); }
+
+CPG_DEV_NOINL void classify_phase2(ReadCtx &R, WCtx &W, RelShared *sh)
+{ if (!(W.status & CPG_ST_EINTVL_OVF)) classify_reliable(R,W,sh); }
+
+CPG_DEV_NOINL int classify_phase3(ReadCtx &R, WCtx &W, uint8_t *cls)
 { const int K = W.M->K;
-  find_walls_and_reliable(R,W);
-  if (!(W.status & CPG_ST_EINTVL_OVF))
-    { classify_reliable(R,W,sh);
-      classify_unreliable(R,W);
-    }
+  if (!(W.status & CPG_ST_EINTVL_OVF)) classify_unreliable(R,W);
   /* emit: 'N' x (K-1), then one class character per k-mer */
   CPG_LOOP for (int j = W.lane; j < K-1; j += CPG_WARP) cls[j] = 'N';
   const cpg_intvl *v = R.S.intvl;
@@ -184,6 +189,12 @@ CPG_DEV_NOINL int classify_read(ReadCtx &R, WCtx &W, RelShared *sh, uint8_t *cls
     }
   CPG_SYNCWARP();
   return W.status;
+}
+
+CPG_DEV int classify_read(ReadCtx &R, WCtx &W, RelShared *sh, uint8_t *cls)
+{ classify_phase1(R,W);
+  classify_phase2(R,W,sh);
+  return classify_phase3(R,W,cls);
 }
 
 #endif

@@ -67,18 +67,18 @@ CPG_DEV unsigned mk_pair(int e) { return e == ET_SELF ? MK_PAIR_S : MK_PAIR_O; }
 /* Lane 0 is the only writer of the scratch words below.  Each helper synchronises the warp BEFORE
  * the write (the other lanes may still be reading the old value: the CUDA memory model does not
  * promise lock-step execution) and AFTER it (so that every lane sees the new one). */
-CPG_DEV_NOINL void mark_or(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
+CPG_DEV_HELPER void mark_or(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
 { CPG_SYNCWARP();
   if (W.lane == 0) R.S.mark[pos] |= bits;
   CPG_SYNCWARP();
 }
-CPG_DEV_NOINL void mark_clear(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
+CPG_DEV_HELPER void mark_clear(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
 { CPG_SYNCWARP();
   if (W.lane == 0) R.S.mark[pos] &= ~bits;
   CPG_SYNCWARP();
 }
 
-CPG_DEV_NOINL double perr_get(const ReadCtx &R, int pos, int e, int w)
+CPG_DEV_HELPER double perr_get(const ReadCtx &R, int pos, int e, int w)
 { unsigned s = R.S.mark[pos] >> 8;
   return s ? R.S.perr[(size_t)(s-1)*4+e*2+w] : -CPG_INF;
 }
@@ -105,7 +105,7 @@ CPG_DEV_NOINL void perr_once(ReadCtx &R, WCtx &W, int pos, int e, int w,
 }
 
 /* src/wall.c:317-322 */
-CPG_DEV_NOINL double lp_diff_pair(const ReadCtx &R, const WCtx &W, int i, int j)
+CPG_DEV_HELPER double lp_diff_pair(const ReadCtx &R, const WCtx &W, int i, int j)
 { const uint16_t *p = R.prof;
   int n_drop = (int)p[i-1]-p[i], n_gain = (int)p[j]-p[j-1];
   uint16_t cov = (uint16_t)imax(p[i-1],p[j]);
@@ -155,14 +155,14 @@ CPG_DEV void pg_counts(const PairGeom &G, const uint16_t *prof, int j, uint16_t 
   cout_j = G.fwd ? prof[j]   : prof[j-1];
 }
 /* count tests of the low-complexity partner (src/wall.c:364-365,455-456) */
-CPG_DEV_NOINL int pg_lc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e)
+CPG_DEV_HELPER int pg_lc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e)
 { uint16_t cin_j, cout_j;
   pg_counts(G,prof,G.lc_j,cin_j,cout_j);
   return cin_j <= cout_j
          && !(cout_j < W.M->cmax && thres_ng(e,cin_j,cthres_at(W,G.t,G.l,cout_j,TH_FINAL,e)));
 }
 /* count tests of a high-complexity partner (src/wall.c:384-389,475-480) */
-CPG_DEV_NOINL int pg_hc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e, int j)
+CPG_DEV_HELPER int pg_hc_ok(const PairGeom &G, const WCtx &W, const uint16_t *prof, int e, int j)
 { uint16_t cin_j, cout_j;
   pg_counts(G,prof,j,cin_j,cout_j);
   const int cmax = W.M->cmax;
@@ -240,7 +240,7 @@ CPG_DEV_NOINL void ei_sort(cpg_eintvl *a, int n, const WCtx &W)
 }
 
 /* src/wall.c:548-568 */
-CPG_DEV_NOINL int ei_unique(cpg_eintvl *a, int n, const WCtx &W)
+CPG_DEV_HELPER int ei_unique(cpg_eintvl *a, int n, const WCtx &W)
 { ei_sort(a,n,W);
   if (n >= 2)
     { int i = 1;
@@ -265,7 +265,7 @@ CPG_DEV_NOINL int ei_unique(cpg_eintvl *a, int n, const WCtx &W)
 }
 
 /* src/wall.c:530-546 */
-CPG_DEV_NOINL int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
+CPG_DEV_HELPER int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
 { CPG_LOOP while (l <= r)
     { int m = (l+r)/2;
       if (a[m].b == b)
@@ -278,14 +278,14 @@ CPG_DEV_NOINL int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
   return -1;
 }
 
-CPG_DEV_NOINL void ei_put(ReadCtx &R, const WCtx &W, int k, int b, int e, double pe)
+CPG_DEV_HELPER void ei_put(ReadCtx &R, const WCtx &W, int k, int b, int e, double pe)
 { CPG_SYNCWARP();
   if (W.lane == 0) { R.S.eint[k].b = b; R.S.eint[k].e = e; R.S.eint[k].pe = pe; }
   CPG_SYNCWARP();
 }
 
 /* clear bits on the open range (b,e), lanes striding */
-CPG_DEV_NOINL void mark_clear_range(ReadCtx &R, const WCtx &W, int b, int e, unsigned bits)
+CPG_DEV_HELPER void mark_clear_range(ReadCtx &R, const WCtx &W, int b, int e, unsigned bits)
 { CPG_SYNCWARP();
   CPG_LOOP for (int j = b+1+W.lane; j < e; j += CPG_WARP) R.S.mark[j] &= ~bits;
   CPG_SYNCWARP();

@@ -128,6 +128,10 @@ int cpg_decode_profiles(cpg_ctx *ctx, int32_t n_reads, const uint8_t *prof, cons
 int cpg_upload(cpg_ctx *ctx, const cpg_batch *batch);
 int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float *ms_classify, int *launches);
 int cpg_download(cpg_ctx *ctx, cpg_result *result);
+/* Summed per-warp clock cycles of the last k_classify launch of slot 0: [0] wall detection +
+ * reliable intervals, [1] reliable-interval DP, [2] unreliable intervals + emit, [3] waiting at the
+ * CTA phase barriers. */
+int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4]);
 
 /* Pinned (page-locked) host memory, so that the copies of cpg_submit/cpg_collect are truly
  * asynchronous DMA transfers; pageable buffers work too but are staged by the driver. */

@@ -52,6 +52,11 @@ unsigned cpg_sim_shfl_up(unsigned v, int d)
   pthread_barrier_wait(&g_bar);
   return r;
 }
+static pthread_barrier_t g_gbar[2];
+void cpg_sim_group_barrier(unsigned mask)
+{ if (mask == 0xffffffffu) pthread_barrier_wait(&g_bar);
+  else pthread_barrier_wait(&g_gbar[mask == 0x0000ffffu ? 0 : 1]);
+}
 int cpg_sim_sum(int v)
 { g_slot[t_lane] = (unsigned)v;
   pthread_barrier_wait(&g_bar);
@@ -65,12 +70,12 @@ int cpg_sim_sum(int v)
 struct HsWork
   { std::vector<uint32_t> mark; std::vector<double> perr; std::vector<cpg_eintvl> eint;
     std::vector<cpg_intvl> intvl, rint, wint; std::vector<uint16_t> bp;
-    std::vector<uint8_t> af, ab, rpos, fixed; std::vector<int32_t> ord;
+    std::vector<uint8_t> af, ab, rpos, fixed; std::vector<int32_t> ord; int mc = 0;
     void size(int P)
       { int MC = P/2+8;
         mark.assign(P+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
-        rint.resize(MC); wint.resize(MC); bp.assign(MC,0); af.assign(MC,0); ab.assign(MC,0);
-        rpos.assign(MC,0); fixed.assign(P+2,0); ord.assign(P+2,0);
+        rint.resize(MC); wint.resize(2*MC); bp.assign(2*MC,0); af.assign(MC,0); ab.assign(MC,0);
+        rpos.assign(2*MC,0); mc = MC; fixed.assign(P+2,0); ord.assign(P+2,0);
       }
   };
 
@@ -87,6 +92,7 @@ static void *lane_classify(void *arg)
   t_lane = J->lane;
 #endif
   WCtx W; W.lane = J->lane; W.M = J->dm; W.cthres = J->dm->cthres; W.ws = J->ws; W.status = 0;
+  W.glane = J->lane; W.gsize = CPG_WARP; W.gmask = 0xffffffffu;
   ReadCtx R = J->R;
   J->status = classify_read(R,W,J->sh,J->cls);
   J->N = R.N; J->M = R.M;
@@ -107,9 +113,11 @@ static void run_lanes(void *(*fn)(void *), LaneJob *jobs)
 #if CPG_HOSTSIM == 32
   pthread_t th[32];
   pthread_barrier_init(&g_bar,NULL,32);
+  pthread_barrier_init(&g_gbar[0],NULL,16); pthread_barrier_init(&g_gbar[1],NULL,16);
   for (int l = 0; l < 32; l++) pthread_create(&th[l],NULL,fn,&jobs[l]);
   for (int l = 0; l < 32; l++) pthread_join(th[l],NULL);
   pthread_barrier_destroy(&g_bar);
+  pthread_barrier_destroy(&g_gbar[0]); pthread_barrier_destroy(&g_gbar[1]);
 #else
   fn(&jobs[0]);
 #endif
@@ -143,17 +151,17 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
 
   static HsWork Wk; static int sized = 0;
   if (sized < plen) { Wk.size(plen+64); sized = plen+64; }
-  static cpg_wshared ws; static RelShared sh;
+  static cpg_wshared ws; static RelShared sh[2];
   LaneJob jobs[CPG_WARP];
   for (int l = 0; l < CPG_WARP; l++)
     { LaneJob &J = jobs[l];
-      J.lane = l; J.dm = &dm; J.ws = &ws; J.sh = &sh; J.cls = (uint8_t *)cls; J.status = 0;
+      J.lane = l; J.dm = &dm; J.ws = &ws; J.sh = sh; J.cls = (uint8_t *)cls; J.status = 0;
       ReadCtx &R = J.R;
       R.prof = prof; R.plen = plen; R.rlen = rlen; R.seq = S; R.nslots = 0; R.N = R.M = 0;
       R.S.mark = Wk.mark.data(); R.S.perr = Wk.perr.data(); R.S.eint = Wk.eint.data();
       R.S.intvl = Wk.intvl.data(); R.S.rint = Wk.rint.data(); R.S.wint = Wk.wint.data();
       R.S.bp = Wk.bp.data(); R.S.asg_f = Wk.af.data(); R.S.asg_b = Wk.ab.data();
-      R.S.rpos = Wk.rpos.data(); R.S.ord = Wk.ord.data(); R.S.fixed = Wk.fixed.data();
+      R.S.rpos = Wk.rpos.data(); R.S.ord = Wk.ord.data(); R.S.fixed = Wk.fixed.data(); R.S.MC = Wk.mc;
     }
   run_lanes(lane_classify,jobs);
   int st = 0;
