@@ -144,6 +144,10 @@ typedef struct { int32_t b, e; double pe; } cpg_eintvl;   /* src/ClassPro.h:153-
 /* Sequence view: 2-bit packed (A,C,G,T = 0..3, base i in bits 2*(i&3) of byte i>>2) or raw bytes */
 typedef struct { const uint8_t *p; int32_t bits; } cpg_seq;
 
+/* One task of an unreliable-interval update (see cpg_unrel.cuh): arguments and result */
+struct cpg_unmemo { double a; double val; int32_t k; int32_t kind; };
+#define CPG_MEMO_CAP 2048      /* intervals per read whose first-sweep results are kept */
+
 /* Per-warp scratch in global memory, sized for the longest profile of the batch */
 typedef struct
   { uint32_t   *mark;     /* [P+2]   flags | (slot+1)<<8 per profile position 0..plen */
@@ -159,6 +163,7 @@ typedef struct
     int32_t     MC;
     int32_t    *ord;      /* [P+2] */
     uint8_t    *fixed;    /* [P+2] */
+    struct cpg_unmemo *memo;   /* [CPG_MEMO_CAP*8] first-sweep results of the unreliable-interval tasks */
   } cpg_scratch;
 
 /* Per-warp exchange block (shared memory on the device) */

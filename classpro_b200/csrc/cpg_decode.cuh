@@ -8,16 +8,22 @@
  *      00rrrrrr            repeat the current count r more times
  *      01sddddd            6-bit signed delta, 16-bit wrap-around add
  *      1sdddddd dddddddd   15-bit two's-complement delta, sum masked to 15 bits
- *  The reference walks it byte by byte.  Here a warp takes 32 bytes per step:
+ *  The reference walks it byte by byte.  Here a warp takes 128 bytes per step, 4 per lane:
  *   1. token boundaries: a byte is the 2nd byte of a long token iff an odd number of
- *      high-bit-set bytes immediately precede it back to the last high-bit-clear byte (or to the
- *      carry of the previous step) -- one ballot + a count-leading-ones per lane;
- *   2. values: inclusive warp scan of the deltas mod 2^16; the 15-bit mask of long tokens is
- *      honoured exactly by restarting from the low 15 bits of the plain sum at the last long
- *      token (a max-scan of lane indices), because the low 15 bits of the running count always
- *      equal those of the plain sum;
- *   3. expansion: exclusive scan of the per-token output counts, then the lanes write the
- *      outputs of the step coalesced, each finding its token by binary search over the 32 offsets.
+ *      high-bit-set bytes immediately precede it back to the last high-bit-clear byte.  Runs that
+ *      span whole lanes have even length, so a lane only needs the trailing run of the nearest
+ *      lower lane that is not all-high (one ballot, one count-leading-ones, one shuffle) or, if
+ *      there is none, the carry of the previous step;
+ *   2. values: inclusive warp scan of the per-lane delta sums mod 2^16.  The 15-bit mask of long
+ *      tokens is honoured exactly: the low 15 bits of the running count always equal those of the
+ *      plain sum, so the count right after the last long token (a max-scan of lane indices) is the
+ *      plain sum up to there masked to 15 bits, and 16-bit wrap-around adds continue from it;
+ *   3. expansion: exclusive scan of the output counts into a per-warp table of (offset, value)
+ *      per token; the lanes then write the step's outputs in aligned groups of eight counts
+ *      (one 16-byte store per group), each finding its first token by binary search in the table
+ *      and walking forward.  The ragged head and tail of a step are written count by count.
+ *  Bit-exact on arbitrary byte streams (wrap-around, mask, zero-length runs), not only on
+ *  well-formed ones.
  *******************************************************************************************/
 #ifndef CPG_DECODE_CUH
 #define CPG_DECODE_CUH
@@ -39,7 +45,7 @@ CPG_DEV int dc_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 #elif defined(CPG_HOSTSIM)
 CPG_DEV unsigned dc_ballot(int p) { return p ? 1u : 0u; }
 CPG_DEV unsigned dc_shfl(unsigned v, int src) { (void)src; return v; }
-CPG_DEV unsigned dc_shfl_up(unsigned v, int d, int lane) { (void)d; (void)lane; return v; }
+CPG_DEV unsigned dc_shfl_up(unsigned v, int d, int lane) { (void)v; (void)d; (void)lane; return 0u; }
 CPG_DEV unsigned dc_scan_add(unsigned v, int lane) { (void)lane; return v; }
 CPG_DEV int      dc_scan_max(int v, int lane) { (void)lane; return v; }
 CPG_DEV int      dc_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
@@ -61,79 +67,140 @@ CPG_DEV int dc_scan_max(int v, int lane)
 CPG_DEV int dc_clz(unsigned v) { return __clz((int)v); }
 #endif
 
-/* Decodes `len` bytes at `src` into at most `cap` counts at `out`; returns the decoded length
- * (which may exceed cap, as Fetch_Profile's return value does).  `offs` is a per-warp shared-memory
- * array of 2*CPG_WARP ints. */
+#define DC_BPL    4                      /* bytes per lane per step */
+#define DC_SLOTS  (DC_BPL*CPG_WARP)      /* token slots per step */
+
+/* owner slot of step-relative output t: the LAST slot whose exclusive offset is <= t (slots that
+ * emit nothing share the offset of their successor) */
+CPG_DEV int dc_owner(const unsigned *tab, int t)
+{ int lo = 0, hi = DC_SLOTS-1;
+  while (lo < hi)
+    { int mid = (lo+hi+1) >> 1;
+      if ((int)(tab[mid] & 0xffffu) <= t) lo = mid; else hi = mid-1;
+    }
+  return lo;
+}
+
+/* Decodes `len` bytes at `src` into at most `cap` counts at `out`; returns the
+ * decoded length (which may exceed cap, as Fetch_Profile's return value does).  `tab` is a
+ * per-warp shared-memory array of DC_SLOTS words: value << 16 | exclusive output offset of each
+ * token slot of the step (a step emits at most 4*32*63 = 8064 < 65536 counts). */
 CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out, int cap,
-                                 int lane, int *offs)
+                                 int lane, unsigned *tab)
 { if (len <= 0) return 0;
-  int *vals = offs+CPG_WARP;
   unsigned x0 = src[0];
   unsigned v_in; int64_t off;
   if (x0 & 0x80) { v_in = ((x0 & 0x7f) << 8) | (len > 1 ? src[1] : 0); off = 2; }
   else           { v_in = x0; off = 1; }
   if (lane == 0 && cap > 0) out[0] = (uint16_t)v_in;
   int n = 1;
-  unsigned carry = 0, carry_hi = 0;      /* lane 0 of the step is the 2nd byte of a long token */
+  unsigned carry = 0, carry_hi = 0;      /* the first byte of the step is the 2nd byte of a long token */
+  const int sh = (int)((((size_t)out) >> 1) & 7);      /* misalignment of the row, in counts */
 
-  for (; off < len; off += CPG_WARP)
-    { const int valid = (off+lane < len);
-      const unsigned x = valid ? src[off+lane] : 0u;
-      const unsigned hi = valid && (x & 0x80);
-      const unsigned H = dc_ballot(hi);
-      /* consecutive high-bit-set bytes right before this lane */
-      int c = 0;
-      if (lane > 0)
-        { unsigned below = H << (32-lane);            /* bit 31 = lane-1 */
-          c = dc_clz(~below);
-          if (c > lane) c = lane;
+  for (; off < len; off += DC_SLOTS)
+    { /* ---- this lane's four bytes ---- */
+      const int64_t p0 = off+(int64_t)lane*DC_BPL;
+      unsigned b[DC_BPL]; int nv = 0;
+      for (int k = 0; k < DC_BPL; k++)
+        { int ok = (p0+k < len);
+          b[k] = ok ? src[p0+k] : 0u;
+          nv += ok;
         }
-      if (c == lane) c += (int)carry;
-      const int second = valid && (c & 1);
-      const unsigned up = dc_shfl_up(x,1,lane);          /* every lane takes part in the shuffle */
-      const unsigned prev = (lane == 0) ? carry_hi : up;
+      /* trailing run of high-bit-set bytes among the valid ones; full = all four present and high */
+      int trail = 0;
+      for (int k = nv-1; k >= 0 && (b[k] & 0x80); k--) trail++;
+      const int full = (nv == DC_BPL && trail == DC_BPL);
+      const unsigned F = dc_ballot(full);
+      int z = 0;
+      if (lane > 0) { z = dc_clz(~(F << (32-lane))); if (z > lane) z = lane; }
+      const int srcl = lane-1-z;
+      const unsigned tsrc = dc_shfl((unsigned)trail,srcl < 0 ? 0 : srcl);
+      int sec = (srcl < 0) ? (int)carry : (int)(tsrc & 1);
+      const unsigned up = dc_shfl_up(b[DC_BPL-1],1,lane);
+      unsigned prev = (lane == 0) ? carry_hi : up;
 
-      unsigned a = 0, cnt = 0; int masked = 0;
-      if (valid)
-        { if (second)
-            { unsigned w = (prev & 0x40) ? ((prev << 8) & 0xffffu) : ((prev << 8) & 0x7fffu);
-              a = (w | x) & 0xffffu; cnt = 1; masked = 1;
+      /* ---- tokens of this lane: output count, delta, mask flag per byte slot ---- */
+      unsigned cnt[DC_BPL], add[DC_BPL]; int msk[DC_BPL];
+      unsigned C = 0, A = 0, A2 = 0; int has_mask = 0;
+      for (int k = 0; k < DC_BPL; k++)
+        { cnt[k] = 0; add[k] = 0; msk[k] = 0;
+          if (k < nv)
+            { const unsigned x = b[k];
+              if (sec)
+                { unsigned w = (prev & 0x40) ? ((prev << 8) & 0xffffu) : ((prev << 8) & 0x7fffu);
+                  add[k] = (w | x) & 0xffffu; cnt[k] = 1; msk[k] = 1; sec = 0;
+                }
+              else if (x & 0x80) sec = 1;
+              else if ((x & 0xc0) == 0) cnt[k] = x;
+              else { add[k] = (x & 0x20) ? ((x & 0x1fu) | 0xffe0u) : (x & 0x1fu); cnt[k] = 1; }
+              prev = x;
             }
-          else if ((x & 0xc0) == 0) cnt = x;
-          else if (!(x & 0x80))
-            { a = (x & 0x20) ? ((x & 0x1fu) | 0xffe0u) : (x & 0x1fu); cnt = 1; }
+          C += cnt[k]; A += add[k];
+          if (msk[k]) { has_mask = 1; A2 = 0; } else A2 += add[k];
         }
-      const unsigned S = dc_scan_add(a,lane) & 0xffffu;
-      const int q = dc_scan_max(masked ? lane : -1,lane);
-      const unsigned Sq = dc_shfl(S,q < 0 ? 0 : q);
+      /* ---- count at the start of this lane ---- */
+      const unsigned S = dc_scan_add(A,lane) & 0xffffu;
+      const unsigned Mk = (S-(A2 & 0xffffu)) & 0xffffu;              /* plain sum up to the lane's last long token */
+      const int q = dc_scan_max(has_mask ? lane : -1,lane);
+      const unsigned Sp = dc_shfl_up(S,1,lane);                      /* 0 for lane 0 */
+      const int qp = (int)dc_shfl_up((unsigned)(q+1),1,lane)-1;      /* -1 for lane 0 */
+      const unsigned Mq = dc_shfl(Mk,qp < 0 ? 0 : qp);
       unsigned v;
-      if (q < 0) v = (v_in+S) & 0xffffu;
-      else       v = ((((v_in+Sq) & 0x7fffu)+((S-Sq) & 0xffffu)) & 0xffffu);
-      const unsigned incl = dc_scan_add(cnt,lane);
-      const unsigned excl = incl-cnt;
+      if (qp < 0) v = (v_in+Sp) & 0xffffu;
+      else        v = ((((v_in+Mq) & 0x7fffu)+((Sp-Mq) & 0xffffu)) & 0xffffu);
+      /* ---- token table: exclusive output offset and count value of every slot ---- */
+      const unsigned incl = dc_scan_add(C,lane);
+      unsigned o = incl-C;
       const int total = (int)dc_shfl(incl,CPG_WARP-1);
-
-      offs[lane] = (int)excl;
-      vals[lane] = (int)v;          /* run tokens leave the count unchanged, so v is what they repeat */
+      for (int k = 0; k < DC_BPL; k++)
+        { v = msk[k] ? ((v+add[k]) & 0x7fffu) : ((v+add[k]) & 0xffffu);
+          tab[lane*DC_BPL+k] = (v << 16) | o;
+          o += cnt[k];
+        }
+      const unsigned v_end = v;
       CPG_SYNCWARP();
-      for (int t = lane; t < total; t += CPG_WARP)
-        { /* owner of output t = LAST lane whose exclusive offset is <= t (tokens that emit
-             nothing share the offset of their successor) */
-          int lo = 0, hi2 = CPG_WARP-1;
-          while (lo < hi2)
-            { int mid = (lo+hi2+1) >> 1;
-              if (offs[mid] <= t) lo = mid; else hi2 = mid-1;
+
+      /* ---- expansion: outputs n .. n+total-1 ---- */
+      if (total > 0)
+        { const int end = n+total;
+          /* groups of 8 counts whose address is 16-byte aligned: positions p with (p+sh) % 8 == 0 */
+          const int g0 = ((n+sh+7) & ~7)-sh, g1 = ((end+sh) & ~7)-sh;
+          if (g0 < g1)
+            { for (int p = g0+8*lane; p < g1; p += 8*CPG_WARP)
+                { int t = p-n, s = dc_owner(tab,t);
+                  unsigned w[4] = {0,0,0,0};
+                  for (int e = 0; e < 8; e++, t++)
+                    { while (s+1 < DC_SLOTS && (int)(tab[s+1] & 0xffffu) <= t) s++;
+                      w[e >> 1] |= (tab[s] >> 16) << ((e & 1)*16);
+                    }
+                  if (p+8 <= cap)
+                    {
+#ifdef CPG_HOSTSIM
+                      for (int e = 0; e < 8; e++) out[p+e] = (uint16_t)((w[e >> 1] >> ((e & 1)*16)) & 0xffffu);
+#else
+                      *reinterpret_cast<uint4 *>(out+p) = make_uint4(w[0],w[1],w[2],w[3]);
+#endif
+                    }
+                  else
+                    for (int e = 0; e < 8; e++)
+                      if (p+e < cap) out[p+e] = (uint16_t)((w[e >> 1] >> ((e & 1)*16)) & 0xffffu);
+                }
             }
-          if (n+t < cap) out[n+t] = (uint16_t)vals[lo];
+          /* ragged head [n,min(g0,end)) and tail [max(g1,g0),end): at most 7 counts each */
+          const int hend = (g0 < end) ? g0 : end;
+          const int tbeg = (g1 > g0) ? g1 : hend;
+          const int nh = hend-n, nt = end-tbeg;
+          for (int i = lane; i < nh+nt; i += CPG_WARP)
+            { const int p = (i < nh) ? n+i : tbeg+(i-nh);
+              if (p < cap) out[p] = (uint16_t)(tab[dc_owner(tab,p-n)] >> 16);
+            }
         }
       CPG_SYNCWARP();
 
       n += total;
-      v_in = dc_shfl(v,CPG_WARP-1);
-      /* carry: the last byte of a full step starts a long token */
-      const unsigned last_first_hi = valid && !second && (x & 0x80);
-      carry = dc_shfl(last_first_hi,CPG_WARP-1);
-      carry_hi = dc_shfl(x,CPG_WARP-1);
+      v_in = dc_shfl(v_end,CPG_WARP-1);
+      carry = dc_shfl((unsigned)sec,CPG_WARP-1);
+      carry_hi = dc_shfl(prev,CPG_WARP-1);
     }
   return n;
 }

@@ -60,7 +60,7 @@ struct ScratchDev
 static inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x+a-1)/a*a; }
 
 /* layout of one warp's scratch; must match scratch_stride() */
-__host__ __device__ static inline size_t scratch_layout(int P, int MC, size_t off[12])
+__host__ __device__ static inline size_t scratch_layout(int P, int MC, size_t off[13])
 { size_t o = 0;
   off[0]  = o; o = align_up(o+sizeof(uint32_t)*(size_t)(P+2),16);        /* mark  */
   off[1]  = o; o = align_up(o+sizeof(double)*4*(size_t)(P+2),16);        /* perr  */
@@ -74,6 +74,7 @@ __host__ __device__ static inline size_t scratch_layout(int P, int MC, size_t of
   off[9]  = o; o = align_up(o+2*(size_t)MC,16);                          /* rpos (fw, bw) */
   off[10] = o; o = align_up(o+sizeof(int32_t)*(size_t)(P+2),16);         /* ord   */
   off[11] = o; o = align_up(o+(size_t)(P+2),16);                         /* fixed */
+  off[12] = o; o = align_up(o+sizeof(cpg_unmemo)*8*(size_t)CPG_MEMO_CAP,16);  /* memo */
   return align_up(o,256);
 }
 
@@ -86,7 +87,7 @@ __device__ __forceinline__ int next_read(int32_t *counter, int lane)
 /* ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(DECODE_THREADS)
 k_decode(BatchDev B, int K)
-{ __shared__ int s_offs[DECODE_THREADS/32][2*CPG_WARP];
+{ __shared__ unsigned s_tab[DECODE_THREADS/32][DC_SLOTS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   for (;;)
     { int q = next_read(B.queue+0,lane);
@@ -95,7 +96,7 @@ k_decode(BatchDev B, int K)
       const int64_t po = B.prof_off[r];
       const int64_t len = B.prof_off[r+1]-po;
       const int cap = B.rlen[r]-K+1;
-      int n = decode_profile(B.prof+po,len,B.cnt+B.cnt_off[r],cap,lane,s_offs[wib]);
+      int n = decode_profile(B.prof+po,len,B.cnt+B.cnt_off[r],cap,lane,s_tab[wib]);
       if (lane == 0)
         { B.plen[r] = n;
           B.status[r] = (n == cap) ? CPG_ST_OK : CPG_ST_BAD_PROFILE;
@@ -124,7 +125,7 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
 
   const size_t gw = (size_t)blockIdx.x*(CLASSIFY_THREADS/32)+wib;
   uint8_t *sb = SC.base+gw*SC.stride;
-  size_t off[12];
+  size_t off[13];
   scratch_layout(SC.P,SC.MC,off);
 
   /* One read per warp, eight/sixteen/thirty-two reads per CTA at a time, taken from the
@@ -167,6 +168,7 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
       R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
       R.S.fixed = sb+off[11];
       R.S.MC = SC.MC;
+      R.S.memo = reinterpret_cast<cpg_unmemo *>(sb+off[12]);
 
       long long t0 = clock64();
       if (active) classify_phase1(R,W);
@@ -352,7 +354,7 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
 /* scratch arena for the persistent classify warps */
 static int ensure_scratch(cpg_ctx *ctx, int P)
 { if (ctx->scratch.p && P <= ctx->SC.P) return CPG_OK;
-  size_t off[12];
+  size_t off[13];
   int MC = P/ctx->model.kmer+8;
   size_t stride = scratch_layout(P,MC,off);
   size_t warps = (size_t)ctx->classify_blocks*(CLASSIFY_THREADS/32);

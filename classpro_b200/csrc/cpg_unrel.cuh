@@ -76,7 +76,7 @@ CPG_DEV_HELPER double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
  *   task 0: E     task 1: R     task 2+4*h+2*side+kind (h: 0=H,1=D; side: 0=left,1=right;
  *   kind 0 = Skellam transition from/to the nearest fixed interval of that state,
  *   kind 1 = log binomial tail of the count against the interpolated coverage) */
-CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N)
+CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *memo, int sweep)
 { const cpg_intvl I = v[idx];
   int ns;
   if (imax(I.cb,I.ce) >= W.M->cov[ST_R]) ns = ST_R;
@@ -84,6 +84,10 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N)
     { double *term = W.ws->term;
       const double *lf = W.M->logfact;
       int bad = 0;
+      /* The second sweep mostly re-asks what the first one computed: the Skellam / binomial
+         arguments of a task change only if a neighbouring interval changed state in between.  The
+         first sweep's arguments and results are kept per interval and reused when they match. */
+      cpg_unmemo *mm = (memo != 0 && idx < CPG_MEMO_CAP) ? memo+(size_t)idx*8 : 0;
       CPG_SYNCWARP();
       CPG_LOOP for (int q = W.lane; q < 10; q += CPG_WARP)
         { double val = -CPG_INF;
@@ -109,9 +113,17 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N)
                   uint16_t c = right ? I.ce : I.cb;
                   if (est >= c) { need_b = 1; bn = est; bc = c; }
                 }
+              const int mkind = need_s ? 1 : (need_b ? 2 : 0);
+              const int mk = need_s ? k : bn;
+              const double ma = need_s ? lambda : (double)bc;
+              if (mm != 0 && sweep == 1 && mm[t].kind == mkind && mm[t].k == mk && mm[t].a == ma)
+                { val = mm[t].val; need_s = need_b = 0; }
+              else
+                { if (need_s) val = cpg_lp_skellam(k,lambda);
+                  if (need_b) val = cpg_log(cpg_p_errorin_lane(lf,ET_OTHERS,0.1,bn,bc,&bad));
+                  if (mm != 0) { mm[t].kind = mkind; mm[t].k = mk; mm[t].a = ma; mm[t].val = val; }
+                }
             }
-          if (need_s) val = cpg_lp_skellam(k,lambda);
-          if (need_b) val = cpg_log(cpg_p_errorin_lane(lf,ET_OTHERS,0.1,bn,bc,&bad));
           term[q] = val;
         }
       CPG_SYNCWARP();
@@ -150,19 +162,21 @@ CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
   const int N = R.N;
   int32_t *ord = R.S.ord;
   uint8_t *fixed = R.S.fixed;
+  /* keys in a compact array first (the wall marks are dead by now), then the ranks */
+  uint32_t *key = R.S.mark;
+  CPG_LOOP for (int i = W.lane; i < N; i += CPG_WARP) key[i] = (uint32_t)imin(v[i].cb,v[i].ce);
+  CPG_SYNCWARP();
   CPG_LOOP for (int i = W.lane; i < N; i += CPG_WARP)
-    { const int key = imin(v[i].cb,v[i].ce);
+    { const uint32_t ki = key[i];
       int rank = 0;
-      CPG_LOOP for (int j = 0; j < N; j++)
-        { int kj = imin(v[j].cb,v[j].ce);
-          rank += (kj < key) || (kj == key && j < i);
-        }
+      for (int j = 0; j < i; j++) rank += (key[j] <= ki);
+      for (int j = i+1; j < N; j++) rank += (key[j] < ki);
       ord[rank] = i;
       fixed[i] = (uint8_t)(v[i].is_rel && (v[i].asgn == ST_H || v[i].asgn == ST_D));
     }
   CPG_SYNCWARP();
-  CPG_LOOP for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
-  CPG_LOOP for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N); }
+  CPG_LOOP for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo,0); }
+  CPG_LOOP for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo,1); }
 }
 
 /* ---- the whole read: src/ClassPro.c:229-271, in three phases.

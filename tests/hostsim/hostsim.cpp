@@ -70,12 +70,12 @@ int cpg_sim_sum(int v)
 struct HsWork
   { std::vector<uint32_t> mark; std::vector<double> perr; std::vector<cpg_eintvl> eint;
     std::vector<cpg_intvl> intvl, rint, wint; std::vector<uint16_t> bp;
-    std::vector<uint8_t> af, ab, rpos, fixed; std::vector<int32_t> ord; int mc = 0;
+    std::vector<uint8_t> af, ab, rpos, fixed; std::vector<int32_t> ord; std::vector<cpg_unmemo> memo; int mc = 0;
     void size(int P)
       { int MC = P/2+8;
         mark.assign(P+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
         rint.resize(MC); wint.resize(2*MC); bp.assign(2*MC,0); af.assign(MC,0); ab.assign(MC,0);
-        rpos.assign(2*MC,0); mc = MC; fixed.assign(P+2,0); ord.assign(P+2,0);
+        rpos.assign(2*MC,0); mc = MC; memo.resize((size_t)CPG_MEMO_CAP*8); fixed.assign(P+2,0); ord.assign(P+2,0);
       }
   };
 
@@ -83,7 +83,7 @@ struct LaneJob
   { int lane; const cpg_dmodel *dm; cpg_wshared *ws; RelShared *sh; ReadCtx R; uint8_t *cls; int status;
     int N, M;
     /* decode job */
-    const uint8_t *src; int64_t len; uint16_t *out; int cap; int *offs; int n;
+    const uint8_t *src; int64_t len; uint16_t *out; int cap; unsigned *offs; int n;
   };
 
 static void *lane_classify(void *arg)
@@ -161,7 +161,7 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
       R.S.mark = Wk.mark.data(); R.S.perr = Wk.perr.data(); R.S.eint = Wk.eint.data();
       R.S.intvl = Wk.intvl.data(); R.S.rint = Wk.rint.data(); R.S.wint = Wk.wint.data();
       R.S.bp = Wk.bp.data(); R.S.asg_f = Wk.af.data(); R.S.asg_b = Wk.ab.data();
-      R.S.rpos = Wk.rpos.data(); R.S.ord = Wk.ord.data(); R.S.fixed = Wk.fixed.data(); R.S.MC = Wk.mc;
+      R.S.rpos = Wk.rpos.data(); R.S.ord = Wk.ord.data(); R.S.fixed = Wk.fixed.data(); R.S.MC = Wk.mc; R.S.memo = Wk.memo.data();
     }
   run_lanes(lane_classify,jobs);
   int st = 0;
@@ -176,7 +176,7 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
 }
 
 int hs_decode_profile(const uint8_t *src, int64_t len, uint16_t *out, int cap)
-{ static int offs[2*CPG_WARP];
+{ static unsigned offs[DC_SLOTS];
   LaneJob jobs[CPG_WARP];
   for (int l = 0; l < CPG_WARP; l++)
     { jobs[l].lane = l; jobs[l].src = src; jobs[l].len = len; jobs[l].out = out; jobs[l].cap = cap;
