@@ -18,10 +18,11 @@
  *      tokens is honoured exactly: the low 15 bits of the running count always equal those of the
  *      plain sum, so the count right after the last long token (a max-scan of lane indices) is the
  *      plain sum up to there masked to 15 bits, and 16-bit wrap-around adds continue from it;
- *   3. expansion: exclusive scan of the output counts into a per-warp table of (offset, value)
- *      per token; the lanes then write the step's outputs in aligned groups of eight counts
- *      (one 16-byte store per group), each finding its first token by binary search in the table
- *      and walking forward.  The ragged head and tail of a step are written count by count.
+ *   3. expansion: scans of the output counts and of the number of emitting tokens give a compact
+ *      per-warp table (value, end offset) in stream order; the lanes then write the step's
+ *      outputs in aligned groups of eight counts (one 16-byte store per group), each finding its
+ *      first token by binary search and moving on at most one token per count.  The ragged head
+ *      and tail of a step are written count by count.
  *  Bit-exact on arbitrary byte streams (wrap-around, mask, zero-length runs), not only on
  *  well-formed ones.
  *******************************************************************************************/
@@ -70,21 +71,22 @@ CPG_DEV int dc_clz(unsigned v) { return __clz((int)v); }
 #define DC_BPL    4                      /* bytes per lane per step */
 #define DC_SLOTS  (DC_BPL*CPG_WARP)      /* token slots per step */
 
-/* owner slot of step-relative output t: the LAST slot whose exclusive offset is <= t (slots that
- * emit nothing share the offset of their successor) */
-CPG_DEV int dc_owner(const unsigned *tab, int t)
-{ int lo = 0, hi = DC_SLOTS-1;
+/* The step's table holds one word per EMITTING token, in stream order: count value << 16 | end
+ * offset (exclusive) of its outputs inside the step.  Owner of step-relative output t = first
+ * token whose end offset is > t. */
+CPG_DEV int dc_owner(const unsigned *tab, int ntok, int t)
+{ int lo = 0, hi = ntok-1;
   while (lo < hi)
-    { int mid = (lo+hi+1) >> 1;
-      if ((int)(tab[mid] & 0xffffu) <= t) lo = mid; else hi = mid-1;
+    { int mid = (lo+hi) >> 1;
+      if ((int)(tab[mid] & 0xffffu) > t) hi = mid; else lo = mid+1;
     }
   return lo;
 }
 
 /* Decodes `len` bytes at `src` into at most `cap` counts at `out`; returns the
  * decoded length (which may exceed cap, as Fetch_Profile's return value does).  `tab` is a
- * per-warp shared-memory array of DC_SLOTS words: value << 16 | exclusive output offset of each
- * token slot of the step (a step emits at most 4*32*63 = 8064 < 65536 counts). */
+ * per-warp shared-memory array of DC_SLOTS words (a step emits at most 4*32*63 = 8064 < 65536
+ * counts, so offsets fit 16 bits). */
 CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out, int cap,
                                  int lane, unsigned *tab)
 { if (len <= 0) return 0;
@@ -101,11 +103,27 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
     { /* ---- this lane's four bytes ---- */
       const int64_t p0 = off+(int64_t)lane*DC_BPL;
       unsigned b[DC_BPL]; int nv = 0;
+#ifdef CPG_HOSTSIM
       for (int k = 0; k < DC_BPL; k++)
         { int ok = (p0+k < len);
           b[k] = ok ? src[p0+k] : 0u;
           nv += ok;
         }
+#else
+      { /* two aligned 32-bit loads + a funnel shift instead of four byte loads; the profile buffer
+           is padded, so reading up to 7 bytes past the read's stream stays inside it */
+        unsigned word = 0;
+        nv = (p0 >= len) ? 0 : ((len-p0 >= DC_BPL) ? DC_BPL : (int)(len-p0));
+        if (nv > 0)
+          { const size_t a = (size_t)(src+p0);
+            const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(size_t)3);
+            const unsigned shb = (unsigned)(a & 3)*8;
+            const unsigned lo32 = wp[0], hi32 = shb ? wp[1] : 0u;
+            word = __funnelshift_r(lo32,hi32,shb);
+          }
+        for (int k = 0; k < DC_BPL; k++) b[k] = (k < nv) ? ((word >> (8*k)) & 0xffu) : 0u;
+      }
+#endif
       /* trailing run of high-bit-set bytes among the valid ones; full = all four present and high */
       int trail = 0;
       for (int k = nv-1; k >= 0 && (b[k] & 0x80); k--) trail++;
@@ -148,14 +166,18 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
       unsigned v;
       if (qp < 0) v = (v_in+Sp) & 0xffffu;
       else        v = ((((v_in+Mq) & 0x7fffu)+((Sp-Mq) & 0xffffu)) & 0xffffu);
-      /* ---- token table: exclusive output offset and count value of every slot ---- */
+      /* ---- token table: one entry per emitting token (value, end offset), compacted ---- */
       const unsigned incl = dc_scan_add(C,lane);
       unsigned o = incl-C;
       const int total = (int)dc_shfl(incl,CPG_WARP-1);
+      unsigned m = 0;
+      for (int k = 0; k < DC_BPL; k++) m += (cnt[k] != 0);
+      const unsigned mincl = dc_scan_add(m,lane);
+      unsigned slot = mincl-m;
+      const int ntok = (int)dc_shfl(mincl,CPG_WARP-1);
       for (int k = 0; k < DC_BPL; k++)
         { v = msk[k] ? ((v+add[k]) & 0x7fffu) : ((v+add[k]) & 0xffffu);
-          tab[lane*DC_BPL+k] = (v << 16) | o;
-          o += cnt[k];
+          if (cnt[k] != 0) { o += cnt[k]; tab[slot++] = (v << 16) | o; }
         }
       const unsigned v_end = v;
       CPG_SYNCWARP();
@@ -167,11 +189,12 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
           const int g0 = ((n+sh+7) & ~7)-sh, g1 = ((end+sh) & ~7)-sh;
           if (g0 < g1)
             { for (int p = g0+8*lane; p < g1; p += 8*CPG_WARP)
-                { int t = p-n, s = dc_owner(tab,t);
+                { int t = p-n, s = dc_owner(tab,ntok,t);
+                  unsigned cur = tab[s], cur_end = cur & 0xffffu;
                   unsigned w[4] = {0,0,0,0};
                   for (int e = 0; e < 8; e++, t++)
-                    { while (s+1 < DC_SLOTS && (int)(tab[s+1] & 0xffffu) <= t) s++;
-                      w[e >> 1] |= (tab[s] >> 16) << ((e & 1)*16);
+                    { if ((unsigned)t >= cur_end) { cur = tab[++s]; cur_end = cur & 0xffffu; }   /* every token emits >= 1 */
+                      w[e >> 1] |= (cur >> 16) << ((e & 1)*16);
                     }
                   if (p+8 <= cap)
                     {
@@ -192,7 +215,7 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
           const int nh = hend-n, nt = end-tbeg;
           for (int i = lane; i < nh+nt; i += CPG_WARP)
             { const int p = (i < nh) ? n+i : tbeg+(i-nh);
-              if (p < cap) out[p] = (uint16_t)(tab[dc_owner(tab,p-n)] >> 16);
+              if (p < cap) out[p] = (uint16_t)(tab[dc_owner(tab,ntok,p-n)] >> 16);
             }
         }
       CPG_SYNCWARP();
