@@ -188,25 +188,39 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
           /* groups of 8 counts whose address is 16-byte aligned: positions p with (p+sh) % 8 == 0 */
           const int g0 = ((n+sh+7) & ~7)-sh, g1 = ((end+sh) & ~7)-sh;
           if (g0 < g1)
-            { for (int p = g0+8*lane; p < g1; p += 8*CPG_WARP)
-                { int t = p-n, s = dc_owner(tab,ntok,t);
+            { /* each lane takes a contiguous range of groups: one table search per lane and step,
+                 then a plain walk (stores of a warp instruction are 16*gc bytes apart; L2 merges them) */
+              const int G = (g1-g0) >> 3, gc = (G+CPG_WARP-1)/CPG_WARP;
+              const int gb = lane*gc, ge = (gb+gc < G) ? gb+gc : G;
+              if (gb < ge)
+                { int p = g0+8*gb, t = p-n, s = dc_owner(tab,ntok,t);
                   unsigned cur = tab[s], cur_end = cur & 0xffffu;
-                  unsigned w[4] = {0,0,0,0};
-                  for (int e = 0; e < 8; e++, t++)
-                    { if ((unsigned)t >= cur_end) { cur = tab[++s]; cur_end = cur & 0xffffu; }   /* every token emits >= 1 */
-                      w[e >> 1] |= (cur >> 16) << ((e & 1)*16);
-                    }
-                  if (p+8 <= cap)
-                    {
+                  for (int g = gb; g < ge; g++, p += 8)
+                    { unsigned w[4] = {0,0,0,0};
+                      if ((unsigned)t >= cur_end) { cur = tab[++s]; cur_end = cur & 0xffffu; }       /* every token emits >= 1 */
+                      if ((unsigned)(t+8) <= cur_end)
+                        { /* the whole group lies inside one token (long runs): splat its value */
+                          const unsigned vv = (cur >> 16) | (cur & 0xffff0000u);
+                          w[0] = w[1] = w[2] = w[3] = vv;
+                          t += 8;
+                        }
+                      else
+                        for (int e = 0; e < 8; e++, t++)
+                          { if ((unsigned)t >= cur_end) { cur = tab[++s]; cur_end = cur & 0xffffu; }
+                            w[e >> 1] |= (cur >> 16) << ((e & 1)*16);
+                          }
+                      if (p+8 <= cap)
+                        {
 #ifdef CPG_HOSTSIM
-                      for (int e = 0; e < 8; e++) out[p+e] = (uint16_t)((w[e >> 1] >> ((e & 1)*16)) & 0xffffu);
+                          for (int e = 0; e < 8; e++) out[p+e] = (uint16_t)((w[e >> 1] >> ((e & 1)*16)) & 0xffffu);
 #else
-                      *reinterpret_cast<uint4 *>(out+p) = make_uint4(w[0],w[1],w[2],w[3]);
+                          *reinterpret_cast<uint4 *>(out+p) = make_uint4(w[0],w[1],w[2],w[3]);
 #endif
+                        }
+                      else
+                        for (int e = 0; e < 8; e++)
+                          if (p+e < cap) out[p+e] = (uint16_t)((w[e >> 1] >> ((e & 1)*16)) & 0xffffu);
                     }
-                  else
-                    for (int e = 0; e < 8; e++)
-                      if (p+e < cap) out[p+e] = (uint16_t)((w[e >> 1] >> ((e & 1)*16)) & 0xffffu);
                 }
             }
           /* ragged head [n,min(g0,end)) and tail [max(g1,g0),end): at most 7 counts each */

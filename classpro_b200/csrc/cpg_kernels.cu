@@ -24,6 +24,9 @@
 #include "cpg_decode.cuh"
 
 #define DECODE_THREADS   256
+#ifndef DECODE_MIN_BLOCKS
+#define DECODE_MIN_BLOCKS 4
+#endif
 #ifndef CLASSIFY_THREADS
 #define CLASSIFY_THREADS 128
 #endif
@@ -85,7 +88,7 @@ __device__ __forceinline__ int next_read(int32_t *counter, int lane)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(DECODE_THREADS)
+__global__ void __launch_bounds__(DECODE_THREADS,DECODE_MIN_BLOCKS)
 k_decode(BatchDev B, int K)
 { __shared__ unsigned s_tab[DECODE_THREADS/32][DC_SLOTS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

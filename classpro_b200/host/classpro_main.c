@@ -434,33 +434,49 @@ static void *reader_main(void *arg)
 
 typedef struct { app_t *A; int device; } gpu_arg_t;
 
+static void check_batch_status(batch_t *b)
+{ for (int i = 0; i < b->n_all; i++)
+    { int k = b->slot_of[i];
+      if (k >= 0 && (b->status[k] & (1|2|4|8|64)))
+        { if (b->status[k] & 1)
+            die("Read %lld: rlen (%d) != plen+Km1",(long long)(b->first_id+i+1),b->rlen_all[i]);
+          die("Read %lld: %s",(long long)(b->first_id+i+1),cpg_status_string(b->status[k]));
+        }
+    }
+}
+
+/* one worker per GPU: two batches in flight (slots 0/1), so the copies of one overlap the kernels
+   of the other; finished batches go to the writer, which restores read order */
 static void *gpu_main(void *arg)
 { gpu_arg_t *G = arg; app_t *A = G->A;
   cpg_ctx *ctx = NULL;
   if (cpg_create(&ctx,G->device,A->model,0,0) != CPG_OK)
     die("%s: %s",PROG,cpg_last_error(NULL));
-  batch_t *b;
-  while ((b = q_pop(&A->q_ready)) != NULL)
-    { if (b->n > 0)
+  batch_t *fly[2] = { NULL, NULL };
+  int slot = 0;
+  for (;;)
+    { batch_t *b = q_pop(&A->q_ready);
+      if (b != NULL && b->n > 0)
         { cpg_batch in = { b->n, b->seq_bits, b->pseq, b->seq_off, b->rlen, b->prof, b->prof_off };
-          cpg_result out = { b->cls, b->cls_off, b->status };
-          int rc = cpg_classify(ctx,&in,&out);
-          if (rc == CPG_EREAD)
-            { for (int i = 0; i < b->n_all; i++)
-                { int k = b->slot_of[i];
-                  if (k >= 0 && (b->status[k] & (1|2|4|8|64)))
-                    { if (b->status[k] & 1)
-                        die("Read %lld: rlen (%d) != plen+Km1",(long long)(b->first_id+i+1),b->rlen_all[i]);
-                      die("Read %lld: %s",(long long)(b->first_id+i+1),cpg_status_string(b->status[k]));
-                    }
-                }
-            }
-          else if (rc != CPG_OK) die("%s: %s",PROG,cpg_last_error(ctx));
+          if (cpg_submit(ctx,slot,&in) != CPG_OK) die("%s: %s",PROG,cpg_last_error(ctx));
         }
-      pthread_mutex_lock(&A->mu);
-      b->next = A->done; A->done = b;
-      pthread_cond_broadcast(&A->cv);
-      pthread_mutex_unlock(&A->mu);
+      batch_t *done = fly[slot ^ 1];          /* the batch submitted before this one */
+      fly[slot ^ 1] = NULL;
+      if (b != NULL) fly[slot] = b;
+      if (done != NULL)
+        { if (done->n > 0)
+            { cpg_result out = { done->cls, done->cls_off, done->status };
+              int rc = cpg_collect(ctx,slot ^ 1,&out);
+              if (rc == CPG_EREAD) check_batch_status(done);
+              else if (rc != CPG_OK) die("%s: %s",PROG,cpg_last_error(ctx));
+            }
+          pthread_mutex_lock(&A->mu);
+          done->next = A->done; A->done = done;
+          pthread_cond_broadcast(&A->cv);
+          pthread_mutex_unlock(&A->mu);
+        }
+      if (b == NULL) break;                  /* queue closed; the last batch in flight was just collected */
+      slot ^= 1;
     }
   cpg_destroy(ctx);
   return NULL;
