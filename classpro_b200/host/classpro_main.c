@@ -47,6 +47,9 @@ static const char *USAGE = "[-vs] [-T<int(4)>] [-c<int>] [-r<int(20000)>] [-P<tm
                            "[-M<model_path>] [-G<int>] [-B<int>] <source>[.f[ast][aq][.gz]]";
 #define MAX_READ_LEN 60000       /* src/const.c:57 */
 
+static double now_s(void);
+static double g_t_reader = 0., g_t_gpu_create = 0., g_t_gpu_busy = 0., g_t_writer = 0.;
+
 static void die(const char *fmt, ...)
 { va_list ap; va_start(ap,fmt); vfprintf(stderr,fmt,ap); va_end(ap); fputc('\n',stderr); exit(1); }
 
@@ -352,6 +355,7 @@ static void *reader_main(void *arg)
   while (!eof && id < A->P.nreads)
     { batch_t *b = q_pop(&A->q_free);
       if (b == NULL) break;
+      const double t_r0 = now_s();
       b->first_id = id; b->n_all = 0; b->n = 0; b->kmers = 0; b->seq_bits = 2;
       int64_t bases = 0; size_t pseq = 0, prof = 0, cls = 0;
       /* pass 1: parse records, keep header + sequence text */
@@ -420,6 +424,7 @@ static void *reader_main(void *arg)
           b->seq_off[k] = so;
           b->seq_bits = 8;
         }
+      g_t_reader += now_s()-t_r0;
       if (b->n_all == 0) { q_push(&A->q_free,b); break; }
       q_push(&A->q_ready,b);
     }
@@ -450,12 +455,15 @@ static void check_batch_status(batch_t *b)
 static void *gpu_main(void *arg)
 { gpu_arg_t *G = arg; app_t *A = G->A;
   cpg_ctx *ctx = NULL;
+  const double t_c0 = now_s();
   if (cpg_create(&ctx,G->device,A->model,0,0) != CPG_OK)
     die("%s: %s",PROG,cpg_last_error(NULL));
+  if (G->device == 0) g_t_gpu_create = now_s()-t_c0;
   batch_t *fly[2] = { NULL, NULL };
   int slot = 0;
   for (;;)
     { batch_t *b = q_pop(&A->q_ready);
+      const double t_g0 = now_s();
       if (b != NULL && b->n > 0)
         { cpg_batch in = { b->n, b->seq_bits, b->pseq, b->seq_off, b->rlen, b->prof, b->prof_off };
           if (cpg_submit(ctx,slot,&in) != CPG_OK) die("%s: %s",PROG,cpg_last_error(ctx));
@@ -475,6 +483,7 @@ static void *gpu_main(void *arg)
           pthread_cond_broadcast(&A->cv);
           pthread_mutex_unlock(&A->mu);
         }
+      if (G->device == 0) g_t_gpu_busy += now_s()-t_g0;
       if (b == NULL) break;                  /* queue closed; the last batch in flight was just collected */
       slot ^= 1;
     }
@@ -505,6 +514,7 @@ static void *writer_main(void *arg)
         }
       pthread_mutex_unlock(&A->mu);
       if (b == NULL) break;
+      const double t_w0 = now_s();
       for (int i = 0; i < b->n_all; i++)
         { const int rlen = b->rlen_all[i], k = b->slot_of[i];
           fputs(b->header[i],out); fputc('\n',out);
@@ -518,6 +528,7 @@ static void *writer_main(void *arg)
           else fprintf(out,"%*s",rlen,rasgn);
           fputc('\n',out);
         }
+      g_t_writer += now_s()-t_w0;
       pthread_mutex_lock(&A->mu);
       A->next_id = b->first_id+b->n_all;
       A->kmers += b->kmers;
@@ -535,6 +546,11 @@ static void *writer_main(void *arg)
  * --------------------------------------------------------------------------------------- */
 static struct timespec T0;
 static struct rusage   R0;
+
+static double now_s(void)
+{ struct timespec t; clock_gettime(CLOCK_MONOTONIC,&t);
+  return (t.tv_sec-T0.tv_sec)+(t.tv_nsec-T0.tv_nsec)*1e-9;
+}
 
 static void time_line(FILE *f, const char *what)
 { struct timespec t; struct rusage r;
@@ -658,6 +674,8 @@ int main(int argc, char **argv)
   if (A->verbose)
     { time_line(stderr,"Resources for phase:");
       fprintf(stderr,"Classified %lld k-mers of %lld reads\n",(long long)A->kmers,(long long)A->total_reads);
+      fprintf(stderr,"    stage seconds: reader %.3f (parse+pack+profile read), GPU0 context %.3f, GPU0 submit/collect %.3f, writer %.3f\n",
+              g_t_reader,g_t_gpu_create,g_t_gpu_busy,g_t_writer);
       time_line(stderr,"Total Resources:");
     }
   return 0;

@@ -252,3 +252,53 @@ def test_full_size_properties(kit, cp):
     kmers, flips = compare_with_oracle(kit, sim, bs, ks, cs, om)
     assert flips <= int(kmers * FLIP_BUDGET)
     ctx.close()
+
+
+def test_cli_fastq_gz_and_header_quirks(kit, cp, tmp_path):
+    """FASTQ.gz input, and the header quirks that are part of the byte contract:
+    no comment on the first record -> "(null)", a tab-separated comment, a comment-less record after
+    one with a comment -> the stale comment is printed again; wrapped sequence lines."""
+    import gzip
+    if not kit.have_reference():
+        pytest.skip("oracle/_ref/ClassPro not present")
+    sim = kit.simulate(write_to=str(tmp_path), root="q", seed=83, genome_len=40000, cov=20., het=0.01, len_mean=7000,
+                       short_reads=1, nparts=2)
+    os.remove(str(tmp_path / "q.fasta"))
+    with gzip.open(str(tmp_path / "q.fastq.gz"), "wb") as f:
+        for i in range(sim.nreads):
+            s = sim.read_ascii(i).tobytes()
+            if i == 0:
+                hdr = b"@r0"
+            elif i % 5 == 1:
+                hdr = b"@r%d\tcomm ent %d" % (i, i)
+            elif i % 5 == 2:
+                hdr = b"@r%d" % i
+            else:
+                hdr = b"@" + sim.headers[i].replace(b"Sim ", b"Sim_", 1)
+            f.write(hdr + b"\n")
+            if i % 3 == 0 and len(s) > 100:          # wrapped sequence (FASTA style wrapping is legal in kseq)
+                f.write(s[:61] + b"\n" + s[61:] + b"\n")
+            else:
+                f.write(s + b"\n")
+            f.write(b"+\n" + b"I" * len(s) + b"\n")
+    fq = str(tmp_path / "q.fastq.gz")
+    ref = kit.run_reference(fq, threads=1)
+    os.rename(ref, ref + ".ref")
+    p = subprocess.run([CLI, fq], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-1500:]
+    assert filecmp.cmp(ref, ref + ".ref", shallow=False)
+    head = open(ref, "rb").read(200)
+    assert head.startswith(b"@r0 (null)\n")
+
+
+def test_cli_errors(kit, cp, tmp_path):
+    """Same failure behaviour as the reference for a missing profile, -M and .db inputs."""
+    kit.simulate(write_to=str(tmp_path), root="e", seed=84, genome_len=20000, cov=12., het=0.01, len_mean=5000)
+    fa = str(tmp_path / "e.fasta")
+    os.remove(str(tmp_path / "e.prof"))
+    p = subprocess.run([CLI, fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 1 and "Cannot open" in p.stderr
+    p = subprocess.run([CLI, "-Mmodel", fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 1 and "-M" in p.stderr
+    p = subprocess.run([CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 1 and p.stderr.startswith("Usage: ClassPro")
