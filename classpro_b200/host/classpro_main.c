@@ -20,7 +20,7 @@
  *                    per-thread part files and concatenates them, src/io.c:70-112).
  *  -T is accepted for compatibility (it no longer selects the degree of parallelism), -P is
  *  accepted and unused (no part files), -G<n> limits the number of GPUs (default: all),
- *  -B<n> sets the batch size in megabases (default 256).
+ *  -B<n> sets the batch size in megabases (default 64).
  *  Not supported, with a clear error: .db/.dam inputs (DAZZ_DB is out of scope), -M (needs GSL).
  *  -s is accepted and ignored with a note: in the reference it never changes .class bytes and
  *  crashes on FASTX input (src/ClassPro.c:281-282, src/seed.c:548-572).
@@ -567,7 +567,7 @@ static const char *EXT[10] = { ".db",".dam",".fastq",".fasta",".fq",".fa",".fast
 int main(int argc, char **argv)
 { clock_gettime(CLOCK_MONOTONIC,&T0); getrusage(RUSAGE_SELF,&R0);
   app_t *A = calloc(1,sizeof(app_t));
-  A->nthreads = 4; A->read_len = 20000; A->ngpus = 0; A->batch_bases = 256000000;
+  A->nthreads = 4; A->read_len = 20000; A->ngpus = 0; A->batch_bases = 64000000;
   int npos = 0; char *pos = NULL;
   for (int i = 1; i < argc; i++)
     { char *a = argv[i];
