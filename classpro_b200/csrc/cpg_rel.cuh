@@ -30,6 +30,7 @@ struct RelState
 struct RelShared
   { RelState col[2][4];
     double   tr[16];
+    int      bpb[4];          /* back pointer of each target state, gathered by lane 0 */
   };
 
 struct RelRun
@@ -129,7 +130,8 @@ CPG_DEV void rl_extend_path(RelState &dst, const RelState &P, int t, int i)
 
 /* src/class_rel.c:279-513 */
 CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelState *prv, RelState *cur)
-{ const int F = U.F;
+{ (void)R;
+  const int F = U.F;
   const cpg_dmodel *M = W.M;
   cpg_intvl *wint = U.wint;
   const cpg_intvl I = wint[i];
@@ -195,11 +197,11 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
       CPG_SYNCGROUP(W);
     }
 
-  uint16_t bpw = 0;
-  CPG_LOOP for (int t = 0; t < 4; t++)
+  /* the four target states are independent: one lane each */
+  CPG_LOOP for (int t = W.glane; t < 4; t += W.gsize)
     { double mlp;
       int ms = rl_best_from(prv,tr,t,&mlp);
-      bpw |= (uint16_t)(ms << (3*t));
+      U.sh->bpb[t] = ms;
       RelState ns;
       ns.dp = mlp; ns.dhr = -CPG_INF;
       CPG_LOOP for (int k = 0; k < 4; k++) { ns.pos[k] = 0; ns.cnt[k] = 0; }
@@ -234,9 +236,11 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
             }
           if (!(ns.cnt[ST_H] < ns.cnt[ST_D] && ns.cnt[ST_D] < ns.cnt[ST_R])) ns.dp = -CPG_INF;
         }
-      if (W.glane == 0) cur[t] = ns;
+      cur[t] = ns;
     }
-  if (W.glane == 0) U.bp[i] = bpw;
+  CPG_SYNCGROUP(W);
+  if (W.glane == 0)
+    U.bp[i] = (uint16_t)(U.sh->bpb[0] | (U.sh->bpb[1] << 3) | (U.sh->bpb[2] << 6) | (U.sh->bpb[3] << 9));
   CPG_SYNCGROUP(W);
 }
 

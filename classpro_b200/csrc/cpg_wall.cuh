@@ -83,27 +83,6 @@ CPG_DEV_HELPER double perr_get(const ReadCtx &R, int pos, int e, int w)
   return s ? R.S.perr[(size_t)(s-1)*4+e*2+w] : -CPG_INF;
 }
 
-/* src/wall.c:310-315: first writer wins, with the caller's error rate */
-CPG_DEV_NOINL void perr_once(ReadCtx &R, WCtx &W, int pos, int e, int w,
-                             uint16_t cout, uint16_t cin, double erate)
-{ if (perr_get(R,pos,e,w) != -CPG_INF) return;
-  double v = cpg_p_errorin(W,e,erate,cout,cin);
-  unsigned m = R.S.mark[pos];
-  unsigned s = m >> 8;
-  CPG_SYNCWARP();
-  if (s == 0)
-    { s = (unsigned)(++R.nslots);
-      if (W.lane == 0)
-        { R.S.mark[pos] = m | (s << 8);
-          double *q = R.S.perr+(size_t)(s-1)*4;
-          q[0] = q[1] = q[2] = q[3] = -CPG_INF;
-        }
-      CPG_SYNCWARP();
-    }
-  if (W.lane == 0) R.S.perr[(size_t)(s-1)*4+e*2+w] = v;
-  CPG_SYNCWARP();
-}
-
 /* src/wall.c:317-322 */
 CPG_DEV_HELPER double lp_diff_pair(const ReadCtx &R, const WCtx &W, int i, int j)
 { const uint16_t *p = R.prof;

@@ -302,3 +302,26 @@ def test_cli_errors(kit, cp, tmp_path):
     assert p.returncode == 1 and "-M" in p.stderr
     p = subprocess.run([CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 1 and p.stderr.startswith("Usage: ClassPro")
+
+
+def test_cli_raw_byte_sequences(kit, cp, tmp_path):
+    """Lower-case bases: the reference compares raw characters (src/context.c), so 'a' != 'A' changes the
+    run lengths; the CLI must ship such batches as bytes (seq_bits = 8) and still match."""
+    if not kit.have_reference():
+        pytest.skip("oracle/_ref/ClassPro not present")
+    kit.simulate(write_to=str(tmp_path), root="lc", seed=85, genome_len=60000, cov=25., het=0.01, repeat_frac=0.5,
+                 len_mean=8000)
+    fa = str(tmp_path / "lc.fasta")
+    rng = np.random.default_rng(3)
+    lines = open(fa, "rb").read().split(b"\n")
+    for i in range(1, len(lines), 2):
+        s = bytearray(lines[i])
+        for p in rng.integers(0, max(1, len(s)), size=max(1, len(s) // 200)):
+            s[p:p + 3] = bytes(s[p:p + 3]).lower()
+        lines[i] = bytes(s)
+    open(fa, "wb").write(b"\n".join(lines))
+    ref = kit.run_reference(fa, threads=1)
+    os.rename(ref, ref + ".ref")
+    p = subprocess.run([CLI, fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-1500:]
+    assert filecmp.cmp(ref, ref + ".ref", shallow=False)
