@@ -36,6 +36,9 @@
     unsigned cpg_sim_shfl(unsigned v, int src);
     unsigned cpg_sim_shfl_up(unsigned v, int d);
     int      cpg_sim_sum(int v);
+    unsigned cpg_sim_gballot(unsigned mask, int pred);
+    int      cpg_sim_gsum(unsigned mask, int v);
+    unsigned cpg_sim_gshfl(unsigned mask, unsigned v, int src);
     #define CPG_SYNCWARP() cpg_sim_barrier()
     void     cpg_sim_group_barrier(unsigned mask);
     #define CPG_SYNCGROUP(W) cpg_sim_group_barrier((W).gmask)
@@ -150,8 +153,9 @@ struct cpg_unmemo { double a; double val; int32_t k; int32_t kind; };
 
 /* Per-warp scratch in global memory, sized for the longest profile of the batch */
 typedef struct
-  { uint32_t   *mark;     /* [P+2]   flags | (slot+1)<<8 per profile position 0..plen */
-    double     *perr;     /* [(P+2)*4] slot-major: [slot][etype][wtype] */
+  { uint8_t    *mark;     /* [P+2+32] flag byte per profile position 0..plen */
+    uint16_t   *slot;     /* [P+2]   probability slot of a position, valid where the flag byte says so */
+    double     *perr;     /* [(P+2)*4] slot-major: [slot][etype][wtype]; sort keys in the last phase */
     cpg_eintvl *eint;     /* [P+2] */
     cpg_intvl  *intvl;    /* [P+2] */
     cpg_intvl  *rint;     /* [MC]  reliable intervals (copy) */
@@ -166,10 +170,9 @@ typedef struct
     struct cpg_unmemo *memo;   /* [CPG_MEMO_CAP*8] first-sweep results of the unreliable-interval tasks */
   } cpg_scratch;
 
-/* Per-warp exchange block (shared memory on the device) */
+/* Exchange block of a lane group (shared memory on the device): task results */
 typedef struct
-  { double term[32];
-    int    iv[32];
+  { double term[24];
   } cpg_wshared;
 
 #endif

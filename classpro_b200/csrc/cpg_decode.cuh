@@ -25,6 +25,13 @@
  *      and tail of a step are written count by count.
  *  Bit-exact on arbitrary byte streams (wrap-around, mask, zero-length runs), not only on
  *  well-formed ones.
+ *
+ *  Fused candidate scan.  find_wall starts from the positions i >= 1 whose count differs from the
+ *  previous one by at least MIN_CNT_CHANGE while the smaller of the two is below the repeat
+ *  threshold (src/wall.c:590-608).  Such a position is always the first output of a token (counts
+ *  do not change inside a run), so the decoder, which has both values in registers, sets bit i of
+ *  the read's candidate bit map right there; k_classify then walks the bit map (1 bit per
+ *  position) instead of sweeping the counts again (16 bits per position).
  *******************************************************************************************/
 #ifndef CPG_DECODE_CUH
 #define CPG_DECODE_CUH
@@ -87,9 +94,26 @@ CPG_DEV int dc_owner(const unsigned *tab, int ntok, int t)
  * decoded length (which may exceed cap, as Fetch_Profile's return value does).  `tab` is a
  * per-warp shared-memory array of DC_SLOTS words (a step emits at most 4*32*63 = 8064 < 65536
  * counts, so offsets fit 16 bits). */
+#if defined(CPG_HOSTSIM)
+CPG_DEV void dc_or(uint32_t *w, uint32_t bit) { __atomic_fetch_or(w,bit,__ATOMIC_RELAXED); }
+#else
+CPG_DEV void dc_or(uint32_t *w, uint32_t bit) { atomicOr(w,bit); }
+#endif
+
+/* the candidate test of src/wall.c:594-608 on two neighbouring counts */
+CPG_DEV int dc_is_cand(unsigned a, unsigned b, int rcov)
+{ const int d = (a > b) ? (int)(a-b) : (int)(b-a);
+  return d >= CPG_MIN_CNT_CHANGE && (int)((a < b) ? a : b) < rcov;
+}
+
+/* `cand` (may be NULL) is the read's candidate bit map, ceil(cap/32) words, zeroed here. */
 CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out, int cap,
-                                 int lane, unsigned *tab)
-{ if (len <= 0) return 0;
+                                 int lane, unsigned *tab, uint32_t *cand, int rcov)
+{ if (cand != 0)
+    { for (int w = lane; w < (cap+31)/32; w += CPG_WARP) cand[w] = 0u;
+      CPG_SYNCWARP();
+    }
+  if (len <= 0) return 0;
   unsigned x0 = src[0];
   unsigned v_in; int64_t off;
   if (x0 & 0x80) { v_in = ((x0 & 0x7f) << 8) | (len > 1 ? src[1] : 0); off = 2; }
@@ -176,8 +200,15 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
       unsigned slot = mincl-m;
       const int ntok = (int)dc_shfl(mincl,CPG_WARP-1);
       for (int k = 0; k < DC_BPL; k++)
-        { v = msk[k] ? ((v+add[k]) & 0x7fffu) : ((v+add[k]) & 0xffffu);
-          if (cnt[k] != 0) { o += cnt[k]; tab[slot++] = (v << 16) | o; }
+        { const unsigned vb = v;
+          v = msk[k] ? ((v+add[k]) & 0x7fffu) : ((v+add[k]) & 0xffffu);
+          if (cnt[k] != 0)
+            { if (cand != 0 && dc_is_cand(vb,v,rcov))
+                { const int p = n+(int)o;                          /* first output of this token */
+                  if (p < cap) dc_or(cand+(p >> 5),1u << (p & 31));
+                }
+              o += cnt[k]; tab[slot++] = (v << 16) | o;
+            }
         }
       const unsigned v_end = v;
       CPG_SYNCWARP();

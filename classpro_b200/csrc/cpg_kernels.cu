@@ -43,7 +43,8 @@ struct BatchDev
     const uint8_t *prof;
     const int64_t *prof_off;
     uint16_t      *cnt;
-    const int64_t *cnt_off;
+    const int64_t *cnt_off;      /* multiples of 32 counts (rows are 64-byte aligned) */
+    uint32_t      *cand;         /* wall-candidate bit map, bit cnt_off[r]+i = position i of read r (NULL: not wanted) */
     int32_t       *plen;
     uint8_t       *cls;
     const int64_t *cls_off;
@@ -63,9 +64,10 @@ struct ScratchDev
 static inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x+a-1)/a*a; }
 
 /* layout of one warp's scratch; must match scratch_stride() */
-__host__ __device__ static inline size_t scratch_layout(int P, int MC, size_t off[13])
+__host__ __device__ static inline size_t scratch_layout(int P, int MC, size_t off[14])
 { size_t o = 0;
-  off[0]  = o; o = align_up(o+sizeof(uint32_t)*(size_t)(P+2),16);        /* mark  */
+  off[0]  = o; o = align_up(o+(size_t)(P+2+32),16);                      /* mark  */
+  off[13] = o; o = align_up(o+sizeof(uint16_t)*(size_t)(P+2),16);        /* slot  */
   off[1]  = o; o = align_up(o+sizeof(double)*4*(size_t)(P+2),16);        /* perr  */
   off[2]  = o; o = align_up(o+sizeof(cpg_eintvl)*(size_t)(P+2),16);      /* eint  */
   off[3]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)(P+2),16);       /* intvl */
@@ -89,7 +91,7 @@ __device__ __forceinline__ int next_read(int32_t *counter, int lane)
 
 /* ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(DECODE_THREADS,DECODE_MIN_BLOCKS)
-k_decode(BatchDev B, int K)
+k_decode(BatchDev B, int K, int rcov)
 { __shared__ unsigned s_tab[DECODE_THREADS/32][DC_SLOTS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   for (;;)
@@ -99,7 +101,8 @@ k_decode(BatchDev B, int K)
       const int64_t po = B.prof_off[r];
       const int64_t len = B.prof_off[r+1]-po;
       const int cap = B.rlen[r]-K+1;
-      int n = decode_profile(B.prof+po,len,B.cnt+B.cnt_off[r],cap,lane,s_tab[wib]);
+      const int64_t co = B.cnt_off[r];
+      int n = decode_profile(B.prof+po,len,B.cnt+co,cap,lane,s_tab[wib],B.cand ? B.cand+(co >> 5) : 0,rcov);
       if (lane == 0)
         { B.plen[r] = n;
           B.status[r] = (n == cap) ? CPG_ST_OK : CPG_ST_BAD_PROFILE;
@@ -108,57 +111,86 @@ k_decode(BatchDev B, int K)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Lanes per read in k_classify: a read is owned by an aligned group of CPG_GROUP lanes, so a warp
+   works on 32/CPG_GROUP reads whose (mostly serial, latency-bound) instruction streams interleave;
+   the lane-parallel task lists of the per-read code are at most 23 long and mostly shorter. */
+#ifndef CPG_GROUP
+#define CPG_GROUP 16
+#endif
+#define CLASSIFY_GROUPS (CLASSIFY_THREADS/CPG_GROUP)
+
+/* the count-threshold table sits in shared memory unless the per-group blocks need the room
+   (groups of 8 lanes: 128 reads per CTA); then it is read through the read-only global path */
+#if CPG_GROUP >= 16
+#define CPG_CTHRES_SMEM 1
+#else
+#define CPG_CTHRES_SMEM 0
+#endif
+
 struct ClassifyShared
-  { uint8_t     cthres[CPG_LROWS*256*4];
+  {
+#if CPG_CTHRES_SMEM
+    uint8_t     cthres[CPG_LROWS*256*4];
+#endif
     cpg_dmodel  model;
-    cpg_wshared ws[CLASSIFY_THREADS/32];
-    RelShared   rel[CLASSIFY_THREADS/32][2];
+    cpg_wshared ws[CLASSIFY_GROUPS];
+    RelShared   rel[CLASSIFY_GROUPS][2];
   };
 
 __global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
 k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { extern __shared__ __align__(16) unsigned char smem_raw[];
   ClassifyShared &sh = *reinterpret_cast<ClassifyShared *>(smem_raw);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int gib = threadIdx.x/CPG_GROUP;              /* group in the CTA */
+  const int glane = threadIdx.x & (CPG_GROUP-1);
+  const int gbase = lane-glane;
+  const unsigned gmask = ((CPG_GROUP >= 32) ? 0xffffffffu : ((1u << CPG_GROUP)-1u)) << gbase;
 
+#if CPG_CTHRES_SMEM
   for (int i = threadIdx.x; i < CPG_LROWS*256; i += blockDim.x)
     reinterpret_cast<uint32_t *>(sh.cthres)[i] = reinterpret_cast<const uint32_t *>(M.cthres)[i];
+  const uint8_t *cthres = sh.cthres;
+#else
+  const uint8_t *cthres = M.cthres;
+#endif
   if (threadIdx.x == 0) sh.model = M;
   __syncthreads();
 
-  const size_t gw = (size_t)blockIdx.x*(CLASSIFY_THREADS/32)+wib;
-  uint8_t *sb = SC.base+gw*SC.stride;
-  size_t off[13];
+  const size_t gg = (size_t)blockIdx.x*CLASSIFY_GROUPS+gib;
+  uint8_t *sb = SC.base+gg*SC.stride;
+  size_t off[14];
   scratch_layout(SC.P,SC.MC,off);
 
-  /* One read per warp, eight/sixteen/thirty-two reads per CTA at a time, taken from the
-     longest-first queue (neighbouring reads have similar lengths, so the phases of a CTA finish
+  /* One read per lane group, CLASSIFY_GROUPS reads per CTA at a time, taken from the queue in
+     processing order (neighbouring reads have similar lengths, so the phases of a CTA finish
      close together). */
   __shared__ int s_base;
-  const int wpc = CLASSIFY_THREADS/32;
   for (;;)
     { __syncthreads();
-      if (threadIdx.x == 0) s_base = atomicAdd(B.queue+1,wpc);
+      if (threadIdx.x == 0) s_base = atomicAdd(B.queue+1,CLASSIFY_GROUPS);
       __syncthreads();
       const int base = s_base;
       if (base >= B.n_reads) break;
-      const int q = base+wib;
+      const int q = base+gib;
       int active = (q < B.n_reads);
       int r = 0, rlen = 0, plen = 0;
       if (active)
         { r = B.order[q];
           rlen = B.rlen[r]; plen = rlen-M.K+1;
           if (B.status[r] != CPG_ST_OK) active = 0;          /* undecodable profile: left to the host */
-          else if (plen > SC.P) { if (lane == 0) B.status[r] = CPG_ST_BAD_PROFILE; active = 0; }
+          else if (plen > SC.P) { if (glane == 0) B.status[r] = CPG_ST_BAD_PROFILE; active = 0; }
         }
       WCtx W;
-      W.lane = lane; W.M = &sh.model; W.cthres = sh.cthres; W.ws = &sh.ws[wib]; W.status = 0;
-      W.glane = lane; W.gsize = 32; W.gmask = 0xffffffffu;
+      W.lane = lane; W.M = &sh.model; W.cthres = cthres; W.ws = &sh.ws[gib]; W.status = 0;
+      W.glane = glane; W.gsize = CPG_GROUP; W.gbase = gbase; W.gmask = gmask;
       ReadCtx R;
       R.prof = B.cnt+(active ? B.cnt_off[r] : 0); R.plen = plen; R.rlen = rlen;
       R.seq.p = B.seq+(active ? B.seq_off[r] : 0); R.seq.bits = B.seq_bits;
       R.nslots = 0; R.N = 0; R.M = 0;
-      R.S.mark  = reinterpret_cast<uint32_t *>(sb+off[0]);
+      R.S.mark  = sb+off[0];
+      R.S.slot  = reinterpret_cast<uint16_t *>(sb+off[13]);
+      R.cand    = B.cand+(active ? (B.cnt_off[r] >> 5) : 0);
       R.S.perr  = reinterpret_cast<double *>(sb+off[1]);
       R.S.eint  = reinterpret_cast<cpg_eintvl *>(sb+off[2]);
       R.S.intvl = reinterpret_cast<cpg_intvl *>(sb+off[3]);
@@ -178,17 +210,17 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
       long long t1 = clock64();
       __syncthreads();
       long long t2 = clock64();
-      if (active) classify_phase2(R,W,sh.rel[wib]);
+      if (active) classify_phase2(R,W,sh.rel[gib]);
       long long t3 = clock64();
       __syncthreads();
       long long t4 = clock64();
       if (active)
         { int st = classify_phase3(R,W,B.cls+B.cls_off[r]);
-          st = __reduce_or_sync(0xffffffffu,st);
-          if (lane == 0) B.status[r] = st;
+          st = __reduce_or_sync(gmask,st);
+          if (glane == 0) B.status[r] = st;
         }
       long long t5 = clock64();
-      if (lane == 0 && B.phase_cycles)
+      if (glane == 0 && B.phase_cycles)
         { atomicAdd(B.phase_cycles+0,(unsigned long long)(t1-t0));
           atomicAdd(B.phase_cycles+1,(unsigned long long)(t3-t2));
           atomicAdd(B.phase_cycles+2,(unsigned long long)(t5-t4));
@@ -204,7 +236,7 @@ struct DevBuf { void *p; size_t cap; };
 
 struct Slot
   { cudaStream_t stream;
-    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, plen, cls, cls_off, status, order, queue;
+    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue;
     /* small host-side (pinned) staging for arrays the library computes itself */
     int64_t *h_cnt_off; int32_t *h_order; size_t h_cap;
     int32_t *h_status; size_t h_status_cap;
@@ -281,7 +313,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   cudaSetDevice(ctx->device);
   for (int s = 0; s < 2; s++)
     { Slot *S = &ctx->slot[s];
-      DevBuf *bufs[] = { &S->seq,&S->seq_off,&S->rlen,&S->prof,&S->prof_off,&S->cnt,&S->cnt_off,&S->plen,
+      DevBuf *bufs[] = { &S->seq,&S->seq_off,&S->rlen,&S->prof,&S->prof_off,&S->cnt,&S->cnt_off,&S->cand,&S->plen,
                          &S->cls,&S->cls_off,&S->status,&S->order,&S->queue };
       for (unsigned i = 0; i < sizeof(bufs)/sizeof(bufs[0]); i++) if (bufs[i]->p) cudaFree(bufs[i]->p);
       if (S->h_cnt_off) cudaFreeHost(S->h_cnt_off);
@@ -356,11 +388,14 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
 
 /* scratch arena for the persistent classify warps */
 static int ensure_scratch(cpg_ctx *ctx, int P)
-{ if (ctx->scratch.p && P <= ctx->SC.P) return CPG_OK;
-  size_t off[13];
+{ { const char *f = getenv("CPG_FORCE_P");            /* experiment knob: oversize the scratch layout */
+    if (f && atoi(f) > P) P = atoi(f);
+  }
+  if (ctx->scratch.p && P <= ctx->SC.P) return CPG_OK;
+  size_t off[14];
   int MC = P/ctx->model.kmer+8;
   size_t stride = scratch_layout(P,MC,off);
-  size_t warps = (size_t)ctx->classify_blocks*(CLASSIFY_THREADS/32);
+  size_t warps = (size_t)ctx->classify_blocks*CLASSIFY_GROUPS;     /* one scratch block per lane group */
   for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->slot[s].stream);
   int rc = reserve(ctx,&ctx->scratch,stride*warps);
   if (rc) return rc;
@@ -399,17 +434,29 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
       if (b->seq_off[i+1]-b->seq_off[i] < need || b->prof_off[i+1] < b->prof_off[i])
         return set_err(ctx,CPG_EINVAL,"read %d of the batch: inconsistent offsets",i);
       S->h_cnt_off[i] = co;
-      co += (rl-K+1+7) & ~7;
+      co += (rl-K+1+31) & ~31;
       if (rl-K+1 > maxP) maxP = rl-K+1;
       if (rl > maxR) maxR = rl;
     }
   S->h_cnt_off[n] = co;
-  /* counting sort by length, longest first */
+  /* Processing order: counting sort by length, longest first, inside chunks of as many consecutive
+     reads as k_classify has resident lane groups (reads in flight).  Reads of one CTA have similar
+     lengths (its phases end together), the reads in flight stay within a few hundred MB of HBM, and
+     the CTAs of a wave differ in length, so they do not all sit in the same phase at the same time.
+     Measured on the 100 Mb workload: chunk = resident warps 465 ms; half 569 ms; twice 525 ms; whole
+     batch (plain longest-first) 608 ms (profiles/r01_history.md).  CPG_ORDER_CHUNK overrides. */
   { int *bucket = (int *)calloc((size_t)maxR+2,sizeof(int));
     if (bucket == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
-    for (int i = 0; i < n; i++) bucket[maxR-b->rlen[i]+1]++;
-    for (int l = 1; l <= maxR+1; l++) bucket[l] += bucket[l-1];
-    for (int i = 0; i < n; i++) S->h_order[bucket[maxR-b->rlen[i]]++] = i;
+    int chunk = ctx->classify_blocks*CLASSIFY_GROUPS;
+    { const char *f = getenv("CPG_ORDER_CHUNK"); if (f && atoi(f) > 0) chunk = atoi(f); }
+    if (chunk < 1) chunk = 1;
+    for (int c0 = 0; c0 < n; c0 += chunk)
+      { const int c1 = (c0+chunk < n) ? c0+chunk : n;
+        memset(bucket,0,sizeof(int)*((size_t)maxR+2));
+        for (int i = c0; i < c1; i++) bucket[maxR-b->rlen[i]+1]++;
+        for (int l = 1; l <= maxR+1; l++) bucket[l] += bucket[l-1];
+        for (int i = c0; i < c1; i++) S->h_order[c0+bucket[maxR-b->rlen[i]]++] = i;
+      }
     free(bucket);
   }
   rc = ensure_scratch(ctx,maxP);
@@ -421,6 +468,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
       || (rc = reserve(ctx,&S->rlen,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->prof,prof_bytes+16))
       || (rc = reserve(ctx,&S->prof_off,sizeof(int64_t)*(n+1))) || (rc = reserve(ctx,&S->cnt,sizeof(uint16_t)*(size_t)co+16))
       || (rc = reserve(ctx,&S->cnt_off,sizeof(int64_t)*(n+1))) || (rc = reserve(ctx,&S->plen,sizeof(int32_t)*(n+1)))
+      || (rc = reserve(ctx,&S->cand,(size_t)co/8+64))
       || (rc = reserve(ctx,&S->cls,cls_bytes+16)) || (rc = reserve(ctx,&S->cls_off,sizeof(int64_t)*(n+1)))
       || (rc = reserve(ctx,&S->status,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->order,sizeof(int32_t)*(n+1)))
       || (rc = reserve(ctx,&S->queue,64)))
@@ -443,6 +491,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   B.rlen = (const int32_t *)S->rlen.p; B.prof = (const uint8_t *)S->prof.p;
   B.prof_off = (const int64_t *)S->prof_off.p; B.cnt = (uint16_t *)S->cnt.p;
   B.cnt_off = (const int64_t *)S->cnt_off.p; B.plen = (int32_t *)S->plen.p;
+  B.cand = (uint32_t *)S->cand.p;
   B.cls = (uint8_t *)S->cls.p; B.cls_off = (const int64_t *)S->cls_off.p;
   B.status = (int32_t *)S->status.p; B.order = (const int32_t *)S->order.p;
   B.queue = (int32_t *)S->queue.p;
@@ -460,7 +509,7 @@ static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
   if (other->kdone_valid) CU(cudaStreamWaitEvent(st,other->kdone,0));
   CU(cudaMemsetAsync(S->queue.p,0,64,st));
   if (timed) CU(cudaEventRecord(ctx->ev[0],st));
-  k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(S->B,ctx->model.kmer);
+  k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(S->B,ctx->model.kmer,(int)ctx->model.cov[1]);
   if (timed) CU(cudaEventRecord(ctx->ev[1],st));
   k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
   if (timed) CU(cudaEventRecord(ctx->ev[2],st));
@@ -621,7 +670,7 @@ extern "C" int cpg_decode_profiles(cpg_ctx *ctx, int32_t n, const uint8_t *prof,
   TRY(cudaMemcpyAsync(S->order.p,S->h_order,sizeof(int32_t)*n,cudaMemcpyHostToDevice,st));
   TRY(cudaMemsetAsync(S->queue.p,0,sizeof(int32_t)*4,st));
   TRY(cudaMemsetAsync(S->cnt.p,0,sizeof(uint16_t)*cnt_n,st));
-  if (e == cudaSuccess) k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(B,K);
+  if (e == cudaSuccess) k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(B,K,0);
   TRY(cudaGetLastError());
   TRY(cudaMemcpyAsync(counts,S->cnt.p,sizeof(uint16_t)*cnt_n,cudaMemcpyDeviceToHost,st));
   TRY(cudaMemcpyAsync(plen,S->plen.p,sizeof(int32_t)*n,cudaMemcpyDeviceToHost,st));

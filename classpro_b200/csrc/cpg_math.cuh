@@ -12,17 +12,17 @@
 #define CPG_MATH_CUH
 #include "cpg_common.h"
 
-/* Warp context: the same values in every lane except `lane` */
+/* Context of the lane group that owns a read: the same values in every lane of the group except
+ * `lane` / `glane`.  The group is a whole warp or an aligned power-of-two part of one; the
+ * reliable-interval DP splits it once more (forward and backward pass on the two halves). */
 struct WCtx
-  { int               lane;
+  { int               lane;      /* lane in the warp */
     const cpg_dmodel *M;
     const uint8_t    *cthres;    /* shared-memory copy of M->cthres (or M->cthres itself) */
     cpg_wshared      *ws;
     int               status;
-    /* lane group: the whole warp, except in the reliable-interval DP where the two half-warps run
-       the forward and the backward pass at the same time */
-    int               glane, gsize;
-    unsigned          gmask;
+    int               glane, gsize, gbase;   /* lane in the group, lanes in the group, warp lane of group lane 0 */
+    unsigned          gmask;                 /* warp-level mask of the group's lanes */
   };
 
 /* one copy of each in the kernel: the per-read code is executed by up to 32 warps per SM that sit in
@@ -141,59 +141,10 @@ CPG_DEV_HELPER double cpg_lp_binom(WCtx &W, uint16_t k16, uint16_t n16, double p
   return CPG_LDG(lf+n)-CPG_LDG(lf+k)-CPG_LDG(lf+(n-k))+k*cpg_log(p)+(n-k)*cpg_log(1-p);
 }
 
-/* src/prob.c:76-112 with exact = false: one-sided binomial tail summed in the reference's order
- * and cut after the first term below a tenth of the first one.  The lanes evaluate CPG_WARP
- * consecutive terms at a time (the exp() calls); the running sum is then formed serially in the
- * reference's order from the shared term buffer, so the rounding sequence is unchanged. */
-CPG_DEV_NOINL double cpg_binom_tail(WCtx &W, int k, int n, double pe)
-{ k = cpg_clamp_cnt(k & 0xffff); n = cpg_clamp_cnt(n & 0xffff);
-  if (k > n) { W.status |= CPG_ST_BINOM; return 0.; }
-  const double *lf = W.M->logfact;
-  const double lpe = cpg_log(pe), l1mpe = cpg_log(1-pe), mean = n*pe;
-  const double lfn = CPG_LDG(lf+n);
-  double *term = W.ws->term;
-  double p, p_first;
-#define CPG_LBP(x) (lfn-CPG_LDG(lf+(x))-CPG_LDG(lf+(n-(x)))+(x)*lpe+(n-(x))*l1mpe)
-  if ((double)k >= mean)
-    { p = p_first = cpg_exp(CPG_LBP(k));
-      CPG_LOOP for (int x0 = k+1; x0 <= n; x0 += CPG_WARP)
-        { int x = x0+W.lane;
-          if (x <= n) term[W.lane] = cpg_exp(CPG_LBP(x));
-          CPG_SYNCWARP();
-          int cnt = imin(CPG_WARP,n-x0+1), stop = 0;
-          CPG_LOOP for (int l = 0; l < cnt; l++)
-            { double t = term[l];
-              p += t;
-              if (10*t < p_first) { stop = 1; break; }
-            }
-          CPG_SYNCWARP();
-          if (stop) break;
-        }
-    }
-  else
-    { p = p_first = (k == 0) ? 0. : cpg_exp(CPG_LBP(k-1));
-      CPG_LOOP for (int x0 = k-2; x0 >= 0; x0 -= CPG_WARP)
-        { int x = x0-W.lane;
-          if (x >= 0) term[W.lane] = cpg_exp(CPG_LBP(x));
-          CPG_SYNCWARP();
-          int cnt = imin(CPG_WARP,x0+1), stop = 0;
-          CPG_LOOP for (int l = 0; l < cnt; l++)
-            { double t = term[l];
-              p += t;
-              if (10*t < p_first) { stop = 1; break; }
-            }
-          CPG_SYNCWARP();
-          if (stop) break;
-        }
-      p = 1-p;
-    }
-#undef CPG_LBP
-  return p;
-}
-
-/* The same tail evaluated by ONE lane, term after term exactly as the reference loops
- * (src/prob.c:76-112).  Used where several independent tails are wanted at once: each lane takes
- * one, instead of the whole warp sharing the terms of a single tail. */
+/* src/prob.c:76-112 with exact = false: one-sided binomial tail summed in the reference's order and
+ * cut after the first term below a tenth of the first one.  Evaluated by ONE lane, term after term
+ * exactly as the reference loops: the callers want several independent tails at once, so each
+ * lane takes one. */
 CPG_DEV_NOINL double cpg_binom_tail_lane(const double *lf, int k, int n, double pe, int *bad)
 { k = cpg_clamp_cnt(k & 0xffff); n = cpg_clamp_cnt(n & 0xffff);
   if (k > n) { *bad = 1; return 0.; }
@@ -223,12 +174,6 @@ CPG_DEV_NOINL double cpg_binom_tail_lane(const double *lf, int k, int n, double 
 /* p_errorin (src/util.c:46-55) for one lane; the caller guarantees cin <= cout */
 CPG_DEV double cpg_p_errorin_lane(const double *lf, int etype, double erate, int cout, int cin, int *bad)
 { return cpg_binom_tail_lane(lf,(etype == ET_SELF) ? cin : cout-cin,cout,erate,bad); }
-
-/* src/util.c:46-55 */
-CPG_DEV double cpg_p_errorin(WCtx &W, int etype, double erate, uint16_t cout, uint16_t cin)
-{ if (!(cin <= cout)) { W.status |= CPG_ST_BINOM; return 0.; }
-  return cpg_binom_tail(W,(etype == ET_SELF) ? cin : (uint16_t)(cout-cin),cout,erate);
-}
 
 /* src/util.c:24-33 */
 CPG_DEV double cpg_lin_interp(WCtx &W, int x, int p1, uint16_t c1, int p2, uint16_t c2)

@@ -139,8 +139,10 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
   const int ip = rl_pred(i,F);
   double *tr = U.sh->tr;
 
-  CPG_LOOP for (int q = W.glane; q < 16; q += W.gsize)
-    { int s = q >> 2, t = q & 3;
+  /* tasks 0..7 are the H/D targets (one Bessel recurrence each), 8..15 the E/R targets, so that a
+     group of eight lanes runs all the recurrences of a step at the same time */
+  CPG_LOOP for (int q0 = W.glane; q0 < 16; q0 += W.gsize)
+    { const int s = (q0 >> 1) & 3, t = ((q0 < 8) ? ST_H : ST_E)+(q0 & 1), q = s*4+t;
       double v = 0.;
       int need = 0, k = 0; double lambda = 0.;
       if (prv[s].dp != -CPG_INF)
@@ -412,15 +414,17 @@ CPG_DEV_NOINL void classify_reliable(ReadCtx &R, WCtx &W, RelShared *sh)
   if (Mrel == 0) return;
   uint8_t *af = R.S.asg_f, *ab = R.S.asg_b;
   double hf, hb;
-  CPG_SYNCWARP();
-  if (CPG_WARP >= 32)
-    { const int h = W.lane >> 4;
+  CPG_SYNCGROUP(W);
+  if (W.gsize >= 2)
+    { const int hs = W.gsize >> 1, h = (W.glane >= hs);
       WCtx G = W;
-      G.glane = W.lane & 15; G.gsize = 16; G.gmask = h ? 0xffff0000u : 0x0000ffffu; G.status = 0;
+      G.glane = W.glane-(h ? hs : 0); G.gsize = hs; G.gbase = W.gbase+(h ? hs : 0);
+      G.gmask = ((hs >= 32) ? 0xffffffffu : ((1u << hs)-1u)) << G.gbase;
+      G.status = 0;
       double hd = rl_direction(R,G,sh+h,h == 0,Mrel,R.plen,h ? ab : af);
       W.status |= G.status;
       if (G.glane == 0) W.ws->term[h] = hd;
-      CPG_SYNCWARP();
+      CPG_SYNCGROUP(W);
       hf = W.ws->term[0]; hb = W.ws->term[1];
     }
   else
@@ -436,8 +440,8 @@ CPG_DEV_NOINL void classify_reliable(ReadCtx &R, WCtx &W, RelShared *sh)
       else use_b = !(fabs(hf-1.) <= fabs(hb-1.));
     }
   const uint8_t *fin = use_b ? ab : af;
-  CPG_SYNCWARP();
-  if (W.lane == 0)
+  CPG_SYNCGROUP(W);
+  if (W.glane == 0)
     { cpg_intvl *v = R.S.intvl;
       CPG_LOOP for (int ri = 0, ii = 0; ri < Mrel; ri++, ii++)
         { CPG_LOOP while (ii < N && !v[ii].is_rel) ii++;
@@ -445,7 +449,7 @@ CPG_DEV_NOINL void classify_reliable(ReadCtx &R, WCtx &W, RelShared *sh)
           v[ii].asgn = (int8_t)fin[ri];
         }
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
 }
 
 #endif

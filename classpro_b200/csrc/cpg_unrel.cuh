@@ -88,8 +88,8 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *
          arguments of a task change only if a neighbouring interval changed state in between.  The
          first sweep's arguments and results are kept per interval and reused when they match. */
       cpg_unmemo *mm = (memo != 0 && idx < CPG_MEMO_CAP) ? memo+(size_t)idx*8 : 0;
-      CPG_SYNCWARP();
-      CPG_LOOP for (int q = W.lane; q < 10; q += CPG_WARP)
+      CPG_SYNCGROUP(W);
+      CPG_LOOP for (int q = W.glane; q < 10; q += W.gsize)
         { double val = -CPG_INF;
           int need_s = 0, need_b = 0, k = 0, bn = 0, bc = 0; double lambda = 0.;
           if (q == 0) val = un_lp_e(W,I);
@@ -126,7 +126,7 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *
             }
           term[q] = val;
         }
-      CPG_SYNCWARP();
+      CPG_SYNCGROUP(W);
       if (bad) W.status |= CPG_ST_BINOM;
       double mx = -CPG_INF; int ms = -1;
       CPG_LOOP for (int s = ST_E; s <= ST_D; s++)
@@ -151,9 +151,9 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *
       if (ms == -1) { W.status |= CPG_ST_NO_PROB; ms = ST_E; }
       ns = ms;
     }
-  CPG_SYNCWARP();
-  if (W.lane == 0 && I.asgn != ns) v[idx].asgn = (int8_t)ns;
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
+  if (W.glane == 0 && I.asgn != ns) v[idx].asgn = (int8_t)ns;
+  CPG_SYNCGROUP(W);
 }
 
 /* src/class_unrel.c:248-275 */
@@ -162,11 +162,11 @@ CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
   const int N = R.N;
   int32_t *ord = R.S.ord;
   uint8_t *fixed = R.S.fixed;
-  /* keys in a compact array first (the wall marks are dead by now), then the ranks */
-  uint32_t *key = R.S.mark;
-  CPG_LOOP for (int i = W.lane; i < N; i += CPG_WARP) key[i] = (uint32_t)imin(v[i].cb,v[i].ce);
-  CPG_SYNCWARP();
-  CPG_LOOP for (int i = W.lane; i < N; i += CPG_WARP)
+  /* keys in a compact array first (the probability slots are dead by now), then the ranks */
+  uint32_t *key = reinterpret_cast<uint32_t *>(R.S.perr);
+  CPG_LOOP for (int i = W.glane; i < N; i += W.gsize) key[i] = (uint32_t)imin(v[i].cb,v[i].ce);
+  CPG_SYNCGROUP(W);
+  CPG_LOOP for (int i = W.glane; i < N; i += W.gsize)
     { const uint32_t ki = key[i];
       int rank = 0;
       for (int j = 0; j < i; j++) rank += (key[j] <= ki);
@@ -174,7 +174,7 @@ CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
       ord[rank] = i;
       fixed[i] = (uint8_t)(v[i].is_rel && (v[i].asgn == ST_H || v[i].asgn == ST_D));
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
   CPG_LOOP for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo,0); }
   CPG_LOOP for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo,1); }
 }
@@ -193,15 +193,15 @@ CPG_DEV_NOINL int classify_phase3(ReadCtx &R, WCtx &W, uint8_t *cls)
 { const int K = W.M->K;
   if (!(W.status & CPG_ST_EINTVL_OVF)) classify_unreliable(R,W);
   /* emit: 'N' x (K-1), then one class character per k-mer */
-  CPG_LOOP for (int j = W.lane; j < K-1; j += CPG_WARP) cls[j] = 'N';
+  CPG_LOOP for (int j = W.glane; j < K-1; j += W.gsize) cls[j] = 'N';
   const cpg_intvl *v = R.S.intvl;
   CPG_LOOP for (int i = 0; i < R.N; i++)
     { const int a = v[i].asgn;
       const char c = (a == ST_E) ? 'E' : (a == ST_R) ? 'R' : (a == ST_H) ? 'H' : (a == ST_D) ? 'D' : '?';
       const int b = v[i].b, e = v[i].e;
-      CPG_LOOP for (int j = b+W.lane; j < e; j += CPG_WARP) cls[K-1+j] = (uint8_t)c;
+      CPG_LOOP for (int j = b+W.glane; j < e; j += W.gsize) cls[K-1+j] = (uint8_t)c;
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
   return W.status;
 }
 

@@ -5,12 +5,16 @@
  *  bs_eintvl) src/wall.c:264-958 and find_rel_intvl/correct_wall_cnt src/wall.c:960-1051.
  *
  *  Layout differences from the reference (results identical):
- *   - one 32-bit word per profile position holds the wall flags and the index of a lazily
- *     allocated slot of four error probabilities; the reference keeps a flag byte plus four
- *     doubles for every position (33 B/position reset per read, here 4 B/position);
- *   - candidates, lone O-walls and interval boundaries are found by lane-parallel sweeps + ballot
- *     and then handled in position order, because pairing, the first-writer-wins probability
- *     cache and the paired flags are order dependent (src/wall.c:310-315,639-640);
+ *   - one flag byte per profile position (the reference's wall flags plus a "has slot" bit); the
+ *     four error probabilities of a position live in a lazily allocated slot whose 16-bit index
+ *     sits in a side array that never needs a reset (it is only read where the flag says so).
+ *     The reference keeps a flag byte plus four doubles for every position (33 B/position reset
+ *     per read, here 1 B/position);
+ *   - wall candidates come as a bit map written by the profile decoder (cpg_decode.cuh: a
+ *     candidate can only arise at a delta token); lone O-walls and interval boundaries are found by
+ *     lane-parallel sweeps over the flag bytes, 16 positions per lane and load.  All of them are
+ *     then handled in position order, because pairing, the first-writer-wins probability cache
+ *     and the paired flags are order dependent (src/wall.c:310-315,639-640);
  *   - pairs explained by errors in others are not stored: their only use in the reference is to
  *     clear the O-wall flag of both ends (src/wall.c:722-726), which commutes with the rest of
  *     pass A and is done at pairing time;
@@ -23,24 +27,44 @@
 #include "cpg_math.cuh"
 #include "cpg_context.cuh"
 
-/* ---- warp primitives (width 1 in the host-side unit-test build) ---- */
+/* ---- lane-group primitives.  A read is owned by a GROUP of lanes (a whole warp, or an aligned
+ *      half / quarter of one: several reads then share a warp and their instruction streams
+ *      interleave).  Ballots are returned relative to the group (bit j = group lane j).
+ *      Width 1 in the host-side unit-test build. ---- */
 #if defined(CPG_HOSTSIM) && CPG_HOSTSIM == 32
-CPG_DEV unsigned cpg_ballot(int pred) { return cpg_sim_ballot(pred); }
-CPG_DEV int      cpg_warp_sum(int v)  { return cpg_sim_sum(v); }
+CPG_DEV unsigned cpg_gballot(const WCtx &W, int pred) { return cpg_sim_gballot(W.gmask,pred) >> W.gbase; }
+CPG_DEV int      cpg_gsum(const WCtx &W, int v)       { return cpg_sim_gsum(W.gmask,v); }
+CPG_DEV unsigned cpg_gshfl(const WCtx &W, unsigned v, int l) { return cpg_sim_gshfl(W.gmask,v,W.gbase+l); }
 CPG_DEV int      cpg_ffs(unsigned m)  { return __builtin_ffs((int)m); }
 #elif defined(CPG_HOSTSIM)
-CPG_DEV unsigned cpg_ballot(int pred) { return pred ? 1u : 0u; }
-CPG_DEV int      cpg_warp_sum(int v)  { return v; }
+CPG_DEV unsigned cpg_gballot(const WCtx &W, int pred) { (void)W; return pred ? 1u : 0u; }
+CPG_DEV int      cpg_gsum(const WCtx &W, int v)       { (void)W; return v; }
+CPG_DEV unsigned cpg_gshfl(const WCtx &W, unsigned v, int l) { (void)W; (void)l; return v; }
 CPG_DEV int      cpg_ffs(unsigned m)  { return __builtin_ffs((int)m); }
 #else
-CPG_DEV unsigned cpg_ballot(int pred) { return __ballot_sync(0xffffffffu,pred); }
-CPG_DEV int      cpg_warp_sum(int v)  { return __reduce_add_sync(0xffffffffu,v); }
+CPG_DEV unsigned cpg_gballot(const WCtx &W, int pred) { return __ballot_sync(W.gmask,pred) >> W.gbase; }
+CPG_DEV int      cpg_gsum(const WCtx &W, int v)       { return __reduce_add_sync(W.gmask,v); }
+CPG_DEV unsigned cpg_gshfl(const WCtx &W, unsigned v, int l) { return __shfl_sync(W.gmask,v,W.gbase+l); }
 CPG_DEV int      cpg_ffs(unsigned m)  { return __ffs((int)m); }
 #endif
 
-/* flag bits (src/wall.c:264-269) in the low byte of a mark word */
+/* 16 flag bytes at a 16-byte aligned address, as four little-endian words */
+CPG_DEV void cpg_ld16(const uint8_t *p, unsigned w[4])
+{
+#ifdef CPG_HOSTSIM
+  memcpy(w,p,16);
+#else
+  const uint4 v = *reinterpret_cast<const uint4 *>(p);
+  w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#endif
+}
+/* bit 0 of each of the four bytes of x -> bits 0..3 */
+CPG_DEV unsigned cpg_pack4(unsigned x) { return ((x & 0x01010101u)*0x00204081u >> 21) & 0xfu; }
+
+/* flag bits (src/wall.c:264-269) of a mark byte, plus MK_SLOT: slot[] holds this position's slot */
 #define MK_BY_S       0x01u
 #define MK_PAIR_S     0x02u
+#define MK_SLOT       0x04u
 #define MK_BY_O       0x10u
 #define MK_PAIR_O     0x20u
 #define MK_PAIR_MULT  0x40u
@@ -51,6 +75,7 @@ struct ReadCtx
   { const uint16_t *prof;
     int             plen, rlen;
     cpg_seq         seq;
+    const uint32_t *cand;     /* wall-candidate bit map of the read (bit i of word i>>5 = position i) */
     cpg_scratch     S;
     int             nslots;
     int             N, M;
@@ -68,19 +93,19 @@ CPG_DEV unsigned mk_pair(int e) { return e == ET_SELF ? MK_PAIR_S : MK_PAIR_O; }
  * the write (the other lanes may still be reading the old value: the CUDA memory model does not
  * promise lock-step execution) and AFTER it (so that every lane sees the new one). */
 CPG_DEV_HELPER void mark_or(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
-{ CPG_SYNCWARP();
-  if (W.lane == 0) R.S.mark[pos] |= bits;
-  CPG_SYNCWARP();
+{ CPG_SYNCGROUP(W);
+  if (W.glane == 0) R.S.mark[pos] |= (uint8_t)bits;
+  CPG_SYNCGROUP(W);
 }
 CPG_DEV_HELPER void mark_clear(ReadCtx &R, const WCtx &W, int pos, unsigned bits)
-{ CPG_SYNCWARP();
-  if (W.lane == 0) R.S.mark[pos] &= ~bits;
-  CPG_SYNCWARP();
+{ CPG_SYNCGROUP(W);
+  if (W.glane == 0) R.S.mark[pos] &= (uint8_t)~bits;
+  CPG_SYNCGROUP(W);
 }
 
 CPG_DEV_HELPER double perr_get(const ReadCtx &R, int pos, int e, int w)
-{ unsigned s = R.S.mark[pos] >> 8;
-  return s ? R.S.perr[(size_t)(s-1)*4+e*2+w] : -CPG_INF;
+{ if (!(R.S.mark[pos] & MK_SLOT)) return -CPG_INF;
+  return R.S.perr[(size_t)R.S.slot[pos]*4+e*2+w];
 }
 
 /* src/wall.c:317-322 */
@@ -100,20 +125,21 @@ CPG_DEV int thres_ng(int e, int cin, int ct)
 
 /* store a freshly computed probability in the first-writer-wins cache (src/wall.c:310-315) */
 CPG_DEV_NOINL void perr_store(ReadCtx &R, WCtx &W, int pos, int e, int w, double v)
-{ unsigned m = R.S.mark[pos];
-  unsigned s = m >> 8;
-  CPG_SYNCWARP();
-  if (s == 0)
-    { s = (unsigned)(++R.nslots);
-      if (W.lane == 0)
-        { R.S.mark[pos] = m | (s << 8);
-          double *q = R.S.perr+(size_t)(s-1)*4;
+{ const unsigned m = R.S.mark[pos];
+  unsigned s = (m & MK_SLOT) ? R.S.slot[pos] : 0u;
+  CPG_SYNCGROUP(W);
+  if (!(m & MK_SLOT))
+    { s = (unsigned)(R.nslots++);
+      if (W.glane == 0)
+        { R.S.mark[pos] = (uint8_t)(m | MK_SLOT);
+          R.S.slot[pos] = (uint16_t)s;
+          double *q = R.S.perr+(size_t)s*4;
           q[0] = q[1] = q[2] = q[3] = -CPG_INF;
         }
-      CPG_SYNCWARP();
+      CPG_SYNCGROUP(W);
     }
-  if (W.lane == 0) R.S.perr[(size_t)(s-1)*4+e*2+w] = v;
-  CPG_SYNCWARP();
+  if (W.glane == 0) R.S.perr[(size_t)s*4+e*2+w] = v;
+  CPG_SYNCGROUP(W);
 }
 
 /* Everything find_gain/find_drop (src/wall.c:331-507) need to know about one candidate.
@@ -207,15 +233,15 @@ CPG_DEV int ei_before(const cpg_eintvl &x, const cpg_eintvl &y)
 
 /* stable insertion sort; the lists are produced almost in order */
 CPG_DEV_NOINL void ei_sort(cpg_eintvl *a, int n, const WCtx &W)
-{ CPG_SYNCWARP();
-  if (W.lane == 0)
+{ CPG_SYNCGROUP(W);
+  if (W.glane == 0)
     CPG_LOOP for (int i = 1; i < n; i++)
       { cpg_eintvl v = a[i];
         int j = i-1;
         CPG_LOOP while (j >= 0 && ei_before(v,a[j])) { a[j+1] = a[j]; j--; }
         a[j+1] = v;
       }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
 }
 
 /* src/wall.c:548-568 */
@@ -230,14 +256,14 @@ CPG_DEV_HELPER int ei_unique(cpg_eintvl *a, int n, const WCtx &W)
       CPG_LOOP for (int j = i+1; j < n; j++)
         if (!(keep_b == a[j].b && keep_e == a[j].e))
           { keep_b = a[j].b; keep_e = a[j].e; cnt++; }
-      CPG_SYNCWARP();
-      if (W.lane == 0)
+      CPG_SYNCGROUP(W);
+      if (W.glane == 0)
         { int w = i;
           CPG_LOOP for (int j = i+1; j < n; j++)
             if (!(a[w-1].b == a[j].b && a[w-1].e == a[j].e))
               a[w++] = a[j];
         }
-      CPG_SYNCWARP();
+      CPG_SYNCGROUP(W);
       n = cnt;
     }
   return n;
@@ -258,16 +284,16 @@ CPG_DEV_HELPER int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
 }
 
 CPG_DEV_HELPER void ei_put(ReadCtx &R, const WCtx &W, int k, int b, int e, double pe)
-{ CPG_SYNCWARP();
-  if (W.lane == 0) { R.S.eint[k].b = b; R.S.eint[k].e = e; R.S.eint[k].pe = pe; }
-  CPG_SYNCWARP();
+{ CPG_SYNCGROUP(W);
+  if (W.glane == 0) { R.S.eint[k].b = b; R.S.eint[k].e = e; R.S.eint[k].pe = pe; }
+  CPG_SYNCGROUP(W);
 }
 
 /* clear bits on the open range (b,e), lanes striding */
 CPG_DEV_HELPER void mark_clear_range(ReadCtx &R, const WCtx &W, int b, int e, unsigned bits)
-{ CPG_SYNCWARP();
-  CPG_LOOP for (int j = b+1+W.lane; j < e; j += CPG_WARP) R.S.mark[j] &= ~bits;
-  CPG_SYNCWARP();
+{ CPG_SYNCGROUP(W);
+  CPG_LOOP for (int j = b+1+W.glane; j < e; j += W.gsize) R.S.mark[j] &= (uint8_t)~bits;
+  CPG_SYNCGROUP(W);
 }
 
 /* ---- pass A for one candidate position (src/wall.c:606-692) ----
@@ -325,10 +351,10 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
   int bad = 0;
   int fresh[2];
   CPG_LOOP for (int e = 0; e < 2; e++) fresh[e] = reach[e] && perr_get(R,i,e,wtype) == -CPG_INF;
-  CPG_SYNCWARP();
-  CPG_LOOP for (int q = W.lane; q < 2; q += CPG_WARP)
+  CPG_SYNCGROUP(W);
+  CPG_LOOP for (int q = W.glane; q < 2; q += W.gsize)
     if (fresh[q]) term[q] = cpg_p_errorin_lane(lf,q,maxpe,cout,cin,&bad);
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
   int go[2];
   CPG_LOOP for (int e = 0; e < 2; e++)
     { if (fresh[e]) perr_store(R,W,i,e,wtype,term[e]);
@@ -355,8 +381,8 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
         else { G.lc_kind = 2; G.lc_j = j; }
       }
       const int wj = G.fwd ? WT_GAIN : WT_DROP;
-      CPG_SYNCWARP();
-      CPG_LOOP for (int q = W.lane; q < 23; q += CPG_WARP)
+      CPG_SYNCGROUP(W);
+      CPG_LOOP for (int q = W.glane; q < 23; q += W.gsize)
         { double val = 0.;
           int need_b = 0, need_s = 0, be = 0, bco = 0, bci = 0, sj = 0; double ber = 0.;
           if (G.lc_kind != 0)
@@ -388,7 +414,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
           if (need_s) val = G.fwd ? lp_diff_pair(R,W,i,sj) : lp_diff_pair(R,W,sj,i);
           term[q] = val;
         }
-      CPG_SYNCWARP();
+      CPG_SYNCGROUP(W);
 
       if (go[ET_SELF] && pair_replay(R,W,G,ET_SELF,&I) && I.pe >= CPG_PE_FINAL)
         { mark_or(R,W,I.b,MK_BY_S|MK_PAIR_S);
@@ -398,12 +424,12 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
         }
       if (go[ET_OTHERS] && pair_replay(R,W,G,ET_OTHERS,&I) && I.pe >= CPG_PE_FINAL)
         { /* paired O-walls stop being walls (src/wall.c:722-726), see header note */
-          CPG_SYNCWARP();
-          if (W.lane == 0)
-            { R.S.mark[I.b] = (R.S.mark[I.b] | MK_PAIR_O) & ~MK_BY_O;
-              R.S.mark[I.e] = (R.S.mark[I.e] | MK_PAIR_O) & ~MK_BY_O;
+          CPG_SYNCGROUP(W);
+          if (W.glane == 0)
+            { R.S.mark[I.b] = (uint8_t)((R.S.mark[I.b] | MK_PAIR_O) & ~MK_BY_O);
+              R.S.mark[I.e] = (uint8_t)((R.S.mark[I.e] | MK_PAIR_O) & ~MK_BY_O);
             }
-          CPG_SYNCWARP();
+          CPG_SYNCGROUP(W);
           reach[ET_OTHERS] = 0;          /* explained by a pair: not a wall */
         }
     }
@@ -422,12 +448,12 @@ CPG_DEV_NOINL int wall_multi(ReadCtx &R, WCtx &W, int i, int NS, int midx)
       const int jend = (w == WT_DROP) ? imin(i+200,plen+1) : imax(i-200,0);   /* DROP: j < jend; GAIN: j >= jend */
       int done = 0;
       CPG_LOOP for (int jb = (w == WT_DROP) ? i+1 : i-1; !done && ((w == WT_DROP) ? (jb < jend) : (jb >= jend));
-           jb += (w == WT_DROP) ? CPG_WARP : -CPG_WARP)
-        { int j = (w == WT_DROP) ? jb+W.lane : jb-W.lane;
+           jb += (w == WT_DROP) ? W.gsize : -W.gsize)
+        { int j = (w == WT_DROP) ? jb+W.glane : jb-W.glane;
           int in = (w == WT_DROP) ? (j < jend) : (j >= jend);
           int edge = in && (j == ((w == WT_DROP) ? plen : 0));
           unsigned f = in ? (R.S.mark[j] & (MK_BY_S|MK_BY_O)) : 0u;
-          unsigned mask = cpg_ballot(f != 0 || edge);
+          unsigned mask = cpg_gballot(W,f != 0 || edge);
           CPG_LOOP while (mask)
             { int l = cpg_ffs(mask)-1; mask &= mask-1;
               j = (w == WT_DROP) ? jb+l : jb-l;
@@ -467,29 +493,29 @@ CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
 
   last = imin(I.b+K-1,I.e-1);
   { int s = 0;
-    CPG_LOOP for (int p = I.b+W.lane; p < last; p += CPG_WARP) s += imax((int)prof[p+1]-prof[p],0);
-    n_gain += cpg_warp_sum(s);
+    CPG_LOOP for (int p = I.b+W.glane; p < last; p += W.gsize) s += imax((int)prof[p+1]-prof[p],0);
+    n_gain += cpg_gsum(W,s);
   }
   if (I.b+K-1 < I.e)
     { lmax = 0;
       CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_rctx(R.seq,R.rlen,I.b+K-1,t)*(t+1));
       last = I.b+lmax;
       int s = 0;
-      CPG_LOOP for (int p = I.b+W.lane; p < last; p += CPG_WARP) s += imax((int)prof[p]-rc_prof(R,W,p+1),0);
-      n_gain -= cpg_warp_sum(s);
+      CPG_LOOP for (int p = I.b+W.glane; p < last; p += W.gsize) s += imax((int)prof[p]-rc_prof(R,W,p+1),0);
+      n_gain -= cpg_gsum(W,s);
     }
   first = imax(I.e-K+1,I.b);
   { int s = 0;
-    CPG_LOOP for (int p = first+W.lane; p < I.e-1; p += CPG_WARP) s += imax((int)prof[p]-prof[p+1],0);
-    n_drop += cpg_warp_sum(s);
+    CPG_LOOP for (int p = first+W.glane; p < I.e-1; p += W.gsize) s += imax((int)prof[p]-prof[p+1],0);
+    n_drop += cpg_gsum(W,s);
   }
   if (I.b < I.e-K+1)
     { lmax = 0;
       CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_lctx(R.seq,R.rlen,I.e-K+1+K-2,t)*(t+1));
       first = I.e-lmax;
       int s = 0;
-      CPG_LOOP for (int p = first+W.lane; p < I.e-1; p += CPG_WARP) s += imax((int)prof[p+1]-prof[p],0);
-      n_drop -= cpg_warp_sum(s);
+      CPG_LOOP for (int p = first+W.glane; p < I.e-1; p += W.gsize) s += imax((int)prof[p+1]-prof[p],0);
+      n_drop -= cpg_gsum(W,s);
     }
   uint16_t ccb = (uint16_t)imin(I.cb+imax(n_gain,0),CPG_MAX_CNT);
   uint16_t cce = (uint16_t)imin(I.ce+imax(n_drop,0),CPG_MAX_CNT);
@@ -499,9 +525,9 @@ CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
      [max(I.e-2K,I.b),I.e) starts at I.b.  Writes to higher slots hit intervals that are either
      recomputed from scratch later or never read. */
   if (I.b == idx && I.e-2*K <= I.b && cce < I.cb) cce = I.cb;
-  CPG_SYNCWARP();
-  if (W.lane == 0) { R.S.intvl[idx].ccb = ccb; R.S.intvl[idx].cce = cce; }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
+  if (W.glane == 0) { R.S.intvl[idx].ccb = ccb; R.S.intvl[idx].cce = cce; }
+  CPG_SYNCGROUP(W);
 }
 
 /* ---- whole wall stage: fills R.S.intvl[0..N) and R.S.rint[0..M) ---- */
@@ -509,27 +535,36 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
 { const cpg_dmodel *M = W.M;
   const int plen = R.plen, K = M->K;
   const uint16_t *prof = R.prof;
-  uint32_t *mark = R.S.mark;
+  uint8_t *mark = R.S.mark;
   cpg_eintvl *eint = R.S.eint;
 
-  CPG_LOOP for (int i = W.lane; i <= plen; i += CPG_WARP) mark[i] = 0;
+  /* flags of positions 0..plen, 16 per store (the array is padded to a multiple of 16) */
+  CPG_LOOP for (int i = 16*W.glane; i <= plen; i += 16*W.gsize)
+    {
+#ifdef CPG_HOSTSIM
+      memset(mark+i,0,16);
+#else
+      *reinterpret_cast<uint4 *>(mark+i) = make_uint4(0u,0u,0u,0u);
+#endif
+    }
   R.nslots = 0;
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
 
-  /* pass A: candidates in position order */
+  /* pass A: candidates in position order, from the decoder's bit map (32 positions per lane) */
   int eidx = 0;
   const int rcov = M->cov[ST_R];
-  CPG_LOOP for (int base = 1; base < plen; base += CPG_WARP)
-    { int i = base+W.lane, cand = 0;
-      if (i < plen)
-        { int a = prof[i-1], b = prof[i];
-          int d = (a > b) ? a-b : b-a;
-          cand = (imin(a,b) < rcov) && (d >= CPG_MIN_CNT_CHANGE);
-        }
-      unsigned mask = cpg_ballot(cand);
-      CPG_LOOP while (mask)
-        { int l = cpg_ffs(mask)-1; mask &= mask-1;
-          wall_candidate(R,W,base+l,eidx);
+  CPG_LOOP for (int base = 0; base < plen; base += 32*W.gsize)
+    { const int p0 = base+32*W.glane;
+      unsigned cw = (p0 < plen) ? R.cand[p0 >> 5] : 0u;
+      if (p0+32 > plen && p0 < plen) cw &= (1u << (plen-p0))-1u;      /* bits past the profile: none are set, but do not rely on it */
+      unsigned lanes = cpg_gballot(W,cw != 0u);
+      CPG_LOOP while (lanes)
+        { const int l = cpg_ffs(lanes)-1; lanes &= lanes-1;
+          unsigned m = cpg_gshfl(W,cw,l);
+          CPG_LOOP while (m)
+            { const int b = cpg_ffs(m)-1; m &= m-1;
+              wall_candidate(R,W,base+32*l+b,eidx);
+            }
         }
     }
   int NS = eidx;
@@ -538,17 +573,29 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
   CPG_LOOP for (int k = 0; k < NS; k++) mark_clear_range(R,W,eint[k].b,eint[k].e,MK_BY_O);
   NS = ei_unique(eint,eidx,W);
 
-  /* pass C */
+  /* pass C: lone O-walls, 16 flag bytes per lane */
   int midx = NS;
-  CPG_LOOP for (int base = 1; base < plen && !(W.status & CPG_ST_EINTVL_OVF); base += CPG_WARP)
-    { int i = base+W.lane;
-      unsigned f = (i < plen) ? mark[i] : 0u;
-      unsigned mask = cpg_ballot((f & MK_BY_O) && !(f & MK_BY_S));
-      CPG_LOOP while (mask)
-        { int l = cpg_ffs(mask)-1; mask &= mask-1;
-          if (mark[base+l] & MK_PAIR_MULT) continue;
-          midx = wall_multi(R,W,base+l,NS,midx);
-          if (W.status & CPG_ST_EINTVL_OVF) break;
+  CPG_LOOP for (int base = 0; base < plen && !(W.status & CPG_ST_EINTVL_OVF); base += 16*W.gsize)
+    { const int p0 = base+16*W.glane;
+      unsigned hit = 0;
+      if (p0 < plen)
+        { unsigned w[4];
+          cpg_ld16(mark+p0,w);
+          CPG_LOOP for (int k = 0; k < 4; k++) hit |= cpg_pack4((w[k] >> 4) & ~w[k]) << (4*k);     /* BY_O and not BY_S */
+          if (p0 == 0) hit &= ~1u;                                    /* positions 1..plen-1 */
+          if (p0+16 > plen) hit &= (1u << (plen-p0))-1u;
+        }
+      unsigned lanes = cpg_gballot(W,hit != 0u);
+      CPG_LOOP while (lanes)
+        { const int l = cpg_ffs(lanes)-1; lanes &= lanes-1;
+          unsigned m = cpg_gshfl(W,hit,l);
+          CPG_LOOP while (m)
+            { const int b = cpg_ffs(m)-1; m &= m-1;
+              const int i = base+16*l+b;
+              if (mark[i] & MK_PAIR_MULT) continue;
+              midx = wall_multi(R,W,i,NS,midx);
+              if (W.status & CPG_ST_EINTVL_OVF) { lanes = 0; break; }
+            }
         }
     }
   if (W.status & CPG_ST_EINTVL_OVF) { R.N = 0; R.M = 0; return; }
@@ -575,43 +622,56 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
       }
   }
   ei_sort(eint,NS,W);
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
   CPG_LOOP for (int k = 0; k < NS; k++)
-    { CPG_LOOP for (int j = eint[k].b+W.lane; j < eint[k].e; j += CPG_WARP) mark[j] |= MK_ERROR;
-      CPG_SYNCWARP();
+    { CPG_LOOP for (int j = eint[k].b+W.glane; j < eint[k].e; j += W.gsize) mark[j] |= (uint8_t)MK_ERROR;
+      CPG_SYNCGROUP(W);
     }
 
   /* pass E (src/wall.c:921-948) */
   int N = 0, b = 0;
   cpg_intvl *intvl = R.S.intvl;
-  CPG_LOOP for (int base = 1; base <= plen; base += CPG_WARP)
-    { int i = base+W.lane, cut = 0;
-      if (i <= plen)
-        { unsigned m1 = mark[i-1], m0 = mark[i];
-          cut = (i == plen) || (((m1 & MK_ERROR) != 0) != ((m0 & MK_ERROR) != 0))
-                || (!(m0 & MK_ERROR) && (m0 & MK_BY_O));
-        }
-      unsigned mask = cpg_ballot(cut);
-      CPG_LOOP while (mask)
-        { int l = cpg_ffs(mask)-1; mask &= mask-1;
-          int e = base+l;
-          int k = ei_find(eint,0,NS-1,b,e);
-          double pe  = (k != -1) ? cpg_log(eint[k].pe) : -CPG_INF;
-          double pob = dmax_ref(perr_get(R,b,ET_OTHERS,WT_DROP),perr_get(R,b,ET_OTHERS,WT_GAIN));
-          double poe = dmax_ref(perr_get(R,e,ET_OTHERS,WT_DROP),perr_get(R,e,ET_OTHERS,WT_GAIN));
-          double lpob = (pob != -CPG_INF) ? cpg_log(pob) : -CPG_INF;
-          double lpoe = (poe != -CPG_INF) ? cpg_log(poe) : -CPG_INF;
-          if (W.lane == 0)
-            { cpg_intvl *I = intvl+N;
-              I->b = b; I->e = e; I->cb = prof[b]; I->ce = prof[e-1];
-              I->ccb = 0; I->cce = 0; I->is_rel = 0; I->asgn = ST_N;
-              I->pe = pe; I->peob = lpob; I->peoe = lpoe;
+  CPG_LOOP for (int base = 0; base <= plen; base += 16*W.gsize)
+    { const int p0 = base+16*W.glane;
+      unsigned cut = 0;
+      if (p0 <= plen)
+        { unsigned w[4];
+          cpg_ld16(mark+p0,w);
+          unsigned carry = (p0 > 0) ? ((unsigned)mark[p0-1] >> 7) : 0u;       /* error bit of the position before */
+          CPG_LOOP for (int k = 0; k < 4; k++)
+            { const unsigned er = (w[k] >> 7) & 0x01010101u, ow = (w[k] >> 4) & 0x01010101u;
+              const unsigned pv = (er << 8) | carry;
+              cut |= cpg_pack4((er ^ pv) | (~er & ow)) << (4*k);
+              carry = er >> 24;
             }
-          N++;
-          b = e;
+          if (p0 == 0) cut &= ~1u;                                    /* positions 1..plen */
+          if (p0+16 > plen) { cut &= (2u << (plen-p0))-1u; cut |= 1u << (plen-p0); }
+        }
+      unsigned lanes = cpg_gballot(W,cut != 0u);
+      CPG_LOOP while (lanes)
+        { const int ll = cpg_ffs(lanes)-1; lanes &= lanes-1;
+          unsigned mm = cpg_gshfl(W,cut,ll);
+          CPG_LOOP while (mm)
+            { const int bb = cpg_ffs(mm)-1; mm &= mm-1;
+              const int e = base+16*ll+bb;
+              int k = ei_find(eint,0,NS-1,b,e);
+              double pe  = (k != -1) ? cpg_log(eint[k].pe) : -CPG_INF;
+              double pob = dmax_ref(perr_get(R,b,ET_OTHERS,WT_DROP),perr_get(R,b,ET_OTHERS,WT_GAIN));
+              double poe = dmax_ref(perr_get(R,e,ET_OTHERS,WT_DROP),perr_get(R,e,ET_OTHERS,WT_GAIN));
+              double lpob = (pob != -CPG_INF) ? cpg_log(pob) : -CPG_INF;
+              double lpoe = (poe != -CPG_INF) ? cpg_log(poe) : -CPG_INF;
+              if (W.glane == 0)
+                { cpg_intvl *I = intvl+N;
+                  I->b = b; I->e = e; I->cb = prof[b]; I->ce = prof[e-1];
+                  I->ccb = 0; I->cce = 0; I->is_rel = 0; I->asgn = ST_N;
+                  I->pe = pe; I->peob = lpob; I->peoe = lpoe;
+                }
+              N++;
+              b = e;
+            }
         }
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
   R.N = N;
 
   /* reliable intervals (src/wall.c:1016-1037).  Three phases: corrected end counts of every
@@ -627,21 +687,21 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
       if (imax(I.cb,I.ce) >= rcov) continue;
       if (I.pe >= logpthres) continue;
       correct_wall_cnt(R,W,i);
-      if (W.lane == 0) cand[ncand] = i;
+      if (W.glane == 0) cand[ncand] = i;
       ncand++;
     }
-  CPG_SYNCWARP();
-  CPG_LOOP for (int q = W.lane; q < ncand; q += CPG_WARP)
+  CPG_SYNCGROUP(W);
+  CPG_LOOP for (int q = W.glane; q < ncand; q += W.gsize)
     { const cpg_intvl I = intvl[cand[q]];
       const int ccb = I.ccb, cce = I.cce;
       int ok = !(cpg_lp_trans(W,I.b,I.e,ccb,cce,(uint16_t)((ccb+cce)/2)) < CPG_THRES_DIFF_REL);
       if (imax(ccb,cce) == CPG_MAX_CNT) ok = 0;
       keep[q] = (uint8_t)ok;
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
   int Mrel = 0;
   CPG_LOOP for (int q = 0; q < ncand; q++) if (keep[q]) Mrel++;
-  if (W.lane == 0)
+  if (W.glane == 0)
     { int m = 0;
       CPG_LOOP for (int q = 0; q < ncand; q++)
         if (keep[q])
@@ -650,7 +710,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
             R.S.rint[m++] = intvl[i];
           }
     }
-  CPG_SYNCWARP();
+  CPG_SYNCGROUP(W);
   R.M = Mrel;
 }
 

@@ -49,6 +49,10 @@ static const char *USAGE = "[-vs] [-T<int(4)>] [-c<int>] [-r<int(20000)>] [-P<tm
 
 static double now_s(void);
 static double g_t_reader = 0., g_t_gpu_create = 0., g_t_gpu_busy = 0., g_t_writer = 0.;
+/* wall-clock marks (seconds since start) printed with -v: model ready, first pinned buffer, GPU0
+   context, first batch parsed, reader done, last batch collected, writer done */
+static double g_tl_model = 0., g_tl_pinned = 0., g_tl_ctx = 0., g_tl_first = 0., g_tl_reader = 0., g_tl_collect = 0.,
+              g_tl_writer = 0.;
 
 static void die(const char *fmt, ...)
 { va_list ap; va_start(ap,fmt); vfprintf(stderr,fmt,ap); va_end(ap); fputc('\n',stderr); exit(1); }
@@ -301,7 +305,7 @@ static void *pinned(size_t n)
   return p;
 }
 
-static void batch_reserve(batch_t *b, int nrec, size_t pseq, size_t prof, size_t cls)
+static void batch_reserve_records(batch_t *b, int nrec)
 { if (nrec > b->rec_cap)
     { int cap = nrec+nrec/2+64;
       b->header = xrealloc(b->header,sizeof(char *)*(size_t)cap);
@@ -311,6 +315,10 @@ static void batch_reserve(batch_t *b, int nrec, size_t pseq, size_t prof, size_t
       b->slot_of = xrealloc(b->slot_of,sizeof(int32_t)*(size_t)cap);
       b->rec_cap = cap;
     }
+}
+
+static void batch_reserve(batch_t *b, int nrec, size_t pseq, size_t prof, size_t cls)
+{ batch_reserve_records(b,nrec);
   if (nrec > b->n_cap)
     { int cap = nrec+nrec/2+64;
       int64_t *so = pinned(sizeof(int64_t)*(size_t)(cap+1)), *po = pinned(sizeof(int64_t)*(size_t)(cap+1)),
@@ -367,7 +375,7 @@ static void *reader_main(void *arg)
             }
           if (rlen > MAX_READ_LEN)
             die("rlen (%d) > MAX_READ_LEN for FASTX inputs (%d)",rlen,MAX_READ_LEN);
-          batch_reserve(b,b->n_all+1,0,0,0);
+          batch_reserve_records(b,b->n_all+1);          /* no pinned memory yet: CUDA may still be starting */
           const int i = b->n_all++;
           const char *cm = X.have_comment ? X.comment.s : "(null)";      /* src/ClassPro.c:188 */
           size_t hl = strlen(X.name.s)+strlen(cm)+3;
@@ -388,7 +396,9 @@ static void *reader_main(void *arg)
           id++;
         }
       /* pass 2: pack + fetch profiles into pinned memory */
+      if (g_tl_first == 0.) g_tl_first = now_s();
       batch_reserve(b,b->n_all,pseq+16,prof+16,cls+16);
+      if (g_tl_pinned == 0.) g_tl_pinned = now_s();
       int64_t so = 0, po = 0, co = 0;
       int k = 0, bad = 0;
       for (int i = 0; i < b->n_all; i++)
@@ -429,6 +439,7 @@ static void *reader_main(void *arg)
       q_push(&A->q_ready,b);
     }
   pthread_mutex_lock(&A->mu);
+  g_tl_reader = now_s();
   A->reader_done = 1; A->total_reads = id;
   pthread_cond_broadcast(&A->cv);
   pthread_mutex_unlock(&A->mu);
@@ -458,7 +469,7 @@ static void *gpu_main(void *arg)
   const double t_c0 = now_s();
   if (cpg_create(&ctx,G->device,A->model,0,0) != CPG_OK)
     die("%s: %s",PROG,cpg_last_error(NULL));
-  if (G->device == 0) g_t_gpu_create = now_s()-t_c0;
+  if (G->device == 0) { g_t_gpu_create = now_s()-t_c0; g_tl_ctx = now_s(); }
   batch_t *fly[2] = { NULL, NULL };
   int slot = 0;
   for (;;)
@@ -487,6 +498,7 @@ static void *gpu_main(void *arg)
       if (b == NULL) break;                  /* queue closed; the last batch in flight was just collected */
       slot ^= 1;
     }
+  if (G->device == 0) g_tl_collect = now_s();
   cpg_destroy(ctx);
   return NULL;
 }
@@ -537,6 +549,7 @@ static void *writer_main(void *arg)
     }
   q_close(&A->q_free);
   if (fclose(out) != 0) die("Cannot write %s",A->out_path);
+  g_tl_writer = now_s();
   free(rasgn);
   return NULL;
 }
@@ -647,6 +660,7 @@ int main(int argc, char **argv)
   if (rc != CPG_OK) exit(1);
   A->model->kmer = A->P.kmer;
   if (A->verbose) fprintf(stderr,"Error model not specified. Using the default error model.\n");
+  g_tl_model = now_s();
 
   int ndev = cpg_device_count();
   if (ndev <= 0) die("%s: no CUDA device found: this program has no CPU fallback",PROG);
@@ -676,6 +690,9 @@ int main(int argc, char **argv)
       fprintf(stderr,"Classified %lld k-mers of %lld reads\n",(long long)A->kmers,(long long)A->total_reads);
       fprintf(stderr,"    stage seconds: reader %.3f (parse+pack+profile read), GPU0 context %.3f, GPU0 submit/collect %.3f, writer %.3f\n",
               g_t_reader,g_t_gpu_create,g_t_gpu_busy,g_t_writer);
+      fprintf(stderr,"    timeline (s): model %.3f, first batch parsed %.3f, first pinned buffer %.3f, GPU0 context %.3f, "
+                     "reader done %.3f, last collect %.3f, writer done %.3f\n",
+              g_tl_model,g_tl_first,g_tl_pinned,g_tl_ctx,g_tl_reader,g_tl_collect,g_tl_writer);
       time_line(stderr,"Total Resources:");
     }
   return 0;

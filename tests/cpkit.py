@@ -273,6 +273,7 @@ def _bind_hostsim(L):
                                    C.c_int, C.c_char_p, C.POINTER(GpuIntvl), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int)]
     L.hs_decode_profile.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    L.hs_decode_profile_cand.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.hs_ctx.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
     assert L.hs_sizeof_intvl() == C.sizeof(GpuIntvl)
     return L
@@ -291,16 +292,7 @@ def hostsim32_lib():
 def hostsim_lib():
     global _hostsim
     if _hostsim is None:
-        L = C.CDLL(build_hostsim())
-        L.cpg_model_from_hist.argtypes = [C.POINTER(GpuModel), C.c_int, C.c_int, C.c_int, C.c_int64,
-                                          C.c_int64, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int]
-        L.cpg_model_from_cov.argtypes = [C.POINTER(GpuModel), C.c_int, C.c_int, C.c_int, C.c_int]
-        L.hs_classify_read.argtypes = [C.POINTER(GpuModel), C.c_char_p, C.c_int, C.c_int, C.c_void_p,
-                                       C.c_int, C.c_char_p, C.POINTER(GpuIntvl), C.POINTER(C.c_int),
-                                       C.POINTER(C.c_int)]
-        L.hs_decode_profile.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
-        L.hs_ctx.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
-        assert L.hs_sizeof_intvl() == C.sizeof(GpuIntvl)
+        L = _bind_hostsim(C.CDLL(build_hostsim()))
         _hostsim = L
     return _hostsim
 
@@ -339,6 +331,26 @@ def hostsim_decode(prof_bytes, cap, lib=None):
     out = np.zeros(max(cap, 1), dtype=np.uint16)
     n = (lib or hostsim_lib()).hs_decode_profile(prof_bytes.ctypes.data, len(prof_bytes), out.ctypes.data, cap)
     return n, out[:min(n, cap)]
+
+
+def hostsim_decode_cand(prof_bytes, cap, rcov, lib=None):
+    """Counts plus the wall-candidate bit map the decoder writes on the side (as a bool array)."""
+    prof_bytes = np.ascontiguousarray(prof_bytes, dtype=np.uint8)
+    out = np.zeros(max(cap, 1), dtype=np.uint16)
+    cand = np.full((max(cap, 1) + 31) // 32, 0xdeadbeef, dtype=np.uint32)       # the decoder zeroes it
+    n = (lib or hostsim_lib()).hs_decode_profile_cand(prof_bytes.ctypes.data, len(prof_bytes), out.ctypes.data, cap,
+                                                      cand.ctypes.data, rcov)
+    bits = np.unpackbits(cand.view(np.uint8), bitorder="little")[:max(cap, 1)].astype(bool)
+    return n, out[:min(n, cap)], bits[:min(n, cap)]
+
+
+def candidate_bits(counts, rcov):
+    """Wall candidates by definition (src/wall.c:594-608): i >= 1, |c[i]-c[i-1]| >= 3, min < rcov."""
+    c = counts.astype(np.int64)
+    bits = np.zeros(len(c), dtype=bool)
+    if len(c) > 1:
+        bits[1:] = (np.abs(np.diff(c)) >= 3) & (np.minimum(c[1:], c[:-1]) < rcov)
+    return bits
 
 
 # ----------------------------------------------------------------------------- reference binary

@@ -29,6 +29,13 @@
 static pthread_barrier_t g_bar;
 static unsigned g_slot[32];
 static thread_local int t_lane = 0;
+/* one barrier per aligned power-of-two lane group: index = log2(size), base/size */
+static pthread_barrier_t g_gbar[6][32];
+static pthread_barrier_t *bar_of(unsigned mask)
+{ if (mask == 0xffffffffu) return &g_bar;
+  int size = __builtin_popcount(mask), base = __builtin_ctz(mask);
+  return &g_gbar[__builtin_ctz((unsigned)size)][base/size];
+}
 void cpg_sim_barrier(void) { pthread_barrier_wait(&g_bar); }
 unsigned cpg_sim_ballot(int pred)
 { g_slot[t_lane] = pred ? 1u : 0u;
@@ -52,38 +59,55 @@ unsigned cpg_sim_shfl_up(unsigned v, int d)
   pthread_barrier_wait(&g_bar);
   return r;
 }
-static pthread_barrier_t g_gbar[2];
-void cpg_sim_group_barrier(unsigned mask)
-{ if (mask == 0xffffffffu) pthread_barrier_wait(&g_bar);
-  else pthread_barrier_wait(&g_gbar[mask == 0x0000ffffu ? 0 : 1]);
+void cpg_sim_group_barrier(unsigned mask) { pthread_barrier_wait(bar_of(mask)); }
+unsigned cpg_sim_gballot(unsigned mask, int pred)
+{ pthread_barrier_t *b = bar_of(mask);
+  g_slot[t_lane] = pred ? 1u : 0u;
+  pthread_barrier_wait(b);
+  unsigned m = 0;
+  for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) m |= g_slot[l] << l;
+  pthread_barrier_wait(b);
+  return m;
 }
-int cpg_sim_sum(int v)
-{ g_slot[t_lane] = (unsigned)v;
-  pthread_barrier_wait(&g_bar);
+int cpg_sim_gsum(unsigned mask, int v)
+{ pthread_barrier_t *b = bar_of(mask);
+  g_slot[t_lane] = (unsigned)v;
+  pthread_barrier_wait(b);
   int s = 0;
-  for (int l = 0; l < 32; l++) s += (int)g_slot[l];
-  pthread_barrier_wait(&g_bar);
+  for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) s += (int)g_slot[l];
+  pthread_barrier_wait(b);
   return s;
+}
+int cpg_sim_sum(int v) { return cpg_sim_gsum(0xffffffffu,v); }
+unsigned cpg_sim_gshfl(unsigned mask, unsigned v, int src)
+{ pthread_barrier_t *b = bar_of(mask);
+  g_slot[t_lane] = v;
+  pthread_barrier_wait(b);
+  unsigned r = g_slot[src & 31];
+  pthread_barrier_wait(b);
+  return r;
 }
 #endif
 
+static int g_group = CPG_WARP;        /* lanes per read (hs_set_group) */
+
 struct HsWork
-  { std::vector<uint32_t> mark; std::vector<double> perr; std::vector<cpg_eintvl> eint;
+  { std::vector<uint8_t> mark; std::vector<uint16_t> slot; std::vector<uint32_t> cand; std::vector<double> perr; std::vector<cpg_eintvl> eint;
     std::vector<cpg_intvl> intvl, rint, wint; std::vector<uint16_t> bp;
     std::vector<uint8_t> af, ab, rpos, fixed; std::vector<int32_t> ord; std::vector<cpg_unmemo> memo; int mc = 0;
     void size(int P)
       { int MC = P/2+8;
-        mark.assign(P+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
+        mark.assign(P+2+32,0xff); slot.assign(P+2,0xffff); cand.assign(P/32+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
         rint.resize(MC); wint.resize(2*MC); bp.assign(2*MC,0); af.assign(MC,0); ab.assign(MC,0);
         rpos.assign(2*MC,0); mc = MC; memo.resize((size_t)CPG_MEMO_CAP*8); fixed.assign(P+2,0); ord.assign(P+2,0);
       }
   };
 
 struct LaneJob
-  { int lane; const cpg_dmodel *dm; cpg_wshared *ws; RelShared *sh; ReadCtx R; uint8_t *cls; int status;
+  { int lane, glane, gsize, gbase; unsigned gmask; const cpg_dmodel *dm; cpg_wshared *ws; RelShared *sh; ReadCtx R; uint8_t *cls; int status;
     int N, M;
     /* decode job */
-    const uint8_t *src; int64_t len; uint16_t *out; int cap; unsigned *offs; int n;
+    const uint8_t *src; int64_t len; uint16_t *out; int cap; unsigned *offs; int n; uint32_t *cand; int rcov;
   };
 
 static void *lane_classify(void *arg)
@@ -92,7 +116,7 @@ static void *lane_classify(void *arg)
   t_lane = J->lane;
 #endif
   WCtx W; W.lane = J->lane; W.M = J->dm; W.cthres = J->dm->cthres; W.ws = J->ws; W.status = 0;
-  W.glane = J->lane; W.gsize = CPG_WARP; W.gmask = 0xffffffffu;
+  W.glane = J->glane; W.gsize = J->gsize; W.gbase = J->gbase; W.gmask = J->gmask;
   ReadCtx R = J->R;
   J->status = classify_read(R,W,J->sh,J->cls);
   J->N = R.N; J->M = R.M;
@@ -104,7 +128,7 @@ static void *lane_decode(void *arg)
 #if CPG_HOSTSIM == 32
   t_lane = J->lane;
 #endif
-  J->n = decode_profile(J->src,J->len,J->out,J->cap,J->lane,J->offs);
+  J->n = decode_profile(J->src,J->len,J->out,J->cap,J->lane,J->offs,J->cand,J->rcov);
   return NULL;
 }
 
@@ -113,11 +137,11 @@ static void run_lanes(void *(*fn)(void *), LaneJob *jobs)
 #if CPG_HOSTSIM == 32
   pthread_t th[32];
   pthread_barrier_init(&g_bar,NULL,32);
-  pthread_barrier_init(&g_gbar[0],NULL,16); pthread_barrier_init(&g_gbar[1],NULL,16);
+  for (int k = 0; k < 6; k++) for (int g = 0; g < (32 >> k); g++) pthread_barrier_init(&g_gbar[k][g],NULL,1u << k);
   for (int l = 0; l < 32; l++) pthread_create(&th[l],NULL,fn,&jobs[l]);
   for (int l = 0; l < 32; l++) pthread_join(th[l],NULL);
   pthread_barrier_destroy(&g_bar);
-  pthread_barrier_destroy(&g_gbar[0]); pthread_barrier_destroy(&g_gbar[1]);
+  for (int k = 0; k < 6; k++) for (int g = 0; g < (32 >> k); g++) pthread_barrier_destroy(&g_gbar[k][g]);
 #else
   fn(&jobs[0]);
 #endif
@@ -149,19 +173,36 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
     }
   else { S.p = (const uint8_t *)seq; S.bits = 8; }
 
-  static HsWork Wk; static int sized = 0;
-  if (sized < plen) { Wk.size(plen+64); sized = plen+64; }
-  static cpg_wshared ws; static RelShared sh[2];
+  /* every lane group of the simulated warp classifies the same read with its own scratch; the
+     outputs of the groups must agree */
+  const int G = g_group, NG = CPG_WARP/G;
+  static HsWork Wk[32]; static int sized[32];
+  static cpg_wshared ws[32]; static RelShared sh[32][2];
+  std::vector<std::vector<char> > cls_g(NG);
   LaneJob jobs[CPG_WARP];
   for (int l = 0; l < CPG_WARP; l++)
     { LaneJob &J = jobs[l];
-      J.lane = l; J.dm = &dm; J.ws = &ws; J.sh = sh; J.cls = (uint8_t *)cls; J.status = 0;
+      const int g = l/G;
+      if (sized[g] < plen) { Wk[g].size(plen+64); sized[g] = plen+64; }
+      if (g > 0 && (int)cls_g[g].size() < rlen+1) cls_g[g].assign((size_t)rlen+1,0);
+      J.lane = l; J.glane = l%G; J.gsize = G; J.gbase = g*G;
+      J.gmask = ((G >= 32) ? 0xffffffffu : ((1u << G)-1u)) << J.gbase;
+      J.dm = &dm; J.ws = &ws[g]; J.sh = sh[g]; J.cls = (g == 0) ? (uint8_t *)cls : (uint8_t *)cls_g[g].data(); J.status = 0;
       ReadCtx &R = J.R;
+      HsWork &K = Wk[g];
       R.prof = prof; R.plen = plen; R.rlen = rlen; R.seq = S; R.nslots = 0; R.N = R.M = 0;
-      R.S.mark = Wk.mark.data(); R.S.perr = Wk.perr.data(); R.S.eint = Wk.eint.data();
-      R.S.intvl = Wk.intvl.data(); R.S.rint = Wk.rint.data(); R.S.wint = Wk.wint.data();
-      R.S.bp = Wk.bp.data(); R.S.asg_f = Wk.af.data(); R.S.asg_b = Wk.ab.data();
-      R.S.rpos = Wk.rpos.data(); R.S.ord = Wk.ord.data(); R.S.fixed = Wk.fixed.data(); R.S.MC = Wk.mc; R.S.memo = Wk.memo.data();
+      /* candidate bit map straight from the definition (src/wall.c:594-608); the decoder's own bit
+         map is checked against the same definition by the decode tests */
+      if (l%G == 0)
+        { std::fill(K.cand.begin(),K.cand.end(),0u);
+          for (int i = 1; i < plen; i++)
+            if (dc_is_cand(prof[i-1],prof[i],dm.cov[ST_R])) K.cand[i >> 5] |= 1u << (i & 31);
+        }
+      R.cand = K.cand.data();
+      R.S.mark = K.mark.data(); R.S.slot = K.slot.data(); R.S.perr = K.perr.data(); R.S.eint = K.eint.data();
+      R.S.intvl = K.intvl.data(); R.S.rint = K.rint.data(); R.S.wint = K.wint.data();
+      R.S.bp = K.bp.data(); R.S.asg_f = K.af.data(); R.S.asg_b = K.ab.data();
+      R.S.rpos = K.rpos.data(); R.S.ord = K.ord.data(); R.S.fixed = K.fixed.data(); R.S.MC = K.mc; R.S.memo = K.memo.data();
     }
   run_lanes(lane_classify,jobs);
   int st = 0;
@@ -169,23 +210,35 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
     { st |= jobs[l].status;
       if (jobs[l].N != jobs[0].N || jobs[l].M != jobs[0].M) st |= 1<<30;      /* lanes disagree */
     }
-  if (ivl_out) for (int i = 0; i < jobs[0].N; i++) ivl_out[i] = Wk.intvl[i];
+  for (int g = 1; g < NG; g++) if (memcmp(cls,cls_g[g].data(),(size_t)rlen) != 0) st |= 1<<29;   /* groups disagree */
+  if (ivl_out) for (int i = 0; i < jobs[0].N; i++) ivl_out[i] = Wk[0].intvl[i];
   if (N_out) *N_out = jobs[0].N;
   if (M_out) *M_out = jobs[0].M;
   return st;
 }
 
-int hs_decode_profile(const uint8_t *src, int64_t len, uint16_t *out, int cap)
+/* lanes per read for the next hs_classify_read calls (a power of two <= the warp width) */
+int hs_set_group(int g)
+{ if (g < 1 || g > CPG_WARP || (g & (g-1))) return -1;
+  g_group = g;
+  return 0;
+}
+
+/* cand: NULL or ceil(cap/32) words for the wall-candidate bit map (rcov = repeat threshold) */
+int hs_decode_profile_cand(const uint8_t *src, int64_t len, uint16_t *out, int cap, uint32_t *cand, int rcov)
 { static unsigned offs[DC_SLOTS];
   LaneJob jobs[CPG_WARP];
   for (int l = 0; l < CPG_WARP; l++)
     { jobs[l].lane = l; jobs[l].src = src; jobs[l].len = len; jobs[l].out = out; jobs[l].cap = cap;
-      jobs[l].offs = offs; jobs[l].n = 0;
+      jobs[l].offs = offs; jobs[l].n = 0; jobs[l].cand = cand; jobs[l].rcov = rcov;
     }
   run_lanes(lane_decode,jobs);
   for (int l = 1; l < CPG_WARP; l++) if (jobs[l].n != jobs[0].n) return -1000000;
   return jobs[0].n;
 }
+
+int hs_decode_profile(const uint8_t *src, int64_t len, uint16_t *out, int cap)
+{ return hs_decode_profile_cand(src,len,out,cap,NULL,0); }
 
 int hs_ctx(const char *seq, int rlen, int p, int right, int t)
 { cpg_seq S; S.p = (const uint8_t *)seq; S.bits = 8;

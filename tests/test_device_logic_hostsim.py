@@ -183,21 +183,56 @@ def test_decode_empty_profile(kit, hostsim):
     assert n == 0
 
 
-def test_warp32_emulation_classify(kit):
+@pytest.mark.parametrize("group", [32, 16, 8])
+def test_warp32_emulation_classify(kit, group):
     """The same device sources with 32 host threads playing the lanes of one warp: every ballot,
-    shuffle, reduction and __syncwarp is a rendezvous, lanes run asynchronously in between.
-    Catches collectives reached by only some lanes (hang) and missing synchronisation (mismatch)."""
+    shuffle, reduction and group barrier is a rendezvous, lanes run asynchronously in between.
+    Catches collectives reached by only some lanes (hang) and missing synchronisation (mismatch).
+    `group` = lanes per read: the warp classifies 32/group copies of the read at the same time, each
+    lane group with its own scratch (k_classify runs with groups of 16), and the groups must agree."""
     L32 = kit.hostsim32_lib()
+    assert L32.hs_set_group(group) == 0
     sim = kit.simulate(seed=47, genome_len=20000, cov=14., het=0.01, repeat_frac=0.4, len_mean=2200, len_sd=400,
                        len_min=500)
     om = kit.oracle_model(sim)
     gm = kit.gpu_model_from_sim(L32, sim)
     ow = kit.OracleWork(clean=True)
-    for i in range(min(sim.nreads, 10)):
-        s, c = sim.read_ascii(i).tobytes(), sim.read_counts(i)
-        a, ia, ma = ow.classify(om, s, c, True)
-        st, b, ib, mb = kit.hostsim_classify(gm, s, c, 2, True, lib=L32)
-        assert st == 0 and a == b and ia == ib and ma == mb, i
+    try:
+        for i in range(min(sim.nreads, 10 if group == 16 else 4)):
+            s, c = sim.read_ascii(i).tobytes(), sim.read_counts(i)
+            a, ia, ma = ow.classify(om, s, c, True)
+            st, b, ib, mb = kit.hostsim_classify(gm, s, c, 2, True, lib=L32)
+            assert st == 0 and a == b and ia == ib and ma == mb, i
+    finally:
+        L32.hs_set_group(32)
+
+
+def test_decoder_candidate_bitmap(kit, hostsim):
+    """The bit map the decoder writes on the side equals the candidate definition applied to the
+    decoded counts, on simulated profiles and on arbitrary byte streams (wrap-around included)."""
+    sim = kit.simulate(seed=5, genome_len=30000, cov=25., het=0.01, repeat_frac=0.3, len_mean=3000, len_sd=600,
+                       len_min=500)
+    for i in range(min(sim.nreads, 40)):
+        c = sim.read_counts(i)
+        for rcov in (12, 60, 40000):
+            n, o, bits = kit.hostsim_decode_cand(sim.read_prof(i), len(c), rcov)
+            assert n == len(c) and np.array_equal(o, c)
+            assert np.array_equal(bits, kit.candidate_bits(c, rcov)), (i, rcov)
+    rng = np.random.default_rng(77)
+    L32 = kit.hostsim32_lib()
+    for it in range(60):
+        s = random_stream(rng, int(rng.integers(1, 400)), bool(it & 1))
+        n1, o1 = kit.oracle_decode(np.frombuffer(s, dtype=np.uint8), 100000)
+        for lib in (None, L32) if it < 12 else (None,):
+            n2, o2, bits = kit.hostsim_decode_cand(np.frombuffer(s, dtype=np.uint8), 100000, 200, lib=lib)
+            assert n2 == n1 and np.array_equal(o2, o1)
+            assert np.array_equal(bits, kit.candidate_bits(o1, 200)), it
+    # a capacity smaller than the stream: bits past the capacity are never written
+    s = random_stream(rng, 300, False)
+    n1, o1 = kit.oracle_decode(np.frombuffer(s, dtype=np.uint8), 100000)
+    cap = max(1, n1 // 2)
+    n2, o2, bits = kit.hostsim_decode_cand(np.frombuffer(s, dtype=np.uint8), cap, 200)
+    assert n2 == n1 and np.array_equal(o2, o1[:cap]) and np.array_equal(bits, kit.candidate_bits(o1[:cap], 200))
 
 
 def test_warp32_emulation_decode(kit):

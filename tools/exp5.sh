@@ -1,0 +1,14 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+B="python bench.py --no-cpu-baseline --steps 3 --warmup 3"
+pick() { python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); k=d['roofline']['kernels']
+        print('$1', 'value %.3e e2e %.3e dec %.2f ms cls %.2f ms' % (d['value'], d['e2e']['value'], k['k_decode']['ms'], k['k_classify']['ms']), k['k_classify']['phase_share'])
+"; }
+for v in g8 g32; do
+CLASSPRO_B200_LIB=$PWD/classpro_b200/build/lib_$v.so $B --genome-mb 100 2>&1 | pick 100mb_$v
+done
+bash tools/prof.sh r1g 2>&1 | tail -3

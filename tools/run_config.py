@@ -96,7 +96,7 @@ def main():
         print(json.dumps(out))
         return 1
     out["gpu_kmers_per_s"] = round(out["kmers"] / out["gpu_s"])
-    out["gpu_stderr_tail"] = pr.stderr.splitlines()[-3:]
+    out["gpu_stderr_tail"] = pr.stderr.splitlines()[-5:]
     mine = os.path.join(tmp, "reads.class")
     if ref_class:
         same = filecmp.cmp(mine, ref_class, shallow=False)
