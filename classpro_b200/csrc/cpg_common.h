@@ -114,6 +114,10 @@ enum { TH_INIT = 0, TH_FINAL = 1 };
 #define CPG_ST_LONG_RUN      32    /* a low-complexity run reached the 127 cap: the reference reads
                                       never-written right-context cells (context.c:26-27) */
 #define CPG_ST_BINOM         64    /* k > n in a binomial (src/prob.c:51-55: exit(1)) */
+/* internal, never reaches the host: the read outgrew the compact scratch block of its lane group
+   and is classified again by the second k_classify launch, which has full-size blocks */
+#define CPG_ST_RETRY    (1<<20)
+#define CPG_ST_ABORT    (CPG_ST_EINTVL_OVF|CPG_ST_RETRY)
 
 /* Device-resident model: host one-shot results (src/ClassPro.c:536-554, src/wall.c:167-244) */
 typedef struct
@@ -125,6 +129,13 @@ typedef struct
     double   dr_ratio;
     double   hc_erate;
     double   pe[3][21];
+    /* logarithms of the model's constants, filled by cpg_model_fill_logs() with the same log() the
+       per-read code uses, so that replacing a log of a constant by its table entry changes no bit */
+    double   lpe[3][21], l1mpe[3][21];   /* log pe[t][l], log(1-pe[t][l]) */
+    double   l_hc, l1m_hc;               /* log hc_erate, log(1-hc_erate) */
+    double   l_p1, l1m_p1;               /* log 0.1, log(1-0.1)   (src/class_unrel.c p_errorin rate) */
+    double   l_p99, l1m_p99;             /* log(1-PE_MEAN), log(1-(1-PE_MEAN)) */
+    double   lcov[4];                    /* log cov[s] */
     /* device pointers */
     const uint8_t *cthres;     /* [CPG_LROWS][256][2(thresT)][2(etype)], row = lrow(t,l) */
     const double  *logfact;    /* [32768] */
@@ -149,15 +160,19 @@ typedef struct { const uint8_t *p; int32_t bits; } cpg_seq;
 
 /* One task of an unreliable-interval update (see cpg_unrel.cuh): arguments and result */
 struct cpg_unmemo { double a; double val; int32_t k; int32_t kind; };
-#define CPG_MEMO_CAP 2048      /* intervals per read whose first-sweep results are kept */
+#define CPG_MEMO_CAP 512       /* intervals per read whose first-sweep results are kept */
 
-/* Per-warp scratch in global memory, sized for the longest profile of the batch */
+/* Scratch block of a lane group in global memory.  P = longest profile of the batch.  The
+ * per-position arrays have P entries; the interval tables have capS/capE/capI entries: a few per
+ * cent of P in the blocks of the main launch (a read that outgrows them is flagged
+ * CPG_ST_RETRY), P+2 -- the worst case -- in the blocks of the retry launch. */
 typedef struct
   { uint8_t    *mark;     /* [P+2+32] flag byte per profile position 0..plen */
     uint16_t   *slot;     /* [P+2]   probability slot of a position, valid where the flag byte says so */
-    double     *perr;     /* [(P+2)*4] slot-major: [slot][etype][wtype]; sort keys in the last phase */
-    cpg_eintvl *eint;     /* [P+2] */
-    cpg_intvl  *intvl;    /* [P+2] */
+    double     *perr;     /* [capS*4] slot-major: [slot][etype][wtype]; sort keys in the last phase */
+    cpg_eintvl *eint;     /* [capE] */
+    cpg_intvl  *intvl;    /* [capI] */
+    int32_t     capS, capE, capI;
     cpg_intvl  *rint;     /* [MC]  reliable intervals (copy) */
     cpg_intvl  *wint;     /* [2*MC] DP working copies (forward, backward) */
     uint16_t   *bp;       /* [2*MC] back pointers: 4 x 3 bits */
@@ -165,8 +180,8 @@ typedef struct
     uint8_t    *asg_b;    /* [MC] */
     uint8_t    *rpos;     /* [2*MC] */
     int32_t     MC;
-    int32_t    *ord;      /* [P+2] */
-    uint8_t    *fixed;    /* [P+2] */
+    int32_t    *ord;      /* [capI] */
+    uint8_t    *fixed;    /* [capI] */
     struct cpg_unmemo *memo;   /* [CPG_MEMO_CAP*8] first-sweep results of the unreliable-interval tasks */
   } cpg_scratch;
 

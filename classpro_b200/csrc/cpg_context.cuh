@@ -15,6 +15,8 @@
  *              trinucleotide ending at p                                       (lctx[p][TS])
  *    R_*(p)  = the mirror images, counted from p to the right                  (rctx[p][*])
  *  all capped at 127.  ctx[DROP][i] = lctx[i+K-2], ctx[GAIN][i] = rctx[i] (src/ClassPro.c:138-142).
+ *  Raw-byte sequences (reads with characters outside ACGT) walk the bases one by one; 2-bit packed
+ *  sequences compare 32 bases at a time (see below).
  *******************************************************************************************/
 #ifndef CPG_CONTEXT_CUH
 #define CPG_CONTEXT_CUH
@@ -26,7 +28,7 @@ CPG_DEV int cpg_base(const cpg_seq S, int i)
 
 CPG_DEV int cpg_cap127(int x) { return x > 127 ? 127 : x; }
 
-CPG_DEV_HELPER int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
+CPG_DEV_HELPER int cpg_lctx_raw(const cpg_seq S, int rlen, int p, int t)
 { (void)rlen;
   if (t == CT_HP)
     { int c = cpg_base(S,p), n = 1;
@@ -50,7 +52,7 @@ CPG_DEV_HELPER int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
   return u;
 }
 
-CPG_DEV_HELPER int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
+CPG_DEV_HELPER int cpg_rctx_raw(const cpg_seq S, int rlen, int p, int t)
 { if (t == CT_HP)
     { int c = cpg_base(S,p), n = 1;
       CPG_LOOP while (n < 127 && p+n < rlen && cpg_base(S,p+n) == c) n++;
@@ -71,6 +73,94 @@ CPG_DEV_HELPER int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
   CPG_LOOP while (u < 127 && q+5 <= rlen-1 && cpg_base(S,q+3) == a && cpg_base(S,q+4) == b && cpg_base(S,q+5) == c)
     { u++; q += 3; }
   return u;
+}
+
+/* ---- 2-bit packed sequences: 32 bases per 64-bit window, runs by XOR + count-zeros ----
+ * With Zb(p,d) = number of consecutive j = p, p-1, ... (j-d >= 0) with s[j] == s[j-d] and Zf(p,d)
+ * its mirror image (j = p, p+1, ..., j+d <= rlen-1, s[j] == s[j+d]) the closed forms above are
+ *   L_HP = 1+Zb(p,1)   L_DS = 1+Zb(p,2)/2   L_TS = 1+Zb(p,3)/3   (R_* with Zf), capped at 127:
+ * a further copy of the unit ends at p exactly when d more positions agree with the base d to
+ * their left. */
+#ifdef CPG_HOSTSIM
+CPG_DEV uint32_t cpg_funnel_r(uint32_t lo, uint32_t hi, unsigned sh)
+{ return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31)); }
+CPG_DEV int cpg_ctz64(uint64_t x) { return __builtin_ctzll(x); }
+CPG_DEV int cpg_clz64(uint64_t x) { return __builtin_clzll(x); }
+#else
+CPG_DEV uint32_t cpg_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo,hi,sh); }
+CPG_DEV int cpg_ctz64(uint64_t x) { return __ffsll((long long)x)-1; }
+CPG_DEV int cpg_clz64(uint64_t x) { return __clzll((long long)x); }
+#endif
+
+/* bases s .. s+31 (s >= 0), base s in bits 0..1.  Reads the three aligned words at and after the
+   byte of base s: up to 3 bytes before it and 11 after it, which the staging buffers pad for. */
+CPG_DEV uint64_t cpg_win(const uint8_t *p, int s)
+{ const size_t ad = (size_t)(p+(s >> 2));
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(ad & ~(size_t)3);
+  const unsigned bo = (unsigned)(ad & 3)*8u+(unsigned)(s & 3)*2u;          /* 0..30 */
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  return (((uint64_t)cpg_funnel_r(w1,w2,bo)) << 32) | cpg_funnel_r(w0,w1,bo);
+}
+/* bases q-31 .. q, base q in the top two bits; bases below 0 read as zeros */
+CPG_DEV uint64_t cpg_win_end(const uint8_t *p, int q)
+{ const int s = q-31;
+  if (s >= 0) return cpg_win(p,s);
+  if (s <= -32) return 0;
+  return cpg_win(p,0) << (2*(-s));
+}
+
+CPG_DEV_HELPER int cpg_zb(const uint8_t *sq, int p, int d, int zmax)
+{ int lim = p-d+1;
+  if (lim > zmax) lim = zmax;
+  int z = 0;
+  CPG_LOOP while (z < lim)
+    { const uint64_t e = cpg_win_end(sq,p-z) ^ cpg_win_end(sq,p-z-d);
+      const int c = e ? (cpg_clz64(e) >> 1) : 32;
+      z += c;
+      if (c < 32) break;
+    }
+  return z < lim ? z : (lim > 0 ? lim : 0);
+}
+
+CPG_DEV_HELPER int cpg_zf(const uint8_t *sq, int rlen, int p, int d, int zmax)
+{ int lim = rlen-d-p;
+  if (lim > zmax) lim = zmax;
+  int z = 0;
+  CPG_LOOP while (z < lim)
+    { const uint64_t e = cpg_win(sq,p+z) ^ cpg_win(sq,p+z+d);
+      const int c = e ? (cpg_ctz64(e) >> 1) : 32;
+      z += c;
+      if (c < 32) break;
+    }
+  return z < lim ? z : (lim > 0 ? lim : 0);
+}
+
+CPG_DEV_HELPER int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
+{ if (S.bits == 8) return cpg_lctx_raw(S,rlen,p,t);
+  if (t == CT_HP) return 1+cpg_zb(S.p,p,1,126);
+  if (t == CT_DS)
+    { if (p == 0 || cpg_base(S,p-1) == cpg_base(S,p)) return 0;
+      return 1+(cpg_zb(S.p,p,2,252) >> 1);
+    }
+  if (p < 2) return 0;
+  { const int a = cpg_base(S,p-2), b = cpg_base(S,p-1), c = cpg_base(S,p);
+    if (a == b && b == c) return 0;
+  }
+  return 1+cpg_zb(S.p,p,3,378)/3;
+}
+
+CPG_DEV_HELPER int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
+{ if (S.bits == 8) return cpg_rctx_raw(S,rlen,p,t);
+  if (t == CT_HP) return 1+cpg_zf(S.p,rlen,p,1,126);
+  if (t == CT_DS)
+    { if (p >= rlen-1 || cpg_base(S,p) == cpg_base(S,p+1)) return 0;
+      return 1+(cpg_zf(S.p,rlen,p,2,252) >> 1);
+    }
+  if (p > rlen-3) return 0;
+  { const int a = cpg_base(S,p), b = cpg_base(S,p+1), c = cpg_base(S,p+2);
+    if (a == b && b == c) return 0;
+  }
+  return 1+cpg_zf(S.p,rlen,p,3,378)/3;
 }
 
 /* ctx[wtype][i][t] of the reference, i a profile position */

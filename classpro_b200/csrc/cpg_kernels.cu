@@ -56,31 +56,50 @@ struct BatchDev
 
 struct ScratchDev
   { uint8_t *base;
-    size_t   stride;             /* bytes per warp */
+    size_t   stride;             /* bytes per lane group */
     int32_t  P;                  /* longest profile the layout is sized for */
     int32_t  MC;                 /* reliable-interval capacity */
+    int32_t  capS, capE, capI;   /* probability slots, E-intervals, intervals (cpg_common.h: cpg_scratch) */
   };
 
 static inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x+a-1)/a*a; }
 
-/* layout of one warp's scratch; must match scratch_stride() */
-__host__ __device__ static inline size_t scratch_layout(int P, int MC, size_t off[14])
-{ size_t o = 0;
+/* layout of one lane group's scratch */
+__host__ __device__ static inline size_t scratch_layout(const ScratchDev &SC, size_t off[14])
+{ const int P = SC.P, MC = SC.MC;
+  size_t o = 0;
   off[0]  = o; o = align_up(o+(size_t)(P+2+32),16);                      /* mark  */
   off[13] = o; o = align_up(o+sizeof(uint16_t)*(size_t)(P+2),16);        /* slot  */
-  off[1]  = o; o = align_up(o+sizeof(double)*4*(size_t)(P+2),16);        /* perr  */
-  off[2]  = o; o = align_up(o+sizeof(cpg_eintvl)*(size_t)(P+2),16);      /* eint  */
-  off[3]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)(P+2),16);       /* intvl */
+  off[1]  = o; o = align_up(o+sizeof(double)*4*(size_t)SC.capS,16);      /* perr  */
+  off[2]  = o; o = align_up(o+sizeof(cpg_eintvl)*(size_t)SC.capE,16);    /* eint  */
+  off[3]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)SC.capI,16);     /* intvl */
   off[4]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)MC,16);          /* rint  */
   off[5]  = o; o = align_up(o+sizeof(cpg_intvl)*2*(size_t)MC,16);        /* wint (fw, bw) */
   off[6]  = o; o = align_up(o+sizeof(uint16_t)*2*(size_t)MC,16);         /* bp   (fw, bw) */
   off[7]  = o; o = align_up(o+(size_t)MC,16);                            /* asg_f */
   off[8]  = o; o = align_up(o+(size_t)MC,16);                            /* asg_b */
   off[9]  = o; o = align_up(o+2*(size_t)MC,16);                          /* rpos (fw, bw) */
-  off[10] = o; o = align_up(o+sizeof(int32_t)*(size_t)(P+2),16);         /* ord   */
-  off[11] = o; o = align_up(o+(size_t)(P+2),16);                         /* fixed */
+  off[10] = o; o = align_up(o+sizeof(int32_t)*(size_t)SC.capI,16);       /* ord   */
+  off[11] = o; o = align_up(o+(size_t)SC.capI,16);                       /* fixed */
   off[12] = o; o = align_up(o+sizeof(cpg_unmemo)*8*(size_t)CPG_MEMO_CAP,16);  /* memo */
   return align_up(o,256);
+}
+
+/* Capacities of the interval tables.  Worst case (full = 1): every position its own interval.
+   Main launch: one interval per 16 positions, one probability slot per 8 -- several times what
+   HiFi profiles need (about one interval per 90 positions); a read that needs more is flagged and
+   classified again by the retry launch. */
+static void scratch_caps(ScratchDev *SC, int P, int K, int full)
+{ SC->P = P; SC->MC = P/K+8;
+  if (full) { SC->capS = SC->capE = SC->capI = P+2; }
+  else
+    { int div = 16;
+      { const char *f = getenv("CPG_SCRATCH_DIV"); if (f && atoi(f) > 0) div = atoi(f); }   /* test knob: force retries */
+      SC->capI = P/div+64; SC->capE = P/div+64; SC->capS = 2*(P/div)+64;
+      if (SC->capI > P+2) SC->capI = P+2;
+      if (SC->capE > P+2) SC->capE = P+2;
+      if (SC->capS > P+2) SC->capS = P+2;
+    }
 }
 
 __device__ __forceinline__ int next_read(int32_t *counter, int lane)
@@ -137,8 +156,10 @@ struct ClassifyShared
     RelShared   rel[CLASSIFY_GROUPS][2];
   };
 
+/* retry = 0: every read of the batch, compact scratch blocks.  retry = 1: the reads the first launch
+   flagged CPG_ST_RETRY, full-size scratch blocks (a handful of CTAs; normally finds nothing). */
 __global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
-k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
+k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
 { extern __shared__ __align__(16) unsigned char smem_raw[];
   ClassifyShared &sh = *reinterpret_cast<ClassifyShared *>(smem_raw);
   const int lane = threadIdx.x & 31;
@@ -156,11 +177,13 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
 #endif
   if (threadIdx.x == 0) sh.model = M;
   __syncthreads();
+  cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
+  __syncthreads();
 
   const size_t gg = (size_t)blockIdx.x*CLASSIFY_GROUPS+gib;
   uint8_t *sb = SC.base+gg*SC.stride;
   size_t off[14];
-  scratch_layout(SC.P,SC.MC,off);
+  scratch_layout(SC,off);
 
   /* One read per lane group, CLASSIFY_GROUPS reads per CTA at a time, taken from the queue in
      processing order (neighbouring reads have similar lengths, so the phases of a CTA finish
@@ -168,7 +191,7 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
   __shared__ int s_base;
   for (;;)
     { __syncthreads();
-      if (threadIdx.x == 0) s_base = atomicAdd(B.queue+1,CLASSIFY_GROUPS);
+      if (threadIdx.x == 0) s_base = atomicAdd(B.queue+1+retry,CLASSIFY_GROUPS);
       __syncthreads();
       const int base = s_base;
       if (base >= B.n_reads) break;
@@ -178,7 +201,10 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
       if (active)
         { r = B.order[q];
           rlen = B.rlen[r]; plen = rlen-M.K+1;
-          if (B.status[r] != CPG_ST_OK) active = 0;          /* undecodable profile: left to the host */
+          const int st0 = B.status[r];
+          if (retry) { if (!(st0 & CPG_ST_RETRY)) active = 0; }
+          else if (st0 != CPG_ST_OK) active = 0;             /* undecodable profile: left to the host */
+          if (!active) { }
           else if (plen > SC.P) { if (glane == 0) B.status[r] = CPG_ST_BAD_PROFILE; active = 0; }
         }
       WCtx W;
@@ -202,7 +228,7 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC)
       R.S.rpos  = sb+off[9];
       R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
       R.S.fixed = sb+off[11];
-      R.S.MC = SC.MC;
+      R.S.MC = SC.MC; R.S.capS = SC.capS; R.S.capE = SC.capE; R.S.capI = SC.capI;
       R.S.memo = reinterpret_cast<cpg_unmemo *>(sb+off[12]);
 
       long long t0 = clock64();
@@ -253,7 +279,8 @@ struct cpg_ctx
     cpg_dmodel dmodel;
     void      *d_cthres, *d_logfact;
     Slot       slot[2];
-    DevBuf     scratch; ScratchDev SC;
+    DevBuf     scratch, scratch_big; ScratchDev SC, SCbig;
+    int        retry_blocks;
     int        n_sm, decode_blocks, classify_blocks;
     size_t     classify_smem;
     cudaEvent_t ev[3];
@@ -302,11 +329,12 @@ extern "C" const char *cpg_status_string(int32_t st)
   if (st & CPG_ST_BINOM)       return "k > n in a binomial";
   if (st & CPG_ST_UNDEF_TRACE) return "all DP states impossible (reference behaviour undefined)";
   if (st & 128)                return "profile[plen] read (reference reads stale memory)";
+  if (st & CPG_ST_RETRY)       return "internal error: read left unclassified by the retry launch";
   return "unknown";
 }
 
 /* fatal = conditions on which the reference exits */
-#define CPG_ST_FATAL (CPG_ST_BAD_PROFILE|CPG_ST_EINTVL_OVF|CPG_ST_NO_PROB|CPG_ST_INTERP|CPG_ST_BINOM)
+#define CPG_ST_FATAL (CPG_ST_BAD_PROFILE|CPG_ST_EINTVL_OVF|CPG_ST_NO_PROB|CPG_ST_INTERP|CPG_ST_BINOM|CPG_ST_RETRY)
 
 extern "C" void cpg_destroy(cpg_ctx *ctx)
 { if (ctx == NULL) return;
@@ -323,6 +351,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
       if (S->stream) cudaStreamDestroy(S->stream);
     }
   if (ctx->scratch.p) cudaFree(ctx->scratch.p);
+  if (ctx->scratch_big.p) cudaFree(ctx->scratch_big.p);
   if (ctx->d_cthres) cudaFree(ctx->d_cthres);
   if (ctx->d_logfact) cudaFree(ctx->d_logfact);
   for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -378,6 +407,7 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
   CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,k_classify,CLASSIFY_THREADS,ctx->classify_smem));
   if (occ < 1) occ = 1;
   ctx->classify_blocks = ctx->n_sm*occ;
+  ctx->retry_blocks = 4;
   CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,k_decode,DECODE_THREADS,0));
   if (occ < 1) occ = 1;
   ctx->decode_blocks = ctx->n_sm*occ;
@@ -386,20 +416,26 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
   return CPG_OK;
 }
 
-/* scratch arena for the persistent classify warps */
+/* scratch arenas: compact blocks for every resident lane group of the main launch, full-size
+   blocks for the few groups of the retry launch */
 static int ensure_scratch(cpg_ctx *ctx, int P)
 { { const char *f = getenv("CPG_FORCE_P");            /* experiment knob: oversize the scratch layout */
     if (f && atoi(f) > P) P = atoi(f);
   }
   if (ctx->scratch.p && P <= ctx->SC.P) return CPG_OK;
   size_t off[14];
-  int MC = P/ctx->model.kmer+8;
-  size_t stride = scratch_layout(P,MC,off);
-  size_t warps = (size_t)ctx->classify_blocks*CLASSIFY_GROUPS;     /* one scratch block per lane group */
+  ScratchDev SC = ctx->SC, SB = ctx->SCbig;
+  scratch_caps(&SC,P,ctx->model.kmer,0);
+  scratch_caps(&SB,P,ctx->model.kmer,1);
+  SC.stride = scratch_layout(SC,off);
+  SB.stride = scratch_layout(SB,off);
   for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->slot[s].stream);
-  int rc = reserve(ctx,&ctx->scratch,stride*warps);
+  int rc = reserve(ctx,&ctx->scratch,SC.stride*(size_t)ctx->classify_blocks*CLASSIFY_GROUPS);
   if (rc) return rc;
-  ctx->SC.base = (uint8_t *)ctx->scratch.p; ctx->SC.stride = stride; ctx->SC.P = P; ctx->SC.MC = MC;
+  rc = reserve(ctx,&ctx->scratch_big,SB.stride*(size_t)ctx->retry_blocks*CLASSIFY_GROUPS);
+  if (rc) return rc;
+  SC.base = (uint8_t *)ctx->scratch.p; SB.base = (uint8_t *)ctx->scratch_big.p;
+  ctx->SC = SC; ctx->SCbig = SB;
   return CPG_OK;
 }
 
@@ -511,7 +547,8 @@ static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
   if (timed) CU(cudaEventRecord(ctx->ev[0],st));
   k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(S->B,ctx->model.kmer,(int)ctx->model.cov[1]);
   if (timed) CU(cudaEventRecord(ctx->ev[1],st));
-  k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+  k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC,0);
+  k_classify<<<ctx->retry_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SCbig,1);
   if (timed) CU(cudaEventRecord(ctx->ev[2],st));
   CU(cudaEventRecord(S->kdone,st));
   S->kdone_valid = 1;
@@ -614,7 +651,7 @@ extern "C" int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float
     }
   if (ms_decode) *ms_decode = (float)(td/iters);
   if (ms_classify) *ms_classify = (float)(tc/iters);
-  if (launches) *launches = 2*iters;
+  if (launches) *launches = 3*iters;
   return CPG_OK;
 }
 

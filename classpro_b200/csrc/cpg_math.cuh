@@ -117,10 +117,40 @@ CPG_DEV_NOINL double cpg_bessi(int n, double x)
 /* src/prob.c:22-31: counts above 32767 are clamped (the reference also prints a note) */
 CPG_DEV int cpg_clamp_cnt(int n) { return n > CPG_MAX_CNT ? CPG_MAX_CNT : n; }
 
-/* src/prob.c:33-39 */
+/* An error rate with its logarithms (taken from the model's tables) */
+struct cpg_rate { double p, lp, l1mp; };
+CPG_DEV cpg_rate cpg_rate_pe(const cpg_dmodel *M, int t, int l) { cpg_rate r = { M->pe[t][l], M->lpe[t][l], M->l1mpe[t][l] }; return r; }
+CPG_DEV cpg_rate cpg_rate_hc(const cpg_dmodel *M) { cpg_rate r = { M->hc_erate, M->l_hc, M->l1m_hc }; return r; }
+CPG_DEV cpg_rate cpg_rate_p1(const cpg_dmodel *M) { cpg_rate r = { 0.1, M->l_p1, M->l1m_p1 }; return r; }
+
+/* Logarithms of the model constants; lane/thread `tid` of `nth` fills its share (the caller
+   synchronises afterwards). */
+CPG_DEV void cpg_model_fill_logs(cpg_dmodel *m, int tid, int nth)
+{ for (int i = tid; i < 63; i += nth)
+    { const int t = i/21, l = i%21;
+      const double p = m->pe[t][l];
+      m->lpe[t][l] = cpg_log(p); m->l1mpe[t][l] = cpg_log(1-p);
+    }
+  if (tid == 0)
+    { const double p = 1-CPG_PE_MEAN;
+      m->l_hc = cpg_log(m->hc_erate); m->l1m_hc = cpg_log(1-m->hc_erate);
+      m->l_p1 = cpg_log(0.1);         m->l1m_p1 = cpg_log(1-0.1);
+      m->l_p99 = cpg_log(p);          m->l1m_p99 = cpg_log(1-p);
+      for (int s = 0; s < 4; s++) m->lcov[s] = cpg_log((double)m->cov[s]);
+    }
+}
+
+/* src/prob.c:33-39; lambda is almost always one of the four global coverages */
 CPG_DEV_HELPER double cpg_lp_poisson(const WCtx &W, uint16_t k16, int lambda)
 { int k = cpg_clamp_cnt(k16);
-  return k*cpg_log((double)lambda)-lambda-CPG_LDG(W.M->logfact+k);
+  const cpg_dmodel *M = W.M;
+  double ll;
+  if      (lambda == M->cov[ST_E]) ll = M->lcov[ST_E];
+  else if (lambda == M->cov[ST_H]) ll = M->lcov[ST_H];
+  else if (lambda == M->cov[ST_D]) ll = M->lcov[ST_D];
+  else if (lambda == M->cov[ST_R]) ll = M->lcov[ST_R];
+  else ll = cpg_log((double)lambda);
+  return k*ll-lambda-CPG_LDG(M->logfact+k);
 }
 
 /* src/prob.c:41-44 */
@@ -133,22 +163,23 @@ CPG_DEV double cpg_lp_trans(const WCtx &W, int b, int e, int cb, int ce, uint16_
   return cpg_lp_skellam(ce-cb,(double)cov*d/W.M->read_len);
 }
 
-/* src/prob.c:59-65 */
-CPG_DEV_HELPER double cpg_lp_binom(WCtx &W, uint16_t k16, uint16_t n16, double p)
+/* src/prob.c:59-65 with p = 1-PE_MEAN, the only value the path uses (src/class_rel.c:186,
+   src/class_unrel.c:98-99) */
+CPG_DEV_HELPER double cpg_lp_binom99(WCtx &W, uint16_t k16, uint16_t n16)
 { int k = cpg_clamp_cnt(k16), n = cpg_clamp_cnt(n16);
   if (k > n) { W.status |= CPG_ST_BINOM; return -CPG_INF; }
   const double *lf = W.M->logfact;
-  return CPG_LDG(lf+n)-CPG_LDG(lf+k)-CPG_LDG(lf+(n-k))+k*cpg_log(p)+(n-k)*cpg_log(1-p);
+  return CPG_LDG(lf+n)-CPG_LDG(lf+k)-CPG_LDG(lf+(n-k))+k*W.M->l_p99+(n-k)*W.M->l1m_p99;
 }
 
 /* src/prob.c:76-112 with exact = false: one-sided binomial tail summed in the reference's order and
  * cut after the first term below a tenth of the first one.  Evaluated by ONE lane, term after term
  * exactly as the reference loops: the callers want several independent tails at once, so each
  * lane takes one. */
-CPG_DEV_NOINL double cpg_binom_tail_lane(const double *lf, int k, int n, double pe, int *bad)
+CPG_DEV_NOINL double cpg_binom_tail_lane(const double *lf, int k, int n, const cpg_rate r, int *bad)
 { k = cpg_clamp_cnt(k & 0xffff); n = cpg_clamp_cnt(n & 0xffff);
   if (k > n) { *bad = 1; return 0.; }
-  const double lpe = cpg_log(pe), l1mpe = cpg_log(1-pe), mean = n*pe;
+  const double lpe = r.lp, l1mpe = r.l1mp, mean = n*r.p;
   const double lfn = CPG_LDG(lf+n);
   double p, p_first, t;
 #define CPG_LBP(x) (lfn-CPG_LDG(lf+(x))-CPG_LDG(lf+(n-(x)))+(x)*lpe+(n-(x))*l1mpe)
@@ -172,7 +203,7 @@ CPG_DEV_NOINL double cpg_binom_tail_lane(const double *lf, int k, int n, double 
 }
 
 /* p_errorin (src/util.c:46-55) for one lane; the caller guarantees cin <= cout */
-CPG_DEV double cpg_p_errorin_lane(const double *lf, int etype, double erate, int cout, int cin, int *bad)
+CPG_DEV double cpg_p_errorin_lane(const double *lf, int etype, const cpg_rate erate, int cout, int cin, int *bad)
 { return cpg_binom_tail_lane(lf,(etype == ET_SELF) ? cin : cout-cin,cout,erate,bad); }
 
 /* src/util.c:24-33 */

@@ -60,7 +60,7 @@ CPG_DEV_HELPER double rl_lp_e(const WCtx &W, const cpg_intvl &I, const uint16_t 
 CPG_DEV_HELPER double rl_lp_r(WCtx &W, const cpg_intvl &I, uint16_t pr_cnt, int F, const uint16_t *COV)
 { uint16_t bc = rl_begcnt(I,F);
   double sf = -CPG_INF;
-  double er = (bc < pr_cnt) ? cpg_lp_binom(W,bc,pr_cnt,1-CPG_PE_MEAN) : -CPG_INF;
+  double er = (bc < pr_cnt) ? cpg_lp_binom99(W,bc,pr_cnt) : -CPG_INF;
   double lp = dmax_ref(sf,er);
   if (lp > CPG_R_LOGP) return lp;
   uint16_t mx = (uint16_t)imax(I.ccb,I.cce);

@@ -14,27 +14,39 @@
 #define CPG_UNREL_CUH
 #include "cpg_rel.cuh"
 
-/* src/class_unrel.c:11-25 */
-CPG_DEV_HELPER void un_nn(int idx, int s, const cpg_intvl *v, int N, int &l, int &r)
-{ l = idx-1;
-  CPG_LOOP while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--;
-  if (l < 0) l = -1;
-  r = idx+1;
-  CPG_LOOP while (r < N && !(v[r].asgn == s && v[r].is_rel)) r++;
-  if (r >= N) r = -1;
+/* src/class_unrel.c:11-25 for both states at once: nb[h][side] = nearest reliable interval
+ * assigned H (h = 0) or D (h = 1) to the left (side 0) / right (side 1) of idx, or -1.  The
+ * reference walks interval by interval, once per use; here the lanes of the group look at
+ * consecutive intervals together and the result is shared by all the tasks of the update. */
+CPG_DEV_HELPER void un_nn_group(const WCtx &W, int idx, const cpg_intvl *v, int N, int nb[2][2])
+{ nb[0][0] = nb[0][1] = nb[1][0] = nb[1][1] = -1;
+  int need = 3;
+  CPG_LOOP for (int base = idx-1; base >= 0 && need; base -= W.gsize)
+    { const int j = base-W.glane;
+      int a = -1;
+      if (j >= 0 && v[j].is_rel) a = v[j].asgn;
+      if (need & 1) { unsigned m = cpg_gballot(W,a == ST_H); if (m) { nb[0][0] = base-(cpg_ffs(m)-1); need &= ~1; } }
+      if (need & 2) { unsigned m = cpg_gballot(W,a == ST_D); if (m) { nb[1][0] = base-(cpg_ffs(m)-1); need &= ~2; } }
+    }
+  need = 3;
+  CPG_LOOP for (int base = idx+1; base < N && need; base += W.gsize)
+    { const int j = base+W.glane;
+      int a = -1;
+      if (j < N && v[j].is_rel) a = v[j].asgn;
+      if (need & 1) { unsigned m = cpg_gballot(W,a == ST_H); if (m) { nb[0][1] = base+(cpg_ffs(m)-1); need &= ~1; } }
+      if (need & 2) { unsigned m = cpg_gballot(W,a == ST_D); if (m) { nb[1][1] = base+(cpg_ffs(m)-1); need &= ~2; } }
+    }
 }
 
 /* src/class_unrel.c:27-51 */
-CPG_DEV_HELPER uint16_t un_est_cov(WCtx &W, int x, int idx, const cpg_intvl *v, int N, int s)
-{ int l, r;
-  un_nn(idx,s,v,N,l,r);
+CPG_DEV_HELPER uint16_t un_est_cov(WCtx &W, int x, const cpg_intvl *v, int s, const int nb[2][2])
+{ int l = nb[s == ST_D][0], r = nb[s == ST_D][1];
   if (l != -1 && r != -1) return (uint16_t)cpg_lin_interp(W,x,v[l].e-1,v[l].cce,v[r].b,v[r].ccb);
   if (l != -1) return v[l].cce;
   if (r != -1) return v[r].ccb;
   /* nothing of state s around: fall back on the other state, once */
-  const int o = (s == ST_H) ? ST_D : ST_H;
   uint16_t c;
-  un_nn(idx,o,v,N,l,r);
+  l = nb[s != ST_D][0]; r = nb[s != ST_D][1];
   if (l != -1 && r != -1) c = (uint16_t)cpg_lin_interp(W,x,v[l].e-1,v[l].cce,v[r].b,v[r].ccb);
   else if (l != -1) c = v[l].cce;
   else if (r != -1) c = v[r].ccb;
@@ -51,12 +63,11 @@ CPG_DEV_HELPER double un_lp_e(const WCtx &W, const cpg_intvl &I)
 }
 
 /* src/class_unrel.c:67-113 */
-CPG_DEV_HELPER double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
+CPG_DEV_HELPER double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, const int nb[2][2])
 { const cpg_intvl &I = v[idx];
   const cpg_dmodel *M = W.M;
   if (imax(I.cb,I.ce) >= M->cov[ST_R]) return 0.;
-  int l, r;
-  un_nn(idx,ST_D,v,N,l,r);
+  const int l = nb[1][0], r = nb[1][1];
   uint16_t dl, dr;
   if (l == -1 && r == -1) dl = dr = M->cov[ST_D];
   else if (l == -1) dl = dr = v[r].cb;
@@ -64,8 +75,8 @@ CPG_DEV_HELPER double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, int N)
   else { dl = v[l].ce; dr = v[r].cb; }
   uint16_t rl = (uint16_t)(M->dr_ratio*dl), rr = (uint16_t)(M->dr_ratio*dr);
   if (I.cb >= rl || I.ce >= rr) return CPG_R_LOGP;
-  double a = cpg_lp_binom(W,I.cb,rl,1-CPG_PE_MEAN);
-  double b = cpg_lp_binom(W,I.ce,rr,1-CPG_PE_MEAN);
+  double a = cpg_lp_binom99(W,I.cb,rl);
+  double b = cpg_lp_binom99(W,I.ce,rr);
   return a+b;
 }
 
@@ -88,17 +99,18 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *
          arguments of a task change only if a neighbouring interval changed state in between.  The
          first sweep's arguments and results are kept per interval and reused when they match. */
       cpg_unmemo *mm = (memo != 0 && idx < CPG_MEMO_CAP) ? memo+(size_t)idx*8 : 0;
+      int nb[2][2];
       CPG_SYNCGROUP(W);
+      un_nn_group(W,idx,v,N,nb);
       CPG_LOOP for (int q = W.glane; q < 10; q += W.gsize)
         { double val = -CPG_INF;
           int need_s = 0, need_b = 0, k = 0, bn = 0, bc = 0; double lambda = 0.;
           if (q == 0) val = un_lp_e(W,I);
-          else if (q == 1) val = un_lp_r(W,idx,v,N);
+          else if (q == 1) val = un_lp_r(W,idx,v,nb);
           else
             { const int t = q-2, s = (t & 4) ? ST_D : ST_H, right = (t >> 1) & 1, kind = t & 1;
               if (kind == 0)
-                { int l, r;
-                  un_nn(idx,s,v,N,l,r);
+                { const int l = nb[s == ST_D][0], r = nb[s == ST_D][1];
                   if (!right && l != -1)
                     { int d = I.b-(v[l].e-1); if (d < 0) d = -d;
                       k = (int)I.cb-(int)v[l].cce; lambda = (double)v[l].cce*d/W.M->read_len; need_s = 1;
@@ -109,7 +121,7 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *
                     }
                 }
               else
-                { uint16_t est = un_est_cov(W,right ? I.e-1 : I.b,idx,v,N,s);
+                { uint16_t est = un_est_cov(W,right ? I.e-1 : I.b,v,s,nb);
                   uint16_t c = right ? I.ce : I.cb;
                   if (est >= c) { need_b = 1; bn = est; bc = c; }
                 }
@@ -120,7 +132,7 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *
                 { val = mm[t].val; need_s = need_b = 0; }
               else
                 { if (need_s) val = cpg_lp_skellam(k,lambda);
-                  if (need_b) val = cpg_log(cpg_p_errorin_lane(lf,ET_OTHERS,0.1,bn,bc,&bad));
+                  if (need_b) val = cpg_log(cpg_p_errorin_lane(lf,ET_OTHERS,cpg_rate_p1(W.M),bn,bc,&bad));
                   if (mm != 0) { mm[t].kind = mkind; mm[t].k = mk; mm[t].a = ma; mm[t].val = val; }
                 }
             }
@@ -187,11 +199,11 @@ CPG_DEV_NOINL void classify_phase1(ReadCtx &R, WCtx &W)
 { find_walls_and_reliable(R,W); }
 
 CPG_DEV_NOINL void classify_phase2(ReadCtx &R, WCtx &W, RelShared *sh)
-{ if (!(W.status & CPG_ST_EINTVL_OVF)) classify_reliable(R,W,sh); }
+{ if (!(W.status & CPG_ST_ABORT)) classify_reliable(R,W,sh); }
 
 CPG_DEV_NOINL int classify_phase3(ReadCtx &R, WCtx &W, uint8_t *cls)
 { const int K = W.M->K;
-  if (!(W.status & CPG_ST_EINTVL_OVF)) classify_unreliable(R,W);
+  if (!(W.status & CPG_ST_ABORT)) classify_unreliable(R,W);
   /* emit: 'N' x (K-1), then one class character per k-mer */
   CPG_LOOP for (int j = W.glane; j < K-1; j += W.gsize) cls[j] = 'N';
   const cpg_intvl *v = R.S.intvl;

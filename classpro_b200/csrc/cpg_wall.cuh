@@ -129,7 +129,8 @@ CPG_DEV_NOINL void perr_store(ReadCtx &R, WCtx &W, int pos, int e, int w, double
   unsigned s = (m & MK_SLOT) ? R.S.slot[pos] : 0u;
   CPG_SYNCGROUP(W);
   if (!(m & MK_SLOT))
-    { s = (unsigned)(R.nslots++);
+    { if (R.nslots >= R.S.capS) { W.status |= CPG_ST_RETRY; return; }       /* uniform in the group */
+      s = (unsigned)(R.nslots++);
       if (W.glane == 0)
         { R.S.mark[pos] = (uint8_t)(m | MK_SLOT);
           R.S.slot[pos] = (uint16_t)s;
@@ -283,8 +284,9 @@ CPG_DEV_HELPER int ei_find(const cpg_eintvl *a, int l, int r, int b, int e)
   return -1;
 }
 
-CPG_DEV_HELPER void ei_put(ReadCtx &R, const WCtx &W, int k, int b, int e, double pe)
-{ CPG_SYNCGROUP(W);
+CPG_DEV_HELPER void ei_put(ReadCtx &R, WCtx &W, int k, int b, int e, double pe)
+{ if (k >= R.S.capE) { W.status |= CPG_ST_RETRY; return; }                  /* uniform in the group */
+  CPG_SYNCGROUP(W);
   if (W.glane == 0) { R.S.eint[k].b = b; R.S.eint[k].e = e; R.S.eint[k].pe = pe; }
   CPG_SYNCGROUP(W);
 }
@@ -353,7 +355,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
   CPG_LOOP for (int e = 0; e < 2; e++) fresh[e] = reach[e] && perr_get(R,i,e,wtype) == -CPG_INF;
   CPG_SYNCGROUP(W);
   CPG_LOOP for (int q = W.glane; q < 2; q += W.gsize)
-    if (fresh[q]) term[q] = cpg_p_errorin_lane(lf,q,maxpe,cout,cin,&bad);
+    if (fresh[q]) term[q] = cpg_p_errorin_lane(lf,q,cpg_rate_pe(M,maxt,maxl),cout,cin,&bad);
   CPG_SYNCGROUP(W);
   int go[2];
   CPG_LOOP for (int e = 0; e < 2; e++)
@@ -384,12 +386,12 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
       CPG_SYNCGROUP(W);
       CPG_LOOP for (int q = W.glane; q < 23; q += W.gsize)
         { double val = 0.;
-          int need_b = 0, need_s = 0, be = 0, bco = 0, bci = 0, sj = 0; double ber = 0.;
+          int need_b = 0, need_s = 0, be = 0, bco = 0, bci = 0, sj = 0, bhc = 1;
           if (G.lc_kind != 0)
             { if (q < 16)
                 { const int e = q >> 3, p = q & 7;
                   if (go[e])
-                    { if (p == 7) { need_b = 1; be = e; ber = M->hc_erate; bco = cout; bci = cin; }
+                    { if (p == 7) { need_b = 1; be = e; bhc = 1; bco = cout; bci = cin; }
                       else
                         { int j = (p == 0) ? G.lc_j : pg_hc_j(G,K,p-1);
                           int ok = (p == 0) ? (G.lc_kind == 2 && pg_lc_ok(G,W,prof,e) && perr_get(R,j,e,wj) == -CPG_INF)
@@ -397,7 +399,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
                           if (ok)
                             { uint16_t cin_j, cout_j;
                               pg_counts(G,prof,j,cin_j,cout_j);
-                              need_b = 1; be = e; ber = (p == 0) ? maxpe : M->hc_erate; bco = cout_j; bci = cin_j;
+                              need_b = 1; be = e; bhc = (p != 0); bco = cout_j; bci = cin_j;
                             }
                         }
                     }
@@ -410,7 +412,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
                   if (ok) { need_s = 1; sj = j; }
                 }
             }
-          if (need_b) val = cpg_p_errorin_lane(lf,be,ber,bco,bci,&bad);
+          if (need_b) val = cpg_p_errorin_lane(lf,be,bhc ? cpg_rate_hc(M) : cpg_rate_pe(M,maxt,maxl),bco,bci,&bad);
           if (need_s) val = G.fwd ? lp_diff_pair(R,W,i,sj) : lp_diff_pair(R,W,sj,i);
           term[q] = val;
         }
@@ -463,6 +465,7 @@ CPG_DEV_NOINL int wall_multi(ReadCtx &R, WCtx &W, int i, int NS, int midx)
                   mark_or(R,W,i,MK_PAIR_MULT);
                   midx++;
                   if (midx >= plen) { W.status |= CPG_ST_EINTVL_OVF; return midx; }
+                  if (W.status & CPG_ST_RETRY) return midx;
                 }
               unsigned mj = R.S.mark[j];
               if (!(mj & (MK_BY_S|MK_BY_O))) continue;
@@ -475,6 +478,7 @@ CPG_DEV_NOINL int wall_multi(ReadCtx &R, WCtx &W, int i, int NS, int midx)
                       mark_or(R,W,j,MK_PAIR_MULT);
                       midx++;
                       if (midx >= plen) { W.status |= CPG_ST_EINTVL_OVF; return midx; }
+                      if (W.status & CPG_ST_RETRY) return midx;
                     }
                 }
               if (mj & MK_BY_O) { done = 1; break; }
@@ -564,6 +568,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
           CPG_LOOP while (m)
             { const int b = cpg_ffs(m)-1; m &= m-1;
               wall_candidate(R,W,base+32*l+b,eidx);
+              if (W.status & CPG_ST_RETRY) { R.N = 0; R.M = 0; return; }
             }
         }
     }
@@ -575,7 +580,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
 
   /* pass C: lone O-walls, 16 flag bytes per lane */
   int midx = NS;
-  CPG_LOOP for (int base = 0; base < plen && !(W.status & CPG_ST_EINTVL_OVF); base += 16*W.gsize)
+  CPG_LOOP for (int base = 0; base < plen && !(W.status & CPG_ST_ABORT); base += 16*W.gsize)
     { const int p0 = base+16*W.glane;
       unsigned hit = 0;
       if (p0 < plen)
@@ -594,11 +599,11 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
               const int i = base+16*l+b;
               if (mark[i] & MK_PAIR_MULT) continue;
               midx = wall_multi(R,W,i,NS,midx);
-              if (W.status & CPG_ST_EINTVL_OVF) { lanes = 0; break; }
+              if (W.status & CPG_ST_ABORT) { lanes = 0; break; }
             }
         }
     }
-  if (W.status & CPG_ST_EINTVL_OVF) { R.N = 0; R.M = 0; return; }
+  if (W.status & CPG_ST_ABORT) { R.N = 0; R.M = 0; return; }
   CPG_LOOP for (int k = NS; k < midx; k++) mark_clear_range(R,W,eint[k].b,eint[k].e,MK_BY_O);
   if (NS < midx) { NS = midx; ei_sort(eint,NS,W); }
 
@@ -617,6 +622,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
           { ei_put(R,W,NS,eint[i].b,max_e,max_pe);
             NS++;
             if (NS >= plen) { W.status |= CPG_ST_EINTVL_OVF; R.N = 0; R.M = 0; return; }
+            if (W.status & CPG_ST_RETRY) { R.N = 0; R.M = 0; return; }
           }
         i = j+1;
       }
@@ -660,7 +666,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
               double poe = dmax_ref(perr_get(R,e,ET_OTHERS,WT_DROP),perr_get(R,e,ET_OTHERS,WT_GAIN));
               double lpob = (pob != -CPG_INF) ? cpg_log(pob) : -CPG_INF;
               double lpoe = (poe != -CPG_INF) ? cpg_log(poe) : -CPG_INF;
-              if (W.glane == 0)
+              if (W.glane == 0 && N < R.S.capI)
                 { cpg_intvl *I = intvl+N;
                   I->b = b; I->e = e; I->cb = prof[b]; I->ce = prof[e-1];
                   I->ccb = 0; I->cce = 0; I->is_rel = 0; I->asgn = ST_N;
@@ -672,6 +678,7 @@ CPG_DEV_NOINL void find_walls_and_reliable(ReadCtx &R, WCtx &W)
         }
     }
   CPG_SYNCGROUP(W);
+  if (N > R.S.capI) { W.status |= CPG_ST_RETRY; R.N = 0; R.M = 0; return; }
   R.N = N;
 
   /* reliable intervals (src/wall.c:1016-1037).  Three phases: corrected end counts of every

@@ -275,6 +275,7 @@ def _bind_hostsim(L):
     L.hs_decode_profile.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
     L.hs_decode_profile_cand.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.hs_ctx.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.hs_ctx2.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     assert L.hs_sizeof_intvl() == C.sizeof(GpuIntvl)
     return L
 

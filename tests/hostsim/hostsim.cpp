@@ -90,11 +90,22 @@ unsigned cpg_sim_gshfl(unsigned mask, unsigned v, int src)
 #endif
 
 static int g_group = CPG_WARP;        /* lanes per read (hs_set_group) */
+static int g_small_caps = 0;          /* > 0: first attempt with interval tables of this many entries (hs_set_small_caps) */
+static int g_retries = 0;
 
 struct HsWork
   { std::vector<uint8_t> mark; std::vector<uint16_t> slot; std::vector<uint32_t> cand; std::vector<double> perr; std::vector<cpg_eintvl> eint;
     std::vector<cpg_intvl> intvl, rint, wint; std::vector<uint16_t> bp;
     std::vector<uint8_t> af, ab, rpos, fixed; std::vector<int32_t> ord; std::vector<cpg_unmemo> memo; int mc = 0;
+    int capS = 0, capE = 0, capI = 0;
+    /* the interval tables are allocated with exactly `cap` entries (heap, so that an access past a
+       compact table is visible to a memory checker) */
+    void set_caps(int P, int small)
+      { capS = capE = capI = P+2;
+        if (small > 0) { capI = capE = small; capS = 2*small; }
+        perr.assign((size_t)capS*4,0.); eint.assign(capE,cpg_eintvl()); intvl.assign(capI,cpg_intvl());
+        fixed.assign(capI,0); ord.assign(capI,0);
+      }
     void size(int P)
       { int MC = P/2+8;
         mark.assign(P+2+32,0xff); slot.assign(P+2,0xffff); cand.assign(P/32+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
@@ -163,13 +174,15 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
   dm.dr_ratio = m->dr_ratio; dm.hc_erate = m->hc_erate;
   for (int t = 0; t < 3; t++) for (int l = 0; l < 21; l++) dm.pe[t][l] = m->pe[t][l];
   dm.cthres = m->cthres; dm.logfact = m->logfact;
+  cpg_model_fill_logs(&dm,0,1);
 
   std::vector<uint8_t> packed;
   cpg_seq S;
   if (seq_bits == 2)
-    { packed.assign((size_t)(rlen+3)/4,0);
-      if (cpg_pack_seq(seq,rlen,packed.data())) return -1;
-      S.p = packed.data(); S.bits = 2;
+    { /* 16 bytes of padding on both sides: cpg_win reads aligned words around the sequence */
+      packed.assign((size_t)(rlen+3)/4+32,0xA5);
+      if (cpg_pack_seq(seq,rlen,packed.data()+16)) return -1;
+      S.p = packed.data()+16; S.bits = 2;
     }
   else { S.p = (const uint8_t *)seq; S.bits = 8; }
 
@@ -180,10 +193,14 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
   static cpg_wshared ws[32]; static RelShared sh[32][2];
   std::vector<std::vector<char> > cls_g(NG);
   LaneJob jobs[CPG_WARP];
+  int st = 0;
+  for (int attempt = (g_small_caps > 0 ? 0 : 1); attempt < 2; attempt++)
+  {
   for (int l = 0; l < CPG_WARP; l++)
     { LaneJob &J = jobs[l];
       const int g = l/G;
       if (sized[g] < plen) { Wk[g].size(plen+64); sized[g] = plen+64; }
+      if (l%G == 0) Wk[g].set_caps(sized[g],attempt == 0 ? g_small_caps : 0);
       if (g > 0 && (int)cls_g[g].size() < rlen+1) cls_g[g].assign((size_t)rlen+1,0);
       J.lane = l; J.glane = l%G; J.gsize = G; J.gbase = g*G;
       J.gmask = ((G >= 32) ? 0xffffffffu : ((1u << G)-1u)) << J.gbase;
@@ -203,9 +220,15 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
       R.S.intvl = K.intvl.data(); R.S.rint = K.rint.data(); R.S.wint = K.wint.data();
       R.S.bp = K.bp.data(); R.S.asg_f = K.af.data(); R.S.asg_b = K.ab.data();
       R.S.rpos = K.rpos.data(); R.S.ord = K.ord.data(); R.S.fixed = K.fixed.data(); R.S.MC = K.mc; R.S.memo = K.memo.data();
+      R.S.capS = K.capS; R.S.capE = K.capE; R.S.capI = K.capI;
     }
   run_lanes(lane_classify,jobs);
-  int st = 0;
+  st = 0;
+  for (int l = 0; l < CPG_WARP; l++) st |= jobs[l].status;
+  if (attempt == 0 && (st & CPG_ST_RETRY)) { g_retries++; continue; }      /* what the retry launch does on the device */
+  break;
+  }
+  st = 0;
   for (int l = 0; l < CPG_WARP; l++)
     { st |= jobs[l].status;
       if (jobs[l].N != jobs[0].N || jobs[l].M != jobs[0].M) st |= 1<<30;      /* lanes disagree */
@@ -216,6 +239,11 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
   if (M_out) *M_out = jobs[0].M;
   return st;
 }
+
+/* first attempt of the next hs_classify_read calls with interval tables of n entries (0: full
+   size only); hs_retries() counts the reads that needed the second, full-size attempt */
+int hs_set_small_caps(int n) { g_small_caps = n; g_retries = 0; return 0; }
+int hs_retries(void) { return g_retries; }
 
 /* lanes per read for the next hs_classify_read calls (a power of two <= the warp width) */
 int hs_set_group(int g)
@@ -242,6 +270,15 @@ int hs_decode_profile(const uint8_t *src, int64_t len, uint16_t *out, int cap)
 
 int hs_ctx(const char *seq, int rlen, int p, int right, int t)
 { cpg_seq S; S.p = (const uint8_t *)seq; S.bits = 8;
+  return right ? cpg_rctx(S,rlen,p,t) : cpg_lctx(S,rlen,p,t);
+}
+
+/* the same query on the 2-bit packed form of the sequence (pad = byte offset of the packed
+   sequence inside its buffer, to exercise every alignment of the window loads) */
+int hs_ctx2(const char *seq, int rlen, int p, int right, int t, int pad)
+{ std::vector<uint8_t> packed((size_t)(rlen+3)/4+48,0x5A);
+  if (cpg_pack_seq(seq,rlen,packed.data()+16+pad)) return -1;
+  cpg_seq S; S.p = packed.data()+16+pad; S.bits = 2;
   return right ? cpg_rctx(S,rlen,p,t) : cpg_lctx(S,rlen,p,t);
 }
 

@@ -89,6 +89,32 @@ def test_minimal_reads(kit, hostsim):
     assert a == b and set(a[39:]) == {ord("R")}
 
 
+def test_compact_scratch_retry(kit, hostsim):
+    """A read that outgrows the compact interval tables of the main launch is flagged and classified
+    again with full-size tables: same result.  Tables of 6 entries force the second attempt for
+    nearly every read; the 32-thread emulation runs the abort paths with lane groups of 16."""
+    sim = kit.simulate(seed=21, genome_len=20000, cov=16., het=0.01, repeat_frac=0.4, len_mean=2500, len_sd=500,
+                       len_min=600)
+    om = kit.oracle_model(sim)
+    ow = kit.OracleWork(clean=True)
+    for lib, nreads, group in ((hostsim, min(sim.nreads, 60), 1), (kit.hostsim32_lib(), 5, 16)):
+        gm = kit.gpu_model_from_sim(lib, sim)
+        if group > 1:
+            lib.hs_set_group(group)
+        lib.hs_set_small_caps(6)
+        try:
+            for i in range(nreads):
+                s, c = sim.read_ascii(i).tobytes(), sim.read_counts(i)
+                a, ia, ma = ow.classify(om, s, c, True)
+                st, b, ib, mb = kit.hostsim_classify(gm, s, c, 2, True, lib=lib)
+                assert st == 0 and a == b and ia == ib and ma == mb, i
+            assert lib.hs_retries() >= nreads // 2
+        finally:
+            lib.hs_set_small_caps(0)
+            if group > 1:
+                lib.hs_set_group(32)
+
+
 def test_context_closed_form_exhaustive(kit, hostsim):
     """cpg_context.cuh's on-demand run lengths equal the reference sweep (src/context.c) at every
     base, for every sequence of length <= 7 over ACGT and <= 12 over a two-letter alphabet."""
@@ -104,6 +130,8 @@ def test_context_closed_form_exhaustive(kit, hostsim):
             for t in range(3):
                 assert hostsim.hs_ctx(seq, n, p, 0, t) == lc[p, t], (seq, p, t, "left")
                 assert hostsim.hs_ctx(seq, n, p, 1, t) == rc[p, t], (seq, p, t, "right")
+                assert hostsim.hs_ctx2(seq, n, p, 0, t, p & 3) == lc[p, t], (seq, p, t, "left, packed")
+                assert hostsim.hs_ctx2(seq, n, p, 1, t, n & 3) == rc[p, t], (seq, p, t, "right, packed")
 
     import itertools
     for n in range(2, 7):
@@ -138,6 +166,25 @@ def test_context_random_low_complexity(kit, hostsim):
             for t in range(3):
                 assert hostsim.hs_ctx(seq, n, p, 0, t) == lc[p, t]
                 assert hostsim.hs_ctx(seq, n, p, 1, t) == rc[p, t]
+                assert hostsim.hs_ctx2(seq, n, p, 0, t, p & 3) == lc[p, t]
+                assert hostsim.hs_ctx2(seq, n, p, 1, t, (p >> 2) & 3) == rc[p, t]
+
+
+def test_context_packed_long_runs(kit, hostsim):
+    """Packed (32 bases per window) and raw (base by base) evaluation agree on runs longer than a
+    window and longer than the 127 cap, at every position and buffer alignment."""
+    rng = np.random.default_rng(11)
+    for unit in (b"A", b"AC", b"ACG", b"T", b"GT", b"TTC"):
+        for copies in (20, 45, 130, 200):
+            seq = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 9))).tolist()) + unit * copies \
+                + bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 9))).tolist())
+            n = len(seq)
+            step = 1 if n < 150 else 5
+            for p in list(range(0, n, step)) + [n - 1]:
+                for t in range(3):
+                    for right in (0, 1):
+                        assert hostsim.hs_ctx2(seq, n, p, right, t, p & 3) == hostsim.hs_ctx(seq, n, p, right, t), \
+                            (unit, copies, p, t, right)
 
 
 def random_stream(rng, n_tokens, adversarial):
