@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--cov", type=float, default=30.)
     ap.add_argument("--chunk-mb", type=float, default=5.)
     ap.add_argument("--gen-threads", type=int, default=0)
-    ap.add_argument("--batches", type=int, default=8)
+    ap.add_argument("--batches", type=int, default=4)
     ap.add_argument("--cpu-sample-mbases", type=float, default=120.)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -366,8 +366,11 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     n, r, c = data.kmers, data.bases, data.prof_bytes
-    bytes_dec = c + 2 * n
-    bytes_cls = 2 * n + (r + 3) // 4 + r
+    # algorithmic bytes.  k_decode is decode + candidate scan fused: compressed
+    # bytes in, counts (2 B/k-mer) and the candidate bit map (1 bit/k-mer) out.  k_classify reads the
+    # counts, the bit map and the 2-bit bases and writes one class byte per base.
+    bytes_dec = c + 2 * n + n // 8
+    bytes_cls = 2 * n + n // 8 + (r + 3) // 4 + r
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -381,10 +384,14 @@ def main():
             "algorithmic_bytes_per_launch": dom_bytes,
             "kernels": {
                 "k_decode": {"ms": ms_dec, "bytes": bytes_dec, "GBps": bytes_dec / (ms_dec * 1e-3) / 1e9,
-                             "frac": bytes_dec / (ms_dec * 1e-3) / 1e9 / peak},
+                             "frac": bytes_dec / (ms_dec * 1e-3) / 1e9 / peak,
+                             "traffic": (traffic or {}).get("k_decode"),
+                             "note": "profile decode + wall-candidate scan fused: c + 2n + n/8 bytes"},
                 "k_classify": {"ms": ms_cls, "bytes": bytes_cls, "GBps": bytes_cls / (ms_cls * 1e-3) / 1e9,
                                "frac": bytes_cls / (ms_cls * 1e-3) / 1e9 / peak,
-                               "note": "FP64-latency / control-flow bound, not a streaming kernel",
+                               "traffic": (traffic or {}).get("k_classify"),
+                               "note": "FP64-latency / control-flow bound, not a streaming kernel: see issue-slot, "
+                                       "FP64-pipe, active-lane and stall counters in profiles/",
                                "phase_share": dict(zip(("wall", "reliable_dp", "unreliable_emit", "barrier_wait"),
                                                        [round(x / max(1, sum(phase)), 3) for x in phase]))}}}
 

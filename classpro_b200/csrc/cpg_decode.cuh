@@ -75,7 +75,9 @@ CPG_DEV int dc_scan_max(int v, int lane)
 CPG_DEV int dc_clz(unsigned v) { return __clz((int)v); }
 #endif
 
-#define DC_BPL    4                      /* bytes per lane per step */
+#ifndef DC_BPL
+#define DC_BPL    4                      /* bytes per lane per step (4 or 8; 8 measured slower: 4.25 vs 3.84 ms) */
+#endif
 #define DC_SLOTS  (DC_BPL*CPG_WARP)      /* token slots per step */
 
 /* The step's table holds one word per EMITTING token, in stream order: count value << 16 | end
@@ -92,8 +94,8 @@ CPG_DEV int dc_owner(const unsigned *tab, int ntok, int t)
 
 /* Decodes `len` bytes at `src` into at most `cap` counts at `out`; returns the
  * decoded length (which may exceed cap, as Fetch_Profile's return value does).  `tab` is a
- * per-warp shared-memory array of DC_SLOTS words (a step emits at most 4*32*63 = 8064 < 65536
- * counts, so offsets fit 16 bits). */
+ * per-warp shared-memory array of DC_SLOTS words (a step emits at most DC_SLOTS*63 <= 16128 <
+ * 65536 counts, so offsets fit 16 bits). */
 #if defined(CPG_HOSTSIM)
 CPG_DEV void dc_or(uint32_t *w, uint32_t bit) { __atomic_fetch_or(w,bit,__ATOMIC_RELAXED); }
 #else
@@ -124,7 +126,7 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
   const int sh = (int)((((size_t)out) >> 1) & 7);      /* misalignment of the row, in counts */
 
   for (; off < len; off += DC_SLOTS)
-    { /* ---- this lane's four bytes ---- */
+    { /* ---- this lane's bytes ---- */
       const int64_t p0 = off+(int64_t)lane*DC_BPL;
       unsigned b[DC_BPL]; int nv = 0;
 #ifdef CPG_HOSTSIM
@@ -134,21 +136,26 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
           nv += ok;
         }
 #else
-      { /* two aligned 32-bit loads + a funnel shift instead of four byte loads; the profile buffer
-           is padded, so reading up to 7 bytes past the read's stream stays inside it */
-        unsigned word = 0;
+      { /* aligned 32-bit loads + funnel shifts instead of byte loads; the profile buffer is padded,
+           so reading up to 7 bytes past the read's stream stays inside it */
+        unsigned word[DC_BPL/4];
+        for (int k = 0; k < DC_BPL/4; k++) word[k] = 0;
         nv = (p0 >= len) ? 0 : ((len-p0 >= DC_BPL) ? DC_BPL : (int)(len-p0));
         if (nv > 0)
           { const size_t a = (size_t)(src+p0);
             const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(size_t)3);
             const unsigned shb = (unsigned)(a & 3)*8;
-            const unsigned lo32 = wp[0], hi32 = shb ? wp[1] : 0u;
-            word = __funnelshift_r(lo32,hi32,shb);
+            unsigned lo32 = wp[0];
+            for (int k = 0; k < DC_BPL/4; k++)
+              { const unsigned hi32 = (shb || k+1 < DC_BPL/4) ? wp[k+1] : 0u;
+                word[k] = __funnelshift_r(lo32,hi32,shb);
+                lo32 = hi32;
+              }
           }
-        for (int k = 0; k < DC_BPL; k++) b[k] = (k < nv) ? ((word >> (8*k)) & 0xffu) : 0u;
+        for (int k = 0; k < DC_BPL; k++) b[k] = (k < nv) ? ((word[k >> 2] >> (8*(k & 3))) & 0xffu) : 0u;
       }
 #endif
-      /* trailing run of high-bit-set bytes among the valid ones; full = all four present and high */
+      /* trailing run of high-bit-set bytes among the valid ones; full = all present and high */
       int trail = 0;
       for (int k = nv-1; k >= 0 && (b[k] & 0x80); k--) trail++;
       const int full = (nv == DC_BPL && trail == DC_BPL);
@@ -236,6 +243,9 @@ CPG_DEV_NOINL int decode_profile(const uint8_t *src, int64_t len, uint16_t *out,
                           t += 8;
                         }
                       else
+                        /* count by count, fully unrolled and predicated.  (Forming the group token by
+                           token -- splat + one XOR per token boundary -- was measured slower, 4.93 vs
+                           3.84 ms: its trip count differs from lane to lane.) */
                         for (int e = 0; e < 8; e++, t++)
                           { if ((unsigned)t >= cur_end) { cur = tab[++s]; cur_end = cur & 0xffffu; }
                             w[e >> 1] |= (cur >> 16) << ((e & 1)*16);

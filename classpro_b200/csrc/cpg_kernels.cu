@@ -50,7 +50,7 @@ struct BatchDev
     const int64_t *cls_off;
     int32_t       *status;
     const int32_t *order;
-    int32_t       *queue;        /* [2] work counters: decode, classify; [2..3] spare */
+    int32_t       *queue;        /* work counters: [0] decode, [1] classify, [2] retry launch; [3] reads flagged for retry */
     unsigned long long *phase_cycles;   /* [4] summed per-warp cycles of the three phases (+ idle at the CTA barriers) */
   };
 
@@ -132,11 +132,20 @@ k_decode(BatchDev B, int K, int rcov)
 /* ------------------------------------------------------------------------------------------ */
 /* Lanes per read in k_classify: a read is owned by an aligned group of CPG_GROUP lanes, so a warp
    works on 32/CPG_GROUP reads whose (mostly serial, latency-bound) instruction streams interleave;
-   the lane-parallel task lists of the per-read code are at most 23 long and mostly shorter. */
+   the lane-parallel task lists of the per-read code are at most 23 long and mostly shorter.
+   Registers cap the kernel at 32 warps per SM, so narrower groups are the way to more independent
+   streams: measured on the 100 Mb workload, k_classify takes 497 / 343 / 309 ms with groups of
+   32 / 16 / 8 lanes (profiles/r01_history.md). */
 #ifndef CPG_GROUP
-#define CPG_GROUP 16
+#define CPG_GROUP 8
 #endif
 #define CLASSIFY_GROUPS (CLASSIFY_THREADS/CPG_GROUP)
+/* CTA-synchronous phases; -DCPG_NO_PHASE_SYNC lets every group run ahead */
+#ifdef CPG_NO_PHASE_SYNC
+#define CPG_PHASE_SYNC() do { } while (0)
+#else
+#define CPG_PHASE_SYNC() __syncthreads()
+#endif
 
 /* the count-threshold table sits in shared memory unless the per-group blocks need the room
    (groups of 8 lanes: 128 reads per CTA); then it is read through the read-only global path */
@@ -189,6 +198,7 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
      processing order (neighbouring reads have similar lengths, so the phases of a CTA finish
      close together). */
   __shared__ int s_base;
+  if (retry && B.queue[3] == 0) return;                /* nothing was flagged (the usual case) */
   for (;;)
     { __syncthreads();
       if (threadIdx.x == 0) s_base = atomicAdd(B.queue+1+retry,CLASSIFY_GROUPS);
@@ -234,16 +244,19 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
       long long t0 = clock64();
       if (active) classify_phase1(R,W);
       long long t1 = clock64();
-      __syncthreads();
+      CPG_PHASE_SYNC();
       long long t2 = clock64();
       if (active) classify_phase2(R,W,sh.rel[gib]);
       long long t3 = clock64();
-      __syncthreads();
+      CPG_PHASE_SYNC();
       long long t4 = clock64();
       if (active)
         { int st = classify_phase3(R,W,B.cls+B.cls_off[r]);
           st = __reduce_or_sync(gmask,st);
-          if (glane == 0) B.status[r] = st;
+          if (glane == 0)
+            { B.status[r] = st;
+              if (st & CPG_ST_RETRY) atomicAdd(B.queue+3,1);
+            }
         }
       long long t5 = clock64();
       if (glane == 0 && B.phase_cycles)

@@ -65,6 +65,23 @@ DATASETS = [
 ]
 
 
+def test_retry_launch_matches_oracle(kit, cp, monkeypatch):
+    """Interval tables of 64 entries in the main launch (CPG_SCRATCH_DIV test knob): nearly every
+    read is flagged and classified by the retry launch with full-size tables; same class strings."""
+    monkeypatch.setenv("CPG_SCRATCH_DIV", "1000000")
+    name, params, cov_opt, read_len = DATASETS[1]
+    sim = kit.simulate(**params)
+    om = kit.oracle_model(sim, cov_opt, read_len)
+    gm = cp.Model.from_hist(sim.kmer, sim.hist[1:32768], sim.hist[32768], sim.hist[32769], cov_opt=cov_opt, read_len=read_len)
+    ctx = cp.Context(gm)
+    batch, keep = make_batch(cp, sim)
+    cls, status = ctx.classify(batch)
+    ctx.close()
+    assert not (status & cp.ST_FATAL).any() and not (status & (1 << 20)).any()
+    kmers, flips = compare_with_oracle(kit, sim, batch, keep, cls, om)
+    assert flips <= max(0, int(kmers * FLIP_BUDGET)), "%d of %d k-mers differ from the oracle" % (flips, kmers)
+
+
 @pytest.mark.parametrize("name,params,cov_opt,read_len", DATASETS, ids=[d[0] for d in DATASETS])
 def test_classify_matches_oracle(kit, cp, name, params, cov_opt, read_len):
     sim = kit.simulate(**params)

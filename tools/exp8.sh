@@ -1,7 +1,5 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/gpu_check.py 2>&1 | grep "^{" | cut -c1-120
 B="python bench.py --no-cpu-baseline --steps 3 --warmup 3"
 pick() { python -c "
 import json,sys
@@ -10,7 +8,7 @@ for l in sys.stdin:
         d=json.loads(l); k=d['roofline']['kernels']
         print('$1', 'value %.3e e2e %.3e dec %.2f ms cls %.2f ms' % (d['value'], d['e2e']['value'], k['k_decode']['ms'], k['k_classify']['ms']), k['k_classify']['phase_share'])
 "; }
-$B --genome-mb 10 2>&1 | pick 10mb
-$B --genome-mb 100 2>&1 | pick 100mb
-CLASSPRO_B200_LIB=$PWD/classpro_b200/build/lib_g8.so $B --genome-mb 100 2>&1 | pick 100mb_g8
-CLASSPRO_B200_LIB=$PWD/classpro_b200/build/lib_g8.so $B --genome-mb 100 --batches 4 2>&1 | pick 100mb_g8_b4
+$B --genome-mb 100 2>&1 | pick 100mb_g8_default
+CLASSPRO_B200_LIB=$PWD/classpro_b200/build/lib_nosync.so $B --genome-mb 100 2>&1 | pick 100mb_g8_nosync
+CPG_ORDER_CHUNK=9472 $B --genome-mb 100 2>&1 | pick 100mb_g8_chunk9472
+CPG_ORDER_CHUNK=37888 $B --genome-mb 100 2>&1 | pick 100mb_g8_chunk37888
