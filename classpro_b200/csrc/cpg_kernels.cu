@@ -50,9 +50,16 @@ struct BatchDev
     const int64_t *cls_off;
     int32_t       *status;
     const int32_t *order;
-    int32_t       *queue;        /* work counters: [0] decode, [1] classify, [2] retry launch; [3] reads flagged for retry */
+    int32_t       *queue;        /* work counters: [0] decode, [1] classify/wall, [2] retry launch; [3] reads flagged
+                                    for retry; [4] reliable DP, [5] unreliable + emit */
+    struct ReadRec *rec;         /* per read: where k_wall left its interval tables */
+    cpg_intvl     *pool;         /* interval pool of the batch: intvl[N] then rint[M] of each read */
+    unsigned long long *pool_cursor;
+    int64_t        pool_cap;     /* entries */
     unsigned long long *phase_cycles;   /* [4] summed per-warp cycles of the three phases (+ idle at the CTA barriers) */
   };
+
+struct ReadRec { int64_t off; int32_t N, M; };
 
 struct ScratchDev
   { uint8_t *base;
@@ -268,6 +275,218 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ *  The main path: one kernel per phase.  The per-read code is large (~150 KB of SASS) and the
+ *  three phases share almost none of it, so each phase as its own persistent kernel keeps the
+ *  instruction working set of an SM small without the CTA-wide barriers k_classify needs for the
+ *  same effect, lets every lane group pull its next read on its own, and gives each phase its own
+ *  register allocation.  Between the kernels a read lives in HBM as its interval table: k_wall
+ *  appends intvl[N] + rint[M] to the batch's pool (one atomicAdd per read) and records the place.
+ *  k_classify above stays as the retry path (reads that outgrow the compact scratch or the pool).
+ * ------------------------------------------------------------------------------------------ */
+/* Lanes per read of each phase kernel (powers of two <= 32).  Measured on the 100 Mb workload
+   (profiles/r01_history.md): k_wall 235 / 198 / 140 / 102 / 96 / 155 ms with 32 / 16 / 8 / 4 / 2 / 1
+   lanes (it waits on DRAM: counts, flags and tables of the reads in flight are far larger than
+   L2, so more reads in flight win until the lane-parallel tasks serialise; 2 lanes cost the other
+   phases and small batches more than they gain); k_rel 79 / 94 ms with 8 / 16; k_unrel 78 ms with
+   4, 8 or 16. */
+#ifndef WALL_GROUP
+#define WALL_GROUP  4
+#endif
+#ifndef REL_GROUP
+#define REL_GROUP   CPG_GROUP
+#endif
+#ifndef UNREL_GROUP
+#define UNREL_GROUP CPG_GROUP
+#endif
+#define CPG_MIN3(a,b,c) ((a) < (b) ? ((a) < (c) ? (a) : (c)) : ((b) < (c) ? (b) : (c)))
+#define PHASE_MAX_GROUPS (CLASSIFY_THREADS/CPG_MIN3(WALL_GROUP,REL_GROUP,UNREL_GROUP))
+
+template<int G> struct PhaseShared
+  { uint8_t     cthres[(G >= 16) ? CPG_LROWS*256*4 : 16];     /* in shared memory when there is room */
+    cpg_dmodel  model;
+    cpg_wshared ws[CLASSIFY_THREADS/G];
+  };
+template<int G> struct RelPhaseShared
+  { cpg_dmodel  model;
+    cpg_wshared ws[CLASSIFY_THREADS/G];
+    RelShared   rel[CLASSIFY_THREADS/G][2];
+  };
+
+struct GroupId { int lane, gib, glane, gbase, gsize; unsigned gmask; };
+template<int G> __device__ __forceinline__ GroupId group_id()
+{ GroupId g;
+  g.lane = threadIdx.x & 31; g.gib = threadIdx.x/G; g.glane = threadIdx.x & (G-1);
+  g.gbase = g.lane-g.glane; g.gsize = G;
+  g.gmask = ((G >= 32) ? 0xffffffffu : ((1u << G)-1u)) << g.gbase;
+  return g;
+}
+/* next position of the processing order for this lane group */
+__device__ __forceinline__ int group_next(int32_t *counter, const GroupId &g)
+{ int q = 0;
+  if (g.glane == 0) q = atomicAdd(counter,1);
+  return __shfl_sync(g.gmask,q,g.gbase);
+}
+__device__ __forceinline__ void bind_scratch(ReadCtx &R, uint8_t *sb, const size_t off[14], const ScratchDev &SC)
+{ R.S.mark  = sb+off[0];
+  R.S.slot  = reinterpret_cast<uint16_t *>(sb+off[13]);
+  R.S.perr  = reinterpret_cast<double *>(sb+off[1]);
+  R.S.eint  = reinterpret_cast<cpg_eintvl *>(sb+off[2]);
+  R.S.intvl = reinterpret_cast<cpg_intvl *>(sb+off[3]);
+  R.S.rint  = reinterpret_cast<cpg_intvl *>(sb+off[4]);
+  R.S.wint  = reinterpret_cast<cpg_intvl *>(sb+off[5]);
+  R.S.bp    = reinterpret_cast<uint16_t *>(sb+off[6]);
+  R.S.asg_f = sb+off[7];
+  R.S.asg_b = sb+off[8];
+  R.S.rpos  = sb+off[9];
+  R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
+  R.S.fixed = sb+off[11];
+  R.S.MC = SC.MC; R.S.capS = SC.capS; R.S.capE = SC.capE; R.S.capI = SC.capI;
+  R.S.memo = reinterpret_cast<cpg_unmemo *>(sb+off[12]);
+}
+__device__ __forceinline__ void init_wctx(WCtx &W, const GroupId &g, const cpg_dmodel *M, const uint8_t *cthres, cpg_wshared *ws, int status)
+{ W.lane = g.lane; W.M = M; W.cthres = cthres; W.ws = ws; W.status = status;
+  W.glane = g.glane; W.gsize = g.gsize; W.gbase = g.gbase; W.gmask = g.gmask;
+}
+
+/* phase 1: wall detection + reliable intervals (cpg_wall.cuh) */
+__global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
+k_wall(BatchDev B, cpg_dmodel M, ScratchDev SC)
+{ constexpr int G = WALL_GROUP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PhaseShared<G> &sh = *reinterpret_cast<PhaseShared<G> *>(smem_raw);
+  const GroupId g = group_id<G>();
+  const uint8_t *cthres = M.cthres;
+  if (G >= 16)
+    { for (int i = threadIdx.x; i < CPG_LROWS*256; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(sh.cthres)[i] = reinterpret_cast<const uint32_t *>(M.cthres)[i];
+      cthres = sh.cthres;
+    }
+  if (threadIdx.x == 0) sh.model = M;
+  __syncthreads();
+  cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
+  __syncthreads();
+
+  uint8_t *sb = SC.base+((size_t)blockIdx.x*(CLASSIFY_THREADS/G)+g.gib)*SC.stride;
+  size_t off[14];
+  scratch_layout(SC,off);
+  for (;;)
+    { const int q = group_next(B.queue+1,g);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      if (B.status[r] != CPG_ST_OK) continue;                 /* undecodable profile: left to the host */
+      const int rlen = B.rlen[r], plen = rlen-M.K+1;
+      if (plen > SC.P) { if (g.glane == 0) B.status[r] = CPG_ST_BAD_PROFILE; continue; }
+      WCtx W; init_wctx(W,g,&sh.model,cthres,&sh.ws[g.gib],0);
+      ReadCtx R;
+      R.prof = B.cnt+B.cnt_off[r]; R.plen = plen; R.rlen = rlen;
+      R.seq.p = B.seq+B.seq_off[r]; R.seq.bits = B.seq_bits;
+      R.cand = B.cand+(B.cnt_off[r] >> 5);
+      R.nslots = 0; R.N = 0; R.M = 0;
+      bind_scratch(R,sb,off,SC);
+      find_walls_and_reliable(R,W);
+      int st = __reduce_or_sync(g.gmask,W.status);
+      const int N = R.N, Mrel = R.M;
+      long long at = 0;
+      if (!(st & CPG_ST_ABORT))
+        { /* a place in the pool for intvl[N] and rint[M] */
+          __syncwarp(g.gmask);
+          if (g.glane == 0) reinterpret_cast<long long *>(W.ws->term)[0] = (long long)atomicAdd(B.pool_cursor,(unsigned long long)(N+Mrel));
+          __syncwarp(g.gmask);
+          at = reinterpret_cast<long long *>(W.ws->term)[0];
+          __syncwarp(g.gmask);
+          if (at+N+Mrel > B.pool_cap) st |= CPG_ST_RETRY;
+          else
+            { /* cpg_intvl is 48 bytes = three 16-byte words */
+              uint4 *dst = reinterpret_cast<uint4 *>(B.pool+at);
+              const uint4 *s1 = reinterpret_cast<const uint4 *>(R.S.intvl), *s2 = reinterpret_cast<const uint4 *>(R.S.rint);
+              for (int i = g.glane; i < 3*N; i += G) dst[i] = s1[i];
+              for (int i = g.glane; i < 3*Mrel; i += G) dst[3*N+i] = s2[i];
+            }
+        }
+      if (g.glane == 0)
+        { ReadRec rc; rc.off = at; rc.N = N; rc.M = Mrel;
+          B.rec[r] = rc;
+          B.status[r] = st;
+          if (st & CPG_ST_RETRY) atomicAdd(B.queue+3,1);
+        }
+      __syncwarp(g.gmask);
+    }
+}
+
+/* phase 2: forward/backward DP over the reliable intervals (cpg_rel.cuh) */
+__global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
+k_rel(BatchDev B, cpg_dmodel M, ScratchDev SC)
+{ constexpr int G = REL_GROUP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RelPhaseShared<G> &sh = *reinterpret_cast<RelPhaseShared<G> *>(smem_raw);
+  const GroupId g = group_id<G>();
+  if (threadIdx.x == 0) sh.model = M;
+  __syncthreads();
+  cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
+  __syncthreads();
+  uint8_t *sb = SC.base+((size_t)blockIdx.x*(CLASSIFY_THREADS/G)+g.gib)*SC.stride;
+  size_t off[14];
+  scratch_layout(SC,off);
+  for (;;)
+    { const int q = group_next(B.queue+4,g);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      const int st0 = B.status[r];
+      if (st0 & (CPG_ST_BAD_PROFILE|CPG_ST_ABORT)) continue;
+      const ReadRec rc = B.rec[r];
+      if (rc.M == 0) continue;
+      WCtx W; init_wctx(W,g,&sh.model,M.cthres,&sh.ws[g.gib],0);
+      ReadCtx R;
+      const int rlen = B.rlen[r];
+      R.prof = B.cnt+B.cnt_off[r]; R.plen = rlen-M.K+1; R.rlen = rlen;
+      R.seq.p = B.seq+B.seq_off[r]; R.seq.bits = B.seq_bits; R.cand = 0;
+      R.nslots = 0; R.N = rc.N; R.M = rc.M;
+      bind_scratch(R,sb,off,SC);
+      R.S.intvl = B.pool+rc.off; R.S.rint = B.pool+rc.off+rc.N;
+      classify_reliable(R,W,sh.rel[g.gib]);
+      const int st = __reduce_or_sync(g.gmask,W.status);
+      if (g.glane == 0 && st != 0) B.status[r] = st0 | st;
+      __syncwarp(g.gmask);
+    }
+}
+
+/* phase 3: unreliable intervals + class string (cpg_unrel.cuh) */
+__global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
+k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
+{ constexpr int G = UNREL_GROUP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PhaseShared<G> &sh = *reinterpret_cast<PhaseShared<G> *>(smem_raw);
+  const GroupId g = group_id<G>();
+  if (threadIdx.x == 0) sh.model = M;
+  __syncthreads();
+  cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
+  __syncthreads();
+  uint8_t *sb = SC.base+((size_t)blockIdx.x*(CLASSIFY_THREADS/G)+g.gib)*SC.stride;
+  size_t off[14];
+  scratch_layout(SC,off);
+  for (;;)
+    { const int q = group_next(B.queue+5,g);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      const int st0 = B.status[r];
+      if (st0 & (CPG_ST_BAD_PROFILE|CPG_ST_RETRY)) continue;
+      const ReadRec rc = B.rec[r];
+      WCtx W; init_wctx(W,g,&sh.model,M.cthres,&sh.ws[g.gib],st0);
+      ReadCtx R;
+      const int rlen = B.rlen[r];
+      R.prof = B.cnt+B.cnt_off[r]; R.plen = rlen-M.K+1; R.rlen = rlen;
+      R.seq.p = B.seq+B.seq_off[r]; R.seq.bits = B.seq_bits; R.cand = 0;
+      R.nslots = 0; R.N = rc.N; R.M = rc.M;
+      bind_scratch(R,sb,off,SC);
+      R.S.intvl = B.pool+rc.off; R.S.rint = B.pool+rc.off+rc.N;
+      int st = classify_phase3(R,W,B.cls+B.cls_off[r]);
+      st = __reduce_or_sync(g.gmask,st);
+      if (g.glane == 0 && st != st0) B.status[r] = st;
+      __syncwarp(g.gmask);
+    }
+}
+
 /* ==========================================================================================
  *  C ABI
  * ========================================================================================== */
@@ -275,7 +494,7 @@ struct DevBuf { void *p; size_t cap; };
 
 struct Slot
   { cudaStream_t stream;
-    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue;
+    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue, rec, pool;
     /* small host-side (pinned) staging for arrays the library computes itself */
     int64_t *h_cnt_off; int32_t *h_order; size_t h_cap;
     int32_t *h_status; size_t h_status_cap;
@@ -294,6 +513,10 @@ struct cpg_ctx
     Slot       slot[2];
     DevBuf     scratch, scratch_big; ScratchDev SC, SCbig;
     int        retry_blocks;
+    int        fused;                 /* CPG_FUSED=1: the single-kernel path (k_classify) for every read */
+    size_t     wall_smem, rel_smem, unrel_smem;
+    cudaEvent_t evp[3];               /* between the phase kernels */
+    uint64_t   phase_ns[4];           /* wall, reliable DP, unreliable + emit, retry launch: last timed run */
     int        n_sm, decode_blocks, classify_blocks;
     size_t     classify_smem;
     cudaEvent_t ev[3];
@@ -355,7 +578,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   for (int s = 0; s < 2; s++)
     { Slot *S = &ctx->slot[s];
       DevBuf *bufs[] = { &S->seq,&S->seq_off,&S->rlen,&S->prof,&S->prof_off,&S->cnt,&S->cnt_off,&S->cand,&S->plen,
-                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue };
+                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue,&S->rec,&S->pool };
       for (unsigned i = 0; i < sizeof(bufs)/sizeof(bufs[0]); i++) if (bufs[i]->p) cudaFree(bufs[i]->p);
       if (S->h_cnt_off) cudaFreeHost(S->h_cnt_off);
       if (S->h_order) cudaFreeHost(S->h_order);
@@ -368,6 +591,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   if (ctx->d_cthres) cudaFree(ctx->d_cthres);
   if (ctx->d_logfact) cudaFree(ctx->d_logfact);
   for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 3; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
   free(ctx);
 }
 
@@ -413,6 +637,13 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
       CU_C(cudaEventCreateWithFlags(&ctx->slot[s].kdone,cudaEventDisableTiming));
     }
   for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->ev[i]));
+  for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->evp[i]));
+  { const char *f = getenv("CPG_FUSED"); ctx->fused = (f && atoi(f) > 0); }
+  ctx->wall_smem = sizeof(PhaseShared<WALL_GROUP>); ctx->rel_smem = sizeof(RelPhaseShared<REL_GROUP>);
+  ctx->unrel_smem = sizeof(PhaseShared<UNREL_GROUP>);
+  CU_C(cudaFuncSetAttribute(k_wall,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->wall_smem));
+  CU_C(cudaFuncSetAttribute(k_unrel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->unrel_smem));
+  CU_C(cudaFuncSetAttribute(k_rel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->rel_smem));
 
   ctx->classify_smem = sizeof(ClassifyShared);
   CU_C(cudaFuncSetAttribute(k_classify,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->classify_smem));
@@ -443,7 +674,8 @@ static int ensure_scratch(cpg_ctx *ctx, int P)
   SC.stride = scratch_layout(SC,off);
   SB.stride = scratch_layout(SB,off);
   for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->slot[s].stream);
-  int rc = reserve(ctx,&ctx->scratch,SC.stride*(size_t)ctx->classify_blocks*CLASSIFY_GROUPS);
+  const size_t groups = (CLASSIFY_GROUPS > PHASE_MAX_GROUPS) ? CLASSIFY_GROUPS : PHASE_MAX_GROUPS;
+  int rc = reserve(ctx,&ctx->scratch,SC.stride*(size_t)ctx->classify_blocks*groups);
   if (rc) return rc;
   rc = reserve(ctx,&ctx->scratch_big,SB.stride*(size_t)ctx->retry_blocks*CLASSIFY_GROUPS);
   if (rc) return rc;
@@ -496,7 +728,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
      batch (plain longest-first) 608 ms (profiles/r01_history.md).  CPG_ORDER_CHUNK overrides. */
   { int *bucket = (int *)calloc((size_t)maxR+2,sizeof(int));
     if (bucket == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
-    int chunk = ctx->classify_blocks*CLASSIFY_GROUPS;
+    int chunk = ctx->classify_blocks*(ctx->fused ? CLASSIFY_GROUPS : CLASSIFY_THREADS/WALL_GROUP);
     { const char *f = getenv("CPG_ORDER_CHUNK"); if (f && atoi(f) > 0) chunk = atoi(f); }
     if (chunk < 1) chunk = 1;
     for (int c0 = 0; c0 < n; c0 += chunk)
@@ -520,8 +752,14 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
       || (rc = reserve(ctx,&S->cand,(size_t)co/8+64))
       || (rc = reserve(ctx,&S->cls,cls_bytes+16)) || (rc = reserve(ctx,&S->cls_off,sizeof(int64_t)*(n+1)))
       || (rc = reserve(ctx,&S->status,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->order,sizeof(int32_t)*(n+1)))
-      || (rc = reserve(ctx,&S->queue,64)))
+      || (rc = reserve(ctx,&S->queue,128)) || (rc = reserve(ctx,&S->rec,sizeof(ReadRec)*(size_t)(n+1))))
     return rc;
+  /* interval pool: one entry per POOL_DIV profile positions (HiFi profiles need about one per 55);
+     a read that does not fit is flagged and goes through the retry launch */
+  int pool_div = 12;
+  { const char *f = getenv("CPG_POOL_DIV"); if (f && atoi(f) > 0) pool_div = atoi(f); }     /* test knob */
+  const int64_t pool_cap = co/pool_div+4096;
+  if ((rc = reserve(ctx,&S->pool,sizeof(cpg_intvl)*(size_t)pool_cap))) return rc;
   cudaStream_t st = S->stream;
   if (n > 0)
     { CU(cudaMemcpyAsync(S->seq.p,b->seq,seq_bytes,cudaMemcpyHostToDevice,st));
@@ -544,7 +782,9 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   B.cls = (uint8_t *)S->cls.p; B.cls_off = (const int64_t *)S->cls_off.p;
   B.status = (int32_t *)S->status.p; B.order = (const int32_t *)S->order.p;
   B.queue = (int32_t *)S->queue.p;
-  B.phase_cycles = (unsigned long long *)((char *)S->queue.p+16);
+  B.phase_cycles = (unsigned long long *)((char *)S->queue.p+32);
+  B.pool_cursor = (unsigned long long *)((char *)S->queue.p+64);
+  B.rec = (ReadRec *)S->rec.p; B.pool = (cpg_intvl *)S->pool.p; B.pool_cap = pool_cap;
   return CPG_OK;
 }
 
@@ -556,11 +796,20 @@ static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
      per-warp scratch arena. */
   Slot *other = &ctx->slot[S == &ctx->slot[0] ? 1 : 0];
   if (other->kdone_valid) CU(cudaStreamWaitEvent(st,other->kdone,0));
-  CU(cudaMemsetAsync(S->queue.p,0,64,st));
+  CU(cudaMemsetAsync(S->queue.p,0,128,st));
   if (timed) CU(cudaEventRecord(ctx->ev[0],st));
   k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(S->B,ctx->model.kmer,(int)ctx->model.cov[1]);
   if (timed) CU(cudaEventRecord(ctx->ev[1],st));
-  k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC,0);
+  if (ctx->fused)
+    k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC,0);
+  else
+    { k_wall<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->wall_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+      if (timed) CU(cudaEventRecord(ctx->evp[0],st));
+      k_rel<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->rel_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+      if (timed) CU(cudaEventRecord(ctx->evp[1],st));
+      k_unrel<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+      if (timed) CU(cudaEventRecord(ctx->evp[2],st));
+    }
   k_classify<<<ctx->retry_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SCbig,1);
   if (timed) CU(cudaEventRecord(ctx->ev[2],st));
   CU(cudaEventRecord(S->kdone,st));
@@ -659,12 +908,21 @@ extern "C" int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float
       if (S->n_reads > 0)
         { CU(cudaEventElapsedTime(&a,ctx->ev[0],ctx->ev[1]));
           CU(cudaEventElapsedTime(&b,ctx->ev[1],ctx->ev[2]));
+          if (!ctx->fused)
+            { float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+              CU(cudaEventElapsedTime(&p0,ctx->ev[1],ctx->evp[0]));
+              CU(cudaEventElapsedTime(&p1,ctx->evp[0],ctx->evp[1]));
+              CU(cudaEventElapsedTime(&p2,ctx->evp[1],ctx->evp[2]));
+              CU(cudaEventElapsedTime(&p3,ctx->evp[2],ctx->ev[2]));
+              ctx->phase_ns[0] = (uint64_t)(p0*1e6); ctx->phase_ns[1] = (uint64_t)(p1*1e6);
+              ctx->phase_ns[2] = (uint64_t)(p2*1e6); ctx->phase_ns[3] = (uint64_t)(p3*1e6);
+            }
         }
       td += a; tc += b;
     }
   if (ms_decode) *ms_decode = (float)(td/iters);
   if (ms_classify) *ms_classify = (float)(tc/iters);
-  if (launches) *launches = 3*iters;
+  if (launches) *launches = (ctx->fused ? 3 : 5)*iters;
   return CPG_OK;
 }
 
@@ -674,7 +932,11 @@ extern "C" int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4])
   Slot *S = &ctx->slot[0];
   if (S->queue.p == NULL) { out[0] = out[1] = out[2] = out[3] = 0; return CPG_OK; }
   CU(cudaStreamSynchronize(S->stream));
-  CU(cudaMemcpy(out,(char *)S->queue.p+16,32,cudaMemcpyDeviceToHost));
+  if (!ctx->fused)
+    { for (int i = 0; i < 4; i++) out[i] = ctx->phase_ns[i];
+      return CPG_OK;
+    }
+  CU(cudaMemcpy(out,(char *)S->queue.p+32,32,cudaMemcpyDeviceToHost));
   return CPG_OK;
 }
 

@@ -18,8 +18,9 @@
  *                    read ranges handed out in order, no data ever moves between GPUs;
  *    writer thread   emits the records of finished batches in read order (the reference writes
  *                    per-thread part files and concatenates them, src/io.c:70-112).
- *  -T is accepted for compatibility (it no longer selects the degree of parallelism), -P is
- *  accepted and unused (no part files), -G<n> limits the number of GPUs (default: all),
+ *  -T<n> is the number of host threads that pack sequences and fetch profiles for the reader
+ *  (the reference's default of 4), -P is accepted and unused (no part files), -G<n> limits the
+ *  number of GPUs (default: all),
  *  -B<n> sets the batch size in megabases (default 64).
  *  Not supported, with a clear error: .db/.dam inputs (DAZZ_DB is out of scope), -M (needs GSL).
  *  -s is accepted and ignored with a note: in the reference it never changes .class bytes and
@@ -349,6 +350,92 @@ static void batch_reserve(batch_t *b, int nrec, size_t pseq, size_t prof, size_t
     }
 }
 
+/* ---------------------------------------------------------------------------------------
+ *  A small fork-join pool: the reader hands the records of a parsed batch to -T host threads
+ *  (itself included) for 2-bit packing and profile reads; chunks are claimed with a counter.
+ * --------------------------------------------------------------------------------------- */
+typedef struct
+  { pthread_mutex_t mu; pthread_cond_t cv_job, cv_done;
+    pthread_t *th; int nth;
+    void (*fn)(void *, int, int); void *arg;
+    int total, chunk, next, busy, gen, stop;
+  } pool_t;
+
+static void pool_work(pool_t *P)                      /* called with P->mu held */
+{ while (P->next < P->total)
+    { int lo = P->next, hi = lo+P->chunk < P->total ? lo+P->chunk : P->total;
+      P->next = hi;
+      pthread_mutex_unlock(&P->mu);
+      P->fn(P->arg,lo,hi);
+      pthread_mutex_lock(&P->mu);
+    }
+}
+
+static void *pool_main(void *arg)
+{ pool_t *P = arg;
+  int seen = 0;
+  pthread_mutex_lock(&P->mu);
+  for (;;)
+    { while (!P->stop && P->gen == seen) pthread_cond_wait(&P->cv_job,&P->mu);
+      if (P->stop) break;
+      seen = P->gen;
+      P->busy++;
+      pool_work(P);
+      if (--P->busy == 0) pthread_cond_broadcast(&P->cv_done);
+    }
+  pthread_mutex_unlock(&P->mu);
+  return NULL;
+}
+
+static void pool_start(pool_t *P, int nthreads)
+{ memset(P,0,sizeof(*P));
+  pthread_mutex_init(&P->mu,NULL); pthread_cond_init(&P->cv_job,NULL); pthread_cond_init(&P->cv_done,NULL);
+  P->nth = nthreads > 1 ? nthreads-1 : 0;
+  P->th = xmalloc(sizeof(pthread_t)*(size_t)(P->nth+1));
+  for (int i = 0; i < P->nth; i++) pthread_create(&P->th[i],NULL,pool_main,P);
+}
+
+static void pool_run(pool_t *P, void (*fn)(void *, int, int), void *arg, int total, int chunk)
+{ pthread_mutex_lock(&P->mu);
+  P->fn = fn; P->arg = arg; P->total = total; P->chunk = chunk > 0 ? chunk : 1; P->next = 0;
+  P->gen++;
+  pthread_cond_broadcast(&P->cv_job);
+  P->busy++;
+  pool_work(P);
+  P->busy--;
+  while (P->busy > 0) pthread_cond_wait(&P->cv_done,&P->mu);
+  pthread_mutex_unlock(&P->mu);
+}
+
+static void pool_stop(pool_t *P)
+{ pthread_mutex_lock(&P->mu); P->stop = 1; pthread_cond_broadcast(&P->cv_job); pthread_mutex_unlock(&P->mu);
+  for (int i = 0; i < P->nth; i++) pthread_join(P->th[i],NULL);
+  free(P->th);
+}
+
+typedef struct { app_t *A; batch_t *b; int bad; } packjob_t;
+
+/* records lo..hi-1 of the batch: 2-bit pack the read, fetch its compressed profile */
+static void pack_records(void *arg, int lo, int hi)
+{ packjob_t *J = arg; app_t *A = J->A; batch_t *b = J->b;
+  int bad = 0;
+  for (int i = lo; i < hi; i++)
+    { const int k = b->slot_of[i];
+      if (k < 0) continue;
+      const int rlen = b->rlen_all[i];
+      bad |= cpg_pack_seq(b->seq[i],rlen,b->pseq+b->seq_off[k]);
+      int part; int64_t off, len;
+      prof_range(&A->P,b->first_id+i,&part,&off,&len);
+      int64_t got = 0;
+      while (got < len)
+        { ssize_t r = pread(A->P.fd[part],b->prof+b->prof_off[k]+got,(size_t)(len-got),off+got);
+          if (r <= 0) die("%s: cannot read profile of read %lld",PROG,(long long)(b->first_id+i+1));
+          got += r;
+        }
+    }
+  if (bad) __atomic_store_n(&J->bad,1,__ATOMIC_RELAXED);
+}
+
 /* reader: FASTX -> batches */
 static void *reader_main(void *arg)
 { app_t *A = arg;
@@ -358,6 +445,8 @@ static void *reader_main(void *arg)
   if (X.f == NULL) die("%s: Cannot open %s",PROG,A->src_path);
   gzbuffer(X.f,1<<20);
   X.buf = xmalloc(FX_BUF);
+  pool_t pool;
+  pool_start(&pool,A->nthreads);
   int64_t id = 0;
   int eof = 0;
   while (!eof && id < A->P.nreads)
@@ -404,21 +493,17 @@ static void *reader_main(void *arg)
       for (int i = 0; i < b->n_all; i++)
         { if (b->slot_of[i] < 0) continue;
           const int rlen = b->rlen_all[i];
-          b->seq_off[k] = so; b->prof_off[k] = po; b->cls_off[k] = co; b->rlen[k] = rlen;
-          bad |= cpg_pack_seq(b->seq[i],rlen,b->pseq+so);
-          so += (rlen+3)/4; co += rlen;
           int part; int64_t off, len;
           prof_range(&A->P,b->first_id+i,&part,&off,&len);
-          int64_t got = 0;
-          while (got < len)
-            { ssize_t r = pread(A->P.fd[part],b->prof+po+got,(size_t)(len-got),off+got);
-              if (r <= 0) die("%s: cannot read profile of read %lld",PROG,(long long)(b->first_id+i+1));
-              got += r;
-            }
-          po += len;
+          b->seq_off[k] = so; b->prof_off[k] = po; b->cls_off[k] = co; b->rlen[k] = rlen;
+          so += (rlen+3)/4; co += rlen; po += len;
           k++;
         }
       b->seq_off[k] = so; b->prof_off[k] = po; b->cls_off[k] = co;
+      { packjob_t J = { A, b, 0 };
+        pool_run(&pool,pack_records,&J,b->n_all,64);
+        bad = J.bad;
+      }
       if (bad)
         { /* a character outside ACGT: ship the raw bytes, compared as the reference compares them */
           size_t raw = 0;
@@ -444,6 +529,7 @@ static void *reader_main(void *arg)
   pthread_cond_broadcast(&A->cv);
   pthread_mutex_unlock(&A->mu);
   q_close(&A->q_ready);
+  pool_stop(&pool);
   gzclose(X.f);
   return NULL;
 }

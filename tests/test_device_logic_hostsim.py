@@ -230,13 +230,13 @@ def test_decode_empty_profile(kit, hostsim):
     assert n == 0
 
 
-@pytest.mark.parametrize("group", [32, 16, 8])
+@pytest.mark.parametrize("group", [32, 16, 8, 4])
 def test_warp32_emulation_classify(kit, group):
     """The same device sources with 32 host threads playing the lanes of one warp: every ballot,
     shuffle, reduction and group barrier is a rendezvous, lanes run asynchronously in between.
     Catches collectives reached by only some lanes (hang) and missing synchronisation (mismatch).
     `group` = lanes per read: the warp classifies 32/group copies of the read at the same time, each
-    lane group with its own scratch (k_classify runs with groups of 16), and the groups must agree."""
+    lane group with its own scratch (the kernels run with groups of 8 and 4), and the groups must agree."""
     L32 = kit.hostsim32_lib()
     assert L32.hs_set_group(group) == 0
     sim = kit.simulate(seed=47, genome_len=20000, cov=14., het=0.01, repeat_frac=0.4, len_mean=2200, len_sd=400,
