@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--chunk-mb", type=float, default=5.)
     ap.add_argument("--gen-threads", type=int, default=0)
     ap.add_argument("--batches", type=int, default=4)
-    ap.add_argument("--cpu-sample-mbases", type=float, default=120.)
+    ap.add_argument("--cpu-sample-mbases", type=float, default=360.)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -376,24 +376,34 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    dom = "k_classify" if ms_cls >= ms_dec else "k_decode"
-    dom_bytes, dom_ms = (bytes_cls, ms_cls) if dom == "k_classify" else (bytes_dec, ms_dec)
+    # classification = k_wall + k_rel + k_unrel (+ the retry launch): device time of each from the
+    # CUDA events between them (cpg_phase_cycles returns nanoseconds of the last timed run)
+    tot_ns = max(1, sum(phase))
+    ms_ph = [ms_cls * x / tot_ns for x in phase]
+    bytes_wall = 2 * n + n // 8 + (r + 3) // 4          # counts + candidate bits + 2-bit bases
+    kern = {
+        "k_decode": {"ms": ms_dec, "bytes": bytes_dec, "GBps": bytes_dec / (ms_dec * 1e-3) / 1e9,
+                     "frac": bytes_dec / (ms_dec * 1e-3) / 1e9 / peak, "traffic": (traffic or {}).get("k_decode"),
+                     "note": "profile decode + wall-candidate scan fused: c + 2n + n/8 bytes; issue bound"},
+        "k_wall": {"ms": ms_ph[0], "bytes": bytes_wall, "GBps": bytes_wall / (max(ms_ph[0], 1e-6) * 1e-3) / 1e9,
+                   "frac": bytes_wall / (max(ms_ph[0], 1e-6) * 1e-3) / 1e9 / peak, "traffic": (traffic or {}).get("k_wall"),
+                   "note": "wall detection + reliable intervals: 2n + n/8 + r/4 bytes in, interval tables out; "
+                           "DRAM-latency / FP64-latency bound (see stall mix in profiles/)"},
+        "k_rel": {"ms": ms_ph[1], "bytes": None, "traffic": (traffic or {}).get("k_rel"),
+                  "note": "reliable-interval DP on the interval tables (48 B per interval): FP64 dependency chains"},
+        "k_unrel": {"ms": ms_ph[2], "bytes": r, "traffic": (traffic or {}).get("k_unrel"),
+                    "note": "unreliable intervals + class string (r bytes out)"},
+        "retry_launch": {"ms": ms_ph[3]},
+    }
+    dom = max(("k_decode", "k_wall", "k_rel", "k_unrel"), key=lambda k: kern[k]["ms"])
+    dom_bytes = kern[dom]["bytes"] if kern[dom]["bytes"] is not None else bytes_cls
+    dom_ms = kern[dom]["ms"]
     roof = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
             "traffic": (traffic or {}).get(dom),
             "algorithmic_bytes_per_launch": dom_bytes,
-            "kernels": {
-                "k_decode": {"ms": ms_dec, "bytes": bytes_dec, "GBps": bytes_dec / (ms_dec * 1e-3) / 1e9,
-                             "frac": bytes_dec / (ms_dec * 1e-3) / 1e9 / peak,
-                             "traffic": (traffic or {}).get("k_decode"),
-                             "note": "profile decode + wall-candidate scan fused: c + 2n + n/8 bytes"},
-                "k_classify": {"ms": ms_cls, "bytes": bytes_cls, "GBps": bytes_cls / (ms_cls * 1e-3) / 1e9,
-                               "frac": bytes_cls / (ms_cls * 1e-3) / 1e9 / peak,
-                               "traffic": (traffic or {}).get("k_classify"),
-                               "note": "FP64-latency / control-flow bound, not a streaming kernel: see issue-slot, "
-                                       "FP64-pipe, active-lane and stall counters in profiles/",
-                               "phase_share": dict(zip(("wall", "reliable_dp", "unreliable_emit", "barrier_wait"),
-                                                       [round(x / max(1, sum(phase)), 3) for x in phase]))}}}
+            "classification_ms": ms_cls, "classification_bytes": bytes_cls,
+            "kernels": kern}
 
     ctx.close()
     if rank == 0:

@@ -1,15 +1,20 @@
 /*******************************************************************************************
  *  cpg_kernels.cu -- sm_100a kernels and the C ABI of libclasspro_b200.so.
  *
- *  Two kernels per batch, both persistent (grid = a multiple of the SM count, warps pull reads
- *  from an atomic queue ordered longest read first, i.e. length-binned LPT scheduling):
+ *  Five launches per batch, all persistent (grid = a multiple of the SM count, warps / lane groups
+ *  pull reads from an atomic queue in processing order):
  *
- *   k_decode    one warp per read: FastK profile bytes -> uint16 counts (cpg_decode.cuh).
- *               Streaming, HBM bound: c + 2n bytes per read (c compressed bytes, n k-mers).
- *   k_classify  one warp per read: candidate sweep over the counts, wall detection, reliable
- *               interval DP, unreliable intervals, class string (cpg_wall/rel/unrel.cuh).
- *               Reads 2n + ~r/4 bytes, writes r bytes; bound by FP64 latency (Bessel
- *               recurrences) and serial control flow, not by bandwidth.
+ *   k_decode    one warp per read: FastK profile bytes -> uint16 counts + the wall-candidate bit
+ *               map (cpg_decode.cuh).  Streaming: c + 2n + n/8 bytes per read.
+ *   k_wall      one lane group per read: wall detection, reliable intervals (cpg_wall.cuh);
+ *               leaves the read's interval tables in the batch's interval pool.
+ *   k_rel       reliable-interval DP, forward and backward (cpg_rel.cuh), on the pooled tables.
+ *   k_unrel     unreliable intervals and the class string (cpg_unrel.cuh): r bytes per read out.
+ *   k_classify  the three phases in one kernel, on 4 CTAs with worst-case scratch: the retry
+ *               launch for reads that outgrew the compact scratch blocks or the pool (normally
+ *               none; it returns at once).  CPG_FUSED=1 runs every read through it instead.
+ *  The classification kernels are bound by FP64 dependency chains (Bessel recurrences), DRAM
+ *  latency and serial control flow, not by bandwidth.
  *
  *  No tensor cores: nothing on this path is a dense contraction (integer/byte scans and scalar
  *  FP64 recurrences).  Compiled with -fmad=false: see cpg_math.cuh.
@@ -126,7 +131,7 @@ k_decode(BatchDev B, int K, int rcov)
       const int r = B.order[q];
       const int64_t po = B.prof_off[r];
       const int64_t len = B.prof_off[r+1]-po;
-      const int cap = B.rlen[r]-K+1;
+      const int cap = (B.rlen[r] >= K) ? B.rlen[r]-K+1 : 0;       /* reads shorter than K have empty profiles */
       const int64_t co = B.cnt_off[r];
       int n = decode_profile(B.prof+po,len,B.cnt+co,cap,lane,s_tab[wib],B.cand ? B.cand+(co >> 5) : 0,rcov);
       if (lane == 0)
@@ -484,6 +489,28 @@ k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
       st = __reduce_or_sync(g.gmask,st);
       if (g.glane == 0 && st != st0) B.status[r] = st;
       __syncwarp(g.gmask);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ *  prof2class (src/prof2class.c:236-258): a RELATIVE profile -- counts of the read's k-mers in a
+ *  genome or haplotype table -- mapped to ground-truth classes, 0 -> E, 1 -> H, 2 -> D, more -> R,
+ *  behind K-1 'N's.  One CTA per read at a time; streaming: 2n bytes in, r bytes out.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256)
+k_count2class(BatchDev B, int K)
+{ for (int r = blockIdx.x; r < B.n_reads; r += gridDim.x)
+    { const uint16_t *c = B.cnt+B.cnt_off[r];
+      uint8_t *o = B.cls+B.cls_off[r];
+      const int rlen = B.rlen[r];
+      for (int i = threadIdx.x; i < rlen; i += blockDim.x)
+        { char ch = 'N';
+          if (i >= K-1)
+            { const unsigned v = c[i-(K-1)];
+              ch = (v == 0) ? 'E' : (v == 1) ? 'H' : (v == 2) ? 'D' : 'R';
+            }
+          o[i] = (uint8_t)ch;
+        }
     }
 }
 
@@ -991,6 +1018,74 @@ extern "C" int cpg_decode_profiles(cpg_ctx *ctx, int32_t n, const uint8_t *prof,
   free(rl);
   if (e != cudaSuccess) return set_err(ctx,CPG_ECUDA,"cpg_decode_profiles: %s",cudaGetErrorString(e));
   return CPG_OK;
+}
+
+extern "C" int cpg_prof2class(cpg_ctx *ctx, int32_t n, const uint8_t *prof, const int64_t *prof_off,
+                              const int32_t *rlen, uint8_t *cls, int32_t *status)
+{ if (ctx == NULL || n < 0 || (n > 0 && (!prof || !prof_off || !rlen || !cls)))
+    return set_err(ctx,CPG_EINVAL,"cpg_prof2class: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) return CPG_OK;
+  Slot *S = &ctx->slot[0];
+  if (S->busy) return set_err(ctx,CPG_EINVAL,"cpg_prof2class: slot 0 busy");
+  const int K = ctx->model.kmer;
+  int rc = host_reserve(ctx,S,n);
+  if (rc) return rc;
+  int64_t *cls_off = (int64_t *)malloc(sizeof(int64_t)*((size_t)n+1));
+  if (cls_off == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
+  int64_t co = 0, lo = 0;
+  for (int i = 0; i < n; i++)
+    { if (rlen[i] < 0 || rlen[i] > CPG_MAX_RLEN || prof_off[i+1] < prof_off[i])
+        { free(cls_off); return set_err(ctx,CPG_EINVAL,"cpg_prof2class: read %d: bad length or offsets",i); }
+      S->h_cnt_off[i] = co; cls_off[i] = lo; S->h_order[i] = i;
+      const int plen = rlen[i] >= K ? rlen[i]-K+1 : 0;
+      co += (plen+31) & ~31; lo += rlen[i];
+    }
+  S->h_cnt_off[n] = co; cls_off[n] = lo;
+  const size_t prof_bytes = (size_t)prof_off[n];
+  if ((rc = reserve(ctx,&S->prof,prof_bytes+16)) || (rc = reserve(ctx,&S->prof_off,sizeof(int64_t)*(n+1)))
+      || (rc = reserve(ctx,&S->cnt,sizeof(uint16_t)*(size_t)co+64)) || (rc = reserve(ctx,&S->cnt_off,sizeof(int64_t)*(n+1)))
+      || (rc = reserve(ctx,&S->rlen,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->plen,sizeof(int32_t)*(n+1)))
+      || (rc = reserve(ctx,&S->status,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->order,sizeof(int32_t)*(n+1)))
+      || (rc = reserve(ctx,&S->cls,(size_t)lo+16)) || (rc = reserve(ctx,&S->cls_off,sizeof(int64_t)*(n+1)))
+      || (rc = reserve(ctx,&S->queue,128)))
+    { free(cls_off); return rc; }
+  cudaStream_t st = S->stream;
+  BatchDev B; memset(&B,0,sizeof(B));
+  B.n_reads = n; B.prof = (const uint8_t *)S->prof.p; B.prof_off = (const int64_t *)S->prof_off.p;
+  B.cnt = (uint16_t *)S->cnt.p; B.cnt_off = (const int64_t *)S->cnt_off.p; B.rlen = (const int32_t *)S->rlen.p;
+  B.plen = (int32_t *)S->plen.p; B.status = (int32_t *)S->status.p; B.order = (const int32_t *)S->order.p;
+  B.cls = (uint8_t *)S->cls.p; B.cls_off = (const int64_t *)S->cls_off.p;
+  B.queue = (int32_t *)S->queue.p;
+  cudaError_t e = cudaSuccess;
+#define TRY(x) if (e == cudaSuccess) e = (x)
+  TRY(cudaMemcpyAsync(S->prof.p,prof,prof_bytes,cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->prof_off.p,prof_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->cnt_off.p,S->h_cnt_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->cls_off.p,cls_off,sizeof(int64_t)*(n+1),cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->rlen.p,rlen,sizeof(int32_t)*n,cudaMemcpyHostToDevice,st));
+  TRY(cudaMemcpyAsync(S->order.p,S->h_order,sizeof(int32_t)*n,cudaMemcpyHostToDevice,st));
+  TRY(cudaMemsetAsync(S->queue.p,0,128,st));
+  if (e == cudaSuccess)
+    { k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(B,K,0);
+      k_count2class<<<ctx->n_sm*8,256,0,st>>>(B,K);
+    }
+  TRY(cudaGetLastError());
+  TRY(cudaMemcpyAsync(cls,S->cls.p,(size_t)lo,cudaMemcpyDeviceToHost,st));
+  TRY(cudaMemcpyAsync(S->h_status,S->status.p,sizeof(int32_t)*n,cudaMemcpyDeviceToHost,st));
+  TRY(cudaStreamSynchronize(st));
+#undef TRY
+  free(cls_off);
+  if (e != cudaSuccess) return set_err(ctx,CPG_ECUDA,"cpg_prof2class: %s",cudaGetErrorString(e));
+  int bad = 0;
+  for (int i = 0; i < n; i++)
+    { if (status) status[i] = S->h_status[i];
+      if (S->h_status[i] & CPG_ST_BAD_PROFILE)
+        { if (!bad) set_err(ctx,CPG_EREAD,"read %d of the batch: %s",i,cpg_status_string(S->h_status[i]));
+          bad = 1;
+        }
+    }
+  return bad ? CPG_EREAD : CPG_OK;
 }
 
 /* pinned host memory for callers that want true asynchronous copies */

@@ -122,15 +122,25 @@ int cpg_collect(cpg_ctx *ctx, int slot, cpg_result *result);
 int cpg_decode_profiles(cpg_ctx *ctx, int32_t n_reads, const uint8_t *prof, const int64_t *prof_off,
                         const int64_t *cnt_off, uint16_t *counts, int32_t *plen);
 
+/* prof2class on the device (src/prof2class.c:165-258): decode the RELATIVE profiles of a batch (counts
+ * of each read's k-mers in a genome / haplotype k-mer table) and map them to ground-truth class
+ * strings, count 0 -> 'E', 1 -> 'H', 2 -> 'D', more -> 'R', behind K-1 'N's.  cls receives rlen[i]
+ * characters per read, reads concatenated; reads shorter than K get rlen[i] 'N's.  K is the model's
+ * k-mer length.  status (may be NULL) flags reads whose profile length is not rlen-K+1. */
+int cpg_prof2class(cpg_ctx *ctx, int32_t n_reads, const uint8_t *prof, const int64_t *prof_off,
+                   const int32_t *rlen, uint8_t *cls, int32_t *status);
+
 /* Device-resident timing: upload once, run the kernels `iters` times on data already in HBM,
  * report the mean device time of each kernel in milliseconds (CUDA events on the context's
  * stream), then fetch the result of the last run. */
 int cpg_upload(cpg_ctx *ctx, const cpg_batch *batch);
 int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float *ms_classify, int *launches);
 int cpg_download(cpg_ctx *ctx, cpg_result *result);
-/* Summed per-warp clock cycles of the last k_classify launch of slot 0: [0] wall detection +
- * reliable intervals, [1] reliable-interval DP, [2] unreliable intervals + emit, [3] waiting at the
- * CTA phase barriers. */
+/* Device time of the classification phases in the last cpg_run_resident iteration, nanoseconds
+ * (CUDA events between the kernels): [0] k_wall (wall detection + reliable intervals), [1] k_rel
+ * (reliable-interval DP), [2] k_unrel (unreliable intervals + class strings), [3] the retry launch.
+ * With CPG_FUSED=1 (single-kernel path): summed per-group clock cycles of the three phases and of
+ * the waits at the CTA phase barriers. */
 int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4]);
 
 /* Pinned (page-locked) host memory, so that the copies of cpg_submit/cpg_collect are truly

@@ -32,6 +32,12 @@ def build_oracle():
     return os.path.join(REF_DIR, "liboracle.so")
 
 
+def build_product():
+    """libclasspro_b200.so + the command-line programs (nvcc cross-compiles without a GPU)."""
+    _run(["make", "-C", os.path.join(ROOT, "classpro_b200"), "--no-print-directory", "all"])
+    build_oracle()
+
+
 def build_cpsim():
     so = os.path.join(TOOLS_DIR, "libcpsim.so")
     src = os.path.join(TOOLS_DIR, "cpsim.c")

@@ -12,10 +12,10 @@ tail -1 $O/bench_full_$TAG.log | cut -c1-300
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$TAG.log 2>&1; tail -1 $O/bench_ref_$TAG.log | cut -c1-300
 python tools/run_config.py c1 > $O/config_c1_$TAG.json 2>&1; tail -1 $O/config_c1_$TAG.json | cut -c1-200
 python tools/run_config.py c4 --scale 0.004 > $O/config_c4_$TAG.json 2>&1; tail -1 $O/config_c4_$TAG.json | cut -c1-200
-# ncu: launch list and source-level capture on the 10 Mb slice, DRAM traffic on the default workload
-S="python bench.py --no-cpu-baseline --genome-mb 10 --steps 2 --warmup 1"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_$TAG.csv $S > $O/ncu_launches_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_ -s 9 -c 3 -f -o $O/prof_$TAG $S > $O/ncu_full_$TAG.log 2>&1
+# ncu: launch list and source-level capture on a 40 Mb slice (60 k reads: enough to fill the 38 k lane groups of k_wall), DRAM traffic on the default workload
+S="python bench.py --no-cpu-baseline --genome-mb 40 --steps 2 --warmup 1"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/launches_$TAG.csv $S > $O/ncu_launches_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_ -s 15 -c 5 -f -o $O/prof_$TAG $S > $O/ncu_full_$TAG.log 2>&1
 F="python bench.py --no-cpu-baseline --steps 1 --warmup 1"
-ncu --set full --clock-control none -k regex:k_ -s 9 -c 3 -f -o $O/prof_full_$TAG $F > $O/ncu_fullwl_$TAG.log 2>&1
+ncu --set full --clock-control none -k regex:k_ -s 15 -c 5 -f -o $O/prof_full_$TAG $F > $O/ncu_fullwl_$TAG.log 2>&1
 ls -la $O/prof_$TAG.ncu-rep $O/prof_full_$TAG.ncu-rep

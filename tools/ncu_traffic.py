@@ -3,8 +3,8 @@
 
     python tools/ncu_traffic.py gpurun_out/prof_full.ncu-rep "<workload description>" > profiles/traffic.json
 
-Launches of one kernel are averaged; k_classify's retry launch (a 4-CTA grid that normally finds
-nothing to do) is skipped.
+Launches of one kernel are averaged; k_classify here is the retry launch (a 4-CTA grid that normally
+finds nothing to do).
 """
 import csv
 import io
@@ -28,7 +28,7 @@ def main():
         name = r[col["Kernel Name"]].split("(")[0]
         grid = int(float(r[col["launch__grid_size"]]))
         if name == "k_classify" and grid < 16:
-            continue
+            name = "retry_launch"
         tot = 0.
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[col[key]]) * UNIT[units[col[key]]]
@@ -36,7 +36,8 @@ def main():
         acc.setdefault(name, []).append((tot, dur, units[col["gpu__time_duration.sum"]]))
     res = {"source": rep.split("/")[-1], "workload": what}
     for name, v in acc.items():
-        res[name] = sum(x[0] for x in v) / len(v)
+        tot = sum(x[0] for x in v) / len(v)
+        res[name] = tot if tot == tot else None        # NaN: ncu could not collect the DRAM counters for this launch
         res[name + "_launches"] = len(v)
         res[name + "_duration_under_ncu"] = "%.3f %s" % (sum(x[1] for x in v) / len(v), v[0][2])
     print(json.dumps(res, indent=1))
