@@ -56,7 +56,7 @@ int main(int argc, char **argv)
   const int K = P.kmer;
 
   cpg_model *model = xmalloc(sizeof(cpg_model));
-  if (cpg_model_from_cov(model,K,20,20000,0) != CPG_OK) die("%s: cannot set up the device context",PROG);
+  if (cpg_model_from_cov(model,K,10,20,20000) != CPG_OK) die("%s: cannot set up the device context",PROG);
   if (cpg_device_count() <= 0) die("%s: no CUDA device found: this program has no CPU fallback",PROG);
   cpg_ctx *ctx = NULL;
   if (cpg_create(&ctx,device,model,0,0) != CPG_OK) die("%s: %s",PROG,cpg_last_error(NULL));
