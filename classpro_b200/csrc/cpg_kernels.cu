@@ -690,10 +690,7 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
 /* scratch arenas: compact blocks for every resident lane group of the main launch, full-size
    blocks for the few groups of the retry launch */
 static int ensure_scratch(cpg_ctx *ctx, int P)
-{ { const char *f = getenv("CPG_FORCE_P");            /* experiment knob: oversize the scratch layout */
-    if (f && atoi(f) > P) P = atoi(f);
-  }
-  if (ctx->scratch.p && P <= ctx->SC.P) return CPG_OK;
+{ if (ctx->scratch.p && P <= ctx->SC.P) return CPG_OK;
   size_t off[14];
   ScratchDev SC = ctx->SC, SB = ctx->SCbig;
   scratch_caps(&SC,P,ctx->model.kmer,0);
