@@ -913,11 +913,31 @@ static inline uint16_t beg_cnt(const cpo_intvl *I, int F) { return F ? I->ccb : 
 static inline int end_pos(const cpo_intvl *I, int F) { return F ? I->e-1 : I->b; }
 static inline uint16_t end_cnt(const cpo_intvl *I, int F) { return F ? I->cce : I->ccb; }
 
+/* Tie tracing: with cpo_set_trace(1) every strict comparison between two
+   log-probabilities that decides an arg-max, and every double -> int truncation of a coverage
+   ratio, is logged to stderr with its relative gap, so that a class character that differs on the
+   GPU (CUDA exp/log vs glibc, <= 1 ulp) can be attributed to the comparison it sits on. */
+static int cpo_trace = 0;
+void cpo_set_trace(int on) { cpo_trace = on; }
+static void trace_cmp(const char *where, int i, int a, int b, double x, double y)
+{ if (!cpo_trace || x == -INFINITY || y == -INFINITY) return;
+  double m = fabs(x) > fabs(y) ? fabs(x) : fabs(y);
+  double g = (m > 0.) ? fabs(x-y)/m : 0.;
+  if (g < 1e-6) fprintf(stderr,"TIE %s @%d: %d vs %d: %.17g vs %.17g rel.gap %.3g\n",where,i,a,b,x,y,g);
+}
+static void trace_trunc(const char *where, int i, double v)
+{ if (!cpo_trace || !(v == v) || fabs(v) > 1e9) return;
+  double f = v-floor(v), d = f < 0.5 ? f : 1.-f;
+  if (d < 1e-6*fabs(v)+1e-12) fprintf(stderr,"TRUNC %s @%d: %.17g is within %.3g of an integer\n",where,i,v,d);
+}
+
 /* class_rel.c:62-73 */
 static int best_state(const double *dp, int i)
 { double mx = -INFINITY; int ms = CPO_NSTATE;
   for (int s = 0; s < 4; s++)
-    if (mx < dp[RIDX(i,s)]) { mx = dp[RIDX(i,s)]; ms = s; }
+    { if (ms != CPO_NSTATE) trace_cmp("best_state",i,ms,s,mx,dp[RIDX(i,s)]);
+      if (mx < dp[RIDX(i,s)]) { mx = dp[RIDX(i,s)]; ms = s; }
+    }
   return ms;
 }
 
@@ -928,6 +948,7 @@ static int best_tr(const double *dp, double tr[4][4], int i, int s, int t, int F
   for (int x = 0; x < 4; x++)
     { int _s = (s < 4) ? s : x, _t = (t < 4) ? t : x;
       double lp = dp[RIDX(ip,_s)]+tr[_s][_t];
+      if (mxx != CPO_NSTATE) trace_cmp(s < 4 ? "best_tr(to)" : "best_tr(from)",i*10+((s < 4) ? s : t),mxx,x,mx,lp);
       if (mx < lp) { mx = lp; mxx = x; }
     }
   if (out_logp) *out_logp = mx;
@@ -989,6 +1010,7 @@ static double rel_lp_h(const cpo_model *M, cpo_work *W, int idx, int s, poscnt *
   double r = W->dh_ratio[RIDX(pred_of(idx,F),s)];
   if (r != -INFINITY)
     { st = sp[CPO_D];
+      trace_trunc("lp_h r*bc",idx,r*bc);
       sf = lp_trans(M,pred_of(st.pos,F),bp,st.cnt,(int)(r*bc),st.cnt);
     }
   return sf+0.;
@@ -1100,13 +1122,14 @@ static void rel_update(const cpo_model *M, cpo_work *W, int i, int Mrel)
           if (t == CPO_H)
             { ch = ec;
               if (r == -INFINITY) cd = has_other ? st[idp][CPO_D].cnt : ch+COV[CPO_H];
-              else { cd = (int)(r*ch); dhr[idx] = r; }
+              else { trace_trunc("r*ch",i,r*ch); cd = (int)(r*ch); dhr[idx] = r; }
             }
           else
             { cd = ec;
               if (r == -INFINITY) ch = has_other ? st[idp][CPO_H].cnt : MAXI(cd/2,cd-COV[CPO_H]);
-              else { ch = (int)((double)cd/r); dhr[idx] = r; }
+              else { trace_trunc("cd/r",i,(double)cd/r); ch = (int)((double)cd/r); dhr[idx] = r; }
             }
+          trace_trunc("dr_ratio*cd",i,M->dr_ratio*cd);
           cr = (int)(M->dr_ratio*cd);
           st[idx][CPO_H].pos = off_pos(ep,F); st[idx][CPO_H].cnt = (uint16_t)ch;
           st[idx][CPO_D].pos = off_pos(ep,F); st[idx][CPO_D].cnt = (uint16_t)cd;
@@ -1276,8 +1299,11 @@ static void classify_reliable(const cpo_model *M, cpo_work *W, int Mrel, int N, 
     { if (eq_prefix(r,Mrel)) { }
       else if (eq_suffix(r,Mrel))
         { for (int i = 0; i < Mrel; i++) r[i].asgn = b.asgn[i]; }
-      else if (!(fabs(f.hdrr-1.) <= fabs(b.hdrr-1.)))
-        { for (int i = 0; i < Mrel; i++) r[i].asgn = b.asgn[i]; }
+      else
+        { trace_cmp("fw/bw |hdrr-1|",0,0,1,fabs(f.hdrr-1.),fabs(b.hdrr-1.));
+          if (!(fabs(f.hdrr-1.) <= fabs(b.hdrr-1.)))
+            for (int i = 0; i < Mrel; i++) r[i].asgn = b.asgn[i];
+        }
     }
   for (int ri = 0, ii = 0; ri < Mrel; ri++, ii++)
     { while (ii < N && !W->intvl[ii].is_rel) ii++;

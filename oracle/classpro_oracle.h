@@ -88,4 +88,7 @@ int  cpo_run_file(const char *fastx, const char *fk_root, int cov_opt, int read_
 #ifdef __cplusplus
 }
 #endif
+/* log near-ties of the order decisions to stderr (see classpro_oracle.c: trace_cmp) */
+void cpo_set_trace(int on);
+
 #endif

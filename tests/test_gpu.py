@@ -65,10 +65,15 @@ DATASETS = [
 ]
 
 
-def test_retry_launch_matches_oracle(kit, cp, monkeypatch):
-    """Interval tables of 64 entries in the main launch (CPG_SCRATCH_DIV test knob): nearly every
-    read is flagged and classified by the retry launch with full-size tables; same class strings."""
-    monkeypatch.setenv("CPG_SCRATCH_DIV", "1000000")
+@pytest.mark.parametrize("knob", ["CPG_SCRATCH_DIV", "CPG_POOL_DIV", "CPG_FUSED"])
+def test_retry_launch_matches_oracle(kit, cp, monkeypatch, knob):
+    """The other routes through the kernels give the same class strings.
+    CPG_SCRATCH_DIV: interval tables of 64 entries in the scratch blocks of the phase kernels, so
+    nearly every read is flagged and classified by the retry launch with full-size tables.
+    CPG_POOL_DIV: an interval pool of 4096 entries for the batch: the first reads fit, the rest are
+    flagged by k_wall (a mix of both routes in one batch).
+    CPG_FUSED: every read through the single-kernel path."""
+    monkeypatch.setenv(knob, "1" if knob == "CPG_FUSED" else "1000000")
     name, params, cov_opt, read_len = DATASETS[1]
     sim = kit.simulate(**params)
     om = kit.oracle_model(sim, cov_opt, read_len)
@@ -154,9 +159,13 @@ def test_cli_matches_live_reference(kit, cp, tmp_path):
     fasta = str(tmp_path / "x.fasta")
     ref = kit.run_reference(fasta, threads=2)
     os.rename(ref, ref + ".ref")
-    p = subprocess.run([CLI, "-B2", fasta], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-    assert p.returncode == 0, p.stderr[-1500:]
-    assert filecmp.cmp(ref, ref + ".ref", shallow=False), "CLI output differs from the reference binary's"
+    # small batches (many hand-overs between reader, GPU worker and writer) and a single big one,
+    # with one and with several packing threads
+    for args in (["-B2"], ["-B1", "-T1"], ["-B1", "-T7"], ["-B500", "-T3"]):
+        p = subprocess.run([CLI] + args + [fasta], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, p.stderr[-1500:]
+        assert filecmp.cmp(ref, ref + ".ref", shallow=False), "CLI %s output differs from the reference binary's" % args
+        os.remove(ref)
 
 
 def test_edge_batches(kit, cp):
