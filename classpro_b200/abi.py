@@ -55,6 +55,7 @@ def lib():
         L.cpg_classify.argtypes = [C.c_void_p, C.POINTER(CBatch), C.POINTER(CResult)]
         L.cpg_submit.argtypes = [C.c_void_p, C.c_int, C.POINTER(CBatch)]
         L.cpg_collect.argtypes = [C.c_void_p, C.c_int, C.POINTER(CResult)]
+        L.cpg_prof2class.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cpg_decode_profiles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]
         L.cpg_upload.argtypes = [C.c_void_p, C.POINTER(CBatch)]
@@ -266,6 +267,23 @@ class Context:
         if rc:
             raise self._err("cpg_decode_profiles", rc)
         return counts, cnt_off, plen[:n]
+
+    def prof2class(self, prof, prof_off, rlen):
+        """prof2class on the device: relative profiles -> ground-truth class strings (reads concatenated).
+        Returns (cls, cls_off, status); raises if a profile length is not rlen-K+1."""
+        prof = np.ascontiguousarray(prof, dtype=np.uint8)
+        prof_off = np.ascontiguousarray(prof_off, dtype=np.int64)
+        rlen = np.ascontiguousarray(rlen, dtype=np.int32)
+        n = len(rlen)
+        cls_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(rlen.astype(np.int64), out=cls_off[1:])
+        cls = np.zeros(int(cls_off[-1]) + 16, dtype=np.uint8)
+        status = np.zeros(n + 1, dtype=np.int32)
+        rc = self.L.cpg_prof2class(self.h, n, prof.ctypes.data, prof_off.ctypes.data, rlen.ctypes.data,
+                                   cls.ctypes.data, status.ctypes.data)
+        if rc:
+            raise self._err("cpg_prof2class", rc)
+        return cls, cls_off, status[:n]
 
     def close(self):
         if self.h:

@@ -304,18 +304,24 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
 #ifndef UNREL_GROUP
 #define UNREL_GROUP CPG_GROUP
 #endif
-#define CPG_MIN3(a,b,c) ((a) < (b) ? ((a) < (c) ? (a) : (c)) : ((b) < (c) ? (b) : (c)))
-#define PHASE_MAX_GROUPS (CLASSIFY_THREADS/CPG_MIN3(WALL_GROUP,REL_GROUP,UNREL_GROUP))
+/* CTA shape of the phase kernels: they have no CTA-wide barrier, so the shape only decides how many
+   warps fit an SM through the register cap (PHASE_THREADS x PHASE_MIN_BLOCKS threads per SM) */
+#ifndef PHASE_THREADS
+#define PHASE_THREADS    CLASSIFY_THREADS
+#endif
+#ifndef PHASE_MIN_BLOCKS
+#define PHASE_MIN_BLOCKS CLASSIFY_MIN_BLOCKS
+#endif
 
 template<int G> struct PhaseShared
   { uint8_t     cthres[(G >= 16) ? CPG_LROWS*256*4 : 16];     /* in shared memory when there is room */
     cpg_dmodel  model;
-    cpg_wshared ws[CLASSIFY_THREADS/G];
+    cpg_wshared ws[PHASE_THREADS/G];
   };
 template<int G> struct RelPhaseShared
   { cpg_dmodel  model;
-    cpg_wshared ws[CLASSIFY_THREADS/G];
-    RelShared   rel[CLASSIFY_THREADS/G][2];
+    cpg_wshared ws[PHASE_THREADS/G];
+    RelShared   rel[PHASE_THREADS/G][2];
   };
 
 struct GroupId { int lane, gib, glane, gbase, gsize; unsigned gmask; };
@@ -355,7 +361,7 @@ __device__ __forceinline__ void init_wctx(WCtx &W, const GroupId &g, const cpg_d
 }
 
 /* phase 1: wall detection + reliable intervals (cpg_wall.cuh) */
-__global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
+__global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
 k_wall(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { constexpr int G = WALL_GROUP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -372,7 +378,7 @@ k_wall(BatchDev B, cpg_dmodel M, ScratchDev SC)
   cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
   __syncthreads();
 
-  uint8_t *sb = SC.base+((size_t)blockIdx.x*(CLASSIFY_THREADS/G)+g.gib)*SC.stride;
+  uint8_t *sb = SC.base+((size_t)blockIdx.x*(PHASE_THREADS/G)+g.gib)*SC.stride;
   size_t off[14];
   scratch_layout(SC,off);
   for (;;)
@@ -420,7 +426,7 @@ k_wall(BatchDev B, cpg_dmodel M, ScratchDev SC)
 }
 
 /* phase 2: forward/backward DP over the reliable intervals (cpg_rel.cuh) */
-__global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
+__global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
 k_rel(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { constexpr int G = REL_GROUP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -430,7 +436,7 @@ k_rel(BatchDev B, cpg_dmodel M, ScratchDev SC)
   __syncthreads();
   cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
   __syncthreads();
-  uint8_t *sb = SC.base+((size_t)blockIdx.x*(CLASSIFY_THREADS/G)+g.gib)*SC.stride;
+  uint8_t *sb = SC.base+((size_t)blockIdx.x*(PHASE_THREADS/G)+g.gib)*SC.stride;
   size_t off[14];
   scratch_layout(SC,off);
   for (;;)
@@ -457,7 +463,7 @@ k_rel(BatchDev B, cpg_dmodel M, ScratchDev SC)
 }
 
 /* phase 3: unreliable intervals + class string (cpg_unrel.cuh) */
-__global__ void __launch_bounds__(CLASSIFY_THREADS,CLASSIFY_MIN_BLOCKS)
+__global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
 k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { constexpr int G = UNREL_GROUP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -467,7 +473,7 @@ k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
   __syncthreads();
   cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
   __syncthreads();
-  uint8_t *sb = SC.base+((size_t)blockIdx.x*(CLASSIFY_THREADS/G)+g.gib)*SC.stride;
+  uint8_t *sb = SC.base+((size_t)blockIdx.x*(PHASE_THREADS/G)+g.gib)*SC.stride;
   size_t off[14];
   scratch_layout(SC,off);
   for (;;)
@@ -541,6 +547,7 @@ struct cpg_ctx
     DevBuf     scratch, scratch_big; ScratchDev SC, SCbig;
     int        retry_blocks;
     int        fused;                 /* CPG_FUSED=1: the single-kernel path (k_classify) for every read */
+    int        wall_blocks, rel_blocks, unrel_blocks;
     size_t     wall_smem, rel_smem, unrel_smem;
     cudaEvent_t evp[3];               /* between the phase kernels */
     uint64_t   phase_ns[4];           /* wall, reliable DP, unreliable + emit, retry launch: last timed run */
@@ -671,6 +678,14 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
   CU_C(cudaFuncSetAttribute(k_wall,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->wall_smem));
   CU_C(cudaFuncSetAttribute(k_unrel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->unrel_smem));
   CU_C(cudaFuncSetAttribute(k_rel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->rel_smem));
+  { int o = 0;
+    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_wall,PHASE_THREADS,ctx->wall_smem));
+    ctx->wall_blocks = ctx->n_sm*(o < 1 ? 1 : o);
+    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_rel,PHASE_THREADS,ctx->rel_smem));
+    ctx->rel_blocks = ctx->n_sm*(o < 1 ? 1 : o);
+    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_unrel,PHASE_THREADS,ctx->unrel_smem));
+    ctx->unrel_blocks = ctx->n_sm*(o < 1 ? 1 : o);
+  }
 
   ctx->classify_smem = sizeof(ClassifyShared);
   CU_C(cudaFuncSetAttribute(k_classify,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->classify_smem));
@@ -698,8 +713,11 @@ static int ensure_scratch(cpg_ctx *ctx, int P)
   SC.stride = scratch_layout(SC,off);
   SB.stride = scratch_layout(SB,off);
   for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->slot[s].stream);
-  const size_t groups = (CLASSIFY_GROUPS > PHASE_MAX_GROUPS) ? CLASSIFY_GROUPS : PHASE_MAX_GROUPS;
-  int rc = reserve(ctx,&ctx->scratch,SC.stride*(size_t)ctx->classify_blocks*groups);
+  size_t groups = (size_t)ctx->classify_blocks*CLASSIFY_GROUPS, g;
+  if ((g = (size_t)ctx->wall_blocks*(PHASE_THREADS/WALL_GROUP)) > groups) groups = g;
+  if ((g = (size_t)ctx->rel_blocks*(PHASE_THREADS/REL_GROUP)) > groups) groups = g;
+  if ((g = (size_t)ctx->unrel_blocks*(PHASE_THREADS/UNREL_GROUP)) > groups) groups = g;
+  int rc = reserve(ctx,&ctx->scratch,SC.stride*groups);
   if (rc) return rc;
   rc = reserve(ctx,&ctx->scratch_big,SB.stride*(size_t)ctx->retry_blocks*CLASSIFY_GROUPS);
   if (rc) return rc;
@@ -752,7 +770,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
      batch (plain longest-first) 608 ms (profiles/r01_history.md).  CPG_ORDER_CHUNK overrides. */
   { int *bucket = (int *)calloc((size_t)maxR+2,sizeof(int));
     if (bucket == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
-    int chunk = ctx->classify_blocks*(ctx->fused ? CLASSIFY_GROUPS : CLASSIFY_THREADS/WALL_GROUP);
+    int chunk = ctx->fused ? ctx->classify_blocks*CLASSIFY_GROUPS : ctx->wall_blocks*(PHASE_THREADS/WALL_GROUP);
     { const char *f = getenv("CPG_ORDER_CHUNK"); if (f && atoi(f) > 0) chunk = atoi(f); }
     if (chunk < 1) chunk = 1;
     for (int c0 = 0; c0 < n; c0 += chunk)
@@ -827,11 +845,11 @@ static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
   if (ctx->fused)
     k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC,0);
   else
-    { k_wall<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->wall_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+    { k_wall<<<ctx->wall_blocks,PHASE_THREADS,ctx->wall_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
       if (timed) CU(cudaEventRecord(ctx->evp[0],st));
-      k_rel<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->rel_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+      k_rel<<<ctx->rel_blocks,PHASE_THREADS,ctx->rel_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
       if (timed) CU(cudaEventRecord(ctx->evp[1],st));
-      k_unrel<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+      k_unrel<<<ctx->unrel_blocks,PHASE_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
       if (timed) CU(cudaEventRecord(ctx->evp[2],st));
     }
   k_classify<<<ctx->retry_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SCbig,1);

@@ -91,3 +91,38 @@ def test_prof2class_matches_reference(kit, tmp_path):
     assert ca == cb
     cls = b"".join(ca.split(b"\n")[3::4])
     assert all(ch in cls for ch in b"HDRN")         # read profiles have no zero counts: no E
+
+
+@pytest.mark.gpu
+def test_prof2class_abi_on_arbitrary_streams(kit):
+    """cpg_prof2class on token streams with zero counts, wrap-around and 15-bit tokens: the class
+    string is the count -> class map of src/prof2class.c:236-258 applied to the oracle's decode."""
+    import numpy as np
+    import classpro_b200 as cp
+    from test_device_logic_hostsim import random_stream
+    rng = np.random.default_rng(3)
+    K = 40
+    streams, lens = [], []
+    for it in range(200):
+        s = random_stream(rng, int(rng.integers(1, 500)), bool(it & 1))
+        n, o = kit.oracle_decode(np.frombuffer(s, dtype=np.uint8), 200000)
+        if n > 50000:
+            continue
+        streams.append((s, o[:n]))
+        lens.append(n + K - 1)
+    streams.append((b"", np.zeros(0, np.uint16)))                 # a read shorter than K: no profile, all 'N'
+    lens.append(17)
+    prof = np.frombuffer(b"".join(s for s, _ in streams), dtype=np.uint8)
+    poff = np.zeros(len(streams) + 1, np.int64)
+    np.cumsum([len(s) for s, _ in streams], out=poff[1:])
+    model = cp.Model.from_cov(K, 10, 20, 20000)
+    ctx = cp.Context(model)
+    cls, coff, status = ctx.prof2class(prof, poff, np.array(lens, np.int32))
+    ctx.close()
+    assert not status.any()
+    lut = np.full(65536, ord("R"), np.uint8)
+    lut[0], lut[1], lut[2] = ord("E"), ord("H"), ord("D")
+    for r, (s, o) in enumerate(streams):
+        got = cls[coff[r]:coff[r + 1]]
+        want = np.concatenate([np.full(min(K - 1, lens[r]), ord("N"), np.uint8), lut[o]])
+        assert np.array_equal(got, want), r
