@@ -93,7 +93,8 @@ CPG_DEV int cpg_clz64(uint64_t x) { return __clzll((long long)x); }
 #endif
 
 /* bases s .. s+31 (s >= 0), base s in bits 0..1.  Reads the three aligned words at and after the
-   byte of base s: up to 3 bytes before it and 11 after it, which the staging buffers pad for. */
+   byte of base s: up to 3 bytes before it and 11 after it; s can be up to 32 bases past the end of
+   the read (cpg_rctx3), so the staging buffers are padded by 64 bytes. */
 CPG_DEV uint64_t cpg_win(const uint8_t *p, int s)
 { const size_t ad = (size_t)(p+(s >> 2));
   const uint32_t *w = reinterpret_cast<const uint32_t *>(ad & ~(size_t)3);
@@ -162,6 +163,58 @@ CPG_DEV_HELPER int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
   }
   return 1+cpg_zf(S.p,rlen,p,3,378)/3;
 }
+
+/* All three run lengths at one base from ONE 128-bit span of the packed sequence (the six
+ * windows of the single-type functions are shifts of it).  A run that fills its 32-base window,
+ * or a raw-byte sequence, falls back on the single-type function. */
+CPG_DEV_HELPER void cpg_lctx3(const cpg_seq S, int rlen, int p, int out[3])
+{ if (S.bits != 2) { for (int t = 0; t < 3; t++) out[t] = cpg_lctx(S,rlen,p,t); return; }
+  const uint64_t x = cpg_win_end(S.p,p), z = cpg_win_end(S.p,p-32);
+  const int b0 = (int)(x >> 62) & 3, b1 = (int)(x >> 60) & 3, b2 = (int)(x >> 58) & 3;     /* s[p], s[p-1], s[p-2] */
+  int zb[3];
+  for (int d = 1; d <= 3; d++)
+    { const uint64_t y = (x << (2*d)) | (z >> (64-2*d));        /* bases p-31-d .. p-d, base p-d on top */
+      const uint64_t e = x ^ y;
+      int c = e ? (cpg_clz64(e) >> 1) : 32;
+      const int lim = p-d+1;
+      if (c >= 32 && lim > 32) c = -1;                          /* the run leaves the window */
+      else if (c > lim) c = lim > 0 ? lim : 0;
+      zb[d-1] = c;
+    }
+  if (zb[0] < 0) out[0] = cpg_lctx(S,rlen,p,CT_HP); else out[0] = cpg_cap127(1+zb[0]);
+  if (p == 0 || b1 == b0) out[1] = 0;
+  else if (zb[1] < 0) out[1] = cpg_lctx(S,rlen,p,CT_DS);
+  else out[1] = 1+(zb[1] >> 1);
+  if (p < 2 || (b2 == b1 && b1 == b0)) out[2] = 0;
+  else if (zb[2] < 0) out[2] = cpg_lctx(S,rlen,p,CT_TS);
+  else out[2] = 1+zb[2]/3;
+}
+
+CPG_DEV_HELPER void cpg_rctx3(const cpg_seq S, int rlen, int p, int out[3])
+{ if (S.bits != 2) { for (int t = 0; t < 3; t++) out[t] = cpg_rctx(S,rlen,p,t); return; }
+  const uint64_t x = cpg_win(S.p,p), z = cpg_win(S.p,p+32);
+  const int b0 = (int)x & 3, b1 = (int)(x >> 2) & 3, b2 = (int)(x >> 4) & 3;                /* s[p], s[p+1], s[p+2] */
+  int zf[3];
+  for (int d = 1; d <= 3; d++)
+    { const uint64_t y = (x >> (2*d)) | (z << (64-2*d));        /* bases p+d .. p+d+31 */
+      const uint64_t e = x ^ y;
+      int c = e ? (cpg_ctz64(e) >> 1) : 32;
+      const int lim = rlen-d-p;
+      if (c >= 32 && lim > 32) c = -1;
+      else if (c > lim) c = lim > 0 ? lim : 0;
+      zf[d-1] = c;
+    }
+  if (zf[0] < 0) out[0] = cpg_rctx(S,rlen,p,CT_HP); else out[0] = cpg_cap127(1+zf[0]);
+  if (p >= rlen-1 || b0 == b1) out[1] = 0;
+  else if (zf[1] < 0) out[1] = cpg_rctx(S,rlen,p,CT_DS);
+  else out[1] = 1+(zf[1] >> 1);
+  if (p > rlen-3 || (b0 == b1 && b1 == b2)) out[2] = 0;
+  else if (zf[2] < 0) out[2] = cpg_rctx(S,rlen,p,CT_TS);
+  else out[2] = 1+zf[2]/3;
+}
+
+CPG_DEV void cpg_ctx3_at(const cpg_seq S, int rlen, int K, int wtype, int i, int out[3])
+{ if (wtype == WT_DROP) cpg_lctx3(S,rlen,i+K-2,out); else cpg_rctx3(S,rlen,i,out); }
 
 /* ctx[wtype][i][t] of the reference, i a profile position */
 CPG_DEV int cpg_ctx_at(const cpg_seq S, int rlen, int K, int wtype, int i, int t)

@@ -787,7 +787,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
 
   const size_t seq_bytes = n ? (size_t)b->seq_off[n] : 0, prof_bytes = n ? (size_t)b->prof_off[n] : 0;
   const size_t cls_bytes = n ? (size_t)cls_off[n] : 0;
-  if ((rc = reserve(ctx,&S->seq,seq_bytes+16)) || (rc = reserve(ctx,&S->seq_off,sizeof(int64_t)*(n+1)))
+  if ((rc = reserve(ctx,&S->seq,seq_bytes+64)) || (rc = reserve(ctx,&S->seq_off,sizeof(int64_t)*(n+1)))
       || (rc = reserve(ctx,&S->rlen,sizeof(int32_t)*(n+1))) || (rc = reserve(ctx,&S->prof,prof_bytes+16))
       || (rc = reserve(ctx,&S->prof_off,sizeof(int64_t)*(n+1))) || (rc = reserve(ctx,&S->cnt,sizeof(uint16_t)*(size_t)co+16))
       || (rc = reserve(ctx,&S->cnt_off,sizeof(int64_t)*(n+1))) || (rc = reserve(ctx,&S->plen,sizeof(int32_t)*(n+1)))

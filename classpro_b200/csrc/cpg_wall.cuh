@@ -317,11 +317,14 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
   else           { wtype = WT_GAIN; cin = cim1; cout = ci;   }
 
   int maxt = -1, maxl = -1; double maxpe = -CPG_INF;
-  CPG_LOOP for (int t = 0; t < CT_N; t++)
-    { int l = imin(cpg_ctx_at(R.seq,R.rlen,K,wtype,i,t),M->lmax[t]);
-      double pe = M->pe[t][l];
-      if (maxpe < pe) { maxpe = pe; maxt = t; maxl = l; }
-    }
+  { int cl[3];
+    cpg_ctx3_at(R.seq,R.rlen,K,wtype,i,cl);
+    CPG_LOOP for (int t = 0; t < CT_N; t++)
+      { int l = imin(cl[t],M->lmax[t]);
+        double pe = M->pe[t][l];
+        if (maxpe < pe) { maxpe = pe; maxt = t; maxl = l; }
+      }
+  }
 
   /* stage 0: how far does each error type get before any probability is needed */
   int reach[2] = {0,0}, o_wall_now = 0;
@@ -502,7 +505,10 @@ CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
   }
   if (I.b+K-1 < I.e)
     { lmax = 0;
-      CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_rctx(R.seq,R.rlen,I.b+K-1,t)*(t+1));
+      { int cl[3];
+        cpg_rctx3(R.seq,R.rlen,I.b+K-1,cl);
+        CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cl[t]*(t+1));
+      }
       last = I.b+lmax;
       int s = 0;
       CPG_LOOP for (int p = I.b+W.glane; p < last; p += W.gsize) s += imax((int)prof[p]-rc_prof(R,W,p+1),0);
@@ -515,7 +521,10 @@ CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
   }
   if (I.b < I.e-K+1)
     { lmax = 0;
-      CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cpg_lctx(R.seq,R.rlen,I.e-K+1+K-2,t)*(t+1));
+      { int cl[3];
+        cpg_lctx3(R.seq,R.rlen,I.e-K+1+K-2,cl);
+        CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cl[t]*(t+1));
+      }
       first = I.e-lmax;
       int s = 0;
       CPG_LOOP for (int p = first+W.glane; p < I.e-1; p += W.gsize) s += imax((int)prof[p+1]-prof[p],0);

@@ -180,7 +180,7 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
   cpg_seq S;
   if (seq_bits == 2)
     { /* 16 bytes of padding on both sides: cpg_win reads aligned words around the sequence */
-      packed.assign((size_t)(rlen+3)/4+32,0xA5);
+      packed.assign((size_t)(rlen+3)/4+64,0xA5);
       if (cpg_pack_seq(seq,rlen,packed.data()+16)) return -1;
       S.p = packed.data()+16; S.bits = 2;
     }
@@ -276,10 +276,15 @@ int hs_ctx(const char *seq, int rlen, int p, int right, int t)
 /* the same query on the 2-bit packed form of the sequence (pad = byte offset of the packed
    sequence inside its buffer, to exercise every alignment of the window loads) */
 int hs_ctx2(const char *seq, int rlen, int p, int right, int t, int pad)
-{ std::vector<uint8_t> packed((size_t)(rlen+3)/4+48,0x5A);
+{ std::vector<uint8_t> packed((size_t)(rlen+3)/4+64,0x5A);
   if (cpg_pack_seq(seq,rlen,packed.data()+16+pad)) return -1;
   cpg_seq S; S.p = packed.data()+16+pad; S.bits = 2;
-  return right ? cpg_rctx(S,rlen,p,t) : cpg_lctx(S,rlen,p,t);
+  /* both forms must agree: the single-type function and the three-at-once span form */
+  int one = right ? cpg_rctx(S,rlen,p,t) : cpg_lctx(S,rlen,p,t);
+  int all[3];
+  if (right) cpg_rctx3(S,rlen,p,all); else cpg_lctx3(S,rlen,p,all);
+  if (all[t] != one) return -1000-all[t];
+  return one;
 }
 
 int hs_sizeof_intvl(void) { return (int)sizeof(cpg_intvl); }
