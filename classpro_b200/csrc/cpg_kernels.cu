@@ -313,8 +313,8 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
 #define PHASE_MIN_BLOCKS CLASSIFY_MIN_BLOCKS
 #endif
 
-template<int G> struct PhaseShared
-  { uint8_t     cthres[(G >= 16) ? CPG_LROWS*256*4 : 16];     /* in shared memory when there is room */
+template<int G, bool CTHRES> struct PhaseShared
+  { uint8_t     cthres[CTHRES ? CPG_LROWS*256*4 : 16];        /* the count-threshold table, for k_wall */
     cpg_dmodel  model;
     cpg_wshared ws[PHASE_THREADS/G];
   };
@@ -365,14 +365,11 @@ __global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
 k_wall(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { constexpr int G = WALL_GROUP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PhaseShared<G> &sh = *reinterpret_cast<PhaseShared<G> *>(smem_raw);
+  PhaseShared<G,true> &sh = *reinterpret_cast<PhaseShared<G,true> *>(smem_raw);
   const GroupId g = group_id<G>();
-  const uint8_t *cthres = M.cthres;
-  if (G >= 16)
-    { for (int i = threadIdx.x; i < CPG_LROWS*256; i += blockDim.x)
-        reinterpret_cast<uint32_t *>(sh.cthres)[i] = reinterpret_cast<const uint32_t *>(M.cthres)[i];
-      cthres = sh.cthres;
-    }
+  for (int i = threadIdx.x; i < CPG_LROWS*256; i += blockDim.x)
+    reinterpret_cast<uint32_t *>(sh.cthres)[i] = reinterpret_cast<const uint32_t *>(M.cthres)[i];
+  const uint8_t *cthres = sh.cthres;
   if (threadIdx.x == 0) sh.model = M;
   __syncthreads();
   cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
@@ -467,7 +464,7 @@ __global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
 k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { constexpr int G = UNREL_GROUP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PhaseShared<G> &sh = *reinterpret_cast<PhaseShared<G> *>(smem_raw);
+  PhaseShared<G,false> &sh = *reinterpret_cast<PhaseShared<G,false> *>(smem_raw);
   const GroupId g = group_id<G>();
   if (threadIdx.x == 0) sh.model = M;
   __syncthreads();
@@ -673,8 +670,8 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
   for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->ev[i]));
   for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->evp[i]));
   { const char *f = getenv("CPG_FUSED"); ctx->fused = (f && atoi(f) > 0); }
-  ctx->wall_smem = sizeof(PhaseShared<WALL_GROUP>); ctx->rel_smem = sizeof(RelPhaseShared<REL_GROUP>);
-  ctx->unrel_smem = sizeof(PhaseShared<UNREL_GROUP>);
+  ctx->wall_smem = sizeof(PhaseShared<WALL_GROUP,true>); ctx->rel_smem = sizeof(RelPhaseShared<REL_GROUP>);
+  ctx->unrel_smem = sizeof(PhaseShared<UNREL_GROUP,false>);
   CU_C(cudaFuncSetAttribute(k_wall,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->wall_smem));
   CU_C(cudaFuncSetAttribute(k_unrel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->unrel_smem));
   CU_C(cudaFuncSetAttribute(k_rel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->rel_smem));

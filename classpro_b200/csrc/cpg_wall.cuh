@@ -496,40 +496,48 @@ CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
 { const int K = W.M->K;
   const cpg_intvl I = R.S.intvl[idx];
   const uint16_t *prof = R.prof;
-  int n_gain = 0, n_drop = 0, last, first, lmax;
+  int n_gain = 0, n_drop = 0;
 
-  last = imin(I.b+K-1,I.e-1);
-  { int s = 0;
-    CPG_LOOP for (int p = I.b+W.glane; p < last; p += W.gsize) s += imax((int)prof[p+1]-prof[p],0);
-    n_gain += cpg_gsum(W,s);
+  /* The four sums of src/wall.c:966-996 -- gains over the first K-1 positions and drops over the
+     last K-1, each minus the part explained by the low-complexity run at that end -- as two
+     loops that work on both ends of the interval at once (twice the loads in flight: the kernel
+     waits on DRAM), then one group reduction per sum. */
+  { const int e1 = imin(I.b+K-1,I.e-1);              /* gains:  p in [I.b,e1)  */
+    const int b3 = imax(I.e-K+1,I.b);                /* drops:  q in [b3,I.e-1) */
+    int sg = 0, sd = 0;
+    CPG_LOOP for (int o = W.glane; o < K-1; o += W.gsize)
+      { const int p = I.b+o, q = b3+o;
+        if (p < e1)    sg += imax((int)prof[p+1]-prof[p],0);
+        if (q < I.e-1) sd += imax((int)prof[q]-prof[q+1],0);
+      }
+    n_gain += cpg_gsum(W,sg);
+    n_drop += cpg_gsum(W,sd);
   }
-  if (I.b+K-1 < I.e)
-    { lmax = 0;
-      { int cl[3];
+  { int e2 = I.b, b4 = I.e-1;                        /* empty ranges unless the interval is longer than K-1 */
+    if (I.b+K-1 < I.e)
+      { int cl[3], lmax = 0;
         cpg_rctx3(R.seq,R.rlen,I.b+K-1,cl);
         CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cl[t]*(t+1));
+        e2 = I.b+lmax;                               /* p in [I.b,e2)  */
       }
-      last = I.b+lmax;
-      int s = 0;
-      CPG_LOOP for (int p = I.b+W.glane; p < last; p += W.gsize) s += imax((int)prof[p]-rc_prof(R,W,p+1),0);
-      n_gain -= cpg_gsum(W,s);
-    }
-  first = imax(I.e-K+1,I.b);
-  { int s = 0;
-    CPG_LOOP for (int p = first+W.glane; p < I.e-1; p += W.gsize) s += imax((int)prof[p]-prof[p+1],0);
-    n_drop += cpg_gsum(W,s);
-  }
-  if (I.b < I.e-K+1)
-    { lmax = 0;
-      { int cl[3];
+    if (I.b < I.e-K+1)
+      { int cl[3], lmax = 0;
         cpg_lctx3(R.seq,R.rlen,I.e-K+1+K-2,cl);
         CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cl[t]*(t+1));
+        b4 = I.e-lmax;                               /* q in [b4,I.e-1) */
       }
-      first = I.e-lmax;
-      int s = 0;
-      CPG_LOOP for (int p = first+W.glane; p < I.e-1; p += W.gsize) s += imax((int)prof[p+1]-prof[p],0);
-      n_drop -= cpg_gsum(W,s);
-    }
+    const int len = imax(e2-I.b,I.e-1-b4);
+    if (len > 0)
+      { int sg = 0, sd = 0;
+        CPG_LOOP for (int o = W.glane; o < len; o += W.gsize)
+          { const int p = I.b+o, q = b4+o;
+            if (p < e2)    sg += imax((int)prof[p]-rc_prof(R,W,p+1),0);
+            if (q < I.e-1) sd += imax((int)prof[q+1]-prof[q],0);
+          }
+        n_gain -= cpg_gsum(W,sg);
+        n_drop -= cpg_gsum(W,sd);
+      }
+  }
   uint16_t ccb = (uint16_t)imin(I.cb+imax(n_gain,0),CPG_MAX_CNT);
   uint16_t cce = (uint16_t)imin(I.ce+imax(n_drop,0),CPG_MAX_CNT);
   /* src/wall.c:999-1006 index intvl[] with a POSITION that hides the interval index; the only
