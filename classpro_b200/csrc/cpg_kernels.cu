@@ -718,6 +718,9 @@ static int ensure_scratch(cpg_ctx *ctx, int P)
   if (rc) return rc;
   rc = reserve(ctx,&ctx->scratch_big,SB.stride*(size_t)ctx->retry_blocks*CLASSIFY_GROUPS);
   if (rc) return rc;
+  /* the memo of the unreliable pass is read before it is written: entries start as "no task" */
+  if (cudaMemset(ctx->scratch.p,0,ctx->scratch.cap) != cudaSuccess || cudaMemset(ctx->scratch_big.p,0,ctx->scratch_big.cap) != cudaSuccess)
+    return set_err(ctx,CPG_ECUDA,"cudaMemset of the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
   SC.base = (uint8_t *)ctx->scratch.p; SB.base = (uint8_t *)ctx->scratch_big.p;
   ctx->SC = SC; ctx->SCbig = SB;
   return CPG_OK;

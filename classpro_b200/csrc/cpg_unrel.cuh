@@ -82,57 +82,100 @@ CPG_DEV_HELPER double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, const int nb
 
 /* src/class_unrel.c:115-237.  The ten independent pieces of an update -- the E and R
  * log-probabilities and, for H and D, the Skellam transition and the error-in-others tail on
- * either side -- are evaluated by ten lanes at once; the arg-max (first maximum wins, order
- * E,R,H,D) is formed uniformly afterwards.
- *   task 0: E     task 1: R     task 2+4*h+2*side+kind (h: 0=H,1=D; side: 0=left,1=right;
+ * either side -- are tasks; the arg-max (first maximum wins, order E,R,H,D) is formed uniformly
+ * afterwards.
+ *   task 0: E     task 1: R     task 2+t, t = 4*h+2*side+kind (h: 0=H,1=D; side: 0=left,1=right;
  *   kind 0 = Skellam transition from/to the nearest fixed interval of that state,
- *   kind 1 = log binomial tail of the count against the interpolated coverage) */
-CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *memo, int sweep)
+ *   kind 1 = log binomial tail of the count against the interpolated coverage)
+ * Tasks 2..9 are pure functions of a small argument triple (what, integer, double), which is how
+ * they are memoised: the triple is formed by un_task_args, the value by un_task_eval. */
+CPG_DEV_HELPER void un_task_args(WCtx &W, const cpg_intvl &I, const cpg_intvl *v, const int nb[2][2], int t,
+                                 int &mkind, int &mk, double &ma)
+{ const int s = (t & 4) ? ST_D : ST_H, right = (t >> 1) & 1, kind = t & 1;
+  mkind = 0; mk = 0; ma = 0.;
+  if (kind == 0)
+    { const int l = nb[s == ST_D][0], r = nb[s == ST_D][1];
+      if (!right && l != -1)
+        { int d = I.b-(v[l].e-1); if (d < 0) d = -d;
+          mk = (int)I.cb-(int)v[l].cce; ma = (double)v[l].cce*d/W.M->read_len; mkind = 1;
+        }
+      if (right && r != -1)
+        { int d = v[r].b-(I.e-1); if (d < 0) d = -d;
+          mk = (int)v[r].ccb-(int)I.ce; ma = (double)v[r].ccb*d/W.M->read_len; mkind = 1;
+        }
+    }
+  else
+    { uint16_t est = un_est_cov(W,right ? I.e-1 : I.b,v,s,nb);
+      uint16_t c = right ? I.ce : I.cb;
+      if (est >= c) { mkind = 2; mk = est; ma = (double)c; }
+    }
+}
+
+CPG_DEV_HELPER double un_task_eval(const WCtx &W, int mkind, int mk, double ma, int *bad)
+{ double val = -CPG_INF;
+  if (mkind == 1) val = cpg_lp_skellam(mk,ma);
+  if (mkind == 2) val = cpg_log(cpg_p_errorin_lane(W.M->logfact,ET_OTHERS,cpg_rate_p1(W.M),mk,(int)ma,bad));
+  return val;
+}
+
+/* Before the sweeps: the tasks of MANY intervals at once, one interval per lane, on the states
+ * as they are now.  The sweeps change few states, so most of their tasks then find their triple
+ * in the memo; evaluated inside un_update the same tasks run on 2-3 lanes of the group (ncu).
+ * A memo entry is (triple, value) and the value depends on nothing else, so an entry left by an
+ * earlier read is as good as a fresh one. */
+CPG_DEV_NOINL void un_precompute(WCtx &W, cpg_intvl *v, int N, const uint8_t *fixed, cpg_unmemo *memo)
+{ const int rcov = W.M->cov[ST_R];
+  const int n = imin(N,CPG_MEMO_CAP);
+  int bad = 0;
+  CPG_LOOP for (int idx = W.glane; idx < n; idx += W.gsize)
+    { if (fixed[idx]) continue;
+      const cpg_intvl I = v[idx];
+      if (imax(I.cb,I.ce) >= rcov) continue;
+      int nb[2][2];
+      CPG_LOOP for (int h = 0; h < 2; h++)
+        { const int s = h ? ST_D : ST_H;
+          int l = idx-1;
+          CPG_LOOP while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--;
+          int r = idx+1;
+          CPG_LOOP while (r < N && !(v[r].asgn == s && v[r].is_rel)) r++;
+          nb[h][0] = l; nb[h][1] = (r >= N) ? -1 : r;
+        }
+      cpg_unmemo *mm = memo+(size_t)idx*8;
+      CPG_LOOP for (int t = 0; t < 8; t++)
+        { int mkind, mk; double ma;
+          un_task_args(W,I,v,nb,t,mkind,mk,ma);
+          if (mkind == 0 || (mm[t].kind == mkind && mm[t].k == mk && mm[t].a == ma)) continue;
+          const double val = un_task_eval(W,mkind,mk,ma,&bad);
+          mm[t].kind = mkind; mm[t].k = mk; mm[t].a = ma; mm[t].val = val;
+        }
+    }
+  if (bad) W.status |= CPG_ST_BINOM;
+  CPG_SYNCGROUP(W);
+}
+
+CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *memo)
 { const cpg_intvl I = v[idx];
   int ns;
   if (imax(I.cb,I.ce) >= W.M->cov[ST_R]) ns = ST_R;
   else
     { double *term = W.ws->term;
-      const double *lf = W.M->logfact;
       int bad = 0;
-      /* The second sweep mostly re-asks what the first one computed: the Skellam / binomial
-         arguments of a task change only if a neighbouring interval changed state in between.  The
-         first sweep's arguments and results are kept per interval and reused when they match. */
       cpg_unmemo *mm = (memo != 0 && idx < CPG_MEMO_CAP) ? memo+(size_t)idx*8 : 0;
       int nb[2][2];
       CPG_SYNCGROUP(W);
       un_nn_group(W,idx,v,N,nb);
       CPG_LOOP for (int q = W.glane; q < 10; q += W.gsize)
-        { double val = -CPG_INF;
-          int need_s = 0, need_b = 0, k = 0, bn = 0, bc = 0; double lambda = 0.;
+        { double val;
           if (q == 0) val = un_lp_e(W,I);
           else if (q == 1) val = un_lp_r(W,idx,v,nb);
           else
-            { const int t = q-2, s = (t & 4) ? ST_D : ST_H, right = (t >> 1) & 1, kind = t & 1;
-              if (kind == 0)
-                { const int l = nb[s == ST_D][0], r = nb[s == ST_D][1];
-                  if (!right && l != -1)
-                    { int d = I.b-(v[l].e-1); if (d < 0) d = -d;
-                      k = (int)I.cb-(int)v[l].cce; lambda = (double)v[l].cce*d/W.M->read_len; need_s = 1;
-                    }
-                  if (right && r != -1)
-                    { int d = v[r].b-(I.e-1); if (d < 0) d = -d;
-                      k = (int)v[r].ccb-(int)I.ce; lambda = (double)v[r].ccb*d/W.M->read_len; need_s = 1;
-                    }
-                }
+            { const int t = q-2;
+              int mkind, mk; double ma;
+              un_task_args(W,I,v,nb,t,mkind,mk,ma);
+              if (mkind == 0) val = -CPG_INF;                      /* no task: never memoised */
+              else if (mm != 0 && mm[t].kind == mkind && mm[t].k == mk && mm[t].a == ma) val = mm[t].val;
               else
-                { uint16_t est = un_est_cov(W,right ? I.e-1 : I.b,v,s,nb);
-                  uint16_t c = right ? I.ce : I.cb;
-                  if (est >= c) { need_b = 1; bn = est; bc = c; }
-                }
-              const int mkind = need_s ? 1 : (need_b ? 2 : 0);
-              const int mk = need_s ? k : bn;
-              const double ma = need_s ? lambda : (double)bc;
-              if (mm != 0 && sweep == 1 && mm[t].kind == mkind && mm[t].k == mk && mm[t].a == ma)
-                { val = mm[t].val; need_s = need_b = 0; }
-              else
-                { if (need_s) val = cpg_lp_skellam(k,lambda);
-                  if (need_b) val = cpg_log(cpg_p_errorin_lane(lf,ET_OTHERS,cpg_rate_p1(W.M),bn,bc,&bad));
+                { val = un_task_eval(W,mkind,mk,ma,&bad);
                   if (mm != 0) { mm[t].kind = mkind; mm[t].k = mk; mm[t].a = ma; mm[t].val = val; }
                 }
             }
@@ -187,8 +230,9 @@ CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
       fixed[i] = (uint8_t)(v[i].is_rel && (v[i].asgn == ST_H || v[i].asgn == ST_D));
     }
   CPG_SYNCGROUP(W);
-  CPG_LOOP for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo,0); }
-  CPG_LOOP for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo,1); }
+  un_precompute(W,v,N,fixed,R.S.memo);
+  CPG_LOOP for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo); }
+  CPG_LOOP for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo); }
 }
 
 /* ---- the whole read: src/ClassPro.c:229-271, in three phases.

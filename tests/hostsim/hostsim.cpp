@@ -110,7 +110,7 @@ struct HsWork
       { int MC = P/2+8;
         mark.assign(P+2+32,0xff); slot.assign(P+2,0xffff); cand.assign(P/32+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
         rint.resize(MC); wint.resize(2*MC); bp.assign(2*MC,0); af.assign(MC,0); ab.assign(MC,0);
-        rpos.assign(2*MC,0); mc = MC; memo.resize((size_t)CPG_MEMO_CAP*8); fixed.assign(P+2,0); ord.assign(P+2,0);
+        rpos.assign(2*MC,0); mc = MC; memo.assign((size_t)CPG_MEMO_CAP*8,cpg_unmemo()); fixed.assign(P+2,0); ord.assign(P+2,0);
       }
   };
 
