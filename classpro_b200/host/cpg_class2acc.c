@@ -1,5 +1,5 @@
 /*******************************************************************************************
- *  class2acc.c -- accuracy of an estimated .class file against a ground-truth .class file.
+ *  cpg_class2acc.c -- the class2acc program: accuracy of an estimated .class file against a ground-truth .class file.
  *
  *      class2acc [-s] [-e<int>] [-f<int(100)>] [-m<int(0)>] [-n<int(100)>] [-r<int(0)>]
  *                <estimate>.class <truth>.class

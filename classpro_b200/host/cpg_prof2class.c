@@ -1,5 +1,5 @@
 /*******************************************************************************************
- *  prof2class.c -- ground-truth .class file from a relative profile.
+ *  cpg_prof2class.c -- the prof2class program: ground-truth .class file from a relative profile.
  *
  *      prof2class [-G<device>] <relative_profile>[.prof] <source>[.f[ast][aq][.gz]]
  *
