@@ -12,3 +12,10 @@ g++ $CF -DCPG_HOSTSIM=1 -c "$here/hostsim.cpp" -o "$here/_build/hostsim.o"
 g++ -shared -o "$here/_build/libhostsim.so" "$here/_build/hostsim.o" "$here/_build/cpg_model.o" "$here/_build/cpg_pack.o" -lm
 g++ $CF -DCPG_HOSTSIM=32 -c "$here/hostsim.cpp" -o "$here/_build/hostsim32.o"
 g++ -shared -o "$here/_build/libhostsim32.so" "$here/_build/hostsim32.o" "$here/_build/cpg_model.o" "$here/_build/cpg_pack.o" -lm -lpthread
+# the command-line programs on top of a TEST-ONLY stand-in for the device (fakedev.cpp): the host
+# side of the product (reader, batching, packing pool, workers, ordered writer) for the CPU suite
+g++ $CF -c "$here/fakedev.cpp" -o "$here/_build/fakedev.o"
+gcc $CF -I"$root/classpro_b200/host" -c "$root/classpro_b200/host/classpro_main.c" -o "$here/_build/classpro_main.o"
+gcc $CF -I"$root/classpro_b200/host" -c "$root/classpro_b200/host/cpg_prof2class.c" -o "$here/_build/cpg_prof2class.o"
+g++ -o "$here/_build/ClassPro" "$here/_build/classpro_main.o" "$here/_build/fakedev.o" "$here/_build/cpg_model.o" "$here/_build/cpg_pack.o" -lz -lpthread -lm
+g++ -o "$here/_build/prof2class" "$here/_build/cpg_prof2class.o" "$here/_build/fakedev.o" "$here/_build/cpg_model.o" "$here/_build/cpg_pack.o" -lz -lpthread -lm

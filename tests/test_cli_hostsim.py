@@ -1,0 +1,116 @@
+"""The host side of the product -- the ClassPro and prof2class programs: option parsing, FASTX
+reader, batching, the packing pool, per-GPU workers, the ordered writer, the byte contract of the
+records -- on machines without a GPU.  tests/hostsim/build.sh links the programs' own sources
+against a TEST-ONLY stand-in for the device (tests/hostsim/fakedev.cpp: the device sources compiled
+for the host, one read at a time); nothing of this is in the product library."""
+import filecmp
+import gzip
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "hostsim", "_build")
+CLI = os.path.join(BUILD, "ClassPro")
+P2C = os.path.join(BUILD, "prof2class")
+
+
+@pytest.fixture(scope="module")
+def progs(kit):
+    kit.build_hostsim()
+    assert os.path.exists(CLI) and os.path.exists(P2C)
+    return CLI
+
+
+def run(cmd, env=None, cwd=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, env=e, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+@pytest.mark.parametrize("opts,devices", [([], 1), (["-B1", "-T1"], 1), (["-B1", "-T5"], 3), (["-B2", "-G2", "-T2"], 4)])
+def test_golden_fixture_through_the_programs_host_side(kit, progs, tmp_path, name, opts, devices):
+    """Golden .class of the reference, reproduced through reader -> pool -> workers -> writer with
+    batches of 1-2 megabases, 1-5 packing threads and 1-3 worker threads ("GPUs")."""
+    from test_oracle import unpack_golden
+    fasta, golden, args = unpack_golden(name, str(tmp_path))
+    p = run([CLI, "-v"] + args + opts + [fasta], env={"CPG_FAKE_DEVICES": str(devices)})
+    assert p.returncode == 0, p.stderr[-1500:]
+    assert filecmp.cmp(fasta[:-6] + ".class", golden, shallow=False)
+    assert "Classified" in p.stderr
+
+
+def test_fastq_gz_header_quirks_and_short_reads(kit, progs, tmp_path):
+    """FASTQ.gz input, wrapped sequence lines, reads shorter than K, and the header quirks that are
+    part of the byte contract: no comment on the first record -> "(null)", a
+    tab-separated comment, a comment-less record after one with a comment -> the stale comment."""
+    if not kit.have_reference():
+        pytest.skip("oracle/_ref/ClassPro not present")
+    sim = kit.simulate(write_to=str(tmp_path), root="q", seed=83, genome_len=40000, cov=20., het=0.01, len_mean=7000,
+                       short_reads=1, nparts=2)
+    os.remove(str(tmp_path / "q.fasta"))
+    with gzip.open(str(tmp_path / "q.fastq.gz"), "wb") as f:
+        for i in range(sim.nreads):
+            s = sim.read_ascii(i).tobytes()
+            if i == 0:
+                hdr = b"@r0"
+            elif i % 5 == 1:
+                hdr = b"@r%d\tcomm ent %d" % (i, i)
+            elif i % 5 == 2:
+                hdr = b"@r%d" % i
+            else:
+                hdr = b"@" + sim.headers[i].replace(b"Sim ", b"Sim_", 1)
+            f.write(hdr + b"\n")
+            if i % 3 == 0 and len(s) > 100:
+                f.write(s[:61] + b"\n" + s[61:] + b"\n")
+            else:
+                f.write(s + b"\n")
+            f.write(b"+\n" + b"I" * len(s) + b"\n")
+    fq = str(tmp_path / "q.fastq.gz")
+    ref = kit.run_reference(fq, threads=1)
+    os.rename(ref, ref + ".ref")
+    for opts in ([], ["-B1", "-T3"]):
+        p = run([CLI] + opts + [fq], env={"CPG_FAKE_DEVICES": "2"})
+        assert p.returncode == 0, p.stderr[-1500:]
+        assert filecmp.cmp(ref, ref + ".ref", shallow=False), opts
+        os.remove(ref)
+
+
+def test_program_errors(kit, progs, tmp_path):
+    from test_oracle import unpack_golden
+    fasta, golden, args = unpack_golden("g1", str(tmp_path))
+    p = run([CLI])
+    assert p.returncode == 1 and "Usage" in p.stderr
+    p = run([CLI, str(tmp_path / "nothing.fasta")])
+    assert p.returncode == 1 and "Cannot open" in p.stderr
+    p = run([CLI, "-Mmodel", fasta])
+    assert p.returncode == 1 and "-M" in p.stderr
+    p = run([CLI, "-Tx", fasta])
+    assert p.returncode == 1 and "not an integer" in p.stderr
+    p = run([CLI, "-q", fasta])
+    assert p.returncode == 1 and "illegal option" in p.stderr
+    p = run([CLI, fasta], env={"CPG_FAKE_DEVICES": "0"})
+    assert p.returncode == 1 and "no CUDA device" in p.stderr
+    os.remove(str(tmp_path / ".g1.prof.1"))
+    p = run([CLI, fasta])
+    assert p.returncode == 1 and "misssing" in p.stderr         # the reference's own spelling (src/libfastk.c:1302)
+
+
+def test_prof2class_host_side(kit, progs, tmp_path):
+    ref = os.path.join(ROOT, "oracle", "_ref", "prof2class")
+    if not os.path.exists(ref):
+        pytest.skip("reference prof2class not built (no /root/reference here)")
+    d1, d2 = tmp_path / "a", tmp_path / "b"
+    d1.mkdir()
+    d2.mkdir()
+    kit.simulate(write_to=str(d1), root="reads", seed=91, genome_len=60000, cov=3., het=0.01, repeat_frac=0.3,
+                 len_mean=6000, len_sd=1500, len_min=30, short_reads=1, nparts=3)
+    for f in os.listdir(d1):
+        shutil.copy(os.path.join(d1, f), os.path.join(d2, f))
+    a = run([ref, "reads", "reads.fasta"], cwd=str(d1))
+    b = run([P2C, "reads.prof", "reads.fasta"], cwd=str(d2))
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+    assert filecmp.cmp(str(d1 / "reads.class"), str(d2 / "reads.class"), shallow=False)
