@@ -300,6 +300,7 @@ static void *reader_main(void *arg)
           bases += rlen;
           id++;
         }
+      if (b->n_all == 0) { g_t_reader += now_s()-t_r0; q_push(&A->q_free,b); break; }     /* nothing left (or an empty input) */
       /* pass 2: pack + fetch profiles into pinned memory */
       if (g_tl_first == 0.) g_tl_first = now_s();
       batch_reserve(b,b->n_all,pseq+16,prof+16,cls+16);

@@ -114,3 +114,47 @@ def test_prof2class_host_side(kit, progs, tmp_path):
     b = run([P2C, "reads.prof", "reads.fasta"], cwd=str(d2))
     assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
     assert filecmp.cmp(str(d1 / "reads.class"), str(d2 / "reads.class"), shallow=False)
+
+
+def test_raw_byte_sequences_and_mixed_batches(kit, progs, tmp_path):
+    """Lower-case bases: the reference compares raw characters (src/context.c), so 'a' != 'A' changes the
+    run lengths; a batch with such a read is shipped as bytes (seq_bits = 8), the others 2-bit packed --
+    with 1 Mbase batches both kinds occur in one run."""
+    import numpy as np
+    if not kit.have_reference():
+        pytest.skip("oracle/_ref/ClassPro not present")
+    kit.simulate(write_to=str(tmp_path), root="lc", seed=85, genome_len=60000, cov=25., het=0.01, repeat_frac=0.5,
+                 len_mean=8000)
+    fa = str(tmp_path / "lc.fasta")
+    rng = np.random.default_rng(3)
+    lines = open(fa, "rb").read().split(b"\n")
+    for i in range(1, len(lines) // 2, 2):                  # first half of the reads only
+        s = bytearray(lines[i])
+        for p in rng.integers(0, max(1, len(s)), size=max(1, len(s) // 200)):
+            s[p:p + 3] = bytes(s[p:p + 3]).lower()
+        lines[i] = bytes(s)
+    open(fa, "wb").write(b"\n".join(lines))
+    ref = kit.run_reference(fa, threads=1)
+    os.rename(ref, ref + ".ref")
+    for opts in (["-B1", "-T2"], []):
+        p = run([CLI] + opts + [fa])
+        assert p.returncode == 0, p.stderr[-1500:]
+        assert filecmp.cmp(ref, ref + ".ref", shallow=False), opts
+        os.remove(ref)
+
+
+def test_empty_and_tiny_inputs(kit, progs, tmp_path):
+    """No reads at all, and a single read shorter than K (src/ClassPro.c:209-226)."""
+    from test_oracle import unpack_golden
+    fasta, golden, args = unpack_golden("g1", str(tmp_path))
+    recs = open(fasta, "rb").read().split(b">")[1:]
+    # the profile index still lists every read; only the FASTA is cut short, as when a run is interrupted
+    open(fasta, "wb").write(b">" + recs[0])
+    p = run([CLI] + args + [fasta])
+    assert p.returncode == 0, p.stderr[-800:]
+    out = open(fasta[:-6] + ".class", "rb").read().split(b"\n")
+    want = open(golden, "rb").read().split(b"\n")
+    assert out[:4] == want[:4] and len(out) == 5
+    open(fasta, "wb").write(b"")
+    p = run([CLI] + args + [fasta])
+    assert p.returncode == 0 and os.path.getsize(fasta[:-6] + ".class") == 0
