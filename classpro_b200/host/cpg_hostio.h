@@ -97,7 +97,7 @@ static int fx_getuntil(fastx_t *x, int line_mode, str_t *s, int *dret, int appen
 static int fx_read(fastx_t *x)
 { int c;
   if (x->last_char == 0)
-    { while ((c = fx_getc(x)) >= 0 && c != '>' && c != '@');
+    { do c = fx_getc(x); while (c >= 0 && c != '>' && c != '@');
       if (c < 0) return -1;
       x->last_char = c;
     }

@@ -2,14 +2,17 @@
 #include <string.h>
 #include "classpro_gpu.h"
 
+/* ASCII -> code, -1 for anything but upper-case ACGT.  Filled when the library is loaded, not on
+   first use: cpg_pack_seq is called from several packing threads at once. */
+static signed char code[256];
+
+__attribute__((constructor)) static void cpg_pack_init(void)
+{ memset(code,-1,sizeof(code));
+  code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3;
+}
+
 int cpg_pack_seq(const char *seq, int32_t rlen, uint8_t *out)
-{ static signed char code[256];
-  static int init = 0;
-  if (!init)
-    { memset(code,-1,sizeof(code));
-      code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3;
-      init = 1;
-    }
+{
   int bad = 0;
   int32_t i = 0;
   for (; i+4 <= rlen; i += 4)

@@ -158,3 +158,31 @@ def test_empty_and_tiny_inputs(kit, progs, tmp_path):
     open(fasta, "wb").write(b"")
     p = run([CLI] + args + [fasta])
     assert p.returncode == 0 and os.path.getsize(fasta[:-6] + ".class") == 0
+
+
+@pytest.mark.parametrize("san", ["address", "thread"])
+def test_host_side_under_sanitizers(kit, progs, tmp_path, san):
+    """The programs' host side (reader, packing pool, three worker threads, writer) built with
+    -fsanitize=address / thread: no report, same bytes.  (Found the lazily initialised table of
+    cpg_pack_seq, which several packing threads raced on.)"""
+    from test_oracle import unpack_golden
+    host, hs = os.path.join(ROOT, "classpro_b200", "host"), os.path.join(ROOT, "tests", "hostsim")
+    cf = ["-O1", "-g", "-ffp-contract=off", "-fsanitize=" + san, "-I" + os.path.join(ROOT, "include"), "-I" + host]
+    objs = []
+    for cc, src in (("gcc", os.path.join(host, "cpg_model.c")), ("gcc", os.path.join(host, "cpg_pack.c")),
+                    ("gcc", os.path.join(host, "classpro_main.c")), ("g++", os.path.join(hs, "fakedev.cpp"))):
+        o = str(tmp_path / (os.path.basename(src) + ".o"))
+        p = run([cc] + cf + ["-w", "-c", src, "-o", o])
+        if p.returncode != 0 and "sanitize" in p.stderr:
+            pytest.skip("no %s sanitizer in this toolchain" % san)
+        assert p.returncode == 0, p.stderr[-800:]
+        objs.append(o)
+    exe = str(tmp_path / "ClassPro_san")
+    p = run(["g++", "-fsanitize=" + san, "-o", exe] + objs + ["-lz", "-lpthread", "-lm"])
+    if p.returncode != 0:
+        pytest.skip("cannot link with -fsanitize=%s: %s" % (san, p.stderr[-200:]))
+    fasta, golden, args = unpack_golden("g1", str(tmp_path / "d"))
+    p = run([exe, "-B1", "-T4"] + args + [fasta], env={"CPG_FAKE_DEVICES": "3", "ASAN_OPTIONS": "detect_leaks=0"})
+    assert p.returncode == 0, p.stderr[-3000:]
+    assert "Sanitizer" not in p.stderr, p.stderr[-3000:]
+    assert filecmp.cmp(fasta[:-6] + ".class", golden, shallow=False)
