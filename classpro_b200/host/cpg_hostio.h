@@ -17,7 +17,7 @@
 #include <strings.h>
 #include <zlib.h>
 
-static void die(const char *fmt, ...)
+__attribute__((noreturn,format(printf,1,2))) static void die(const char *fmt, ...)
 { va_list ap; va_start(ap,fmt); vfprintf(stderr,fmt,ap); va_end(ap); fputc('\n',stderr); exit(1); }
 
 static void *xmalloc(size_t n)
@@ -141,7 +141,7 @@ static void split_path(const char *name, char *dir, size_t dn, char *base, size_
   else    { snprintf(dir,dn,"."); snprintf(base,bn,"%s",name); }
 }
 
-static int profidx_open(profidx_t *P, const char *fk_root)
+__attribute__((unused)) static int profidx_open(profidx_t *P, const char *fk_root)
 { char dir[4096], root[1024], path[8192];
   split_path(fk_root,dir,sizeof(dir),root,sizeof(root));
   size_t rl = strlen(root);
@@ -192,7 +192,7 @@ static int profidx_open(profidx_t *P, const char *fk_root)
 }
 
 /* byte range of read id inside its part (src/libfastk.c:1444-1454) */
-static void prof_range(const profidx_t *P, int64_t id, int *part, int64_t *off, int64_t *len)
+__attribute__((unused)) static void prof_range(const profidx_t *P, int64_t id, int *part, int64_t *off, int64_t *len)
 { int w = 0;
   while (w < P->nparts && id >= P->nbase[w]) w++;
   if (w >= P->nparts) die("Id %lld is out of range [1,%lld]",(long long)id,(long long)P->nbase[P->nparts-1]);
