@@ -58,9 +58,13 @@ int cpg_create(cpg_ctx **out, int device, const cpg_model *model, int64_t, int32
 }
 void cpg_destroy(cpg_ctx *c) { delete c; }
 
-/* one read: the per-read calls of k_decode and of the classification kernels */
+/* one read: the per-read calls of k_decode and of the classification kernels.
+   CPG_FAKE_NULL=1 skips them (class string of 'X's): then a run of the program times its host side
+   alone -- parser, packing pool, queues, writer -- on inputs of any size. */
 static int fake_read(cpg_ctx *c, const cpg_batch *b, int i, uint8_t *cls)
 { const int K = c->dm.K, rlen = b->rlen[i], cap = rlen-K+1;
+  static const int null_dev = (getenv("CPG_FAKE_NULL") != 0);
+  if (null_dev) { memset(cls,'N',(size_t)K-1); memset(cls+K-1,'X',(size_t)cap); return 0; }
   static thread_local std::vector<uint16_t> cnt; static thread_local std::vector<uint32_t> cand;
   static thread_local std::vector<uint8_t> sq; static thread_local HsWork Wk; static thread_local int sized = 0;
   static thread_local unsigned tab[DC_SLOTS];

@@ -160,7 +160,7 @@ def test_empty_and_tiny_inputs(kit, progs, tmp_path):
     assert p.returncode == 0 and os.path.getsize(fasta[:-6] + ".class") == 0
 
 
-@pytest.mark.parametrize("san", ["address", "thread"])
+@pytest.mark.parametrize("san", ["address,undefined", "thread"])
 def test_host_side_under_sanitizers(kit, progs, tmp_path, san):
     """The programs' host side (reader, packing pool, three worker threads, writer) built with
     -fsanitize=address / thread: no report, same bytes.  (Found the lazily initialised table of
