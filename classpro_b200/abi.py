@@ -240,6 +240,8 @@ class Context:
         return a.value, b.value, n.value
 
     def phase_cycles(self):
+        """Device time of k_wall, k_rel, k_unrel and the retry launch in the last timed resident run,
+        nanoseconds (per-phase clock cycles with CPG_FUSED=1)."""
         out = (C.c_uint64 * 4)()
         rc = self.L.cpg_phase_cycles(self.h, out)
         if rc:
