@@ -10,7 +10,10 @@
  *  the kernels make.  Built by tests/hostsim/build.sh into tests/hostsim/_build/ only; it is not a
  *  fallback: the product library has none and fails without a CUDA device.
  *******************************************************************************************/
-#define CPG_HOSTSIM 1
+#ifndef CPG_HOSTSIM
+#define CPG_HOSTSIM 1            /* -DCPG_HOSTSIM=32: every read on the 32-thread warp emulation (slow; used
+                                    with -fsanitize=thread to look for missing group barriers) */
+#endif
 #include "hostsim.cpp"
 #include <string.h>
 
@@ -65,6 +68,21 @@ static int fake_read(cpg_ctx *c, const cpg_batch *b, int i, uint8_t *cls)
 { const int K = c->dm.K, rlen = b->rlen[i], cap = rlen-K+1;
   static const int null_dev = (getenv("CPG_FAKE_NULL") != 0);
   if (null_dev) { memset(cls,'N',(size_t)K-1); memset(cls+K-1,'X',(size_t)cap); return 0; }
+#if CPG_HOSTSIM == 32
+  { /* the warp emulation: 32 host threads per read, lane groups of CPG_FAKE_GROUP lanes (default 4) */
+    static const int grp = getenv("CPG_FAKE_GROUP") ? atoi(getenv("CPG_FAKE_GROUP")) : 4;
+    hs_set_group(grp);
+    std::vector<uint16_t> cnt((size_t)cap+64,0);
+    const int64_t po = b->prof_off[i];
+    int n = hs_decode_profile(b->prof+po,b->prof_off[i+1]-po,cnt.data(),cap);
+    if (n != cap) return CPG_ST_BAD_PROFILE;
+    std::vector<char> asc((size_t)rlen+1,0);
+    const uint8_t *sp = b->seq+b->seq_off[i];
+    for (int j = 0; j < rlen; j++)
+      asc[j] = (b->seq_bits == 2) ? "ACGT"[(sp[j >> 2] >> ((j & 3)*2)) & 3] : (char)sp[j];
+    return hs_classify_read(&c->model,asc.data(),rlen,b->seq_bits,cnt.data(),cap,(char *)cls,NULL,NULL,NULL);
+  }
+#else
   static thread_local std::vector<uint16_t> cnt; static thread_local std::vector<uint32_t> cand;
   static thread_local std::vector<uint8_t> sq; static thread_local HsWork Wk; static thread_local int sized = 0;
   static thread_local unsigned tab[DC_SLOTS];
@@ -90,6 +108,7 @@ static int fake_read(cpg_ctx *c, const cpg_batch *b, int i, uint8_t *cls)
   R.S.rpos = Kk.rpos.data(); R.S.ord = Kk.ord.data(); R.S.fixed = Kk.fixed.data(); R.S.MC = Kk.mc; R.S.memo = Kk.memo.data();
   R.S.capS = Kk.capS; R.S.capE = Kk.capE; R.S.capI = Kk.capI;
   return classify_read(R,W,sh,cls);
+#endif
 }
 
 int cpg_submit(cpg_ctx *c, int slot, const cpg_batch *b)

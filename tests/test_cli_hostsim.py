@@ -186,3 +186,36 @@ def test_host_side_under_sanitizers(kit, progs, tmp_path, san):
     assert p.returncode == 0, p.stderr[-3000:]
     assert "Sanitizer" not in p.stderr, p.stderr[-3000:]
     assert filecmp.cmp(fasta[:-6] + ".class", golden, shallow=False)
+
+
+@pytest.mark.parametrize("group", [4, 8])
+def test_warp_emulation_under_thread_sanitizer(kit, progs, tmp_path, group):
+    """The device sources with 32 host threads playing the lanes of a warp (lane groups of 4 / 8, as
+    in k_wall / k_rel, k_unrel), built with -fsanitize=thread: a scratch or shared word written by one
+    lane and read by another without a group barrier in between is a data race it reports.  30 reads
+    of the golden fixture through decode and all three phases: no report, same bytes."""
+    from test_oracle import unpack_golden
+    host, hs = os.path.join(ROOT, "classpro_b200", "host"), os.path.join(ROOT, "tests", "hostsim")
+    cf = ["-O1", "-g", "-ffp-contract=off", "-fsanitize=thread", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + host]
+    objs = []
+    for cc, src, extra in (("gcc", os.path.join(host, "cpg_model.c"), []), ("gcc", os.path.join(host, "cpg_pack.c"), []),
+                           ("gcc", os.path.join(host, "classpro_main.c"), []),
+                           ("g++", os.path.join(hs, "fakedev.cpp"), ["-DCPG_HOSTSIM=32"])):
+        o = str(tmp_path / (os.path.basename(src) + ".o"))
+        p = run([cc] + cf + extra + ["-c", src, "-o", o])
+        if p.returncode != 0 and "sanitize" in p.stderr:
+            pytest.skip("no thread sanitizer in this toolchain")
+        assert p.returncode == 0, p.stderr[-800:]
+        objs.append(o)
+    exe = str(tmp_path / "ClassPro_t32")
+    p = run(["g++", "-fsanitize=thread", "-o", exe] + objs + ["-lz", "-lpthread", "-lm"])
+    if p.returncode != 0:
+        pytest.skip("cannot link with -fsanitize=thread: %s" % p.stderr[-200:])
+    fasta, golden, args = unpack_golden("g1", str(tmp_path / "d"))
+    recs = open(fasta, "rb").read().split(b">")[1:31]
+    open(fasta, "wb").write(b"".join(b">" + r for r in recs))
+    p = run([exe, "-T2"] + args + [fasta], env={"CPG_FAKE_GROUP": str(group)})
+    assert p.returncode == 0, p.stderr[-3000:]
+    assert "Sanitizer" not in p.stderr, p.stderr[-3000:]
+    want = b"\n".join(open(golden, "rb").read().split(b"\n")[:4 * len(recs)]) + b"\n"
+    assert open(fasta[:-6] + ".class", "rb").read() == want
