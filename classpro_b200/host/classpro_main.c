@@ -430,18 +430,26 @@ static void *writer_main(void *arg)
       pthread_mutex_unlock(&A->mu);
       if (b == NULL) break;
       const double t_w0 = now_s();
+      int last = -1;                          /* last classified record of this batch so far */
       for (int i = 0; i < b->n_all; i++)
         { const int rlen = b->rlen_all[i], k = b->slot_of[i];
           fputs(b->header[i],out); fputc('\n',out);
           fwrite(b->seq[i],1,(size_t)rlen,out);
           fputs("\n+\n",out);
-          if (k >= 0)
-            { const uint8_t *c = b->cls+b->cls_off[k];
-              fwrite(c,1,(size_t)rlen,out);
-              memcpy(rasgn,c,(size_t)rlen); rasgn[rlen] = 0;
+          if (k >= 0) { fwrite(b->cls+b->cls_off[k],1,(size_t)rlen,out); last = i; }
+          else
+            { if (last >= 0)                    /* rasgn is brought up to date only when it is needed */
+                { const int ll = b->rlen_all[last];
+                  memcpy(rasgn,b->cls+b->cls_off[b->slot_of[last]],(size_t)ll); rasgn[ll] = 0;
+                  last = -1;
+                }
+              fprintf(out,"%*s",rlen,rasgn);
             }
-          else fprintf(out,"%*s",rlen,rasgn);
           fputc('\n',out);
+        }
+      if (last >= 0)
+        { const int ll = b->rlen_all[last];
+          memcpy(rasgn,b->cls+b->cls_off[b->slot_of[last]],(size_t)ll); rasgn[ll] = 0;
         }
       g_t_writer += now_s()-t_w0;
       pthread_mutex_lock(&A->mu);
