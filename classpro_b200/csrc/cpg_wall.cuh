@@ -319,6 +319,7 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
   int maxt = -1, maxl = -1; double maxpe = -CPG_INF;
   { int cl[3];
     cpg_ctx3_at(R.seq,R.rlen,K,wtype,i,cl);
+    if (imax(imax(cl[0],cl[1]),cl[2]) >= 127) W.status |= CPG_ST_LONG_RUN;
     CPG_LOOP for (int t = 0; t < CT_N; t++)
       { int l = imin(cl[t],M->lmax[t]);
         double pe = M->pe[t][l];
@@ -377,7 +378,9 @@ CPG_DEV_NOINL void wall_candidate(ReadCtx &R, WCtx &W, int i, int &eidx)
           { int idx = G.fwd ? i+ulen*(n+1) : i-ulen*(n+1);
             if (G.fwd) { if (idx >= plen) break; }
             else       { if (idx <= 0) break; }
-            if (cpg_ctx_at(R.seq,R.rlen,K,wtype,idx,maxt) != m+n+1) break;
+            const int cx = cpg_ctx_at(R.seq,R.rlen,K,wtype,idx,maxt);
+            if (cx >= 127) W.status |= CPG_ST_LONG_RUN;
+            if (cx != m+n+1) break;
             n++;
           }
         int j = G.fwd ? i+K-1+n-m : i-K+1-n+m;
@@ -517,12 +520,14 @@ CPG_DEV_NOINL void correct_wall_cnt(ReadCtx &R, WCtx &W, int idx)
     if (I.b+K-1 < I.e)
       { int cl[3], lmax = 0;
         cpg_rctx3(R.seq,R.rlen,I.b+K-1,cl);
+        if (imax(imax(cl[0],cl[1]),cl[2]) >= 127) W.status |= CPG_ST_LONG_RUN;
         CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cl[t]*(t+1));
         e2 = I.b+lmax;                               /* p in [I.b,e2)  */
       }
     if (I.b < I.e-K+1)
       { int cl[3], lmax = 0;
         cpg_lctx3(R.seq,R.rlen,I.e-K+1+K-2,cl);
+        if (imax(imax(cl[0],cl[1]),cl[2]) >= 127) W.status |= CPG_ST_LONG_RUN;
         CPG_LOOP for (int t = 0; t < CT_N; t++) lmax = imax(lmax,cl[t]*(t+1));
         b4 = I.e-lmax;                               /* q in [b4,I.e-1) */
       }
