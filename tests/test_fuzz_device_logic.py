@@ -75,3 +75,37 @@ def test_adversarial_profiles_match_the_oracle(kit, hostsim, seed):
                 continue
             assert (st & ~128) == 0 and a == b, (seed, cov_opt, r, n, st)
     assert flagged < total // 10
+
+
+@pytest.mark.parametrize("group,small_caps", [(4, 0), (8, 0), (16, 5), (0, 4)])
+def test_adversarial_profiles_on_lane_groups_and_the_retry_path(kit, hostsim, group, small_caps):
+    """The same inputs on the 32-thread warp emulation with lane groups of 4 / 8 / 16 (group = 0: the
+    width-1 build), and with interval tables of a few entries in the first attempt, so that most
+    reads take the abort paths of the phase code and are classified again with full-size tables."""
+    lib = kit.hostsim32_lib() if group else hostsim
+    rng = np.random.default_rng(100 + group + small_caps)
+    sim = kit.simulate(seed=5, genome_len=30000, cov=20., het=0.01, len_mean=3000)
+    if group:
+        assert lib.hs_set_group(group) == 0
+    lib.hs_set_small_caps(small_caps)
+    try:
+        for cov_opt, read_len in ((0, 20000), (12, 8000)):
+            om = kit.oracle_model(sim, cov_opt, read_len)
+            gm = kit.gpu_model_from_sim(lib, sim, cov_opt, read_len)
+            H, D, R = om.cov[2], om.cov[3], om.cov[1]
+            ow = kit.OracleWork(clean=True)
+            for r in range(80):
+                n = int(rng.integers(1, 1500))
+                s = rand_seq(rng, n + 39)
+                c = rand_counts(rng, n, H, D, R)
+                a = ow.classify(om, s, c)
+                st, b = kit.hostsim_classify(gm, s, c, 2, lib=lib)
+                if st & 32:
+                    continue
+                assert (st & ~128) == 0 and a == b, (group, small_caps, cov_opt, r, n, st)
+        if small_caps:
+            assert lib.hs_retries() > 40
+    finally:
+        lib.hs_set_small_caps(0)
+        if group:
+            lib.hs_set_group(32)
