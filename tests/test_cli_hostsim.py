@@ -219,3 +219,47 @@ def test_warp_emulation_under_thread_sanitizer(kit, progs, tmp_path, group):
     assert "Sanitizer" not in p.stderr, p.stderr[-3000:]
     want = b"\n".join(open(golden, "rb").read().split(b"\n")[:4 * len(recs)]) + b"\n"
     assert open(fasta[:-6] + ".class", "rb").read() == want
+
+
+def test_fasta_format_variants(kit, progs, tmp_path):
+    """Record formats kseq accepts (src/kseq.h:177-218) and the program must echo byte for byte like
+    the reference: wrapped sequence lines of several widths, CRLF line ends, blank lines between
+    records, no comment / tab separator / extra blanks in the header."""
+    import numpy as np
+    if not kit.have_reference():
+        pytest.skip("oracle/_ref/ClassPro not present")
+    rng = np.random.default_rng(1)
+    d = str(tmp_path)
+    sim = kit.simulate(write_to=d, root="q", seed=1, genome_len=30000, cov=12., het=0.01, len_mean=4000,
+                       short_reads=1, nparts=2)
+    fa = os.path.join(d, "q.fasta")
+    for variant in range(6):
+        out = bytearray()
+        for i in range(sim.nreads):
+            s = sim.read_ascii(i).tobytes()
+            hdr = sim.headers[i]
+            k = rng.integers(0, 8)
+            if k == 0:
+                hdr = hdr.split(b" ")[0]
+            elif k == 1:
+                hdr = hdr.replace(b" ", b"\t", 1)
+            elif k == 2:
+                hdr = hdr + b"  trailing  "
+            elif k == 3:
+                hdr = hdr.replace(b" ", b"  ", 1)
+            nl = b"\r\n" if rng.random() < 0.15 else b"\n"
+            out += b">" + hdr + nl
+            w = int(rng.choice([0, 0, 60, 80, 7, 1000]))
+            if w and len(s) > 0:
+                for a in range(0, len(s), w):
+                    out += s[a:a + w] + nl
+            else:
+                out += s + nl
+            if rng.random() < 0.1:
+                out += nl
+        open(fa, "wb").write(bytes(out))
+        ref = kit.run_reference(fa, threads=1)
+        os.replace(ref, ref + ".ref")
+        p = run([CLI, "-B1", "-T2", fa])
+        assert p.returncode == 0, p.stderr[-1500:]
+        assert filecmp.cmp(ref, ref + ".ref", shallow=False), variant
