@@ -39,7 +39,8 @@ typedef struct { char *s; size_t l, m; } str_t;
 typedef struct
   { gzFile  f;
     uint8_t *buf;
-    int      beg, end, eof;
+    int64_t  beg, end;              /* window of buf; int64: in memory mode buf is a whole mapped file */
+    int      eof;
     int      last_char;
     str_t    name, comment, seq, qual;
     int      have_comment;          /* comment.s non-NULL in kseq terms */
@@ -76,8 +77,8 @@ static int fx_getuntil(fastx_t *x, int line_mode, str_t *s, int *dret, int appen
           x->end = gzread(x->f,x->buf,FX_BUF);
           if (x->end <= 0) { x->eof = 1; x->end = 0; break; }
         }
-      int i = x->beg;
-      if (line_mode) { uint8_t *q = memchr(x->buf+i,'\n',(size_t)(x->end-i)); i = q ? (int)(q-x->buf) : x->end; }
+      int64_t i = x->beg;
+      if (line_mode) { uint8_t *q = memchr(x->buf+i,'\n',(size_t)(x->end-i)); i = q ? (int64_t)(q-x->buf) : x->end; }
       else while (i < x->end && !isspace(x->buf[i])) i++;
       str_reserve(s,(size_t)(i-x->beg));
       got = 1;
@@ -93,7 +94,23 @@ static int fx_getuntil(fastx_t *x, int line_mode, str_t *s, int *dret, int appen
   return (int)s->l;
 }
 
-/* >= 0 sequence length, -1 end of file */
+/* Memory mode: the stream is the byte range [pos,len) of mem (a mapped file), never refilled.
+   Several fastx_t can parse different ranges of the same mapping at the same time. */
+__attribute__((unused)) static void fx_set_memory(fastx_t *x, const uint8_t *mem, int64_t pos, int64_t len)
+{ x->f = NULL; x->buf = (uint8_t *)mem; x->beg = pos; x->end = len; x->eof = 1; x->last_char = 0; }
+
+/* Memory mode: position of the record marker ('>' or '@') the next fx_read starts from (= end at the
+   end of the stream).  With the comment carried from earlier records this is the whole parser state
+   between two records (src/kseq.h:181-186: either the marker was already consumed as the character
+   that ended the previous sequence, or the reader skips to the next one). */
+__attribute__((unused)) static int64_t fx_next_marker(const fastx_t *x)
+{ if (x->last_char) return x->beg-1;
+  int64_t i = x->beg;
+  while (i < x->end && x->buf[i] != '>' && x->buf[i] != '@') i++;
+  return i < x->end ? i : x->end;
+}
+
+/* >= 0 sequence length, -1 end of file, -2 truncated quality string */
 static int fx_read(fastx_t *x)
 { int c;
   if (x->last_char == 0)

@@ -4,6 +4,7 @@ records -- on machines without a GPU.  tests/hostsim/build.sh links the programs
 against a TEST-ONLY stand-in for the device (tests/hostsim/fakedev.cpp: the device sources compiled
 for the host, one read at a time); nothing of this is in the product library."""
 import filecmp
+import re
 import gzip
 import os
 import shutil
@@ -263,3 +264,66 @@ def test_fasta_format_variants(kit, progs, tmp_path):
         p = run([CLI, "-B1", "-T2", fa])
         assert p.returncode == 0, p.stderr[-1500:]
         assert filecmp.cmp(ref, ref + ".ref", shallow=False), variant
+
+
+def test_parallel_parse_and_mapped_writer(kit, progs, tmp_path):
+    """The chunk-parallel FASTX parser and the mapped, parallel writer against the
+    reference binary: FASTQ whose quality lines begin with / contain '@', '>' and '+' (a guessed
+    piece start that is not a record start must be caught and parsed again), wrapped records,
+    comments that a later comment-less record repeats across piece boundaries, reads shorter than
+    K, CRLF; windows of 30-200 kb cut into 1-9 pieces.  Same bytes as with the serial reader /
+    write() writer (CPG_SERIAL_IO=1) and as the reference."""
+    import numpy as np
+    if not kit.have_reference():
+        pytest.skip("oracle/_ref/ClassPro not present")
+    rng = np.random.default_rng(7)
+    d = str(tmp_path)
+    sim = kit.simulate(write_to=d, root="q", seed=5, genome_len=40000, cov=15., het=0.01, len_mean=3000,
+                       short_reads=1, nparts=3)
+    os.remove(os.path.join(d, "q.fasta"))
+    qchars = np.frombuffer(b"@>+I!~5@@>", dtype=np.uint8)
+    stats = {}
+    for variant, ext in enumerate(["fastq", "fastq", "fasta", "fastq"]):
+        out = bytearray()
+        for i in range(sim.nreads):
+            s = sim.read_ascii(i).tobytes()
+            name = b"r%d" % i
+            k = rng.integers(0, 4) if variant != 3 else (1 if i == sim.nreads // 2 else 0)
+            hdr = name if k == 0 else name + b" c%d x" % i if k == 1 else name + b"\tt%d" % i if k == 2 else name + b" "
+            nl = b"\r\n" if (variant == 2 and rng.random() < 0.2) else b"\n"
+            mark = b"@" if ext == "fastq" else b">"
+            out += mark + hdr + nl
+            w = int(rng.choice([0, 0, 0, 50, 211])) if variant != 0 else 0
+            lines = [s[a:a + w] for a in range(0, len(s), w)] if (w and s) else [s]
+            for ln in lines:
+                out += ln + nl
+            if ext == "fastq":
+                q = qchars[rng.integers(0, len(qchars), len(s))].tobytes()
+                if len(s) and rng.random() < 0.5:
+                    q = b"@" + q[1:]
+                out += b"+" + (name if rng.random() < 0.3 else b"") + b"\n"
+                qlines = [q[a:a + w] for a in range(0, len(q), w)] if (w and q) else [q]
+                for ln in qlines:
+                    out += ln + b"\n"
+        src = os.path.join(d, "q." + ext)
+        open(src, "wb").write(bytes(out))
+        ref = kit.run_reference(src, threads=1)
+        os.replace(ref, ref + ".ref")
+        for env in ({"CPG_SERIAL_IO": "1"},
+                    {"CPG_BATCH_BASES": "30000", "CPG_PARSE_PIECES": "9"},
+                    {"CPG_BATCH_BASES": "200000", "CPG_PARSE_PIECES": "4"},
+                    {"CPG_BATCH_BASES": "70001", "CPG_PARSE_PIECES": "1"},
+                    {}):
+            e = dict(env)
+            e["CPG_FAKE_DEVICES"] = "2"
+            p = run([CLI, "-v", "-T3", src], env=e)
+            assert p.returncode == 0, p.stderr[-1500:]
+            assert ("Parsing" in p.stderr) == ("CPG_SERIAL_IO" not in env)
+            m = re.search(r"parser: (\d+) pieces parsed again from their true start, (\d+) headers completed", p.stderr)
+            stats[(variant, env.get("CPG_PARSE_PIECES", "serial" if "CPG_SERIAL_IO" in env else "default"))] = (int(m.group(1)), int(m.group(2)))
+            assert filecmp.cmp(ref, ref + ".ref", shallow=False), (variant, env)
+            os.remove(ref)
+        os.remove(src)
+    # the cases the test is about did occur: wrong guesses in wrapped FASTQ (none in FASTA), carried comments
+    assert stats[(1, "9")][0] > 0 and stats[(2, "9")][0] == 0 and stats[(1, "serial")] == (0, 0)
+    assert stats[(3, "9")][1] > 0 and stats[(2, "9")][1] > 0, stats
