@@ -1,0 +1,244 @@
+/*******************************************************************************************
+ *  cpg_count.cu -- profile producer on the GPU: cpg_count_kmers and
+ *  cpg_encode_profiles of include/classpro_gpu.h.  sm_100a; grid-stride kernels around the element
+ *  functions of cpg_count.cuh, CUB (the toolkit's) for the radix sort and the two prefix sums.
+ *
+ *  All of this is HBM-bound integer work.  Algorithmic bytes per k-mer, n k-mers, r reads
+ *  (K <= 32: the second sort pass falls away):
+ *    k_kmer_keys      r/4 in (2-bit bases, every 64-bit word read by <= 33 neighbouring threads: L1),
+ *                     16 out (64 low key bits; high key bits << 48 | index)
+ *    sort             16 in + 16 out per radix pass; 8 passes of 8 bits for the low word, 2 for
+ *                     the 16 high bits of a 40-mer: 320 B per k-mer, the bulk of the whole job
+ *    k_run_heads      16 in, 4 out;  inclusive sum 4 in, 4 out;  k_run_starts 8 in, <= 4 out
+ *    k_scatter_counts 16 in, 2 out (scattered: the index order of a sorted run is random)
+ *    encoder          k_enc_change 2 in, 4 out; max-scan 4+4; k_enc_size 6 in, 1 out; sum 1 in,
+ *                     8 out; k_enc_write 15 in, c out  (a fused one-warp-per-read encoder, the mirror
+ *                     image of k_decode, would read 2 and write c: next step)
+ *  Device memory: 2 x 16 B per k-mer for the sort's double buffers plus its histogram scratch,
+ *  4 + 4 B for run ids and run starts (the latter in the idle half of a double buffer), 2 B for the
+ *  counts: ~40 B per k-mer, i.e. ~4 * 10^9 k-mers in 180 GB (BASELINE config 2 has 3 * 10^9).
+ *  Larger read sets need key-range passes (equal keys always land in the same pass) and, over
+ *  several GPUs, an all-to-all of keys by range: the one real exchange step of this row.
+ *******************************************************************************************/
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include "../../include/classpro_gpu.h"
+#include "cpg_count.cuh"
+
+static thread_local char t_err[512] = "";
+
+static int cnt_err(int code, const char *fmt, ...)
+{ va_list ap; va_start(ap,fmt); vsnprintf(t_err,sizeof(t_err),fmt,ap); va_end(ap);
+  return code;
+}
+
+extern "C" const char *cpg_count_error(void) { return t_err; }
+
+#define CT_THREADS 256
+#define HIDX_SHIFT CPG_HIDX_SHIFT
+
+/* one CTA per read at a time (reads are handed out round robin), threads stride the positions */
+__global__ void __launch_bounds__(CT_THREADS)
+k_kmer_keys(int n_reads, const uint64_t *__restrict__ W, const int64_t *__restrict__ seq_off,
+            const int64_t *__restrict__ cnt_off, int K, uint64_t *__restrict__ klo, uint64_t *__restrict__ khidx)
+{ for (int r = blockIdx.x; r < n_reads; r += gridDim.x)
+    { const int64_t m0 = cnt_off[r]; const int n = (int)(cnt_off[r+1]-m0);
+      const int64_t bit0 = 8*seq_off[r];
+      for (int p = threadIdx.x; p < n; p += CT_THREADS) cpg_key_element(W,bit0,p,m0+p,K,klo,khidx);
+    }
+}
+
+__global__ void __launch_bounds__(CT_THREADS)
+k_run_heads(int64_t n, const uint64_t *__restrict__ klo, const uint64_t *__restrict__ khidx, uint32_t *__restrict__ head)
+{ for (int64_t i = blockIdx.x*(int64_t)CT_THREADS+threadIdx.x; i < n; i += (int64_t)gridDim.x*CT_THREADS)
+    head[i] = cpg_run_head(i,klo,khidx);
+}
+
+__global__ void __launch_bounds__(CT_THREADS)
+k_run_starts(int64_t n, const uint32_t *__restrict__ rid, uint32_t *__restrict__ start)
+{ for (int64_t i = blockIdx.x*(int64_t)CT_THREADS+threadIdx.x; i < n; i += (int64_t)gridDim.x*CT_THREADS)
+    cpg_run_start(i,n,rid,start);
+}
+
+/* counts back to read order + the histogram of distinct k-mers: the low bins (where nearly all
+   distinct k-mers are) in shared memory, flushed once per CTA */
+#define HIST_SMEM 1024
+__global__ void __launch_bounds__(CT_THREADS)
+k_scatter_counts(int64_t n, const uint64_t *__restrict__ khidx, const uint32_t *__restrict__ rid,
+                 const uint32_t *__restrict__ start, uint16_t *__restrict__ counts, unsigned long long *__restrict__ hist)
+{ __shared__ unsigned int sh[HIST_SMEM];
+  for (int j = threadIdx.x; j < HIST_SMEM; j += CT_THREADS) sh[j] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x*(int64_t)CT_THREADS+threadIdx.x; i < n; i += (int64_t)gridDim.x*CT_THREADS)
+    { const uint32_t c = cpg_scatter_count(i,khidx,rid,start,counts);
+      if (c)                                               /* once per distinct k-mer */
+        { if (c < HIST_SMEM) atomicAdd(&sh[c],1u);
+          else if (c < CPG_CNT_MAX) atomicAdd(&hist[c],1ull);
+          else { atomicAdd(&hist[CPG_CNT_MAX],1ull); atomicAdd(&hist[32769],(unsigned long long)c); }   /* + instances of the top bin */
+        }
+    }
+  __syncthreads();
+  for (int j = threadIdx.x; j < HIST_SMEM; j += CT_THREADS)
+    if (sh[j]) atomicAdd(&hist[j],(unsigned long long)sh[j]);
+}
+
+/* ---- encoder ---- */
+__global__ void __launch_bounds__(CT_THREADS)
+k_enc_change(int n_reads, const uint16_t *__restrict__ counts, const int64_t *__restrict__ cnt_off, uint32_t *__restrict__ chg)
+{ for (int r = blockIdx.x; r < n_reads; r += gridDim.x)
+    { const int64_t m0 = cnt_off[r]; const int n = (int)(cnt_off[r+1]-m0);
+      for (int p = threadIdx.x; p < n; p += CT_THREADS) chg[m0+p] = cpg_enc_change(counts+m0,p,m0+p);
+    }
+}
+
+template<bool WRITE>
+__global__ void __launch_bounds__(CT_THREADS)
+k_enc_tokens(int n_reads, const uint16_t *__restrict__ counts, const int64_t *__restrict__ cnt_off,
+             const uint32_t *__restrict__ last, uint8_t *__restrict__ nbytes, const int64_t *__restrict__ boff,
+             uint8_t *__restrict__ prof, int64_t *__restrict__ prof_off)
+{ for (int r = blockIdx.x; r < n_reads; r += gridDim.x)
+    { const int64_t m0 = cnt_off[r]; const int n = (int)(cnt_off[r+1]-m0);
+      if (WRITE && threadIdx.x == 0) prof_off[r] = boff[m0];       /* boff has one entry past the last count */
+      for (int p = threadIdx.x; p < n; p += CT_THREADS)
+        { const int k = cpg_enc_position(counts+m0,p,n,m0+p,last,boff,WRITE ? prof : NULL);
+          if (!WRITE) nbytes[m0+p] = (uint8_t)k;
+        }
+    }
+}
+
+struct Sum64 { __host__ __device__ __forceinline__ int64_t operator()(int64_t a, int64_t b) const { return a+b; } };
+struct MaxOp { __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = cnt_err(CPG_ECUDA,"%s: %s",#x,cudaGetErrorString(e_)); goto done; } } while (0)
+#define DMALLOC(p,bytes) do { cudaError_t e_ = cudaMalloc((void **)&(p),(bytes)); \
+    if (e_ != cudaSuccess) { rc = cnt_err(CPG_ENOMEM,"cannot allocate %zu bytes of device memory (%s)",(size_t)(bytes),cudaGetErrorString(e_)); goto done; } } while (0)
+
+static int grid_for(int device, int64_t work_items)
+{ int sms = 148;
+  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,device);
+  int64_t want = (work_items+CT_THREADS-1)/CT_THREADS, cap = (int64_t)sms*8;        /* 8 CTAs of 256 threads per SM */
+  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const uint8_t *seq, const int64_t *seq_off,
+                               const int32_t *rlen, int64_t *cnt_off, uint16_t *counts, int64_t *hist)
+{ if (n_reads < 0 || kmer < 1 || (n_reads > 0 && (!seq || !seq_off || !rlen)) || !cnt_off || !hist || 2*kmer > 64+(64-HIDX_SHIFT))
+    return cnt_err(CPG_EINVAL,"cpg_count_kmers: bad argument (1 <= K <= %d)",(64+64-HIDX_SHIFT)/2);
+  int rc = CPG_OK;
+  cnt_off[0] = 0;
+  for (int i = 0; i < n_reads; i++) cnt_off[i+1] = cnt_off[i]+(rlen[i] >= kmer ? rlen[i]-kmer+1 : 0);
+  const int64_t n = cnt_off[n_reads];
+  memset(hist,0,sizeof(int64_t)*32770);
+  if (n == 0) return CPG_OK;
+  if (counts == NULL) return cnt_err(CPG_EINVAL,"cpg_count_kmers: counts is NULL");
+  if (n >= (int64_t)0xfffffff0u) return cnt_err(CPG_EINVAL,"cpg_count_kmers: %lld k-mers in one call (limit 2^32)",(long long)n);
+  if (cudaSetDevice(device) != cudaSuccess) return cnt_err(CPG_ECUDA,"no CUDA device %d: the profile producer has no CPU fallback",device);
+
+  const size_t seq_bytes = (size_t)seq_off[n_reads];
+  uint8_t *d_seq = NULL; int64_t *d_seq_off = NULL, *d_cnt_off = NULL;
+  uint64_t *d_lo[2] = { NULL, NULL }, *d_hx[2] = { NULL, NULL };
+  uint32_t *d_rid = NULL; uint16_t *d_counts = NULL; unsigned long long *d_hist = NULL; void *d_tmp = NULL;
+  cudaStream_t st = 0;
+  { CU(cudaStreamCreate(&st));
+    DMALLOC(d_seq,seq_bytes+32); DMALLOC(d_seq_off,sizeof(int64_t)*(size_t)(n_reads+1)); DMALLOC(d_cnt_off,sizeof(int64_t)*(size_t)(n_reads+1));
+    for (int b = 0; b < 2; b++) { DMALLOC(d_lo[b],sizeof(uint64_t)*(size_t)(n+2)); DMALLOC(d_hx[b],sizeof(uint64_t)*(size_t)(n+2)); }
+    DMALLOC(d_rid,sizeof(uint32_t)*(size_t)(n+2)); DMALLOC(d_counts,sizeof(uint16_t)*(size_t)n); DMALLOC(d_hist,sizeof(unsigned long long)*32770);
+    CU(cudaMemsetAsync(d_seq+seq_bytes,0,32,st));
+    CU(cudaMemcpyAsync(d_seq,seq,seq_bytes,cudaMemcpyHostToDevice,st));
+    CU(cudaMemcpyAsync(d_seq_off,seq_off,sizeof(int64_t)*(size_t)(n_reads+1),cudaMemcpyHostToDevice,st));
+    CU(cudaMemcpyAsync(d_cnt_off,cnt_off,sizeof(int64_t)*(size_t)(n_reads+1),cudaMemcpyHostToDevice,st));
+    CU(cudaMemsetAsync(d_hist,0,sizeof(unsigned long long)*32770,st));
+
+    k_kmer_keys<<<grid_for(device,(int64_t)n_reads*CT_THREADS),CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,d_lo[0],d_hx[0]);
+    CU(cudaGetLastError());
+
+    cub::DoubleBuffer<uint64_t> B_lo(d_lo[0],d_lo[1]), B_hx(d_hx[0],d_hx[1]);
+    const int lo_bits = 2*kmer < 64 ? 2*kmer : 64, hi_bits = 2*kmer > 64 ? 2*kmer-64 : 0;
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    CU(cub::DeviceRadixSort::SortPairs(NULL,t1,B_lo,B_hx,n,0,lo_bits,st));
+    if (hi_bits) CU(cub::DeviceRadixSort::SortPairs(NULL,t2,B_hx,B_lo,n,HIDX_SHIFT,HIDX_SHIFT+hi_bits,st));
+    CU(cub::DeviceScan::InclusiveSum(NULL,t3,d_rid,d_rid,n,st));
+    size_t tmp_bytes = t1 > t2 ? t1 : t2; if (t3 > tmp_bytes) tmp_bytes = t3;
+    DMALLOC(d_tmp,tmp_bytes+16);
+    CU(cub::DeviceRadixSort::SortPairs(d_tmp,tmp_bytes,B_lo,B_hx,n,0,lo_bits,st));
+    if (hi_bits) CU(cub::DeviceRadixSort::SortPairs(d_tmp,tmp_bytes,B_hx,B_lo,n,HIDX_SHIFT,HIDX_SHIFT+hi_bits,st));
+    const uint64_t *s_lo = B_lo.Current(), *s_hx = B_hx.Current();
+    uint32_t *d_start = (uint32_t *)B_lo.Alternate();              /* idle half of a double buffer: n+1 entries fit in 8(n+2) bytes */
+
+    const int g = grid_for(device,n);
+    k_run_heads<<<g,CT_THREADS,0,st>>>(n,s_lo,s_hx,d_rid);
+    CU(cudaGetLastError());
+    CU(cub::DeviceScan::InclusiveSum(d_tmp,tmp_bytes,d_rid,d_rid,n,st));
+    k_run_starts<<<g,CT_THREADS,0,st>>>(n,d_rid,d_start);
+    CU(cudaGetLastError());
+    k_scatter_counts<<<g,CT_THREADS,0,st>>>(n,s_hx,d_rid,d_start,d_counts,d_hist);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts,d_counts,sizeof(uint16_t)*(size_t)n,cudaMemcpyDeviceToHost,st));
+    CU(cudaMemcpyAsync(hist,d_hist,sizeof(int64_t)*32770,cudaMemcpyDeviceToHost,st));
+    CU(cudaStreamSynchronize(st));
+    hist[32768] = hist[1];                                          /* instances of the low bin (count 1) */
+  }
+done:
+  cudaFree(d_seq); cudaFree(d_seq_off); cudaFree(d_cnt_off);
+  for (int b = 0; b < 2; b++) { cudaFree(d_lo[b]); cudaFree(d_hx[b]); }
+  cudaFree(d_rid); cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_tmp);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}
+
+extern "C" int cpg_encode_profiles(int device, int32_t n_reads, const uint16_t *counts, const int64_t *cnt_off,
+                                   uint8_t *prof, int64_t prof_cap, int64_t *prof_off)
+{ if (n_reads < 0 || !cnt_off || !prof_off || (n_reads > 0 && cnt_off[n_reads] > 0 && (!counts || !prof)))
+    return cnt_err(CPG_EINVAL,"cpg_encode_profiles: bad argument");
+  int rc = CPG_OK;
+  const int64_t n = n_reads > 0 ? cnt_off[n_reads] : 0;
+  if (n == 0) { for (int i = 0; i <= n_reads; i++) prof_off[i] = 0; return CPG_OK; }
+  if (n >= (int64_t)0xfffffff0u) return cnt_err(CPG_EINVAL,"cpg_encode_profiles: %lld counts in one call (limit 2^32)",(long long)n);
+  if (cudaSetDevice(device) != cudaSuccess) return cnt_err(CPG_ECUDA,"no CUDA device %d: the profile producer has no CPU fallback",device);
+
+  uint16_t *d_counts = NULL; int64_t *d_cnt_off = NULL, *d_boff = NULL, *d_prof_off = NULL;
+  uint32_t *d_last = NULL; uint8_t *d_nb = NULL, *d_prof = NULL; void *d_tmp = NULL;
+  cudaStream_t st = 0;
+  int64_t total = 0;
+  { CU(cudaStreamCreate(&st));
+    DMALLOC(d_counts,sizeof(uint16_t)*(size_t)(n+1)); DMALLOC(d_cnt_off,sizeof(int64_t)*(size_t)(n_reads+1));
+    DMALLOC(d_last,sizeof(uint32_t)*(size_t)n); DMALLOC(d_nb,(size_t)n+1); DMALLOC(d_boff,sizeof(int64_t)*(size_t)(n+1));
+    DMALLOC(d_prof_off,sizeof(int64_t)*(size_t)(n_reads+1));
+    CU(cudaMemcpyAsync(d_counts,counts,sizeof(uint16_t)*(size_t)n,cudaMemcpyHostToDevice,st));
+    CU(cudaMemcpyAsync(d_cnt_off,cnt_off,sizeof(int64_t)*(size_t)(n_reads+1),cudaMemcpyHostToDevice,st));
+    CU(cudaMemsetAsync(d_nb+n,0,1,st));
+    size_t t1 = 0, t2 = 0;
+    CU(cub::DeviceScan::InclusiveScan(NULL,t1,d_last,d_last,MaxOp(),n,st));
+    CU(cub::DeviceScan::ExclusiveScan(NULL,t2,d_nb,d_boff,Sum64(),(int64_t)0,n+1,st));
+    size_t tmp_bytes = t1 > t2 ? t1 : t2;
+    DMALLOC(d_tmp,tmp_bytes+16);
+    const int g = grid_for(device,(int64_t)n_reads*CT_THREADS);
+    k_enc_change<<<g,CT_THREADS,0,st>>>(n_reads,d_counts,d_cnt_off,d_last);
+    CU(cudaGetLastError());
+    CU(cub::DeviceScan::InclusiveScan(d_tmp,tmp_bytes,d_last,d_last,MaxOp(),n,st));
+    k_enc_tokens<false><<<g,CT_THREADS,0,st>>>(n_reads,d_counts,d_cnt_off,d_last,d_nb,NULL,NULL,NULL);
+    CU(cudaGetLastError());
+    CU(cub::DeviceScan::ExclusiveScan(d_tmp,tmp_bytes,d_nb,d_boff,Sum64(),(int64_t)0,n+1,st));   /* uint8 in, int64 sums */
+    CU(cudaMemcpyAsync(&total,d_boff+n,sizeof(int64_t),cudaMemcpyDeviceToHost,st));
+    CU(cudaStreamSynchronize(st));
+    if (total > prof_cap)
+      { rc = cnt_err(CPG_EINVAL,"cpg_encode_profiles: %lld bytes needed, capacity %lld",(long long)total,(long long)prof_cap); goto done; }
+    DMALLOC(d_prof,(size_t)total+16);
+    k_enc_tokens<true><<<g,CT_THREADS,0,st>>>(n_reads,d_counts,d_cnt_off,d_last,NULL,d_boff,d_prof,d_prof_off);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(prof,d_prof,(size_t)total,cudaMemcpyDeviceToHost,st));
+    CU(cudaMemcpyAsync(prof_off,d_prof_off,sizeof(int64_t)*(size_t)n_reads,cudaMemcpyDeviceToHost,st));
+    CU(cudaStreamSynchronize(st));
+    prof_off[n_reads] = total;
+  }
+done:
+  cudaFree(d_counts); cudaFree(d_cnt_off); cudaFree(d_last); cudaFree(d_nb); cudaFree(d_boff); cudaFree(d_prof_off);
+  cudaFree(d_prof); cudaFree(d_tmp);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}

@@ -143,6 +143,31 @@ int cpg_download(cpg_ctx *ctx, cpg_result *result);
  * the waits at the CTA phase barriers. */
 int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4]);
 
+/* ---- profile producer (what FastK does before ClassPro runs) ----------------
+ * FastK is not part of the reference tree; the reference only reads its files (src/libfastk.c:51-96
+ * histogram, :1238-1386 profile index, :1414-1562 Fetch_Profile).  These two calls produce what
+ * those readers expect, on the GPU, from the 2-bit packed reads; they need no model and no cpg_ctx.
+ *
+ * cpg_count_kmers: exact counts of the canonical k-mers (a k-mer and its reverse complement are
+ * one) of the whole read set at every read position, saturated at 32767.
+ *   seq, seq_off, rlen : as in cpg_batch with seq_bits = 2
+ *   cnt_off  : [n_reads+1] OUT, prefix sums of max(rlen-K+1,0)
+ *   counts   : [cnt_off[n_reads]] OUT, counts of read r at counts[cnt_off[r] ..)  (= what
+ *              Fetch_Profile decodes, src/libfastk.c:1414-1562)
+ *   hist     : [32770] OUT, hist[c] = number of DISTINCT k-mers with count c, 1 <= c <= 32767 (the
+ *              bins of <root>.hist with low = 1, high = 32767, src/libfastk.c:72-83); hist[32768] and
+ *              hist[32769] = the instance-mode values of the two boundary bins (the file's two
+ *              hidden words, src/libfastk.c:91-93)
+ * 1 <= K <= 40; fewer than 2^32 k-mers per call; needs ~40 bytes of device memory per k-mer. */
+int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const uint8_t *seq, const int64_t *seq_off,
+                    const int32_t *rlen, int64_t *cnt_off, uint16_t *counts, int64_t *hist);
+/* cpg_encode_profiles: the encoder side of the profile codec (decoder: src/libfastk.c:1467-1535):
+ * prof receives the token streams read after read, prof_off[n_reads+1] their byte offsets (= the
+ * .pidx index of a part).  prof_cap = capacity of prof in bytes (2 bytes per count always suffice). */
+int cpg_encode_profiles(int device, int32_t n_reads, const uint16_t *counts, const int64_t *cnt_off,
+                        uint8_t *prof, int64_t prof_cap, int64_t *prof_off);
+const char *cpg_count_error(void);      /* text of the last error of the two calls above (per thread) */
+
 /* Pinned (page-locked) host memory, so that the copies of cpg_submit/cpg_collect are truly
  * asynchronous DMA transfers; pageable buffers work too but are staged by the driver. */
 void *cpg_host_alloc(size_t bytes);

@@ -19,3 +19,8 @@ gcc $CF -I"$root/classpro_b200/host" -c "$root/classpro_b200/host/classpro_main.
 gcc $CF -I"$root/classpro_b200/host" -c "$root/classpro_b200/host/cpg_prof2class.c" -o "$here/_build/cpg_prof2class.o"
 g++ -o "$here/_build/ClassPro" "$here/_build/classpro_main.o" "$here/_build/fakedev.o" "$here/_build/cpg_model.o" "$here/_build/cpg_pack.o" -lz -lpthread -lm
 g++ -o "$here/_build/prof2class" "$here/_build/cpg_prof2class.o" "$here/_build/fakedev.o" "$here/_build/cpg_model.o" "$here/_build/cpg_pack.o" -lz -lpthread -lm
+# TEST-ONLY host build of the profile producer's element functions (countsim.cpp)
+g++ $CF -shared -o "$here/_build/libcountsim.so" "$here/countsim.cpp"
+g++ $CF -DCOUNTSIM_AS_ABI -c "$here/countsim.cpp" -o "$here/_build/countsim_abi.o"
+gcc $CF -I"$root/classpro_b200/host" -c "$root/classpro_b200/host/cpg_profiler.c" -o "$here/_build/cpg_profiler.o"
+g++ -o "$here/_build/profiler" "$here/_build/cpg_profiler.o" "$here/_build/countsim_abi.o" "$here/_build/cpg_pack.o" -lz
