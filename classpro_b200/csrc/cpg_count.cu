@@ -154,9 +154,6 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
     CU(cudaMemcpyAsync(d_cnt_off,cnt_off,sizeof(int64_t)*(size_t)(n_reads+1),cudaMemcpyHostToDevice,st));
     CU(cudaMemsetAsync(d_hist,0,sizeof(unsigned long long)*32770,st));
 
-    k_kmer_keys<<<grid_for(device,(int64_t)n_reads*CT_THREADS),CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,d_lo[0],d_hx[0]);
-    CU(cudaGetLastError());
-
     cub::DoubleBuffer<uint64_t> B_lo(d_lo[0],d_lo[1]), B_hx(d_hx[0],d_hx[1]);
     const int lo_bits = 2*kmer < 64 ? 2*kmer : 64, hi_bits = 2*kmer > 64 ? 2*kmer-64 : 0;
     size_t t1 = 0, t2 = 0, t3 = 0;
@@ -165,23 +162,45 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
     CU(cub::DeviceScan::InclusiveSum(NULL,t3,d_rid,d_rid,n,st));
     size_t tmp_bytes = t1 > t2 ? t1 : t2; if (t3 > tmp_bytes) tmp_bytes = t3;
     DMALLOC(d_tmp,tmp_bytes+16);
+    const int timing = getenv("CPG_COUNT_TIMING") != NULL;
+    cudaEvent_t ev[6];
+    if (timing) for (int i = 0; i < 6; i++) CU(cudaEventCreate(&ev[i]));
+#define MARK(i) if (timing) CU(cudaEventRecord(ev[i],st))
+    MARK(0);
+    k_kmer_keys<<<grid_for(device,(int64_t)n_reads*CT_THREADS),CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,d_lo[0],d_hx[0]);
+    CU(cudaGetLastError());
+
+    MARK(1);
     CU(cub::DeviceRadixSort::SortPairs(d_tmp,tmp_bytes,B_lo,B_hx,n,0,lo_bits,st));
     if (hi_bits) CU(cub::DeviceRadixSort::SortPairs(d_tmp,tmp_bytes,B_hx,B_lo,n,HIDX_SHIFT,HIDX_SHIFT+hi_bits,st));
     const uint64_t *s_lo = B_lo.Current(), *s_hx = B_hx.Current();
     uint32_t *d_start = (uint32_t *)B_lo.Alternate();              /* idle half of a double buffer: n+1 entries fit in 8(n+2) bytes */
 
     const int g = grid_for(device,n);
+    MARK(2);
     k_run_heads<<<g,CT_THREADS,0,st>>>(n,s_lo,s_hx,d_rid);
     CU(cudaGetLastError());
     CU(cub::DeviceScan::InclusiveSum(d_tmp,tmp_bytes,d_rid,d_rid,n,st));
     k_run_starts<<<g,CT_THREADS,0,st>>>(n,d_rid,d_start);
     CU(cudaGetLastError());
+    MARK(3);
     k_scatter_counts<<<g,CT_THREADS,0,st>>>(n,s_hx,d_rid,d_start,d_counts,d_hist);
     CU(cudaGetLastError());
+    MARK(4);
     CU(cudaMemcpyAsync(counts,d_counts,sizeof(uint16_t)*(size_t)n,cudaMemcpyDeviceToHost,st));
     CU(cudaMemcpyAsync(hist,d_hist,sizeof(int64_t)*32770,cudaMemcpyDeviceToHost,st));
     CU(cudaStreamSynchronize(st));
     hist[32768] = hist[1];                                          /* instances of the low bin (count 1) */
+    if (timing)
+      { float ms[4];
+        for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i],ev[i],ev[i+1]));
+        fprintf(stderr,"cpg_count_kmers: n = %lld, K = %d: keys %.3f ms (%.0f GB/s of 16 B/k-mer out), sort %.3f ms (%.0f GB/s of %d B/k-mer), "
+                       "runs %.3f ms, scatter+hist %.3f ms; %.2f G k-mers/s on the device\n",
+                (long long)n,kmer,ms[0],16e-6*n/ms[0],ms[1],1e-6*n*32*((lo_bits+7)/8+(hi_bits+7)/8)/ms[1],32*((lo_bits+7)/8+(hi_bits+7)/8),
+                ms[2],ms[3],1e-6*n/(ms[0]+ms[1]+ms[2]+ms[3]));
+        for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
+      }
+#undef MARK
   }
 done:
   cudaFree(d_seq); cudaFree(d_seq_off); cudaFree(d_cnt_off);
