@@ -53,6 +53,58 @@ k_kmer_keys(int n_reads, const uint64_t *__restrict__ W, const int64_t *__restri
     }
 }
 
+/* several passes (cpg_key_pass): how many k-mers each pass will hold */
+#define MAX_PASSES 64
+__global__ void __launch_bounds__(CT_THREADS)
+k_pass_sizes(int n_reads, const uint64_t *__restrict__ W, const int64_t *__restrict__ seq_off,
+             const int64_t *__restrict__ cnt_off, int K, int npass, unsigned long long *__restrict__ sizes)
+{ __shared__ unsigned int sh[MAX_PASSES];
+  if (threadIdx.x < MAX_PASSES) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int r = blockIdx.x; r < n_reads; r += gridDim.x)
+    { const int n = (int)(cnt_off[r+1]-cnt_off[r]);
+      const int64_t bit0 = 8*seq_off[r];
+      for (int p = threadIdx.x; p < n; p += CT_THREADS)
+        { uint64_t hi, lo;
+          cpg_kmer_key(W,bit0+2*(int64_t)p,K,&hi,&lo);
+          atomicAdd(&sh[cpg_key_pass(hi,lo,(uint32_t)npass)],1u);
+        }
+      __syncthreads();                                   /* flush per read: a 32-bit counter cannot overflow */
+      if (threadIdx.x < npass && sh[threadIdx.x]) { atomicAdd(&sizes[threadIdx.x],(unsigned long long)sh[threadIdx.x]); sh[threadIdx.x] = 0; }
+      __syncthreads();
+    }
+}
+
+/* the keys of one pass, appended in any order (the sort does not care): one atomic per warp and step */
+__global__ void __launch_bounds__(CT_THREADS)
+k_kmer_keys_pass(int n_reads, const uint64_t *__restrict__ W, const int64_t *__restrict__ seq_off,
+                 const int64_t *__restrict__ cnt_off, int K, int pass, int npass, unsigned long long *__restrict__ fill,
+                 uint64_t *__restrict__ klo, uint64_t *__restrict__ khidx)
+{ const unsigned lane = threadIdx.x & 31u;
+  for (int r = blockIdx.x; r < n_reads; r += gridDim.x)
+    { const int64_t m0 = cnt_off[r]; const int n = (int)(cnt_off[r+1]-m0);
+      const int64_t bit0 = 8*seq_off[r];
+      for (int p0 = 0; p0 < n; p0 += CT_THREADS)          /* every thread of the CTA runs every step: full-warp ballots */
+        { const int p = p0+(int)threadIdx.x;
+          uint64_t hi = 0, lo = 0; bool keep = false;
+          if (p < n)
+            { cpg_kmer_key(W,bit0+2*(int64_t)p,K,&hi,&lo);
+              keep = cpg_key_pass(hi,lo,(uint32_t)npass) == (uint32_t)pass;
+            }
+          const unsigned bal = __ballot_sync(0xffffffffu,keep);
+          if (bal == 0) continue;
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(fill,(unsigned long long)__popc(bal));
+          base = __shfl_sync(0xffffffffu,base,0);
+          if (keep)
+            { const unsigned long long o = base+(unsigned long long)__popc(bal & ((1u << lane)-1u));
+              klo[o] = lo;
+              khidx[o] = (hi << HIDX_SHIFT) | (uint64_t)(m0+p);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CT_THREADS)
 k_run_heads(int64_t n, const uint64_t *__restrict__ klo, const uint64_t *__restrict__ khidx, uint32_t *__restrict__ head)
 { for (int64_t i = blockIdx.x*(int64_t)CT_THREADS+threadIdx.x; i < n; i += (int64_t)gridDim.x*CT_THREADS)
@@ -136,76 +188,129 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
   memset(hist,0,sizeof(int64_t)*32770);
   if (n == 0) return CPG_OK;
   if (counts == NULL) return cnt_err(CPG_EINVAL,"cpg_count_kmers: counts is NULL");
-  if (n >= (int64_t)0xfffffff0u) return cnt_err(CPG_EINVAL,"cpg_count_kmers: %lld k-mers in one call (limit 2^32)",(long long)n);
+  if (n >= ((int64_t)1 << HIDX_SHIFT)) return cnt_err(CPG_EINVAL,"cpg_count_kmers: %lld k-mers in one call (limit 2^%d)",(long long)n,HIDX_SHIFT);
   if (cudaSetDevice(device) != cudaSuccess) return cnt_err(CPG_ECUDA,"no CUDA device %d: the profile producer has no CPU fallback",device);
 
   const size_t seq_bytes = (size_t)seq_off[n_reads];
   uint8_t *d_seq = NULL; int64_t *d_seq_off = NULL, *d_cnt_off = NULL;
   uint64_t *d_lo[2] = { NULL, NULL }, *d_hx[2] = { NULL, NULL };
-  uint32_t *d_rid = NULL; uint16_t *d_counts = NULL; unsigned long long *d_hist = NULL; void *d_tmp = NULL;
+  uint32_t *d_rid = NULL; uint16_t *d_counts = NULL; unsigned long long *d_hist = NULL, *d_sizes = NULL; void *d_tmp = NULL;
   cudaStream_t st = 0;
+  cudaEvent_t ev[5] = { NULL, NULL, NULL, NULL, NULL };
   { CU(cudaStreamCreate(&st));
     DMALLOC(d_seq,seq_bytes+32); DMALLOC(d_seq_off,sizeof(int64_t)*(size_t)(n_reads+1)); DMALLOC(d_cnt_off,sizeof(int64_t)*(size_t)(n_reads+1));
-    for (int b = 0; b < 2; b++) { DMALLOC(d_lo[b],sizeof(uint64_t)*(size_t)(n+2)); DMALLOC(d_hx[b],sizeof(uint64_t)*(size_t)(n+2)); }
-    DMALLOC(d_rid,sizeof(uint32_t)*(size_t)(n+2)); DMALLOC(d_counts,sizeof(uint16_t)*(size_t)n); DMALLOC(d_hist,sizeof(unsigned long long)*32770);
+    DMALLOC(d_counts,sizeof(uint16_t)*(size_t)n); DMALLOC(d_hist,sizeof(unsigned long long)*32770);
+    DMALLOC(d_sizes,sizeof(unsigned long long)*(MAX_PASSES+1));
     CU(cudaMemsetAsync(d_seq+seq_bytes,0,32,st));
     CU(cudaMemcpyAsync(d_seq,seq,seq_bytes,cudaMemcpyHostToDevice,st));
     CU(cudaMemcpyAsync(d_seq_off,seq_off,sizeof(int64_t)*(size_t)(n_reads+1),cudaMemcpyHostToDevice,st));
     CU(cudaMemcpyAsync(d_cnt_off,cnt_off,sizeof(int64_t)*(size_t)(n_reads+1),cudaMemcpyHostToDevice,st));
     CU(cudaMemsetAsync(d_hist,0,sizeof(unsigned long long)*32770,st));
+    const int gr = grid_for(device,(int64_t)n_reads*CT_THREADS);
 
-    cub::DoubleBuffer<uint64_t> B_lo(d_lo[0],d_lo[1]), B_hx(d_hx[0],d_hx[1]);
+    /* passes: all keys at once if 36 bytes per k-mer (two 16-byte sort buffers in double, run ids) plus the
+       sort's scratch fit in what is left of the device memory.  Key-range passes for larger sets are
+       written (k_pass_sizes, k_kmer_keys_pass) but EXPERIMENTAL: their first run on a B200 gave wrong counts
+       (profiles/r01_producer_passes.log) while the host build of the same logic is right, so they are only
+       taken when CPG_COUNT_PASSES=<p> asks for them; without it a set that does not fit is an error */
+    unsigned long long sizes[MAX_PASSES]; int npass = 1; int64_t cap = n;
+    { size_t mfree = 0, mtotal = 0;
+      CU(cudaMemGetInfo(&mfree,&mtotal));
+      const double budget = 0.92*(double)mfree;
+      const char *e = getenv("CPG_COUNT_PASSES");
+      int forced = e ? atoi(e) : 0;
+      if (forced > MAX_PASSES) forced = MAX_PASSES;
+      if (forced > 0) npass = forced;
+      else if (37.0*(double)n*1.02 > budget)
+        { rc = cnt_err(CPG_ENOMEM,"cpg_count_kmers: %lld k-mers need ~%.1f GB of device memory, %.1f GB free",(long long)n,37e-9*(double)n,1e-9*(double)mfree);
+          goto done;
+        }
+      for (;;)
+        { sizes[0] = (unsigned long long)n;
+          if (npass > 1)
+            { CU(cudaMemsetAsync(d_sizes,0,sizeof(unsigned long long)*MAX_PASSES,st));
+              k_pass_sizes<<<gr,CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,npass,d_sizes);
+              CU(cudaGetLastError());
+              CU(cudaMemcpyAsync(sizes,d_sizes,sizeof(unsigned long long)*(size_t)npass,cudaMemcpyDeviceToHost,st));
+              CU(cudaStreamSynchronize(st));
+            }
+          cap = 0;
+          for (int p = 0; p < npass; p++) if ((int64_t)sizes[p] > cap) cap = (int64_t)sizes[p];
+          if (forced > 0 || npass >= MAX_PASSES || 37.0*(double)cap <= budget) break;
+          npass++;                                               /* a heavy repeat made one pass larger than its share */
+        }
+      if (cap >= (int64_t)0xfffffff0u)
+        { rc = cnt_err(CPG_EINVAL,"cpg_count_kmers: %lld k-mers in one pass (limit 2^32); use more passes",(long long)cap); goto done; }
+    }
+    for (int b = 0; b < 2; b++) { DMALLOC(d_lo[b],sizeof(uint64_t)*(size_t)(cap+2)); DMALLOC(d_hx[b],sizeof(uint64_t)*(size_t)(cap+2)); }
+    DMALLOC(d_rid,sizeof(uint32_t)*(size_t)(cap+2));
     const int lo_bits = 2*kmer < 64 ? 2*kmer : 64, hi_bits = 2*kmer > 64 ? 2*kmer-64 : 0;
-    size_t t1 = 0, t2 = 0, t3 = 0;
-    CU(cub::DeviceRadixSort::SortPairs(NULL,t1,B_lo,B_hx,n,0,lo_bits,st));
-    if (hi_bits) CU(cub::DeviceRadixSort::SortPairs(NULL,t2,B_hx,B_lo,n,HIDX_SHIFT,HIDX_SHIFT+hi_bits,st));
-    CU(cub::DeviceScan::InclusiveSum(NULL,t3,d_rid,d_rid,n,st));
-    size_t tmp_bytes = t1 > t2 ? t1 : t2; if (t3 > tmp_bytes) tmp_bytes = t3;
+    size_t tmp_bytes = 0;
+    { cub::DoubleBuffer<uint64_t> Q_lo(d_lo[0],d_lo[1]), Q_hx(d_hx[0],d_hx[1]);
+      size_t t1 = 0, t2 = 0, t3 = 0;
+      CU(cub::DeviceRadixSort::SortPairs(NULL,t1,Q_lo,Q_hx,cap,0,lo_bits,st));
+      if (hi_bits) CU(cub::DeviceRadixSort::SortPairs(NULL,t2,Q_hx,Q_lo,cap,HIDX_SHIFT,HIDX_SHIFT+hi_bits,st));
+      CU(cub::DeviceScan::InclusiveSum(NULL,t3,d_rid,d_rid,cap,st));
+      tmp_bytes = t1 > t2 ? t1 : t2; if (t3 > tmp_bytes) tmp_bytes = t3;
+    }
     DMALLOC(d_tmp,tmp_bytes+16);
     const int timing = getenv("CPG_COUNT_TIMING") != NULL;
-    cudaEvent_t ev[6];
-    if (timing) for (int i = 0; i < 6; i++) CU(cudaEventCreate(&ev[i]));
+    float ms[4] = { 0.f, 0.f, 0.f, 0.f };
+    if (timing) for (int i = 0; i < 5; i++) CU(cudaEventCreate(&ev[i]));
 #define MARK(i) if (timing) CU(cudaEventRecord(ev[i],st))
-    MARK(0);
-    k_kmer_keys<<<grid_for(device,(int64_t)n_reads*CT_THREADS),CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,d_lo[0],d_hx[0]);
-    CU(cudaGetLastError());
 
-    MARK(1);
-    CU(cub::DeviceRadixSort::SortPairs(d_tmp,tmp_bytes,B_lo,B_hx,n,0,lo_bits,st));
-    if (hi_bits) CU(cub::DeviceRadixSort::SortPairs(d_tmp,tmp_bytes,B_hx,B_lo,n,HIDX_SHIFT,HIDX_SHIFT+hi_bits,st));
-    const uint64_t *s_lo = B_lo.Current(), *s_hx = B_hx.Current();
-    uint32_t *d_start = (uint32_t *)B_lo.Alternate();              /* idle half of a double buffer: n+1 entries fit in 8(n+2) bytes */
-
-    const int g = grid_for(device,n);
-    MARK(2);
-    k_run_heads<<<g,CT_THREADS,0,st>>>(n,s_lo,s_hx,d_rid);
-    CU(cudaGetLastError());
-    CU(cub::DeviceScan::InclusiveSum(d_tmp,tmp_bytes,d_rid,d_rid,n,st));
-    k_run_starts<<<g,CT_THREADS,0,st>>>(n,d_rid,d_start);
-    CU(cudaGetLastError());
-    MARK(3);
-    k_scatter_counts<<<g,CT_THREADS,0,st>>>(n,s_hx,d_rid,d_start,d_counts,d_hist);
-    CU(cudaGetLastError());
-    MARK(4);
+    for (int pass = 0; pass < npass; pass++)
+      { const int64_t m = (int64_t)sizes[pass];
+        if (m == 0) continue;
+        MARK(0);
+        if (npass == 1)
+          k_kmer_keys<<<gr,CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,d_lo[0],d_hx[0]);
+        else
+          { CU(cudaMemsetAsync(d_sizes+MAX_PASSES,0,sizeof(unsigned long long),st));
+            k_kmer_keys_pass<<<gr,CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,pass,npass,d_sizes+MAX_PASSES,d_lo[0],d_hx[0]);
+          }
+        CU(cudaGetLastError());
+        MARK(1);
+        cub::DoubleBuffer<uint64_t> B_lo(d_lo[0],d_lo[1]), B_hx(d_hx[0],d_hx[1]);
+        size_t tb = tmp_bytes;
+        CU(cub::DeviceRadixSort::SortPairs(d_tmp,tb,B_lo,B_hx,m,0,lo_bits,st));
+        tb = tmp_bytes;
+        if (hi_bits) CU(cub::DeviceRadixSort::SortPairs(d_tmp,tb,B_hx,B_lo,m,HIDX_SHIFT,HIDX_SHIFT+hi_bits,st));
+        const uint64_t *s_lo = B_lo.Current(), *s_hx = B_hx.Current();
+        uint32_t *d_start = (uint32_t *)B_lo.Alternate();          /* idle half of a double buffer: m+1 entries fit in 8(m+2) bytes */
+        const int g = grid_for(device,m);
+        MARK(2);
+        k_run_heads<<<g,CT_THREADS,0,st>>>(m,s_lo,s_hx,d_rid);
+        CU(cudaGetLastError());
+        tb = tmp_bytes;
+        CU(cub::DeviceScan::InclusiveSum(d_tmp,tb,d_rid,d_rid,m,st));
+        k_run_starts<<<g,CT_THREADS,0,st>>>(m,d_rid,d_start);
+        CU(cudaGetLastError());
+        MARK(3);
+        k_scatter_counts<<<g,CT_THREADS,0,st>>>(m,s_hx,d_rid,d_start,d_counts,d_hist);
+        CU(cudaGetLastError());
+        MARK(4);
+        if (timing)
+          { CU(cudaStreamSynchronize(st));
+            for (int i = 0; i < 4; i++) { float t; CU(cudaEventElapsedTime(&t,ev[i],ev[i+1])); ms[i] += t; }
+          }
+      }
     CU(cudaMemcpyAsync(counts,d_counts,sizeof(uint16_t)*(size_t)n,cudaMemcpyDeviceToHost,st));
     CU(cudaMemcpyAsync(hist,d_hist,sizeof(int64_t)*32770,cudaMemcpyDeviceToHost,st));
     CU(cudaStreamSynchronize(st));
     hist[32768] = hist[1];                                          /* instances of the low bin (count 1) */
     if (timing)
-      { float ms[4];
-        for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i],ev[i],ev[i+1]));
-        fprintf(stderr,"cpg_count_kmers: n = %lld, K = %d: keys %.3f ms (%.0f GB/s of 16 B/k-mer out), sort %.3f ms (%.0f GB/s of %d B/k-mer), "
-                       "runs %.3f ms, scatter+hist %.3f ms; %.2f G k-mers/s on the device\n",
-                (long long)n,kmer,ms[0],16e-6*n/ms[0],ms[1],1e-6*n*32*((lo_bits+7)/8+(hi_bits+7)/8)/ms[1],32*((lo_bits+7)/8+(hi_bits+7)/8),
-                ms[2],ms[3],1e-6*n/(ms[0]+ms[1]+ms[2]+ms[3]));
-        for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
-      }
+      fprintf(stderr,"cpg_count_kmers: n = %lld, K = %d, %d pass%s: keys %.3f ms (%.0f GB/s of 16 B/k-mer out), sort %.3f ms (%.0f GB/s of %d B/k-mer), "
+                     "runs %.3f ms, scatter+hist %.3f ms; %.2f G k-mers/s on the device\n",
+              (long long)n,kmer,npass,npass > 1 ? "es" : "",ms[0],16e-6*n/ms[0],ms[1],1e-6*n*32*((lo_bits+7)/8+(hi_bits+7)/8)/ms[1],
+              32*((lo_bits+7)/8+(hi_bits+7)/8),ms[2],ms[3],1e-6*n/(ms[0]+ms[1]+ms[2]+ms[3]));
 #undef MARK
   }
 done:
+  for (int i = 0; i < 5; i++) if (ev[i]) cudaEventDestroy(ev[i]);
   cudaFree(d_seq); cudaFree(d_seq_off); cudaFree(d_cnt_off);
   for (int b = 0; b < 2; b++) { cudaFree(d_lo[b]); cudaFree(d_hx[b]); }
-  cudaFree(d_rid); cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_tmp);
+  cudaFree(d_rid); cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_sizes); cudaFree(d_tmp);
   if (st) cudaStreamDestroy(st);
   return rc;
 }

@@ -76,6 +76,15 @@ CPG_HD void cpg_key_element(const uint64_t *W, int64_t bit0, int p, int64_t m, i
   khidx[m] = (hi << CPG_HIDX_SHIFT) | (uint64_t)m;
 }
 
+/* Key-range passes for read sets whose keys do not fit in device memory at once: pass of a key =
+   a hash of it scaled to [0,npass), so equal keys always meet in the same pass and a pass holds about
+   1/npass of the k-mers whatever the composition of the reads */
+CPG_HD uint32_t cpg_key_pass(uint64_t hi, uint64_t lo, uint32_t npass)
+{ uint64_t x = lo ^ (hi * 0x9e3779b97f4a7c15ull);
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return (uint32_t)(((x >> 32) * (uint64_t)npass) >> 32);
+}
+
 /* sorted element i starts a run of equal keys */
 CPG_HD uint32_t cpg_run_head(int64_t i, const uint64_t *klo, const uint64_t *khidx)
 { return (i == 0 || klo[i] != klo[i-1] || (khidx[i] >> CPG_HIDX_SHIFT) != (khidx[i-1] >> CPG_HIDX_SHIFT)) ? 1u : 0u; }

@@ -9,6 +9,7 @@
 #define CPG_HOSTSIM 1
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 #include <numeric>
@@ -26,29 +27,47 @@ extern "C" int sim_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
   /* the device copy of seq: 8-byte aligned and readable 32 bytes past its end */
   std::vector<uint64_t> W((size_t)(seq_off[n_reads]+32+7)/8,0);
   memcpy(W.data(),seq,(size_t)seq_off[n_reads]);
-  std::vector<uint64_t> klo((size_t)n), khx((size_t)n);
-  for (int r = 0; r < n_reads; r++)                                                  /* k_kmer_keys */
-    for (int p = 0; p < (int)(cnt_off[r+1]-cnt_off[r]); p++)
-      cpg_key_element(W.data(),8*seq_off[r],p,cnt_off[r]+p,kmer,klo.data(),khx.data());
-  /* SortPairs(keys = low word, bits [0,min(64,2K))), then SortPairs(keys = value word, bits [48,48+2K-64)) */
-  std::vector<int64_t> perm((size_t)n);
-  std::iota(perm.begin(),perm.end(),(int64_t)0);
-  const int lo_bits = 2*kmer < 64 ? 2*kmer : 64;
-  const uint64_t lomask = lo_bits == 64 ? ~0ull : ((1ull << lo_bits)-1);
-  std::stable_sort(perm.begin(),perm.end(),[&](int64_t a, int64_t b) { return (klo[a] & lomask) < (klo[b] & lomask); });
-  if (2*kmer > 64)
-    std::stable_sort(perm.begin(),perm.end(),[&](int64_t a, int64_t b) { return (khx[a] >> CPG_HIDX_SHIFT) < (khx[b] >> CPG_HIDX_SHIFT); });
-  std::vector<uint64_t> slo((size_t)n), shx((size_t)n);
-  for (int64_t i = 0; i < n; i++) { slo[i] = klo[perm[i]]; shx[i] = khx[perm[i]]; }
-  std::vector<uint32_t> rid((size_t)n), start((size_t)n+1);
-  for (int64_t i = 0; i < n; i++) rid[i] = cpg_run_head(i,slo.data(),shx.data());    /* k_run_heads */
-  for (int64_t i = 1; i < n; i++) rid[i] += rid[i-1];                                 /* InclusiveSum */
-  for (int64_t i = n-1; i >= 0; i--) cpg_run_start(i,n,rid.data(),start.data());      /* k_run_starts (any order) */
-  for (int64_t i = 0; i < n; i++)                                                     /* k_scatter_counts */
-    { const uint32_t c = cpg_scatter_count(i,shx.data(),rid.data(),start.data(),counts);
-      if (c)
-        { if (c < CPG_CNT_MAX) hist[c] += 1;
-          else { hist[CPG_CNT_MAX] += 1; hist[32769] += c; }
+  /* passes (CPG_COUNT_PASSES, as in cpg_count.cu): the keys of one pass appended in read order */
+  const char *e = getenv("CPG_COUNT_PASSES");
+  const int npass = (e && atoi(e) > 0) ? (atoi(e) > 64 ? 64 : atoi(e)) : 1;
+  for (int pass = 0; pass < npass; pass++)
+    { std::vector<uint64_t> klo, khx;
+      if (npass == 1)
+        { klo.resize((size_t)n); khx.resize((size_t)n);
+          for (int r = 0; r < n_reads; r++)                                              /* k_kmer_keys */
+            for (int p = 0; p < (int)(cnt_off[r+1]-cnt_off[r]); p++)
+              cpg_key_element(W.data(),8*seq_off[r],p,cnt_off[r]+p,kmer,klo.data(),khx.data());
+        }
+      else
+        for (int r = 0; r < n_reads; r++)                                                /* k_kmer_keys_pass */
+          for (int p = 0; p < (int)(cnt_off[r+1]-cnt_off[r]); p++)
+            { uint64_t hi, lo;
+              cpg_kmer_key(W.data(),8*seq_off[r]+2*(int64_t)p,kmer,&hi,&lo);
+              if (cpg_key_pass(hi,lo,(uint32_t)npass) != (uint32_t)pass) continue;
+              klo.push_back(lo); khx.push_back((hi << CPG_HIDX_SHIFT) | (uint64_t)(cnt_off[r]+p));
+            }
+      const int64_t m = (int64_t)klo.size();
+      if (m == 0) continue;
+      /* SortPairs(keys = low word, bits [0,min(64,2K))), then SortPairs(keys = value word, bits [48,48+2K-64)) */
+      std::vector<int64_t> perm((size_t)m);
+      std::iota(perm.begin(),perm.end(),(int64_t)0);
+      const int lo_bits = 2*kmer < 64 ? 2*kmer : 64;
+      const uint64_t lomask = lo_bits == 64 ? ~0ull : ((1ull << lo_bits)-1);
+      std::stable_sort(perm.begin(),perm.end(),[&](int64_t a, int64_t b) { return (klo[a] & lomask) < (klo[b] & lomask); });
+      if (2*kmer > 64)
+        std::stable_sort(perm.begin(),perm.end(),[&](int64_t a, int64_t b) { return (khx[a] >> CPG_HIDX_SHIFT) < (khx[b] >> CPG_HIDX_SHIFT); });
+      std::vector<uint64_t> slo((size_t)m), shx((size_t)m);
+      for (int64_t i = 0; i < m; i++) { slo[i] = klo[perm[i]]; shx[i] = khx[perm[i]]; }
+      std::vector<uint32_t> rid((size_t)m), start((size_t)m+1);
+      for (int64_t i = 0; i < m; i++) rid[i] = cpg_run_head(i,slo.data(),shx.data());    /* k_run_heads */
+      for (int64_t i = 1; i < m; i++) rid[i] += rid[i-1];                                 /* InclusiveSum */
+      for (int64_t i = m-1; i >= 0; i--) cpg_run_start(i,m,rid.data(),start.data());      /* k_run_starts (any order) */
+      for (int64_t i = 0; i < m; i++)                                                     /* k_scatter_counts */
+        { const uint32_t c = cpg_scatter_count(i,shx.data(),rid.data(),start.data(),counts);
+          if (c)
+            { if (c < CPG_CNT_MAX) hist[c] += 1;
+              else { hist[CPG_CNT_MAX] += 1; hist[32769] += c; }
+            }
         }
     }
   hist[32768] = hist[1];
