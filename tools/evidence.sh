@@ -19,3 +19,10 @@ ncu --set full --clock-control none --import-source on -k regex:k_ -s 15 -c 5 -f
 F="python bench.py --no-cpu-baseline --steps 1 --warmup 1"
 ncu --set full --clock-control none -k regex:k_ -s 15 -c 5 -f -o $O/prof_full_$TAG $F > $O/ncu_fullwl_$TAG.log 2>&1
 ls -la $O/prof_$TAG.ncu-rep $O/prof_full_$TAG.ncu-rep
+# profile producer: parity with the harness counter + stage times, then the launch list and one
+# full capture of its kernels; the forced 3-pass run is the open bug of round 1
+CPG_COUNT_TIMING=1 python tools/producer_check.py 2000000 30 40,32,21 > $O/producer_$TAG.log 2>&1; tail -4 $O/producer_$TAG.log
+CPG_COUNT_PASSES=3 python tools/producer_check.py 300000 20 40 > $O/producer_passes_$TAG.log 2>&1; tail -2 $O/producer_passes_$TAG.log
+P="python tools/producer_check.py 1000000 30 40"
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/producer_launches_$TAG.csv $P > $O/ncu_producer_launches_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_kmer|k_run|k_scatter|k_enc' -c 8 -f -o $O/prof_producer_$TAG $P > $O/ncu_producer_$TAG.log 2>&1

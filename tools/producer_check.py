@@ -42,5 +42,13 @@ for K in KS:
           np.array_equal(prof_off, sim.prof_off), np.array_equal(prof[:prof_off[n]], sim.prof))
     print("K=%d: %d k-mers, counts/hist/offsets/bytes equal to the harness: %s; count %.3f s, encode %.3f s (host wall, incl. copies and allocation)"
           % (K, sim.total_kmers, ok, t1 - t0, t2 - t1), flush=True)
+    if not all(ok):                                        # what a debugging session wants to see first
+        got, want = counts[:sim.total_kmers], sim.counts
+        bad = np.flatnonzero(got != want)
+        print("  %d of %d counts differ; first: %s" % (len(bad), len(want), [(int(i), int(got[i]), int(want[i])) for i in bad[:8]]))
+        print("  sum over distinct k-mers of count: got %d, harness %d, k-mers %d; distinct: got %d, harness %d"
+              % (int((hist[1:32767] * np.arange(1, 32767)).sum()) + int(hist[32769]), int((sim.hist[1:32767] * np.arange(1, 32767)).sum()) + int(sim.hist[32769]),
+                 sim.total_kmers, int(hist[1:32768].sum()), int(sim.hist[1:32768].sum())))
+        print("  got < want at %d positions, got > want at %d, got == 0 at %d" % (int((got < want).sum()), int((got > want).sum()), int((got == 0).sum())))
     assert all(ok)
 print("producer_check: OK")
