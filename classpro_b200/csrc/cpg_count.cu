@@ -79,7 +79,7 @@ k_pass_sizes(int n_reads, const uint64_t *__restrict__ W, const int64_t *__restr
 __global__ void __launch_bounds__(CT_THREADS)
 k_kmer_keys_pass(int n_reads, const uint64_t *__restrict__ W, const int64_t *__restrict__ seq_off,
                  const int64_t *__restrict__ cnt_off, int K, int pass, int npass, unsigned long long *__restrict__ fill,
-                 uint64_t *__restrict__ klo, uint64_t *__restrict__ khidx)
+                 unsigned long long cap, uint64_t *__restrict__ klo, uint64_t *__restrict__ khidx)
 { const unsigned lane = threadIdx.x & 31u;
   for (int r = blockIdx.x; r < n_reads; r += gridDim.x)
     { const int64_t m0 = cnt_off[r]; const int n = (int)(cnt_off[r+1]-m0);
@@ -98,8 +98,10 @@ k_kmer_keys_pass(int n_reads, const uint64_t *__restrict__ W, const int64_t *__r
           base = __shfl_sync(0xffffffffu,base,0);
           if (keep)
             { const unsigned long long o = base+(unsigned long long)__popc(bal & ((1u << lane)-1u));
-              klo[o] = lo;
-              khidx[o] = (hi << HIDX_SHIFT) | (uint64_t)(m0+p);
+              if (o < cap)                                 /* the host compares the fill count with the capacity */
+                { klo[o] = lo;
+                  khidx[o] = (hi << HIDX_SHIFT) | (uint64_t)(m0+p);
+                }
             }
         }
     }
@@ -260,14 +262,25 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
 #define MARK(i) if (timing) CU(cudaEventRecord(ev[i],st))
 
     for (int pass = 0; pass < npass; pass++)
-      { const int64_t m = (int64_t)sizes[pass];
+      { int64_t m = (int64_t)sizes[pass];
         if (m == 0) continue;
         MARK(0);
         if (npass == 1)
           k_kmer_keys<<<gr,CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,d_lo[0],d_hx[0]);
         else
           { CU(cudaMemsetAsync(d_sizes+MAX_PASSES,0,sizeof(unsigned long long),st));
-            k_kmer_keys_pass<<<gr,CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,pass,npass,d_sizes+MAX_PASSES,d_lo[0],d_hx[0]);
+            k_kmer_keys_pass<<<gr,CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,pass,npass,d_sizes+MAX_PASSES,(unsigned long long)cap,d_lo[0],d_hx[0]);
+            /* the number of keys of the pass is what was appended; k_pass_sizes only sized the buffers */
+            unsigned long long filled = 0;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(&filled,d_sizes+MAX_PASSES,sizeof(filled),cudaMemcpyDeviceToHost,st));
+            CU(cudaStreamSynchronize(st));
+            if ((int64_t)filled != m)
+              { fprintf(stderr,"cpg_count_kmers: pass %d of %d: %llu keys appended, %lld expected\n",pass,npass,filled,(long long)m);
+                if ((int64_t)filled > cap) { rc = cnt_err(CPG_ECUDA,"cpg_count_kmers: pass %d overflowed its buffers",pass); goto done; }
+                m = (int64_t)filled;
+                if (m == 0) continue;
+              }
           }
         CU(cudaGetLastError());
         MARK(1);
