@@ -50,8 +50,24 @@ def build_cpsim():
 
 
 def build_hostsim():
-    _run(["bash", os.path.join(HOSTSIM_DIR, "build.sh")])
-    return os.path.join(HOSTSIM_DIR, "_build", "libhostsim.so")
+    """tests/hostsim/build.sh, once: skipped when every output is newer than every source, and under a
+    file lock, because the two ranks of the gloo test (and parallel test workers) call this at the same
+    time and must not load a library another process is still writing."""
+    import fcntl
+    import glob
+    bdir = os.path.join(HOSTSIM_DIR, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    so = os.path.join(bdir, "libhostsim.so")
+    outs = [so] + [os.path.join(bdir, f) for f in ("libhostsim32.so", "libcountsim.so", "ClassPro", "prof2class", "profiler")]
+    srcs = (glob.glob(os.path.join(ROOT, "classpro_b200", "csrc", "*")) + glob.glob(os.path.join(ROOT, "classpro_b200", "host", "*"))
+            + glob.glob(os.path.join(ROOT, "include", "*.h")) + glob.glob(os.path.join(HOSTSIM_DIR, "*.cpp"))
+            + [os.path.join(HOSTSIM_DIR, "build.sh")])
+    with open(os.path.join(bdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        newest = max(os.path.getmtime(f) for f in srcs)
+        if not all(os.path.exists(o) and os.path.getmtime(o) >= newest for o in outs):
+            _run(["bash", os.path.join(HOSTSIM_DIR, "build.sh")])
+    return so
 
 
 # ----------------------------------------------------------------------------- cpsim
