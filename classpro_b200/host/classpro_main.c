@@ -124,6 +124,15 @@ static batch_t *q_pop(queue_t *q)
   return b;
 }
 
+/* without waiting: NULL when nothing is queued right now */
+static batch_t *q_trypop(queue_t *q)
+{ pthread_mutex_lock(&q->mu);
+  batch_t *b = q->head;
+  if (b) { q->head = b->next; if (q->head == NULL) q->tail = NULL; }
+  pthread_mutex_unlock(&q->mu);
+  return b;
+}
+
 typedef struct
   { /* options */
     int verbose, find_seeds, nthreads, cov, read_len, ngpus; int64_t batch_bases;
@@ -583,7 +592,10 @@ static void check_batch_status(batch_t *b)
 }
 
 /* one worker per GPU: two batches in flight (slots 0/1), so the copies of one overlap the kernels
-   of the other; finished batches go to the writer, which restores read order */
+   of the other; finished batches go to the writer, which restores read order.  A worker never
+   sleeps on the queue with a batch in flight: the writer may be waiting for exactly that batch while
+   every other batch sits, out of order, behind it (with several workers and batches that take no
+   time that is a deadlock -- found by the parser fuzz of the CPU suite). */
 static void *gpu_main(void *arg)
 { gpu_arg_t *G = arg; app_t *A = G->A;
   cpg_ctx *ctx = NULL;
@@ -594,7 +606,8 @@ static void *gpu_main(void *arg)
   batch_t *fly[2] = { NULL, NULL };
   int slot = 0;
   for (;;)
-    { batch_t *b = q_pop(&A->q_ready);
+    { const int in_flight = fly[slot ^ 1] != NULL;
+      batch_t *b = in_flight ? q_trypop(&A->q_ready) : q_pop(&A->q_ready);
       const double t_g0 = now_s();
       if (b != NULL && b->n > 0)
         { cpg_batch in = { b->n, b->seq_bits, b->pseq, b->seq_off, b->rlen, b->prof, b->prof_off };
@@ -616,7 +629,10 @@ static void *gpu_main(void *arg)
           pthread_mutex_unlock(&A->mu);
         }
       if (G->device == 0) g_t_gpu_busy += now_s()-t_g0;
-      if (b == NULL) break;                  /* queue closed; the last batch in flight was just collected */
+      if (b == NULL)
+        { if (!in_flight) break;              /* queue closed and nothing in flight */
+          continue;                           /* nothing was ready: the batch in flight is finished, now wait */
+        }
       slot ^= 1;
     }
   if (G->device == 0) g_tl_collect = now_s();

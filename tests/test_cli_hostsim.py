@@ -327,3 +327,53 @@ def test_parallel_parse_and_mapped_writer(kit, progs, tmp_path):
     # the cases the test is about did occur: wrong guesses in wrapped FASTQ (none in FASTA), carried comments
     assert stats[(1, "9")][0] > 0 and stats[(2, "9")][0] == 0 and stats[(1, "serial")] == (0, 0)
     assert stats[(3, "9")][1] > 0 and stats[(2, "9")][1] > 0, stats
+
+
+def test_parallel_parse_fuzz(kit, progs, tmp_path):
+    """Differential fuzz of the chunk-parallel parser + mapped writer against the serial parser +
+    write() of the same program (CPG_SERIAL_IO=1; that pair is checked against the reference binary
+    above) on randomly formatted FASTA/FASTQ: windows smaller than a read, more pieces than records,
+    no newline at the end of the file, blank lines, CRLF, '>' and '@' inside headers and quality
+    strings, reads shorter than K.  Null device (class strings of 'X'): the test is about records,
+    offsets and order."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    d = str(tmp_path)
+    sim = kit.simulate(write_to=d, root="f", seed=2, genome_len=20000, cov=8., het=0.01, len_mean=2500,
+                       short_reads=1, nparts=2)
+    os.remove(os.path.join(d, "f.fasta"))
+    qchars = np.frombuffer(b"@>+#I5", dtype=np.uint8)
+    for trial in range(24):
+        fastq = trial % 2 == 1
+        out = bytearray()
+        for i in range(sim.nreads):
+            s = sim.read_ascii(i).tobytes()
+            nl = b"\r\n" if rng.random() < 0.1 else b"\n"
+            hdr = b"r%d" % i + [b"", b" a>b @c", b"\t@x", b" "][int(rng.integers(0, 4))]
+            out += (b"@" if fastq else b">") + hdr + nl
+            w = int(rng.choice([0, 0, 37, 120]))
+            for ln in ([s[a:a + w] for a in range(0, len(s), w)] if (w and s) else [s]):
+                out += ln + nl
+            if fastq:
+                q = qchars[rng.integers(0, len(qchars), len(s))].tobytes()
+                out += b"+\n"
+                for ln in ([q[a:a + w] for a in range(0, len(q), w)] if (w and q) else [q]):
+                    out += ln + b"\n"
+            if rng.random() < 0.1:
+                out += nl
+        if trial % 3 == 0:
+            out = out.rstrip(b"\r\n")                              # no newline at the end of the file
+        src = os.path.join(d, "f.fastq" if fastq else "f.fasta")
+        open(src, "wb").write(bytes(out))
+        cls = os.path.join(d, "f.class")
+        base = {"CPG_FAKE_NULL": "1", "CPG_FAKE_DEVICES": "2"}
+        p = run([CLI, "-T2", "-c8", src], env=dict(base, CPG_SERIAL_IO="1"))
+        assert p.returncode == 0, p.stderr[-800:]
+        want = open(cls, "rb").read()
+        assert want.count(b"\n") == 4 * sim.nreads
+        env = dict(base, CPG_BATCH_BASES=str(int(rng.choice([700, 5000, 40000, 10**7]))),
+                   CPG_PARSE_PIECES=str(int(rng.choice([1, 2, 5, 16, 40]))))
+        p = run([CLI, "-T%d" % rng.integers(1, 5), "-c8", src], env=env)
+        assert p.returncode == 0, (env, p.stderr[-800:])
+        assert open(cls, "rb").read() == want, (trial, env)
+        os.remove(src)
