@@ -58,7 +58,7 @@ def build_hostsim():
     bdir = os.path.join(HOSTSIM_DIR, "_build")
     os.makedirs(bdir, exist_ok=True)
     so = os.path.join(bdir, "libhostsim.so")
-    outs = [so] + [os.path.join(bdir, f) for f in ("libhostsim32.so", "libcountsim.so", "ClassPro", "prof2class", "profiler")]
+    outs = [so] + [os.path.join(bdir, f) for f in ("libhostsim32.so", "libcountsim.so", "libpassemu.so", "ClassPro", "prof2class", "profiler")]
     srcs = (glob.glob(os.path.join(ROOT, "classpro_b200", "csrc", "*")) + glob.glob(os.path.join(ROOT, "classpro_b200", "host", "*"))
             + glob.glob(os.path.join(ROOT, "include", "*.h")) + glob.glob(os.path.join(HOSTSIM_DIR, "*.cpp"))
             + [os.path.join(HOSTSIM_DIR, "build.sh")])

@@ -24,3 +24,5 @@ g++ $CF -shared -o "$here/_build/libcountsim.so" "$here/countsim.cpp"
 g++ $CF -DCOUNTSIM_AS_ABI -c "$here/countsim.cpp" -o "$here/_build/countsim_abi.o"
 gcc $CF -I"$root/classpro_b200/host" -c "$root/classpro_b200/host/cpg_profiler.c" -o "$here/_build/cpg_profiler.o"
 g++ -o "$here/_build/profiler" "$here/_build/cpg_profiler.o" "$here/_build/countsim_abi.o" "$here/_build/cpg_pack.o" -lz
+# TEST-ONLY: the key-range-pass kernels of the profile producer on host threads (passemu.cpp)
+g++ $CF -shared -o "$here/_build/libpassemu.so" "$here/passemu.cpp" -lpthread

@@ -207,6 +207,49 @@ def test_key_range_passes_hostsim(kit, hostsim, monkeypatch, passes):
     check_strands(hostsim)
 
 
+@pytest.mark.parametrize("npass,grid", [(3, 5), (7, 2)])
+def test_pass_kernels_on_host_threads(kit, hostsim, npass, grid):
+    """The source text of k_pass_sizes / k_kmer_keys_pass (the only producer kernels that are not loops
+    around an element function) on host threads: 256 threads per CTA, warp votes and shuffles as
+    rendezvous (tests/hostsim/passemu.cpp).  Every k-mer is appended in exactly one pass, equal keys
+    in the same pass, as many as the sizing kernel says, and counting the appended keys gives the
+    harness counts."""
+    from classpro_b200 import abi
+    L = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "_build", "libpassemu.so"))
+    L.pe_pass_sizes.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.pe_keys_pass.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.c_uint64, C.c_void_p, C.c_void_p]
+    L.pe_keys_pass.restype = C.c_uint64
+    K = 40
+    sim = kit.simulate(kmer=K, seed=4, genome_len=6000, cov=8., het=0.01, len_mean=1500, short_reads=1, repeat_frac=0.3)
+    pseq, seq_off = abi.pack_codes(sim.seq, sim.seq_off, sim.rlen)
+    n, nr = sim.total_kmers, sim.nreads
+    cnt_off = np.ascontiguousarray(sim.cnt_off, np.int64)
+    sizes = np.zeros(64, np.uint64)
+    L.pe_pass_sizes(grid, nr, pseq.ctypes.data, seq_off.ctypes.data, cnt_off.ctypes.data, K, npass, sizes.ctypes.data)
+    assert int(sizes.sum()) == n and not sizes[npass:].any()
+    seen = np.zeros(n, np.int32)
+    where = {}
+    counts = np.zeros(n, np.int64)
+    for p in range(npass):
+        cap = int(sizes[p])
+        klo = np.zeros(cap + 2, np.uint64); khx = np.zeros(cap + 2, np.uint64)
+        got = L.pe_keys_pass(grid, nr, pseq.ctypes.data, seq_off.ctypes.data, cnt_off.ctypes.data, K, p, npass, cap,
+                             klo.ctypes.data, khx.ctypes.data)
+        assert got == cap, (p, got, cap)
+        klo, khx = klo[:cap], khx[:cap]
+        idx = (khx & np.uint64((1 << 48) - 1)).astype(np.int64)
+        np.add.at(seen, idx, 1)
+        keys = list(zip(klo.tolist(), (khx >> np.uint64(48)).tolist()))
+        tally = {}
+        for k in keys:
+            assert where.setdefault(k, p) == p
+            tally[k] = tally.get(k, 0) + 1
+        counts[idx] = [tally[k] for k in keys]
+    assert (seen == 1).all()
+    assert np.array_equal(np.minimum(counts, 32767).astype(np.uint16), sim.counts)
+
+
 def test_encoder_hostsim(kit, hostsim):
     check_encoder(hostsim, kit, np.random.default_rng(5))
 
