@@ -70,6 +70,10 @@ def lib():
         L.cpg_status_string.restype = C.c_char_p
         L.cpg_version.restype = C.c_char_p
         L.cpg_device_count.restype = C.c_int
+        L.cpg_count_kmers.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+        L.cpg_encode_profiles.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.cpg_count_error.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -297,3 +301,37 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+# ---- profile producer (include/classpro_gpu.h: cpg_count_kmers / cpg_encode_profiles) ----
+def count_kmers(kmer, pseq, seq_off, rlen, device=0):
+    """Exact canonical k-mer counts of a 2-bit packed read set on the GPU: (counts, cnt_off, hist)."""
+    L = lib()
+    n = len(rlen)
+    rlen = np.ascontiguousarray(rlen, dtype=np.int32)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    pseq = np.ascontiguousarray(pseq, dtype=np.uint8)
+    cnt_off = np.zeros(n + 1, dtype=np.int64)
+    total = int(np.maximum(rlen.astype(np.int64) - kmer + 1, 0).sum())
+    counts = np.zeros(max(total, 1), dtype=np.uint16)
+    hist = np.zeros(32770, dtype=np.int64)
+    rc = L.cpg_count_kmers(device, kmer, n, pseq.ctypes.data, seq_off.ctypes.data, rlen.ctypes.data,
+                           cnt_off.ctypes.data, counts.ctypes.data, hist.ctypes.data)
+    if rc:
+        raise CpgError("cpg_count_kmers: rc %d: %s" % (rc, L.cpg_count_error().decode()))
+    return counts[:total], cnt_off, hist
+
+
+def encode_profiles(counts, cnt_off, device=0):
+    """FastK token streams of the counts of every read on the GPU: (prof, prof_off)."""
+    L = lib()
+    n = len(cnt_off) - 1
+    counts = np.ascontiguousarray(counts, dtype=np.uint16)
+    cnt_off = np.ascontiguousarray(cnt_off, dtype=np.int64)
+    cap = 2 * len(counts) + 16
+    prof = np.zeros(cap, dtype=np.uint8)
+    prof_off = np.zeros(n + 1, dtype=np.int64)
+    rc = L.cpg_encode_profiles(device, n, counts.ctypes.data, cnt_off.ctypes.data, prof.ctypes.data, cap, prof_off.ctypes.data)
+    if rc:
+        raise CpgError("cpg_encode_profiles: rc %d: %s" % (rc, L.cpg_count_error().decode()))
+    return prof[:prof_off[n]], prof_off

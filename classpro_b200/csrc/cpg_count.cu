@@ -89,6 +89,17 @@ k_scatter_counts(int64_t n, const uint64_t *__restrict__ khidx, const uint32_t *
     if (sh[j]) atomicAdd(&hist[j],(unsigned long long)sh[j]);
 }
 
+/* invariant of a finished count: every position was written by exactly one pass (the array starts as 0xffff,
+   which no count can be: they saturate at 32767) */
+__global__ void __launch_bounds__(CT_THREADS)
+k_count_unwritten(int64_t n, const uint16_t *__restrict__ counts, unsigned long long *__restrict__ bad)
+{ unsigned int c = 0;
+  for (int64_t i = blockIdx.x*(int64_t)CT_THREADS+threadIdx.x; i < n; i += (int64_t)gridDim.x*CT_THREADS)
+    c += (counts[i] == 0xffffu);
+  c = __reduce_add_sync(0xffffffffu,c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(bad,(unsigned long long)c);
+}
+
 /* ---- encoder ---- */
 __global__ void __launch_bounds__(CT_THREADS)
 k_enc_change(int n_reads, const uint16_t *__restrict__ counts, const int64_t *__restrict__ cnt_off, uint32_t *__restrict__ chg)
@@ -119,6 +130,22 @@ struct MaxOp { __host__ __device__ __forceinline__ uint32_t operator()(uint32_t 
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = cnt_err(CPG_ECUDA,"%s: %s",#x,cudaGetErrorString(e_)); goto done; } } while (0)
 #define DMALLOC(p,bytes) do { cudaError_t e_ = cudaMalloc((void **)&(p),(bytes)); \
     if (e_ != cudaSuccess) { rc = cnt_err(CPG_ENOMEM,"cannot allocate %zu bytes of device memory (%s)",(size_t)(bytes),cudaGetErrorString(e_)); goto done; } } while (0)
+
+/* CPG_COUNT_DEBUG_DIR=<dir>: every stage of every pass is copied back and written to <dir>/<name>.<pass>.bin
+   (tools/producer_debug.py compares the passes with the single-pass arrays) */
+static void dbg_dump(cudaStream_t st, const char *name, int pass, const void *dptr, size_t bytes)
+{ const char *dir = getenv("CPG_COUNT_DEBUG_DIR");
+  if (dir == NULL) return;
+  void *h = malloc(bytes ? bytes : 1);
+  if (h == NULL) return;
+  cudaStreamSynchronize(st);
+  cudaError_t e = cudaMemcpy(h,dptr,bytes,cudaMemcpyDeviceToHost);
+  char path[4096]; snprintf(path,sizeof(path),"%s/%s.%d.bin",dir,name,pass);
+  FILE *f = fopen(path,"wb");
+  if (f) { fwrite(h,1,bytes,f); fclose(f); }
+  if (e != cudaSuccess) fprintf(stderr,"dbg_dump %s pass %d: %s\n",name,pass,cudaGetErrorString(e));
+  free(h);
+}
 
 static int grid_for(int device, int64_t work_items)
 { int sms = 148;
@@ -156,6 +183,7 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
     CU(cudaMemcpyAsync(d_seq_off,seq_off,sizeof(int64_t)*(size_t)(n_reads+1),cudaMemcpyHostToDevice,st));
     CU(cudaMemcpyAsync(d_cnt_off,cnt_off,sizeof(int64_t)*(size_t)(n_reads+1),cudaMemcpyHostToDevice,st));
     CU(cudaMemsetAsync(d_hist,0,sizeof(unsigned long long)*32770,st));
+    CU(cudaMemsetAsync(d_counts,0xff,sizeof(uint16_t)*(size_t)n,st));
     const int gr = grid_for(device,(int64_t)n_reads*CT_THREADS);
 
     /* passes: all keys at once if 36 bytes per k-mer (two 16-byte sort buffers in double, run ids) plus the
@@ -224,14 +252,13 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
             CU(cudaMemcpyAsync(&filled,d_sizes+MAX_PASSES,sizeof(filled),cudaMemcpyDeviceToHost,st));
             CU(cudaStreamSynchronize(st));
             if ((int64_t)filled != m)
-              { fprintf(stderr,"cpg_count_kmers: pass %d of %d: %llu keys appended, %lld expected\n",pass,npass,filled,(long long)m);
-                if ((int64_t)filled > cap) { rc = cnt_err(CPG_ECUDA,"cpg_count_kmers: pass %d overflowed its buffers",pass); goto done; }
-                m = (int64_t)filled;
-                if (m == 0) continue;
+              { rc = cnt_err(CPG_ECUDA,"cpg_count_kmers: pass %d of %d: %llu keys appended, %lld expected",pass,npass,filled,(long long)m);
+                goto done;
               }
           }
         CU(cudaGetLastError());
         MARK(1);
+        dbg_dump(st,"keys_lo",pass,d_lo[0],sizeof(uint64_t)*(size_t)m); dbg_dump(st,"keys_hx",pass,d_hx[0],sizeof(uint64_t)*(size_t)m);
         cub::DoubleBuffer<uint64_t> B_lo(d_lo[0],d_lo[1]), B_hx(d_hx[0],d_hx[1]);
         size_t tb = tmp_bytes;
         CU(cub::DeviceRadixSort::SortPairs(d_tmp,tb,B_lo,B_hx,m,0,lo_bits,st));
@@ -241,6 +268,7 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
         uint32_t *d_start = (uint32_t *)B_lo.Alternate();          /* idle half of a double buffer: m+1 entries fit in 8(m+2) bytes */
         const int g = grid_for(device,m);
         MARK(2);
+        dbg_dump(st,"sort_lo",pass,s_lo,sizeof(uint64_t)*(size_t)m); dbg_dump(st,"sort_hx",pass,s_hx,sizeof(uint64_t)*(size_t)m);
         k_run_heads<<<g,CT_THREADS,0,st>>>(m,s_lo,s_hx,d_rid);
         CU(cudaGetLastError());
         tb = tmp_bytes;
@@ -248,16 +276,33 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
         k_run_starts<<<g,CT_THREADS,0,st>>>(m,d_rid,d_start);
         CU(cudaGetLastError());
         MARK(3);
+        dbg_dump(st,"rid",pass,d_rid,sizeof(uint32_t)*(size_t)m); dbg_dump(st,"start",pass,d_start,sizeof(uint32_t)*(size_t)(m+1));
         k_scatter_counts<<<g,CT_THREADS,0,st>>>(m,s_hx,d_rid,d_start,d_counts,d_hist);
         CU(cudaGetLastError());
         MARK(4);
+        dbg_dump(st,"counts",pass,d_counts,sizeof(uint16_t)*(size_t)n);
         if (timing)
           { CU(cudaStreamSynchronize(st));
             for (int i = 0; i < 4; i++) { float t; CU(cudaEventElapsedTime(&t,ev[i],ev[i+1])); ms[i] += t; }
           }
       }
+    /* fail closed: every position counted exactly once, and the histogram accounts for every k-mer */
+    { unsigned long long unwritten = 0;
+      CU(cudaMemsetAsync(d_sizes,0,sizeof(unsigned long long),st));
+      k_count_unwritten<<<grid_for(device,n),CT_THREADS,0,st>>>(n,d_counts,d_sizes);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(&unwritten,d_sizes,sizeof(unwritten),cudaMemcpyDeviceToHost,st));
+      CU(cudaMemcpyAsync(hist,d_hist,sizeof(int64_t)*32770,cudaMemcpyDeviceToHost,st));
+      CU(cudaStreamSynchronize(st));
+      int64_t inst = hist[32769];
+      for (int c = 1; c < CPG_CNT_MAX; c++) inst += (int64_t)c*hist[c];
+      if (unwritten != 0 || inst != n)
+        { rc = cnt_err(CPG_ECUDA,"cpg_count_kmers: inconsistent result (%llu positions never counted; histogram accounts for %lld of %lld k-mers, %d pass%s)",
+                       unwritten,(long long)inst,(long long)n,npass,npass > 1 ? "es" : "");
+          goto done;
+        }
+    }
     CU(cudaMemcpyAsync(counts,d_counts,sizeof(uint16_t)*(size_t)n,cudaMemcpyDeviceToHost,st));
-    CU(cudaMemcpyAsync(hist,d_hist,sizeof(int64_t)*32770,cudaMemcpyDeviceToHost,st));
     CU(cudaStreamSynchronize(st));
     hist[32768] = hist[1];                                          /* instances of the low bin (count 1) */
     if (timing)

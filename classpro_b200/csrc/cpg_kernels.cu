@@ -721,6 +721,10 @@ static int ensure_scratch(cpg_ctx *ctx, int P)
   /* the memo of the unreliable pass is read before it is written: entries start as "no task" */
   if (cudaMemset(ctx->scratch.p,0,ctx->scratch.cap) != cudaSuccess || cudaMemset(ctx->scratch_big.p,0,ctx->scratch_big.cap) != cudaSuccess)
     return set_err(ctx,CPG_ECUDA,"cudaMemset of the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
+  /* the memsets run on the legacy default stream, which the (non-blocking) slot streams do not wait for:
+     nothing may be launched on them before the arenas are really zero */
+  if (cudaDeviceSynchronize() != cudaSuccess)
+    return set_err(ctx,CPG_ECUDA,"zeroing the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
   SC.base = (uint8_t *)ctx->scratch.p; SB.base = (uint8_t *)ctx->scratch_big.p;
   ctx->SC = SC; ctx->SCbig = SB;
   return CPG_OK;
@@ -909,10 +913,11 @@ extern "C" int cpg_collect(cpg_ctx *ctx, int slot, cpg_result *res)
   CU(cudaSetDevice(ctx->device));
   Slot *S = &ctx->slot[slot];
   if (!S->busy) return set_err(ctx,CPG_EINVAL,"cpg_collect: slot %d has no batch in flight",slot);
-  S->busy = 0;
+  /* a rejected result leaves the batch in flight (the slot stays busy): call again with a valid one */
   if (res->cls == NULL && S->cls_bytes > 0) return set_err(ctx,CPG_EINVAL,"cpg_result.cls is NULL");
   if (res->cls_off && (res->cls_off[0] != 0 || res->cls_off[S->n_reads] != S->cls_bytes))
     return set_err(ctx,CPG_EINVAL,"cpg_result.cls_off must be the prefix sums of rlen");
+  S->busy = 0;
   return fetch_result(ctx,S,res);
 }
 

@@ -59,6 +59,8 @@ static const char *USAGE = "[-vs] [-T<int(4)>] [-c<int>] [-r<int(20000)>] [-P<tm
 static double now_s(void);
 static long   g_reparsed = 0, g_patched = 0;      /* pieces parsed again after a wrong guess, headers completed in flatten_chunks */
 static double g_t_reader = 0., g_t_gpu_create = 0., g_t_gpu_busy = 0., g_t_writer = 0.;
+#define MAX_GPUS 64
+static long   g_gpu_batches[MAX_GPUS]; static long long g_gpu_kmers[MAX_GPUS];     /* per device: batches and k-mers classified */
 /* wall-clock marks (seconds since start) printed with -v: model ready, first pinned buffer, GPU0
    context, first batch parsed, reader done, last batch collected, writer done */
 static double g_tl_model = 0., g_tl_pinned = 0., g_tl_ctx = 0., g_tl_first = 0., g_tl_reader = 0., g_tl_collect = 0.,
@@ -612,6 +614,7 @@ static void *gpu_main(void *arg)
       if (b != NULL && b->n > 0)
         { cpg_batch in = { b->n, b->seq_bits, b->pseq, b->seq_off, b->rlen, b->prof, b->prof_off };
           if (cpg_submit(ctx,slot,&in) != CPG_OK) die("%s: %s",PROG,cpg_last_error(ctx));
+          if (G->device < MAX_GPUS) { g_gpu_batches[G->device]++; g_gpu_kmers[G->device] += b->kmers; }
         }
       batch_t *done = fly[slot ^ 1];          /* the batch submitted before this one */
       fly[slot ^ 1] = NULL;
@@ -872,6 +875,7 @@ int main(int argc, char **argv)
   const char *env = getenv("CLASSPRO_GPUS");
   if (A->ngpus == 0 && env && atoi(env) > 0) A->ngpus = atoi(env);
   if (A->ngpus == 0 || A->ngpus > ndev) A->ngpus = ndev;
+  if (A->ngpus > MAX_GPUS) A->ngpus = MAX_GPUS;
   if (A->verbose)
     fprintf(stderr,"Classifying %d-mers on %d GPU%s...\n",A->P.kmer,A->ngpus,A->ngpus > 1 ? "s" : "");
 
@@ -895,6 +899,9 @@ int main(int argc, char **argv)
       fprintf(stderr,"Classified %lld k-mers of %lld reads\n",(long long)A->kmers,(long long)A->total_reads);
       fprintf(stderr,"    stage seconds: reader %.3f (parse+pack+profile read), GPU0 context %.3f, GPU0 submit/collect %.3f, writer %.3f\n",
               g_t_reader,g_t_gpu_create,g_t_gpu_busy,g_t_writer);
+      fprintf(stderr,"    per GPU (batches/k-mers):");
+      for (int g = 0; g < A->ngpus && g < MAX_GPUS; g++) fprintf(stderr," %ld/%lld",g_gpu_batches[g],g_gpu_kmers[g]);
+      fprintf(stderr,"\n");
       fprintf(stderr,"    parser: %ld pieces parsed again from their true start, %ld headers completed with a carried comment\n",
               g_reparsed,g_patched);
       fprintf(stderr,"    timeline (s): model %.3f, first batch parsed %.3f, first pinned buffer %.3f, GPU0 context %.3f, "

@@ -33,3 +33,25 @@ def reference_thread_ranges(nreads, nthreads):
     (src/ClassPro.c:529-530, src/io.c:353-354)."""
     per = nreads // nthreads + (0 if nreads % nthreads == 0 else 1)
     return [(min(t * per, nreads), min((t + 1) * per, nreads)) for t in range(nthreads)]
+
+
+def plan_chunk_shards(chunk_weights, nranks):
+    """The shards of a read set that exists as chunks (FastK profile parts, or the chromosomes bench.py
+    generates): chunk_weights = [(chunk id, per-read weights of the chunk)] in global read order.
+    Returns (plans, total_reads); plans[r] = (beg, end, [(chunk id, a, b)]) -- the global read range of
+    rank r and, chunk by chunk, the local read range [a,b) of the chunks it touches.  A rank only
+    ever needs those chunks; borders fall inside a chunk, so neighbours may both need it."""
+    first, at = [], 0
+    for c, w in chunk_weights:
+        first.append(at)
+        at += len(w)
+    allw = np.concatenate([np.asarray(w, dtype=np.int64) for c, w in chunk_weights]) if chunk_weights else np.zeros(0, np.int64)
+    plans = []
+    for beg, end in shard_ranges(allw, nranks):
+        need = []
+        for (c, w), f in zip(chunk_weights, first):
+            a, b = max(beg - f, 0), min(end - f, len(w))
+            if a < b:
+                need.append((c, int(a), int(b)))
+        plans.append((int(beg), int(end), need))
+    return plans, at

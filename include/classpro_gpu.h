@@ -109,9 +109,14 @@ int cpg_pack_seq(const char *seq, int32_t rlen, uint8_t *out);
  * Stands in for steps 2-6 of the per-read loop, src/ClassPro.c:229-271, for a whole batch. */
 int cpg_classify(cpg_ctx *ctx, const cpg_batch *batch, cpg_result *result);
 
-/* Asynchronous pair on one of two slots (double buffering: slot 0/1): cpg_submit stages the
- * batch into pinned memory and enqueues copies + kernels; cpg_collect waits for that slot and
- * copies the classes out.  A slot must be collected before it is submitted again. */
+/* Asynchronous pair on one of two slots (double buffering: slot 0/1): cpg_submit enqueues the
+ * host->device copies STRAIGHT FROM THE CALLER'S ARRAYS (no staging copy) and the kernels;
+ * cpg_collect waits for that slot and copies the classes out.  The arrays of the batch must
+ * therefore stay valid and unchanged until cpg_collect of that slot has returned (pinned arrays,
+ * cpg_host_alloc, make the copies true DMA transfers).  A slot must be collected before it is
+ * submitted again.  cpg_result.cls_off, when given, must be the prefix sums of rlen; a result that
+ * cpg_collect rejects (CPG_EINVAL) leaves the batch in flight: call again with a valid one.
+ * One host thread per context: the calls on one cpg_ctx are not re-entrant. */
 int cpg_submit(cpg_ctx *ctx, int slot, const cpg_batch *batch);
 int cpg_collect(cpg_ctx *ctx, int slot, cpg_result *result);
 

@@ -104,6 +104,91 @@ def test_shard_ranges_properties():
     assert reference_thread_ranges(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
 
 
+def test_plan_chunk_shards_properties():
+    """The bench's shard plan over a read set that exists as chunks: ranges cover everything once, the chunk
+    pieces of a rank add up to its range, and a rank only touches chunks that overlap its range."""
+    from classpro_b200.shard import plan_chunk_shards, shard_ranges
+    rng = np.random.default_rng(9)
+    for nchunks, ranks in ((1, 1), (3, 2), (8, 8), (5, 8), (20, 3)):
+        cw = [(100 + c, rng.integers(50, 4000, size=int(rng.integers(1, 300)))) for c in range(nchunks)]
+        plans, total = plan_chunk_shards(cw, ranks)
+        assert total == sum(len(w) for c, w in cw) and len(plans) == ranks
+        allw = np.concatenate([w for c, w in cw])
+        assert [(b, e) for b, e, _ in plans] == shard_ranges(allw, ranks)
+        seen = []
+        first = dict(zip([c for c, w in cw], np.cumsum([0] + [len(w) for c, w in cw[:-1]])))
+        for beg, end, need in plans:
+            assert sum(b - a for c, a, b in need) == end - beg
+            for c, a, b in need:
+                seen.extend(range(first[c] + a, first[c] + b))
+        assert seen == list(range(total))
+
+
+BENCH_SHARD_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import bench
+from classpro_b200.shard import plan_chunk_shards
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+wl = dict(bench.WORKLOADS["c2"]); wl["cov"] = 8.
+C = 3                                            # chromosomes of the global set: rank 0 is home to 1, rank 1 to 2
+home = list(range(C * rank // world, C * (rank + 1) // world))
+sims = bench.gen_chunks(home, wl, 0.05, 2)
+mine = [(c, np.diff(sims[c].prof_off)) for c in home]
+g = [None] * world
+dist.all_gather_object(g, mine)
+allw = sorted([cw for x in g for cw in x], key=lambda cw: cw[0])
+plans, total = plan_chunk_shards(allw, world)
+beg, end, need = plans[rank]
+extra = [c for c, a, b in need if c not in sims]
+sims.update(bench.gen_chunks(extra, wl, 0.05, 2))
+# what this rank holds: per global read id, a checksum of its sequence and profile bytes
+out = {}
+first = {}
+at = 0
+for c, w in allw:
+    first[c] = at; at += len(w)
+for c, a, b in need:
+    s = sims[c]
+    for i in range(a, b):
+        out[first[c] + i] = (int(s.rlen[i]), int(s.read_prof(i).astype(np.int64).sum()), int(s.seq[s.seq_off[i]:s.seq_off[i + 1]].astype(np.int64).sum()))
+assert sorted(out) == list(range(beg, end))
+g2 = [None] * world
+dist.all_gather_object(g2, (out, extra))
+if rank == 0:
+    whole = bench.gen_chunks(range(C), wl, 0.05, 2)       # the same set generated in one place
+    want = {}
+    at = 0
+    for c in range(C):
+        s = whole[c]
+        for i in range(s.nreads):
+            want[at + i] = (int(s.rlen[i]), int(s.read_prof(i).astype(np.int64).sum()), int(s.seq[s.seq_off[i]:s.seq_off[i + 1]].astype(np.int64).sum()))
+        at += s.nreads
+    got = {}
+    for o, e in g2:
+        assert not (set(o) & set(got))
+        got.update(o)
+    assert got == want and at == total
+    print("BENCH_SHARD_OK", world, total, [e for o, e in g2])
+dist.destroy_process_group()
+"""
+
+
+def test_bench_shard_plan_two_ranks_gloo(kit, tmp_path):
+    """bench.py's N>1 flow on CPU: every rank generates its home chromosomes, the per-read profile sizes are
+    all-gathered, the ranges are cut, a rank whose range reaches into a neighbour's chromosome generates that one
+    too -- together the ranks hold exactly the reads of the set generated in one place, each once."""
+    script = tmp_path / "worker.py"
+    script.write_text(BENCH_SHARD_WORKER % {"root": ROOT})
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:]
+    assert "BENCH_SHARD_OK 2" in p.stdout
+
+
 WORKER = r"""
 import os, sys
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))

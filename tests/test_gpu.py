@@ -168,6 +168,31 @@ def test_cli_matches_live_reference(kit, cp, tmp_path):
         os.remove(ref)
 
 
+def test_cli_every_gpu_count_matches_reference(kit, cp, tmp_path):
+    """The real multi-GPU shape: ONE read set, contiguous batches of reads handed to one worker per
+    GPU, one writer that restores read order.  For every n <= devices present: ClassPro -G<n> gives the bytes
+    of the reference binary, and every one of the n GPUs classified some of the reads."""
+    import re
+    if not kit.have_reference():
+        pytest.skip("oracle/_ref/ClassPro not present")
+    ndev = cp.lib().cpg_device_count()
+    kit.simulate(write_to=str(tmp_path), root="m", seed=91, genome_len=1500000, cov=30., het=0.01, repeat_frac=0.2,
+                 len_mean=15000, len_sd=3000, short_reads=1, nparts=5)
+    fasta = str(tmp_path / "m.fasta")
+    ref = kit.run_reference(fasta, threads=4)
+    os.rename(ref, ref + ".ref")
+    for n in range(1, ndev + 1):
+        p = subprocess.run([CLI, "-v", "-G%d" % n, "-B1", "-T4", fasta], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, p.stderr[-1500:]
+        assert filecmp.cmp(ref, ref + ".ref", shallow=False), "ClassPro -G%d output differs from the reference binary's" % n
+        os.remove(ref)
+        m = re.search(r"per GPU \(batches/k-mers\):((?: \d+/\d+)+)", p.stderr)
+        assert m, p.stderr[-800:]
+        per = [tuple(int(x) for x in t.split("/")) for t in m.group(1).split()]
+        assert len(per) == n and all(b > 0 and k > 0 for b, k in per), "a GPU stayed idle: %s" % per
+        print("-G%d: per GPU (batches, k-mers) %s" % (n, per))
+
+
 def test_edge_batches(kit, cp):
     sim = kit.simulate(seed=79, genome_len=60000, cov=25., het=0.01, len_mean=9000)
     om = kit.oracle_model(sim)

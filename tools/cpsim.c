@@ -358,7 +358,11 @@ int cpsim_generate(const cpsim_params *P, cpsim_data *D)
   D->counts = xmalloc(sizeof(uint16_t)*(size_t)(NK+1));
   D->hist = calloc(32768+2,sizeof(int64_t));
 
-  if (P->exact)
+  if (P->exact == 2)
+    { /* reads only: the counts come from somewhere else (the GPU profile producer, classpro_b200/profiler) */
+      memset(D->counts,0,sizeof(uint16_t)*(size_t)(NK+1));
+    }
+  else if (P->exact)
     { kent *a = xmalloc(sizeof(kent)*(size_t)(NK+1)), *tmp = xmalloc(sizeof(kent)*(size_t)(NK+1));
       const u128 mask = (K == 64) ? ~(u128)0 : (((u128)1 << (2*K))-1);
       int64_t m = 0;
@@ -502,6 +506,7 @@ int cpsim_write_files(const cpsim_params *P, const cpsim_data *D, const char *di
     }
   free(line);
   fclose(f);
+  if (P->exact == 2) return 0;                     /* reads only */
   /* histogram: kmer, low=1, high=32767, ilowcnt, ihighcnt, hist[1..32767] */
   snprintf(path,sizeof(path),"%s/%s.hist",dir,root);
   f = xopen(path);
@@ -544,7 +549,7 @@ static void usage(void)
   "usage: cpsim [options] <out_dir> <root>\n"
   "  --seed N --genome-len N --het F --snp-only --repeat-frac F --seg-dups N\n"
   "  --cov F --len-mean N --len-sd N --len-min N --len-max N\n"
-  "  --err-sub F --err-indel-base F --err-indel-hp F --kmer N --nparts N --fast --short-reads\n");
+  "  --err-sub F --err-indel-base F --err-indel-hp F --kmer N --nparts N --fast --reads-only --short-reads\n");
   exit(1);
 }
 
@@ -563,6 +568,7 @@ int main(int argc, char **argv)
       OPTI("--kmer",kmer) OPTI("--nparts",nparts)
       if (!strcmp(a,"--snp-only")) { P.snp_only = 1; continue; }
       if (!strcmp(a,"--fast")) { P.exact = 0; P.snp_only = 1; continue; }
+      if (!strcmp(a,"--reads-only")) { P.exact = 2; continue; }
       if (!strcmp(a,"--short-reads")) { P.short_reads = 1; continue; }
       if (a[0] == '-') usage();
       if (np < 2) pos[np++] = a; else usage();

@@ -18,7 +18,7 @@ typedef struct
     double  err_sub, err_indel_base, err_indel_hp;
     int64_t kmer;
     int64_t nparts;          /* number of FastK profile parts written */
-    int     exact;           /* 1: exact canonical k-mer counts; 0: ground-truth coverage */
+    int     exact;           /* 1: exact canonical k-mer counts; 0: ground-truth coverage; 2: reads only (no counts) */
     int     short_reads;     /* 1: sprinkle reads shorter than k (edge-case tests) */
   } cpsim_params;
 
