@@ -187,10 +187,8 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
     const int gr = grid_for(device,(int64_t)n_reads*CT_THREADS);
 
     /* passes: all keys at once if 36 bytes per k-mer (two 16-byte sort buffers in double, run ids) plus the
-       sort's scratch fit in what is left of the device memory.  Key-range passes for larger sets are
-       written (k_pass_sizes, k_kmer_keys_pass) but EXPERIMENTAL: their first run on a B200 gave wrong counts
-       (profiles/r01_producer_passes.log) while the host build of the same logic is right, so they are only
-       taken when CPG_COUNT_PASSES=<p> asks for them; without it a set that does not fit is an error */
+       sort's scratch fit in what is left of the device memory; otherwise key-range passes (equal keys always land
+       in the same pass): as many as it takes for the largest pass to fit.  CPG_COUNT_PASSES=<p> forces p passes. */
     unsigned long long sizes[MAX_PASSES]; int npass = 1; int64_t cap = n;
     { size_t mfree = 0, mtotal = 0;
       CU(cudaMemGetInfo(&mfree,&mtotal));
@@ -199,22 +197,36 @@ extern "C" int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const 
       int forced = e ? atoi(e) : 0;
       if (forced > MAX_PASSES) forced = MAX_PASSES;
       if (forced > 0) npass = forced;
-      else if (37.0*(double)n*1.02 > budget)
-        { rc = cnt_err(CPG_ENOMEM,"cpg_count_kmers: %lld k-mers need ~%.1f GB of device memory, %.1f GB free",(long long)n,37e-9*(double)n,1e-9*(double)mfree);
-          goto done;
+      else if (37.0*(double)n*1.02 > budget || n >= (int64_t)0xfffffff0u)
+        { npass = (int)(37.0*(double)n*1.05/budget)+1;
+          if (npass < 2) npass = 2;
+          if (npass > MAX_PASSES)
+            { rc = cnt_err(CPG_ENOMEM,"cpg_count_kmers: %lld k-mers need ~%.1f GB of device memory per pass even with %d passes, %.1f GB free",
+                           (long long)n,37e-9*(double)n/MAX_PASSES,MAX_PASSES,1e-9*(double)mfree);
+              goto done;
+            }
         }
       for (;;)
         { sizes[0] = (unsigned long long)n;
           if (npass > 1)
-            { CU(cudaMemsetAsync(d_sizes,0,sizeof(unsigned long long)*MAX_PASSES,st));
-              k_pass_sizes<<<gr,CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,npass,d_sizes);
+            { /* sizes of the passes: the append kernel itself with a capacity of 0 (it counts, stores nothing), one
+                 launch per pass -- the very code that fills the buffers afterwards.  (A separate sizing kernel with
+                 a shared-memory histogram, k_pass_sizes, put every key in pass 0 on a B200 although its source is
+                 right on host threads: profiles/r02_producer_debug.log; it is kept for the CPU suite only.) */
+              CU(cudaMemsetAsync(d_sizes,0,sizeof(unsigned long long)*MAX_PASSES,st));
+              for (int p = 0; p < npass; p++)
+                k_kmer_keys_pass<<<gr,CT_THREADS,0,st>>>(n_reads,(const uint64_t *)d_seq,d_seq_off,d_cnt_off,kmer,p,npass,d_sizes+p,0ull,NULL,NULL);
               CU(cudaGetLastError());
               CU(cudaMemcpyAsync(sizes,d_sizes,sizeof(unsigned long long)*(size_t)npass,cudaMemcpyDeviceToHost,st));
               CU(cudaStreamSynchronize(st));
+              unsigned long long tot = 0;
+              for (int p = 0; p < npass; p++) tot += sizes[p];
+              if ((int64_t)tot != n)
+                { rc = cnt_err(CPG_ECUDA,"cpg_count_kmers: the %d passes hold %llu of %lld k-mers",npass,tot,(long long)n); goto done; }
             }
           cap = 0;
           for (int p = 0; p < npass; p++) if ((int64_t)sizes[p] > cap) cap = (int64_t)sizes[p];
-          if (forced > 0 || npass >= MAX_PASSES || 37.0*(double)cap <= budget) break;
+          if (forced > 0 || npass >= MAX_PASSES || (37.0*(double)cap <= budget && cap < (int64_t)0xfffffff0u)) break;
           npass++;                                               /* a heavy repeat made one pass larger than its share */
         }
       if (cap >= (int64_t)0xfffffff0u)

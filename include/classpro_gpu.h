@@ -163,7 +163,9 @@ int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4]);
  *              bins of <root>.hist with low = 1, high = 32767, src/libfastk.c:72-83); hist[32768] and
  *              hist[32769] = the instance-mode values of the two boundary bins (the file's two
  *              hidden words, src/libfastk.c:91-93)
- * 1 <= K <= 40; fewer than 2^32 k-mers per call; needs ~40 bytes of device memory per k-mer. */
+ * 1 <= K <= 40.  Needs ~40 bytes of device memory per k-mer; a read set that does not fit is counted in
+ * key-range passes (every pass extracts the keys again and sorts the ones whose hash falls in its range:
+ * equal k-mers always meet in the same pass), fewer than 2^32 k-mers per pass. */
 int cpg_count_kmers(int device, int32_t kmer, int32_t n_reads, const uint8_t *seq, const int64_t *seq_off,
                     const int32_t *rlen, int64_t *cnt_off, uint16_t *counts, int64_t *hist);
 /* cpg_encode_profiles: the encoder side of the profile codec (decoder: src/libfastk.c:1467-1535):

@@ -338,8 +338,6 @@ def test_counts_and_histogram_gpu(kit, device, K):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="key-range passes: wrong counts in their first run on a B200 (profiles/r01_producer_passes.log), "
-                                        "not diagnosed yet; the library only takes them when CPG_COUNT_PASSES asks")
 @pytest.mark.parametrize("passes", [3, 64])
 def test_key_range_passes_gpu(kit, device, monkeypatch, passes):
     monkeypatch.setenv("CPG_COUNT_PASSES", str(passes))
