@@ -629,6 +629,7 @@ def main():
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
     phase = ctx.phase_cycles()
+    wall_ns = ctx.wall_ns()
     cls_res, status = ctx.download(data.whole)
     n_bad = int(sum_over_ranks(float((status & cp.ST_FATAL != 0).sum())))
     my_ms = ms_dec + ms_cls
@@ -701,8 +702,11 @@ def main():
                      "note": "profile decode + wall-candidate scan fused: c + 2n + n/8 bytes; issue bound"},
         "k_wall": {"ms": ms_ph[0], "bytes": bytes_wall, "GBps": bytes_wall / (max(ms_ph[0], 1e-6) * 1e-3) / 1e9,
                    "frac": bytes_wall / (max(ms_ph[0], 1e-6) * 1e-3) / 1e9 / peak, "traffic": traffic.get("k_wall"),
-                   "note": "wall detection + reliable intervals: 2n + n/8 + r/4 bytes in, interval tables out; "
-                           "DRAM-latency / FP64-latency bound (see stall mix in profiles/)"},
+                   "launches": {"k_wall_a": ms_ph[0] * wall_ns[0] / max(1, sum(wall_ns)),
+                                "k_wall_b": ms_ph[0] * wall_ns[1] / max(1, sum(wall_ns)),
+                                "k_wall_c": ms_ph[0] * wall_ns[2] / max(1, sum(wall_ns))},
+                   "note": "wall detection + reliable intervals as three launches (pure per candidate / replay per read / "
+                           "pure per interval): 2n + n/8 + r/4 bytes in, interval tables out"},
         "k_rel": {"ms": ms_ph[1], "bytes": None, "traffic": traffic.get("k_rel"),
                   "note": "reliable-interval DP on the interval tables (48 B per interval): FP64 dependency chains"},
         "k_unrel": {"ms": ms_ph[2], "bytes": r, "traffic": traffic.get("k_unrel"),

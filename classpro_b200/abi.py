@@ -63,6 +63,7 @@ def lib():
                                        C.POINTER(C.c_int)]
         L.cpg_download.argtypes = [C.c_void_p, C.POINTER(CResult)]
         L.cpg_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.cpg_wall_ns.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.cpg_host_alloc.argtypes = [C.c_size_t]
         L.cpg_host_alloc.restype = C.c_void_p
         L.cpg_host_free.argtypes = [C.c_void_p]
@@ -250,6 +251,14 @@ class Context:
         rc = self.L.cpg_phase_cycles(self.h, out)
         if rc:
             raise self._err("cpg_phase_cycles", rc)
+        return list(out)
+
+    def wall_ns(self):
+        """Device time of k_wall_a, k_wall_b, k_wall_c in the last timed resident run, nanoseconds."""
+        out = (C.c_uint64 * 3)()
+        rc = self.L.cpg_wall_ns(self.h, out)
+        if rc:
+            raise self._err("cpg_wall_ns", rc)
         return list(out)
 
     def download(self, batch, allow_read_errors=True):

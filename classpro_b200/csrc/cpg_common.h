@@ -162,17 +162,52 @@ typedef struct { const uint8_t *p; int32_t bits; } cpg_seq;
 struct cpg_unmemo { double a; double val; int32_t k; int32_t kind; };
 #define CPG_MEMO_CAP 512       /* intervals per read whose first-sweep results are kept */
 
+/* ---- wall stage, step 1 -> step 2: what the pure, candidate-parallel step (k_wall_a, cpg_wall.cuh "wa_")
+ *      leaves for the order-dependent replay of a read (k_wall_b, "wb_").  One header per wall candidate of
+ *      the read, in position order; one big record for every candidate that gets past the count thresholds
+ *      of src/wall.c:643-675 for at least one error type (about one in ten on HiFi profiles). ---- */
+typedef struct
+  { int32_t  pos;       /* profile position i of the candidate */
+    uint32_t info;      /* CH_* bits */
+    uint32_t big;       /* index of its cpg_cbig record (valid iff info & (CH_REACH_S|CH_REACH_O)) */
+    uint32_t pad;
+  } cpg_chdr;
+#define CH_REACH_S  0x01u   /* SELF gets past the thresholds (before the paired flags are looked at) */
+#define CH_REACH_O  0x02u   /* OTHERS likewise */
+#define CH_ONOW     0x04u   /* OTHERS: a wall by the thresholds alone (src/wall.c:672-675) */
+#define CH_GAIN     0x08u   /* wall type: count gain (else drop) */
+#define CH_LONG     0x10u   /* a context run at the candidate reached the 127 cap */
+
+typedef struct
+  { double   own[2];    /* p_errorin of the candidate itself under its context's error rate, per error type */
+    double   term[23];  /* partner probabilities, layout in cpg_wall.cuh */
+    int32_t  lc_j;      /* low-complexity partner position */
+    uint8_t  lc_kind;   /* 0 = no partner, 1 = read boundary, 2 = regular */
+    uint8_t  nhc;       /* high-complexity partners inside the profile (the reference's loop stops at the first outside) */
+    uint8_t  bad;       /* k > n in a binomial */
+    uint8_t  lr_walk;   /* the low-complexity walk met a run at the 127 cap */
+    uint16_t ok;        /* bit e*7: the low-complexity partner passes the count tests of error type e;
+                           bit e*7+1+n: high-complexity partner n does */
+    uint16_t pad[3];
+  } cpg_cbig;           /* 216 bytes */
+
 /* Scratch block of a lane group in global memory.  P = longest profile of the batch.  The
- * per-position arrays have P entries; the interval tables have capS/capE/capI entries: a few per
+ * per-position arrays have P entries; the tables have capS/capE/capI/capC entries: a few per
  * cent of P in the blocks of the main launch (a read that outgrows them is flagged
- * CPG_ST_RETRY), P+2 -- the worst case -- in the blocks of the retry launch. */
+ * CPG_ST_RETRY), P+2 -- the worst case -- in the blocks of the retry launch.
+ * mark[] is CLEAN (all zero) between reads: the replay logs every position it touches and zeroes
+ * exactly those when the read is done, so no per-position sweep is ever needed. */
 typedef struct
   { uint8_t    *mark;     /* [P+2+32] flag byte per profile position 0..plen */
     uint16_t   *slot;     /* [P+2]   probability slot of a position, valid where the flag byte says so */
-    double     *perr;     /* [capS*4] slot-major: [slot][etype][wtype]; sort keys in the last phase */
+    double     *perr;     /* [capS*4] slot-major: [slot][etype][wtype] */
     cpg_eintvl *eint;     /* [capE] */
     cpg_intvl  *intvl;    /* [capI] */
     int32_t     capS, capE, capI;
+    int32_t    *tlog;     /* [capT] positions whose flag byte is not zero (may hold duplicates) */
+    int32_t     capT, capC;
+    cpg_chdr   *hdr;      /* [capC] candidate headers (single-kernel path; the phase kernels read the batch's arrays) */
+    cpg_cbig   *big;      /* [capC] */
     cpg_intvl  *rint;     /* [MC]  reliable intervals (copy) */
     cpg_intvl  *wint;     /* [2*MC] DP working copies (forward, backward) */
     uint16_t   *bp;       /* [2*MC] back pointers: 4 x 3 bits */
@@ -182,6 +217,7 @@ typedef struct
     int32_t     MC;
     int32_t    *ord;      /* [capI] */
     uint8_t    *fixed;    /* [capI] */
+    uint32_t   *key;      /* [capI] sort keys of the unreliable pass */
     struct cpg_unmemo *memo;   /* [CPG_MEMO_CAP*8] first-sweep results of the unreliable-interval tasks */
   } cpg_scratch;
 

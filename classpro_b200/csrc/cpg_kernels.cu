@@ -1,13 +1,19 @@
 /*******************************************************************************************
  *  cpg_kernels.cu -- sm_100a kernels and the C ABI of libclasspro_b200.so.
  *
- *  Five launches per batch, all persistent (grid = a multiple of the SM count, warps / lane groups
+ *  Seven launches per batch, all persistent (grid = a multiple of the SM count, warps / lane groups
  *  pull reads from an atomic queue in processing order):
  *
  *   k_decode    one warp per read: FastK profile bytes -> uint16 counts + the wall-candidate bit
  *               map (cpg_decode.cuh).  Streaming: c + 2n + n/8 bytes per read.
- *   k_wall      one lane group per read: wall detection, reliable intervals (cpg_wall.cuh);
- *               leaves the read's interval tables in the batch's interval pool.
+ *   k_wall_a    one warp per read, one wall CANDIDATE per lane: the pure part of wall detection
+ *               (context, count thresholds, every probability pass A can ask for) -> a 16-byte
+ *               header per candidate, a 216-byte record for the one in ten that needs it.
+ *   k_wall_b    one lane group per read: the order-dependent replay of find_wall on those records
+ *               (probability cache, paired flags, E-intervals, cuts) -> the read's interval table
+ *               in the batch's interval pool.  Touches no count and no base.
+ *   k_wall_c    one interval per lane: end counts, corrected counts, Skellam plausibility; the
+ *               reliable intervals are appended to the read's table (cpg_wall.cuh).
  *   k_rel       reliable-interval DP, forward and backward (cpg_rel.cuh), on the pooled tables.
  *   k_unrel     unreliable intervals and the class string (cpg_unrel.cuh): r bytes per read out.
  *   k_classify  the three phases in one kernel, on 4 CTAs with worst-case scratch: the retry
@@ -55,63 +61,105 @@ struct BatchDev
     const int64_t *cls_off;
     int32_t       *status;
     const int32_t *order;
-    int32_t       *queue;        /* work counters: [0] decode, [1] classify/wall, [2] retry launch; [3] reads flagged
-                                    for retry; [4] reliable DP, [5] unreliable + emit */
-    struct ReadRec *rec;         /* per read: where k_wall left its interval tables */
+    int32_t       *queue;        /* work counters: [0] decode, [1] classify/wall_a, [2] retry launch; [3] reads flagged
+                                    for retry; [4] reliable DP, [5] unreliable + emit, [6] wall_b, [7] wall_c */
+    struct ReadRec *rec;         /* per read: where the wall kernels left its candidate records and interval tables */
     cpg_intvl     *pool;         /* interval pool of the batch: intvl[N] then rint[M] of each read */
     unsigned long long *pool_cursor;
     int64_t        pool_cap;     /* entries */
+    cpg_chdr      *hdr;          /* candidate headers of the batch, a read's in position order */
+    cpg_cbig      *big;          /* big candidate records */
+    unsigned long long *hdr_cursor, *big_cursor;
+    int64_t        hdr_cap, big_cap;
     unsigned long long *phase_cycles;   /* [4] summed per-warp cycles of the three phases (+ idle at the CTA barriers) */
   };
 
-struct ReadRec { int64_t off; int32_t N, M; };
+struct ReadRec { int64_t off, hoff; int32_t N, M, ncand, mcap; };
 
+/* Each kind of kernel has its own region of the scratch arena, laid out for what it uses:
+   SM_WALL  k_wall_b: flag bytes, slot indices, probability slots, E-intervals, touch log
+   SM_REL   k_rel:    DP working copies, back pointers, path strings
+   SM_UNREL k_unrel:  order, fixed flags, sort keys, task memo
+   SM_FULL  k_classify (retry launch): all of it, worst-case capacities */
+enum { SM_WALL = 0, SM_REL = 1, SM_UNREL = 2, SM_FULL = 3 };
+#define N_OFF 18
 struct ScratchDev
   { uint8_t *base;
     size_t   stride;             /* bytes per lane group */
+    int32_t  mode;
     int32_t  P;                  /* longest profile the layout is sized for */
     int32_t  MC;                 /* reliable-interval capacity */
     int32_t  capS, capE, capI;   /* probability slots, E-intervals, intervals (cpg_common.h: cpg_scratch) */
+    int32_t  capT, capC;         /* touch log, candidate records (SM_FULL only) */
   };
 
 static inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x+a-1)/a*a; }
 
 /* layout of one lane group's scratch */
-__host__ __device__ static inline size_t scratch_layout(const ScratchDev &SC, size_t off[14])
-{ const int P = SC.P, MC = SC.MC;
+__host__ __device__ static inline size_t scratch_layout(const ScratchDev &SC, size_t off[N_OFF])
+{ const int P = SC.P, MC = SC.MC, md = SC.mode;
+  const bool w = (md == SM_WALL || md == SM_FULL), r = (md == SM_REL || md == SM_FULL), u = (md == SM_UNREL || md == SM_FULL);
+  const bool f = (md == SM_FULL);
   size_t o = 0;
-  off[0]  = o; o = align_up(o+(size_t)(P+2+32),16);                      /* mark  */
-  off[13] = o; o = align_up(o+sizeof(uint16_t)*(size_t)(P+2),16);        /* slot  */
-  off[1]  = o; o = align_up(o+sizeof(double)*4*(size_t)SC.capS,16);      /* perr  */
-  off[2]  = o; o = align_up(o+sizeof(cpg_eintvl)*(size_t)SC.capE,16);    /* eint  */
-  off[3]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)SC.capI,16);     /* intvl */
-  off[4]  = o; o = align_up(o+sizeof(cpg_intvl)*(size_t)MC,16);          /* rint  */
-  off[5]  = o; o = align_up(o+sizeof(cpg_intvl)*2*(size_t)MC,16);        /* wint (fw, bw) */
-  off[6]  = o; o = align_up(o+sizeof(uint16_t)*2*(size_t)MC,16);         /* bp   (fw, bw) */
-  off[7]  = o; o = align_up(o+(size_t)MC,16);                            /* asg_f */
-  off[8]  = o; o = align_up(o+(size_t)MC,16);                            /* asg_b */
-  off[9]  = o; o = align_up(o+2*(size_t)MC,16);                          /* rpos (fw, bw) */
-  off[10] = o; o = align_up(o+sizeof(int32_t)*(size_t)SC.capI,16);       /* ord   */
-  off[11] = o; o = align_up(o+(size_t)SC.capI,16);                       /* fixed */
-  off[12] = o; o = align_up(o+sizeof(cpg_unmemo)*8*(size_t)CPG_MEMO_CAP,16);  /* memo */
+  off[0]  = o; o = align_up(o+(w ? (size_t)(P+2+32) : 0),16);                      /* mark  */
+  off[13] = o; o = align_up(o+(w ? sizeof(uint16_t)*(size_t)(P+2) : 0),16);        /* slot  */
+  off[1]  = o; o = align_up(o+(w ? sizeof(double)*4*(size_t)SC.capS : 0),16);      /* perr  */
+  off[2]  = o; o = align_up(o+(w ? sizeof(cpg_eintvl)*(size_t)SC.capE : 0),16);    /* eint  */
+  off[14] = o; o = align_up(o+(w ? sizeof(int32_t)*(size_t)SC.capT : 0),16);       /* tlog  */
+  off[3]  = o; o = align_up(o+(f ? sizeof(cpg_intvl)*(size_t)SC.capI : 0),16);     /* intvl */
+  off[4]  = o; o = align_up(o+(f ? sizeof(cpg_intvl)*(size_t)MC : 0),16);          /* rint  */
+  off[15] = o; o = align_up(o+(f ? sizeof(cpg_chdr)*(size_t)SC.capC : 0),16);      /* hdr   */
+  off[16] = o; o = align_up(o+(f ? sizeof(cpg_cbig)*(size_t)SC.capC : 0),16);      /* big   */
+  off[5]  = o; o = align_up(o+(r ? sizeof(cpg_intvl)*2*(size_t)MC : 0),16);        /* wint (fw, bw) */
+  off[6]  = o; o = align_up(o+(r ? sizeof(uint16_t)*2*(size_t)MC : 0),16);         /* bp   (fw, bw) */
+  off[7]  = o; o = align_up(o+(r ? (size_t)MC : 0),16);                            /* asg_f */
+  off[8]  = o; o = align_up(o+(r ? (size_t)MC : 0),16);                            /* asg_b */
+  off[9]  = o; o = align_up(o+(r ? 2*(size_t)MC : 0),16);                          /* rpos (fw, bw) */
+  off[10] = o; o = align_up(o+(u ? sizeof(int32_t)*(size_t)SC.capI : 0),16);       /* ord   */
+  off[11] = o; o = align_up(o+(u ? (size_t)SC.capI : 0),16);                       /* fixed */
+  off[17] = o; o = align_up(o+(u ? sizeof(uint32_t)*(size_t)SC.capI : 0),16);      /* key   */
+  off[12] = o; o = align_up(o+(u ? sizeof(cpg_unmemo)*8*(size_t)CPG_MEMO_CAP : 0),16);  /* memo */
   return align_up(o,256);
 }
 
-/* Capacities of the interval tables.  Worst case (full = 1): every position its own interval.
-   Main launch: one interval per 16 positions, one probability slot per 8 -- several times what
-   HiFi profiles need (about one interval per 90 positions); a read that needs more is flagged and
-   classified again by the retry launch. */
-static void scratch_caps(ScratchDev *SC, int P, int K, int full)
-{ SC->P = P; SC->MC = P/K+8;
-  if (full) { SC->capS = SC->capE = SC->capI = P+2; }
+/* Capacities of the tables.  Worst case (SM_FULL): every position its own interval.  Main
+   launches: one interval per 16 positions (HiFi profiles need about one per 70), one probability
+   slot per 32 (they need one per 500); a read that needs more is flagged and classified again by
+   the retry launch. */
+static void scratch_caps(ScratchDev *SC, int P, int K, int mode)
+{ SC->P = P; SC->MC = P/K+8; SC->mode = mode;
+  if (mode == SM_FULL) { SC->capS = SC->capE = SC->capI = SC->capC = P+2; SC->capT = 3*(P+2); }
   else
     { int div = 16;
       { const char *f = getenv("CPG_SCRATCH_DIV"); if (f && atoi(f) > 0) div = atoi(f); }   /* test knob: force retries */
-      SC->capI = P/div+64; SC->capE = P/div+64; SC->capS = 2*(P/div)+64;
+      SC->capI = P/div+64; SC->capE = P/div+64; SC->capS = P/(2*div)+64; SC->capT = P/div+192; SC->capC = 0;
       if (SC->capI > P+2) SC->capI = P+2;
       if (SC->capE > P+2) SC->capE = P+2;
       if (SC->capS > P+2) SC->capS = P+2;
     }
+}
+
+__device__ __forceinline__ void bind_scratch(ReadCtx &R, uint8_t *sb, const size_t off[N_OFF], const ScratchDev &SC)
+{ R.S.mark  = sb+off[0];
+  R.S.slot  = reinterpret_cast<uint16_t *>(sb+off[13]);
+  R.S.perr  = reinterpret_cast<double *>(sb+off[1]);
+  R.S.eint  = reinterpret_cast<cpg_eintvl *>(sb+off[2]);
+  R.S.tlog  = reinterpret_cast<int32_t *>(sb+off[14]);
+  R.S.intvl = reinterpret_cast<cpg_intvl *>(sb+off[3]);
+  R.S.rint  = reinterpret_cast<cpg_intvl *>(sb+off[4]);
+  R.S.hdr   = reinterpret_cast<cpg_chdr *>(sb+off[15]);
+  R.S.big   = reinterpret_cast<cpg_cbig *>(sb+off[16]);
+  R.S.wint  = reinterpret_cast<cpg_intvl *>(sb+off[5]);
+  R.S.bp    = reinterpret_cast<uint16_t *>(sb+off[6]);
+  R.S.asg_f = sb+off[7];
+  R.S.asg_b = sb+off[8];
+  R.S.rpos  = sb+off[9];
+  R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
+  R.S.fixed = sb+off[11];
+  R.S.key   = reinterpret_cast<uint32_t *>(sb+off[17]);
+  R.S.MC = SC.MC; R.S.capS = SC.capS; R.S.capE = SC.capE; R.S.capI = SC.capI; R.S.capT = SC.capT; R.S.capC = SC.capC;
+  R.S.memo = reinterpret_cast<cpg_unmemo *>(sb+off[12]);
+  R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0;
 }
 
 __device__ __forceinline__ int next_read(int32_t *counter, int lane)
@@ -203,7 +251,7 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
 
   const size_t gg = (size_t)blockIdx.x*CLASSIFY_GROUPS+gib;
   uint8_t *sb = SC.base+gg*SC.stride;
-  size_t off[14];
+  size_t off[N_OFF];
   scratch_layout(SC,off);
 
   /* One read per lane group, CLASSIFY_GROUPS reads per CTA at a time, taken from the queue in
@@ -236,22 +284,8 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
       R.prof = B.cnt+(active ? B.cnt_off[r] : 0); R.plen = plen; R.rlen = rlen;
       R.seq.p = B.seq+(active ? B.seq_off[r] : 0); R.seq.bits = B.seq_bits;
       R.nslots = 0; R.N = 0; R.M = 0;
-      R.S.mark  = sb+off[0];
-      R.S.slot  = reinterpret_cast<uint16_t *>(sb+off[13]);
       R.cand    = B.cand+(active ? (B.cnt_off[r] >> 5) : 0);
-      R.S.perr  = reinterpret_cast<double *>(sb+off[1]);
-      R.S.eint  = reinterpret_cast<cpg_eintvl *>(sb+off[2]);
-      R.S.intvl = reinterpret_cast<cpg_intvl *>(sb+off[3]);
-      R.S.rint  = reinterpret_cast<cpg_intvl *>(sb+off[4]);
-      R.S.wint  = reinterpret_cast<cpg_intvl *>(sb+off[5]);
-      R.S.bp    = reinterpret_cast<uint16_t *>(sb+off[6]);
-      R.S.asg_f = sb+off[7];
-      R.S.asg_b = sb+off[8];
-      R.S.rpos  = sb+off[9];
-      R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
-      R.S.fixed = sb+off[11];
-      R.S.MC = SC.MC; R.S.capS = SC.capS; R.S.capE = SC.capE; R.S.capI = SC.capI;
-      R.S.memo = reinterpret_cast<cpg_unmemo *>(sb+off[12]);
+      bind_scratch(R,sb,off,SC);
 
       long long t0 = clock64();
       if (active) classify_phase1(R,W);
@@ -281,22 +315,21 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
 }
 
 /* ------------------------------------------------------------------------------------------
- *  The main path: one kernel per phase.  The per-read code is large (~150 KB of SASS) and the
- *  three phases share almost none of it, so each phase as its own persistent kernel keeps the
- *  instruction working set of an SM small without the CTA-wide barriers k_classify needs for the
- *  same effect, lets every lane group pull its next read on its own, and gives each phase its own
- *  register allocation.  Between the kernels a read lives in HBM as its interval table: k_wall
- *  appends intvl[N] + rint[M] to the batch's pool (one atomicAdd per read) and records the place.
- *  k_classify above stays as the retry path (reads that outgrow the compact scratch or the pool).
+ *  The main path: one kernel per phase.  The per-read code is large and branchy and the phases
+ *  share almost none of it, so each phase as its own persistent kernel keeps the instruction
+ *  working set of an SM small without the CTA-wide barriers k_classify needs for the same effect,
+ *  lets every lane group pull its next read on its own, and gives each phase its own register
+ *  allocation and its own lane mapping (candidate / read / interval per lane).  Between the
+ *  kernels a read lives in HBM as its candidate records, then as its interval table in the
+ *  batch's pool (one atomicAdd per read).  k_classify above stays as the retry path (reads that
+ *  outgrow the compact scratch, the record arrays or the pool).
  * ------------------------------------------------------------------------------------------ */
-/* Lanes per read of each phase kernel (powers of two <= 32).  Measured on the 100 Mb workload
-   (profiles/r01_history.md): k_wall 235 / 198 / 140 / 102 / 96 / 155 ms with 32 / 16 / 8 / 4 / 2 / 1
-   lanes (it waits on DRAM: counts, flags and tables of the reads in flight are far larger than
-   L2, so more reads in flight win until the lane-parallel tasks serialise; 2 lanes cost the other
-   phases and small batches more than they gain); k_rel 79 / 94 ms with 8 / 16; k_unrel 78 ms with
-   4, 8 or 16. */
-#ifndef WALL_GROUP
-#define WALL_GROUP  4
+/* Lanes per read of each phase kernel (powers of two <= 32); profiles/README.md has the sweeps. */
+#ifndef WALLB_GROUP
+#define WALLB_GROUP 4
+#endif
+#ifndef WALLC_GROUP
+#define WALLC_GROUP 8
 #endif
 #ifndef REL_GROUP
 #define REL_GROUP   CPG_GROUP
@@ -312,9 +345,16 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
 #ifndef PHASE_MIN_BLOCKS
 #define PHASE_MIN_BLOCKS CLASSIFY_MIN_BLOCKS
 #endif
+#ifndef WALLA_THREADS
+#define WALLA_THREADS    256
+#endif
+#ifndef WALLA_MIN_BLOCKS
+#define WALLA_MIN_BLOCKS 2
+#endif
+#define WALLA_QCAP (1024+32)     /* candidate positions queued per warp: one 1024-position chunk plus a remainder */
 
 template<int G, bool CTHRES> struct PhaseShared
-  { uint8_t     cthres[CTHRES ? CPG_LROWS*256*4 : 16];        /* the count-threshold table, for k_wall */
+  { uint8_t     cthres[CTHRES ? CPG_LROWS*256*4 : 16];        /* the count-threshold table */
     cpg_dmodel  model;
     cpg_wshared ws[PHASE_THREADS/G];
   };
@@ -322,6 +362,11 @@ template<int G> struct RelPhaseShared
   { cpg_dmodel  model;
     cpg_wshared ws[PHASE_THREADS/G];
     RelShared   rel[PHASE_THREADS/G][2];
+  };
+struct WallAShared
+  { uint8_t     cthres[CPG_LROWS*256*4];
+    cpg_dmodel  model;
+    int32_t     q[WALLA_THREADS/32][WALLA_QCAP];
   };
 
 struct GroupId { int lane, gib, glane, gbase, gsize; unsigned gmask; };
@@ -338,85 +383,192 @@ __device__ __forceinline__ int group_next(int32_t *counter, const GroupId &g)
   if (g.glane == 0) q = atomicAdd(counter,1);
   return __shfl_sync(g.gmask,q,g.gbase);
 }
-__device__ __forceinline__ void bind_scratch(ReadCtx &R, uint8_t *sb, const size_t off[14], const ScratchDev &SC)
-{ R.S.mark  = sb+off[0];
-  R.S.slot  = reinterpret_cast<uint16_t *>(sb+off[13]);
-  R.S.perr  = reinterpret_cast<double *>(sb+off[1]);
-  R.S.eint  = reinterpret_cast<cpg_eintvl *>(sb+off[2]);
-  R.S.intvl = reinterpret_cast<cpg_intvl *>(sb+off[3]);
-  R.S.rint  = reinterpret_cast<cpg_intvl *>(sb+off[4]);
-  R.S.wint  = reinterpret_cast<cpg_intvl *>(sb+off[5]);
-  R.S.bp    = reinterpret_cast<uint16_t *>(sb+off[6]);
-  R.S.asg_f = sb+off[7];
-  R.S.asg_b = sb+off[8];
-  R.S.rpos  = sb+off[9];
-  R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
-  R.S.fixed = sb+off[11];
-  R.S.MC = SC.MC; R.S.capS = SC.capS; R.S.capE = SC.capE; R.S.capI = SC.capI;
-  R.S.memo = reinterpret_cast<cpg_unmemo *>(sb+off[12]);
-}
 __device__ __forceinline__ void init_wctx(WCtx &W, const GroupId &g, const cpg_dmodel *M, const uint8_t *cthres, cpg_wshared *ws, int status)
 { W.lane = g.lane; W.M = M; W.cthres = cthres; W.ws = ws; W.status = status;
   W.glane = g.glane; W.gsize = g.gsize; W.gbase = g.gbase; W.gmask = g.gmask;
 }
 
-/* phase 1: wall detection + reliable intervals (cpg_wall.cuh) */
-__global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
-k_wall(BatchDev B, cpg_dmodel M, ScratchDev SC)
-{ constexpr int G = WALL_GROUP;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  PhaseShared<G,true> &sh = *reinterpret_cast<PhaseShared<G,true> *>(smem_raw);
-  const GroupId g = group_id<G>();
+/* phase 1a: the pure step of wall detection, one wall candidate per lane (cpg_wall.cuh, wa_).
+   A warp takes a read, streams its candidate bit map (1024 positions per step), queues the candidate
+   positions in shared memory and works them off 32 at a time, so that the lanes stay full although
+   only one position in ~80 is a candidate.  Reads: 2 counts, the bases around the k-mer's end, the
+   threshold table (shared memory) per candidate; writes: a header per candidate, in position order. */
+__global__ void __launch_bounds__(WALLA_THREADS,WALLA_MIN_BLOCKS)
+k_wall_a(BatchDev B, cpg_dmodel M)
+{ extern __shared__ __align__(16) unsigned char smem_raw[];
+  WallAShared &sh = *reinterpret_cast<WallAShared *>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < CPG_LROWS*256; i += blockDim.x)
     reinterpret_cast<uint32_t *>(sh.cthres)[i] = reinterpret_cast<const uint32_t *>(M.cthres)[i];
-  const uint8_t *cthres = sh.cthres;
   if (threadIdx.x == 0) sh.model = M;
   __syncthreads();
   cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
   __syncthreads();
-
-  uint8_t *sb = SC.base+((size_t)blockIdx.x*(PHASE_THREADS/G)+g.gib)*SC.stride;
-  size_t off[14];
-  scratch_layout(SC,off);
+  int32_t *pq = sh.q[wib];
+  WCtx W;
+  W.lane = lane; W.M = &sh.model; W.cthres = sh.cthres; W.ws = 0; W.status = 0;
+  W.glane = 0; W.gsize = 1; W.gbase = lane; W.gmask = 1u << lane;
+  const unsigned lt = (1u << lane)-1u;
   for (;;)
-    { const int q = group_next(B.queue+1,g);
+    { const int q = next_read(B.queue+1,lane);
       if (q >= B.n_reads) break;
       const int r = B.order[q];
-      if (B.status[r] != CPG_ST_OK) continue;                 /* undecodable profile: left to the host */
+      ReadRec rc; rc.off = 0; rc.hoff = 0; rc.N = 0; rc.M = 0; rc.ncand = 0; rc.mcap = 0;
+      const int rlen = B.rlen[r], plen = rlen-M.K+1;
+      if (B.status[r] != CPG_ST_OK) { if (lane == 0) B.rec[r] = rc; continue; }     /* undecodable profile: left to the host */
+      const uint16_t *prof = B.cnt+B.cnt_off[r];
+      const uint32_t *cand = B.cand+(B.cnt_off[r] >> 5);
+      cpg_seq seq; seq.p = B.seq+B.seq_off[r]; seq.bits = B.seq_bits;
+      const int nwords = (plen+31) >> 5;
+      const unsigned tail = (plen & 31) ? ((1u << (plen & 31))-1u) : 0xffffffffu;
+      int ncand = 0;
+      for (int w = lane; w < nwords; w += 32) ncand += __popc(cand[w] & (w == nwords-1 ? tail : 0xffffffffu));
+      ncand = __reduce_add_sync(0xffffffffu,ncand);
+      long long hoff = 0;
+      if (lane == 0) hoff = (long long)atomicAdd(B.hdr_cursor,(unsigned long long)ncand);
+      hoff = __shfl_sync(0xffffffffu,hoff,0);
+      if (hoff+ncand > B.hdr_cap)
+        { if (lane == 0) { B.rec[r] = rc; B.status[r] = CPG_ST_RETRY; atomicAdd(B.queue+3,1); }
+          continue;
+        }
+      cpg_chdr *hdr = B.hdr+hoff;
+      int npend = 0, done = 0, overflow = 0;
+      for (int wb = 0; wb < nwords || npend > 0; wb += 32)
+        { int total = 0;
+          if (wb < nwords)
+            { const int w = wb+lane;
+              unsigned cw = (w < nwords) ? (cand[w] & (w == nwords-1 ? tail : 0xffffffffu)) : 0u;
+              int incl = __popc(cw);
+              const int mine = incl;
+              #pragma unroll
+              for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu,incl,d); if (lane >= d) incl += t; }
+              total = __shfl_sync(0xffffffffu,incl,31);
+              int k = npend+incl-mine;
+              while (cw) { const int bit = __ffs((int)cw)-1; cw &= cw-1; pq[k++] = (w << 5)+bit; }
+              __syncwarp();
+              npend += total;
+            }
+          const int flush = (wb+32 >= nwords);          /* last chunk: work off the remainder too */
+          int head = 0;
+          while (npend-head >= 32 || (flush && npend-head > 0))
+            { const int nact = min(32,npend-head);
+              const int active = lane < nact;
+              const int pos = active ? pq[head+lane] : 0;
+              unsigned info = 0; WaCand C;
+              if (active) info = wa_stage0(prof,seq,rlen,W,pos,C);
+              int need = active && (info & (CH_REACH_S|CH_REACH_O));
+              const unsigned m = __ballot_sync(0xffffffffu,need);
+              unsigned long long bb = 0;
+              if (lane == 0 && m) bb = atomicAdd(B.big_cursor,(unsigned long long)__popc(m));
+              bb = __shfl_sync(0xffffffffu,bb,0);
+              const unsigned long long idx = bb+(unsigned)__popc(m & lt);
+              if (need && (long long)idx >= B.big_cap) { overflow = 1; need = 0; }
+              if (active)
+                { cpg_chdr H; H.pos = pos; H.info = info; H.big = (uint32_t)idx; H.pad = 0;
+                  *reinterpret_cast<uint4 *>(hdr+done+lane) = *reinterpret_cast<const uint4 *>(&H);
+                }
+              if (need) wa_tasks(prof,plen,seq,rlen,W,pos,C,info,B.big+idx);
+              done += nact; head += nact;
+            }
+          /* bring the remainder to the front of the queue */
+          const int left = npend-head;
+          if (head > 0 && left > 0)
+            { const int v = (lane < left) ? pq[head+lane] : 0;
+              __syncwarp();
+              if (lane < left) pq[lane] = v;
+            }
+          __syncwarp();
+          npend = left;
+          if (flush) break;
+        }
+      overflow = __any_sync(0xffffffffu,overflow);
+      if (lane == 0)
+        { rc.hoff = hoff; rc.ncand = ncand;
+          B.rec[r] = rc;
+          if (overflow) { B.status[r] = CPG_ST_RETRY; atomicAdd(B.queue+3,1); }
+        }
+    }
+}
+
+/* phase 1b: the order-dependent replay of find_wall for one read per lane group (cpg_wall.cuh, wb_):
+   candidate records in, interval table (without counts) out, straight into the pool. */
+__global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
+k_wall_b(BatchDev B, cpg_dmodel M, ScratchDev SC)
+{ constexpr int G = WALLB_GROUP;
+  __shared__ cpg_dmodel s_model;
+  const GroupId g = group_id<G>();
+  if (threadIdx.x == 0) s_model = M;
+  __syncthreads();
+  uint8_t *sb = SC.base+((size_t)blockIdx.x*(PHASE_THREADS/G)+g.gib)*SC.stride;
+  size_t off[N_OFF];
+  scratch_layout(SC,off);
+  for (;;)
+    { const int q = group_next(B.queue+6,g);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      if (B.status[r] != CPG_ST_OK) continue;                 /* undecodable profile, or flagged for the retry launch */
       const int rlen = B.rlen[r], plen = rlen-M.K+1;
       if (plen > SC.P) { if (g.glane == 0) B.status[r] = CPG_ST_BAD_PROFILE; continue; }
-      WCtx W; init_wctx(W,g,&sh.model,cthres,&sh.ws[g.gib],0);
+      ReadRec rc = B.rec[r];
+      WCtx W; init_wctx(W,g,&s_model,M.cthres,0,0);
       ReadCtx R;
-      R.prof = B.cnt+B.cnt_off[r]; R.plen = plen; R.rlen = rlen;
-      R.seq.p = B.seq+B.seq_off[r]; R.seq.bits = B.seq_bits;
-      R.cand = B.cand+(B.cnt_off[r] >> 5);
+      R.prof = 0; R.plen = plen; R.rlen = rlen; R.seq.p = 0; R.seq.bits = B.seq_bits; R.cand = 0;
       R.nslots = 0; R.N = 0; R.M = 0;
       bind_scratch(R,sb,off,SC);
-      find_walls_and_reliable(R,W);
-      int st = __reduce_or_sync(g.gmask,W.status);
-      const int N = R.N, Mrel = R.M;
+      R.hdr = B.hdr+rc.hoff; R.big = B.big; R.ncand = rc.ncand;
+      const int NS = wb_walls(R,W);
+      int N = 0, mcap = 0;
       long long at = 0;
-      if (!(st & CPG_ST_ABORT))
-        { /* a place in the pool for intvl[N] and rint[M] */
-          __syncwarp(g.gmask);
-          if (g.glane == 0) reinterpret_cast<long long *>(W.ws->term)[0] = (long long)atomicAdd(B.pool_cursor,(unsigned long long)(N+Mrel));
-          __syncwarp(g.gmask);
-          at = reinterpret_cast<long long *>(W.ws->term)[0];
-          __syncwarp(g.gmask);
-          if (at+N+Mrel > B.pool_cap) st |= CPG_ST_RETRY;
+      if (!(W.status & CPG_ST_ABORT))
+        { N = wb_cuts(R,W,NS,0,0,&mcap);
+          /* the per-interval arrays of k_unrel's scratch blocks hold capI entries */
+          if (N > SC.capI) W.status |= CPG_ST_RETRY;
           else
-            { /* cpg_intvl is 48 bytes = three 16-byte words */
-              uint4 *dst = reinterpret_cast<uint4 *>(B.pool+at);
-              const uint4 *s1 = reinterpret_cast<const uint4 *>(R.S.intvl), *s2 = reinterpret_cast<const uint4 *>(R.S.rint);
-              for (int i = g.glane; i < 3*N; i += G) dst[i] = s1[i];
-              for (int i = g.glane; i < 3*Mrel; i += G) dst[3*N+i] = s2[i];
+            { /* a place in the pool for intvl[N] and the (at most mcap) reliable ones behind them */
+              if (g.glane == 0) at = (long long)atomicAdd(B.pool_cursor,(unsigned long long)(N+mcap));
+              at = __shfl_sync(g.gmask,at,g.gbase);
+              if (at+N+mcap > B.pool_cap) W.status |= CPG_ST_RETRY;
+              else wb_cuts(R,W,NS,B.pool+at,N,0);
             }
         }
+      wb_clean(R,W);
+      const int st = __reduce_or_sync(g.gmask,W.status);
       if (g.glane == 0)
-        { ReadRec rc; rc.off = at; rc.N = N; rc.M = Mrel;
+        { rc.off = at; rc.N = (st & CPG_ST_ABORT) ? 0 : N; rc.M = 0; rc.mcap = mcap;
           B.rec[r] = rc;
-          B.status[r] = st;
+          if (st) B.status[r] = st;
           if (st & CPG_ST_RETRY) atomicAdd(B.queue+3,1);
+        }
+      __syncwarp(g.gmask);
+    }
+}
+
+/* phase 1c: one interval per lane: end counts, corrected counts, plausibility (cpg_wall.cuh, wc_);
+   the reliable intervals of a read go behind its table, in order. */
+__global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
+k_wall_c(BatchDev B, cpg_dmodel M)
+{ constexpr int G = WALLC_GROUP;
+  __shared__ cpg_dmodel s_model;
+  const GroupId g = group_id<G>();
+  if (threadIdx.x == 0) s_model = M;
+  __syncthreads();
+  for (;;)
+    { const int q = group_next(B.queue+7,g);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      const int st0 = B.status[r];
+      if (st0 & (CPG_ST_BAD_PROFILE|CPG_ST_ABORT)) continue;
+      ReadRec rc = B.rec[r];
+      if (rc.N == 0) continue;
+      const int rlen = B.rlen[r], plen = rlen-M.K+1;
+      WCtx W; init_wctx(W,g,&s_model,M.cthres,0,0);
+      cpg_seq seq; seq.p = B.seq+B.seq_off[r]; seq.bits = B.seq_bits;
+      cpg_intvl *v = B.pool+rc.off;
+      const int Mrel = wc_read(B.cnt+B.cnt_off[r],plen,seq,rlen,W,v,rc.N,v+rc.N);
+      const int st = __reduce_or_sync(g.gmask,W.status);
+      if (g.glane == 0)
+        { B.rec[r].M = Mrel;
+          if (st) B.status[r] = st0 | st;
         }
       __syncwarp(g.gmask);
     }
@@ -434,7 +586,7 @@ k_rel(BatchDev B, cpg_dmodel M, ScratchDev SC)
   cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
   __syncthreads();
   uint8_t *sb = SC.base+((size_t)blockIdx.x*(PHASE_THREADS/G)+g.gib)*SC.stride;
-  size_t off[14];
+  size_t off[N_OFF];
   scratch_layout(SC,off);
   for (;;)
     { const int q = group_next(B.queue+4,g);
@@ -471,7 +623,7 @@ k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
   cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
   __syncthreads();
   uint8_t *sb = SC.base+((size_t)blockIdx.x*(PHASE_THREADS/G)+g.gib)*SC.stride;
-  size_t off[14];
+  size_t off[N_OFF];
   scratch_layout(SC,off);
   for (;;)
     { const int q = group_next(B.queue+5,g);
@@ -524,7 +676,7 @@ struct DevBuf { void *p; size_t cap; };
 
 struct Slot
   { cudaStream_t stream;
-    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue, rec, pool;
+    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue, rec, pool, hdr, big;
     /* small host-side (pinned) staging for arrays the library computes itself */
     int64_t *h_cnt_off; int32_t *h_order; size_t h_cap;
     int32_t *h_status; size_t h_status_cap;
@@ -541,13 +693,16 @@ struct cpg_ctx
     cpg_dmodel dmodel;
     void      *d_cthres, *d_logfact;
     Slot       slot[2];
-    DevBuf     scratch, scratch_big; ScratchDev SC, SCbig;
+    DevBuf     scratch, scratch_big; ScratchDev SC, SCbig;      /* SC: k_classify as the main launch (CPG_FUSED) */
+    ScratchDev SCw, SCr, SCu;                                   /* regions of `scratch` for k_wall_b, k_rel, k_unrel */
+    int        scratch_P;
     int        retry_blocks;
     int        fused;                 /* CPG_FUSED=1: the single-kernel path (k_classify) for every read */
-    int        wall_blocks, rel_blocks, unrel_blocks;
-    size_t     wall_smem, rel_smem, unrel_smem;
-    cudaEvent_t evp[3];               /* between the phase kernels */
+    int        walla_blocks, wallb_blocks, wallc_blocks, rel_blocks, unrel_blocks;
+    size_t     walla_smem, rel_smem, unrel_smem;
+    cudaEvent_t evp[5];               /* between the phase kernels */
     uint64_t   phase_ns[4];           /* wall, reliable DP, unreliable + emit, retry launch: last timed run */
+    uint64_t   wall_ns[3];            /* k_wall_a, k_wall_b, k_wall_c of that run */
     int        n_sm, decode_blocks, classify_blocks;
     size_t     classify_smem;
     cudaEvent_t ev[3];
@@ -609,7 +764,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   for (int s = 0; s < 2; s++)
     { Slot *S = &ctx->slot[s];
       DevBuf *bufs[] = { &S->seq,&S->seq_off,&S->rlen,&S->prof,&S->prof_off,&S->cnt,&S->cnt_off,&S->cand,&S->plen,
-                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue,&S->rec,&S->pool };
+                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue,&S->rec,&S->pool,&S->hdr,&S->big };
       for (unsigned i = 0; i < sizeof(bufs)/sizeof(bufs[0]); i++) if (bufs[i]->p) cudaFree(bufs[i]->p);
       if (S->h_cnt_off) cudaFreeHost(S->h_cnt_off);
       if (S->h_order) cudaFreeHost(S->h_order);
@@ -622,7 +777,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   if (ctx->d_cthres) cudaFree(ctx->d_cthres);
   if (ctx->d_logfact) cudaFree(ctx->d_logfact);
   for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  for (int i = 0; i < 3; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
+  for (int i = 0; i < 5; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
   free(ctx);
 }
 
@@ -668,16 +823,20 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
       CU_C(cudaEventCreateWithFlags(&ctx->slot[s].kdone,cudaEventDisableTiming));
     }
   for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->ev[i]));
-  for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->evp[i]));
+  for (int i = 0; i < 5; i++) CU_C(cudaEventCreate(&ctx->evp[i]));
   { const char *f = getenv("CPG_FUSED"); ctx->fused = (f && atoi(f) > 0); }
-  ctx->wall_smem = sizeof(PhaseShared<WALL_GROUP,true>); ctx->rel_smem = sizeof(RelPhaseShared<REL_GROUP>);
+  ctx->walla_smem = sizeof(WallAShared); ctx->rel_smem = sizeof(RelPhaseShared<REL_GROUP>);
   ctx->unrel_smem = sizeof(PhaseShared<UNREL_GROUP,false>);
-  CU_C(cudaFuncSetAttribute(k_wall,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->wall_smem));
+  CU_C(cudaFuncSetAttribute(k_wall_a,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->walla_smem));
   CU_C(cudaFuncSetAttribute(k_unrel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->unrel_smem));
   CU_C(cudaFuncSetAttribute(k_rel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->rel_smem));
   { int o = 0;
-    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_wall,PHASE_THREADS,ctx->wall_smem));
-    ctx->wall_blocks = ctx->n_sm*(o < 1 ? 1 : o);
+    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_wall_a,WALLA_THREADS,ctx->walla_smem));
+    ctx->walla_blocks = ctx->n_sm*(o < 1 ? 1 : o);
+    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_wall_b,PHASE_THREADS,0));
+    ctx->wallb_blocks = ctx->n_sm*(o < 1 ? 1 : o);
+    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_wall_c,PHASE_THREADS,0));
+    ctx->wallc_blocks = ctx->n_sm*(o < 1 ? 1 : o);
     CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_rel,PHASE_THREADS,ctx->rel_smem));
     ctx->rel_blocks = ctx->n_sm*(o < 1 ? 1 : o);
     CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_unrel,PHASE_THREADS,ctx->unrel_smem));
@@ -702,31 +861,42 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
 /* scratch arenas: compact blocks for every resident lane group of the main launch, full-size
    blocks for the few groups of the retry launch */
 static int ensure_scratch(cpg_ctx *ctx, int P)
-{ if (ctx->scratch.p && P <= ctx->SC.P) return CPG_OK;
-  size_t off[14];
-  ScratchDev SC = ctx->SC, SB = ctx->SCbig;
-  scratch_caps(&SC,P,ctx->model.kmer,0);
-  scratch_caps(&SB,P,ctx->model.kmer,1);
-  SC.stride = scratch_layout(SC,off);
-  SB.stride = scratch_layout(SB,off);
+{ if (ctx->scratch.p && P <= ctx->scratch_P) return CPG_OK;
+  size_t off[N_OFF];
+  const int K = ctx->model.kmer;
+  ScratchDev SC = ctx->SC, SB = ctx->SCbig, Sw = ctx->SCw, Sr = ctx->SCr, Su = ctx->SCu;
+  scratch_caps(&SB,P,K,SM_FULL); SB.stride = scratch_layout(SB,off);
+  size_t total = 0, o_r = 0, o_u = 0;
+  if (ctx->fused)
+    { /* the single-kernel path as the main launch: compact tables, every array */
+      scratch_caps(&SC,P,K,SM_WALL); SC.mode = SM_FULL; SC.capC = SC.capI; SC.stride = scratch_layout(SC,off);
+      total = SC.stride*(size_t)ctx->classify_blocks*CLASSIFY_GROUPS;
+    }
+  else
+    { scratch_caps(&Sw,P,K,SM_WALL);  Sw.stride = scratch_layout(Sw,off);
+      scratch_caps(&Sr,P,K,SM_REL);   Sr.stride = scratch_layout(Sr,off);
+      scratch_caps(&Su,P,K,SM_UNREL); Su.stride = scratch_layout(Su,off);
+      o_r = Sw.stride*(size_t)ctx->wallb_blocks*(PHASE_THREADS/WALLB_GROUP);
+      o_u = o_r+Sr.stride*(size_t)ctx->rel_blocks*(PHASE_THREADS/REL_GROUP);
+      total = o_u+Su.stride*(size_t)ctx->unrel_blocks*(PHASE_THREADS/UNREL_GROUP);
+    }
   for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->slot[s].stream);
-  size_t groups = (size_t)ctx->classify_blocks*CLASSIFY_GROUPS, g;
-  if ((g = (size_t)ctx->wall_blocks*(PHASE_THREADS/WALL_GROUP)) > groups) groups = g;
-  if ((g = (size_t)ctx->rel_blocks*(PHASE_THREADS/REL_GROUP)) > groups) groups = g;
-  if ((g = (size_t)ctx->unrel_blocks*(PHASE_THREADS/UNREL_GROUP)) > groups) groups = g;
-  int rc = reserve(ctx,&ctx->scratch,SC.stride*groups);
+  int rc = reserve(ctx,&ctx->scratch,total);
   if (rc) return rc;
   rc = reserve(ctx,&ctx->scratch_big,SB.stride*(size_t)ctx->retry_blocks*CLASSIFY_GROUPS);
   if (rc) return rc;
-  /* the memo of the unreliable pass is read before it is written: entries start as "no task" */
+  /* the flag bytes of the wall replay are zero between reads, and the memo of the unreliable pass is read
+     before it is written (entries start as "no task"): the arenas start as zeros */
   if (cudaMemset(ctx->scratch.p,0,ctx->scratch.cap) != cudaSuccess || cudaMemset(ctx->scratch_big.p,0,ctx->scratch_big.cap) != cudaSuccess)
     return set_err(ctx,CPG_ECUDA,"cudaMemset of the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
   /* the memsets run on the legacy default stream, which the (non-blocking) slot streams do not wait for:
      nothing may be launched on them before the arenas are really zero */
   if (cudaDeviceSynchronize() != cudaSuccess)
     return set_err(ctx,CPG_ECUDA,"zeroing the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
-  SC.base = (uint8_t *)ctx->scratch.p; SB.base = (uint8_t *)ctx->scratch_big.p;
-  ctx->SC = SC; ctx->SCbig = SB;
+  uint8_t *base = (uint8_t *)ctx->scratch.p;
+  SC.base = base; Sw.base = base; Sr.base = base+o_r; Su.base = base+o_u; SB.base = (uint8_t *)ctx->scratch_big.p;
+  ctx->SC = SC; ctx->SCbig = SB; ctx->SCw = Sw; ctx->SCr = Sr; ctx->SCu = Su;
+  ctx->scratch_P = P;
   return CPG_OK;
 }
 
@@ -774,7 +944,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
      batch (plain longest-first) 608 ms (profiles/r01_history.md).  CPG_ORDER_CHUNK overrides. */
   { int *bucket = (int *)calloc((size_t)maxR+2,sizeof(int));
     if (bucket == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
-    int chunk = ctx->fused ? ctx->classify_blocks*CLASSIFY_GROUPS : ctx->wall_blocks*(PHASE_THREADS/WALL_GROUP);
+    int chunk = ctx->fused ? ctx->classify_blocks*CLASSIFY_GROUPS : ctx->wallb_blocks*(PHASE_THREADS/WALLB_GROUP);
     { const char *f = getenv("CPG_ORDER_CHUNK"); if (f && atoi(f) > 0) chunk = atoi(f); }
     if (chunk < 1) chunk = 1;
     for (int c0 = 0; c0 < n; c0 += chunk)
@@ -806,6 +976,14 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   { const char *f = getenv("CPG_POOL_DIV"); if (f && atoi(f) > 0) pool_div = atoi(f); }     /* test knob */
   const int64_t pool_cap = co/pool_div+4096;
   if ((rc = reserve(ctx,&S->pool,sizeof(cpg_intvl)*(size_t)pool_cap))) return rc;
+  /* candidate records: a header for one position in HDR_DIV (HiFi profiles have a candidate per 65-100
+     positions), a big record for one in BIG_DIV (they need one per ~700); same fallback */
+  int hdr_div = 24, big_div = 160;
+  { const char *f = getenv("CPG_HDR_DIV"); if (f && atoi(f) > 0) hdr_div = atoi(f); }       /* test knobs */
+  { const char *f = getenv("CPG_BIG_DIV"); if (f && atoi(f) > 0) big_div = atoi(f); }
+  const int64_t hdr_cap = co/hdr_div+4096, big_cap = co/big_div+4096;
+  if (!ctx->fused && ((rc = reserve(ctx,&S->hdr,sizeof(cpg_chdr)*(size_t)hdr_cap)) || (rc = reserve(ctx,&S->big,sizeof(cpg_cbig)*(size_t)big_cap))))
+    return rc;
   cudaStream_t st = S->stream;
   if (n > 0)
     { CU(cudaMemcpyAsync(S->seq.p,b->seq,seq_bytes,cudaMemcpyHostToDevice,st));
@@ -831,6 +1009,9 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   B.phase_cycles = (unsigned long long *)((char *)S->queue.p+32);
   B.pool_cursor = (unsigned long long *)((char *)S->queue.p+64);
   B.rec = (ReadRec *)S->rec.p; B.pool = (cpg_intvl *)S->pool.p; B.pool_cap = pool_cap;
+  B.hdr_cursor = (unsigned long long *)((char *)S->queue.p+72);
+  B.big_cursor = (unsigned long long *)((char *)S->queue.p+80);
+  B.hdr = (cpg_chdr *)S->hdr.p; B.big = (cpg_cbig *)S->big.p; B.hdr_cap = hdr_cap; B.big_cap = big_cap;
   return CPG_OK;
 }
 
@@ -849,11 +1030,15 @@ static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
   if (ctx->fused)
     k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC,0);
   else
-    { k_wall<<<ctx->wall_blocks,PHASE_THREADS,ctx->wall_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+    { k_wall_a<<<ctx->walla_blocks,WALLA_THREADS,ctx->walla_smem,st>>>(S->B,ctx->dmodel);
+      if (timed) CU(cudaEventRecord(ctx->evp[3],st));
+      k_wall_b<<<ctx->wallb_blocks,PHASE_THREADS,0,st>>>(S->B,ctx->dmodel,ctx->SCw);
+      if (timed) CU(cudaEventRecord(ctx->evp[4],st));
+      k_wall_c<<<ctx->wallc_blocks,PHASE_THREADS,0,st>>>(S->B,ctx->dmodel);
       if (timed) CU(cudaEventRecord(ctx->evp[0],st));
-      k_rel<<<ctx->rel_blocks,PHASE_THREADS,ctx->rel_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+      k_rel<<<ctx->rel_blocks,PHASE_THREADS,ctx->rel_smem,st>>>(S->B,ctx->dmodel,ctx->SCr);
       if (timed) CU(cudaEventRecord(ctx->evp[1],st));
-      k_unrel<<<ctx->unrel_blocks,PHASE_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SC);
+      k_unrel<<<ctx->unrel_blocks,PHASE_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SCu);
       if (timed) CU(cudaEventRecord(ctx->evp[2],st));
     }
   k_classify<<<ctx->retry_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SCbig,1);
@@ -963,13 +1148,17 @@ extern "C" int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float
               CU(cudaEventElapsedTime(&p3,ctx->evp[2],ctx->ev[2]));
               ctx->phase_ns[0] = (uint64_t)(p0*1e6); ctx->phase_ns[1] = (uint64_t)(p1*1e6);
               ctx->phase_ns[2] = (uint64_t)(p2*1e6); ctx->phase_ns[3] = (uint64_t)(p3*1e6);
+              CU(cudaEventElapsedTime(&p0,ctx->ev[1],ctx->evp[3]));
+              CU(cudaEventElapsedTime(&p1,ctx->evp[3],ctx->evp[4]));
+              CU(cudaEventElapsedTime(&p2,ctx->evp[4],ctx->evp[0]));
+              ctx->wall_ns[0] = (uint64_t)(p0*1e6); ctx->wall_ns[1] = (uint64_t)(p1*1e6); ctx->wall_ns[2] = (uint64_t)(p2*1e6);
             }
         }
       td += a; tc += b;
     }
   if (ms_decode) *ms_decode = (float)(td/iters);
   if (ms_classify) *ms_classify = (float)(tc/iters);
-  if (launches) *launches = (ctx->fused ? 3 : 5)*iters;
+  if (launches) *launches = (ctx->fused ? 3 : 7)*iters;
   return CPG_OK;
 }
 
@@ -984,6 +1173,12 @@ extern "C" int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4])
       return CPG_OK;
     }
   CU(cudaMemcpy(out,(char *)S->queue.p+32,32,cudaMemcpyDeviceToHost));
+  return CPG_OK;
+}
+
+extern "C" int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[3])
+{ if (ctx == NULL || out == NULL) return set_err(ctx,CPG_EINVAL,"cpg_wall_ns: bad argument");
+  for (int i = 0; i < 3; i++) out[i] = ctx->fused ? 0 : ctx->wall_ns[i];
   return CPG_OK;
 }
 

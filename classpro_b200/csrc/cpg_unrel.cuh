@@ -217,8 +217,8 @@ CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
   const int N = R.N;
   int32_t *ord = R.S.ord;
   uint8_t *fixed = R.S.fixed;
-  /* keys in a compact array first (the probability slots are dead by now), then the ranks */
-  uint32_t *key = reinterpret_cast<uint32_t *>(R.S.perr);
+  /* keys in a compact array first, then the ranks */
+  uint32_t *key = R.S.key;
   CPG_LOOP for (int i = W.glane; i < N; i += W.gsize) key[i] = (uint32_t)imin(v[i].cb,v[i].ce);
   CPG_SYNCGROUP(W);
   CPG_LOOP for (int i = W.glane; i < N; i += W.gsize)

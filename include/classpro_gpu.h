@@ -142,11 +142,14 @@ int cpg_upload(cpg_ctx *ctx, const cpg_batch *batch);
 int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float *ms_classify, int *launches);
 int cpg_download(cpg_ctx *ctx, cpg_result *result);
 /* Device time of the classification phases in the last cpg_run_resident iteration, nanoseconds
- * (CUDA events between the kernels): [0] k_wall (wall detection + reliable intervals), [1] k_rel
+ * (CUDA events between the kernels): [0] the three wall kernels (wall detection + reliable intervals), [1] k_rel
  * (reliable-interval DP), [2] k_unrel (unreliable intervals + class strings), [3] the retry launch.
  * With CPG_FUSED=1 (single-kernel path): summed per-group clock cycles of the three phases and of
  * the waits at the CTA phase barriers. */
 int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4]);
+/* ... and of the three wall kernels of that iteration: [0] k_wall_a (pure, one candidate per lane), [1] k_wall_b
+ * (order-dependent replay, one read per lane group), [2] k_wall_c (one interval per lane). */
+int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[3]);
 
 /* ---- profile producer (what FastK does before ClassPro runs) ----------------
  * FastK is not part of the reference tree; the reference only reads its files (src/libfastk.c:51-96

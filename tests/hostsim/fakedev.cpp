@@ -107,6 +107,9 @@ static int fake_read(cpg_ctx *c, const cpg_batch *b, int i, uint8_t *cls)
   R.S.bp = Kk.bp.data(); R.S.asg_f = Kk.af.data(); R.S.asg_b = Kk.ab.data();
   R.S.rpos = Kk.rpos.data(); R.S.ord = Kk.ord.data(); R.S.fixed = Kk.fixed.data(); R.S.MC = Kk.mc; R.S.memo = Kk.memo.data();
   R.S.capS = Kk.capS; R.S.capE = Kk.capE; R.S.capI = Kk.capI;
+  R.S.tlog = Kk.tlog.data(); R.S.capT = Kk.capT; R.S.capC = Kk.capC; R.S.hdr = Kk.hdr.data(); R.S.big = Kk.big.data();
+  R.S.key = Kk.key.data();
+  R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0;
   return classify_read(R,W,sh,cls);
 #endif
 }

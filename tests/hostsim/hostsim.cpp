@@ -94,7 +94,8 @@ static int g_small_caps = 0;          /* > 0: first attempt with interval tables
 static int g_retries = 0;
 
 struct HsWork
-  { std::vector<uint8_t> mark; std::vector<uint16_t> slot; std::vector<uint32_t> cand; std::vector<double> perr; std::vector<cpg_eintvl> eint;
+  { std::vector<uint8_t> mark; std::vector<uint16_t> slot; std::vector<uint32_t> cand, key; std::vector<double> perr; std::vector<cpg_eintvl> eint;
+    std::vector<int32_t> tlog; std::vector<cpg_chdr> hdr; std::vector<cpg_cbig> big; int capT = 0, capC = 0;
     std::vector<cpg_intvl> intvl, rint, wint; std::vector<uint16_t> bp;
     std::vector<uint8_t> af, ab, rpos, fixed; std::vector<int32_t> ord; std::vector<cpg_unmemo> memo; int mc = 0;
     int capS = 0, capE = 0, capI = 0;
@@ -103,12 +104,14 @@ struct HsWork
     void set_caps(int P, int small)
       { capS = capE = capI = P+2;
         if (small > 0) { capI = capE = small; capS = 2*small; }
+        capT = 3*capS; capC = capI;
         perr.assign((size_t)capS*4,0.); eint.assign(capE,cpg_eintvl()); intvl.assign(capI,cpg_intvl());
-        fixed.assign(capI,0); ord.assign(capI,0);
+        fixed.assign(capI,0); ord.assign(capI,0); key.assign(capI,0);
+        tlog.assign(capT,0); hdr.assign(capC,cpg_chdr()); big.assign(capC,cpg_cbig());
       }
     void size(int P)
       { int MC = P/2+8;
-        mark.assign(P+2+32,0xff); slot.assign(P+2,0xffff); cand.assign(P/32+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
+        mark.assign(P+2+32,0); slot.assign(P+2,0xffff);        /* the flag bytes are zero between reads (checked below) */ cand.assign(P/32+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
         rint.resize(MC); wint.resize(2*MC); bp.assign(2*MC,0); af.assign(MC,0); ab.assign(MC,0);
         rpos.assign(2*MC,0); mc = MC; memo.assign((size_t)CPG_MEMO_CAP*8,cpg_unmemo()); fixed.assign(P+2,0); ord.assign(P+2,0);
       }
@@ -221,6 +224,9 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
       R.S.bp = K.bp.data(); R.S.asg_f = K.af.data(); R.S.asg_b = K.ab.data();
       R.S.rpos = K.rpos.data(); R.S.ord = K.ord.data(); R.S.fixed = K.fixed.data(); R.S.MC = K.mc; R.S.memo = K.memo.data();
       R.S.capS = K.capS; R.S.capE = K.capE; R.S.capI = K.capI;
+      R.S.tlog = K.tlog.data(); R.S.capT = K.capT; R.S.capC = K.capC; R.S.hdr = K.hdr.data(); R.S.big = K.big.data();
+      R.S.key = K.key.data();
+      R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0;
     }
   run_lanes(lane_classify,jobs);
   st = 0;
@@ -234,6 +240,8 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
       if (jobs[l].N != jobs[0].N || jobs[l].M != jobs[0].M) st |= 1<<30;      /* lanes disagree */
     }
   for (int g = 1; g < NG; g++) if (memcmp(cls,cls_g[g].data(),(size_t)rlen) != 0) st |= 1<<29;   /* groups disagree */
+  for (int g = 0; g < NG; g++)                                   /* the wall stage must leave its flag bytes clean */
+    for (size_t q = 0; q < Wk[g].mark.size(); q++) if (Wk[g].mark[q]) { st |= 1<<28; break; }
   if (ivl_out) for (int i = 0; i < jobs[0].N; i++) ivl_out[i] = Wk[0].intvl[i];
   if (N_out) *N_out = jobs[0].N;
   if (M_out) *M_out = jobs[0].M;

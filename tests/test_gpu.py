@@ -65,13 +65,15 @@ DATASETS = [
 ]
 
 
-@pytest.mark.parametrize("knob", ["CPG_SCRATCH_DIV", "CPG_POOL_DIV", "CPG_FUSED"])
+@pytest.mark.parametrize("knob", ["CPG_SCRATCH_DIV", "CPG_POOL_DIV", "CPG_HDR_DIV", "CPG_BIG_DIV", "CPG_FUSED"])
 def test_retry_launch_matches_oracle(kit, cp, monkeypatch, knob):
     """The other routes through the kernels give the same class strings.
     CPG_SCRATCH_DIV: interval tables of 64 entries in the scratch blocks of the phase kernels, so
     nearly every read is flagged and classified by the retry launch with full-size tables.
     CPG_POOL_DIV: an interval pool of 4096 entries for the batch: the first reads fit, the rest are
-    flagged by k_wall (a mix of both routes in one batch).
+    flagged by k_wall_b (a mix of both routes in one batch).
+    CPG_HDR_DIV / CPG_BIG_DIV: 4096 candidate headers / big candidate records for the batch: the reads that
+    find the arrays full are flagged by k_wall_a.
     CPG_FUSED: every read through the single-kernel path."""
     monkeypatch.setenv(knob, "1" if knob == "CPG_FUSED" else "1000000")
     name, params, cov_opt, read_len = DATASETS[1]
