@@ -702,15 +702,17 @@ def main():
                      "note": "profile decode + wall-candidate scan fused: c + 2n + n/8 bytes; issue bound"},
         "k_wall": {"ms": ms_ph[0], "bytes": bytes_wall, "GBps": bytes_wall / (max(ms_ph[0], 1e-6) * 1e-3) / 1e9,
                    "frac": bytes_wall / (max(ms_ph[0], 1e-6) * 1e-3) / 1e9 / peak, "traffic": traffic.get("k_wall"),
-                   "launches": {"k_wall_a": ms_ph[0] * wall_ns[0] / max(1, sum(wall_ns)),
-                                "k_wall_b": ms_ph[0] * wall_ns[1] / max(1, sum(wall_ns)),
-                                "k_wall_c": ms_ph[0] * wall_ns[2] / max(1, sum(wall_ns))},
+                   "launches": {"k_wall_a": ms_ph[0] * wall_ns[0] / max(1, sum(wall_ns[:3])),
+                                "k_wall_b": ms_ph[0] * wall_ns[1] / max(1, sum(wall_ns[:3])),
+                                "k_wall_c": ms_ph[0] * wall_ns[2] / max(1, sum(wall_ns[:3]))},
                    "note": "wall detection + reliable intervals as three launches (pure per candidate / replay per read / "
                            "pure per interval): 2n + n/8 + r/4 bytes in, interval tables out"},
         "k_rel": {"ms": ms_ph[1], "bytes": None, "traffic": traffic.get("k_rel"),
                   "note": "reliable-interval DP on the interval tables (48 B per interval): FP64 dependency chains"},
         "k_unrel": {"ms": ms_ph[2], "bytes": r, "traffic": traffic.get("k_unrel"),
-                    "note": "unreliable intervals + class string (r bytes out)"},
+                    "launches": {"k_unrel_a": ms_ph[2] * wall_ns[3] / max(1, sum(wall_ns[3:])),
+                                 "k_unrel_b": ms_ph[2] * wall_ns[4] / max(1, sum(wall_ns[3:]))},
+                    "note": "unreliable intervals (pure per interval, then the sweeps per read) + class string (r bytes out)"},
         "retry_launch": {"ms": ms_ph[3]},
     }
     dom = max(("k_decode", "k_wall", "k_rel", "k_unrel"), key=lambda k: kern[k]["ms"])

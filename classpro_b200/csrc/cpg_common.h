@@ -158,9 +158,14 @@ typedef struct { int32_t b, e; double pe; } cpg_eintvl;   /* src/ClassPro.h:153-
 /* Sequence view: 2-bit packed (A,C,G,T = 0..3, base i in bits 2*(i&3) of byte i>>2) or raw bytes */
 typedef struct { const uint8_t *p; int32_t bits; } cpg_seq;
 
-/* One task of an unreliable-interval update (see cpg_unrel.cuh): arguments and result */
-struct cpg_unmemo { double a; double val; int32_t k; int32_t kind; };
-#define CPG_MEMO_CAP 512       /* intervals per read whose first-sweep results are kept */
+/* What the pure step of the unreliable pass (k_unrel_a, cpg_unrel.cuh) records for an interval the sweeps
+   will visit: its four nearest reliable H / D neighbours and the ten task values under them */
+typedef struct
+  { int32_t nb[4];      /* H left, H right, D left, D right (interval index, -1 = none; -2 = forced R, no values) */
+    double  val[10];
+    int32_t st;         /* status bits the evaluation raised: they count only if the values are used */
+    int32_t pad;
+  } cpg_upre;           /* 104 bytes */
 
 /* ---- wall stage, step 1 -> step 2: what the pure, candidate-parallel step (k_wall_a, cpg_wall.cuh "wa_")
  *      leaves for the order-dependent replay of a read (k_wall_b, "wb_").  One header per wall candidate of
@@ -215,10 +220,10 @@ typedef struct
     uint8_t    *asg_b;    /* [MC] */
     uint8_t    *rpos;     /* [2*MC] */
     int32_t     MC;
-    int32_t    *ord;      /* [capI] */
-    uint8_t    *fixed;    /* [capI] */
-    uint32_t   *key;      /* [capI] sort keys of the unreliable pass */
-    struct cpg_unmemo *memo;   /* [CPG_MEMO_CAP*8] first-sweep results of the unreliable-interval tasks */
+    int32_t    *ord;      /* [capI] unreliable pass: the intervals the sweeps visit, in index order */
+    int32_t    *srt;      /* [capI] ... their positions in ord[], in sweep order */
+    uint32_t   *key;      /* [capI] ... their sort keys */
+    cpg_upre   *upre;     /* [capI] ... their recorded task values (single-kernel path; the phase kernels read the batch's array) */
   } cpg_scratch;
 
 /* Exchange block of a lane group (shared memory on the device): task results */

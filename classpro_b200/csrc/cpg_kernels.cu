@@ -1,7 +1,7 @@
 /*******************************************************************************************
  *  cpg_kernels.cu -- sm_100a kernels and the C ABI of libclasspro_b200.so.
  *
- *  Seven launches per batch, all persistent (grid = a multiple of the SM count, warps / lane groups
+ *  Eight launches per batch, all persistent (grid = a multiple of the SM count, warps / lane groups
  *  pull reads from an atomic queue in processing order):
  *
  *   k_decode    one warp per read: FastK profile bytes -> uint16 counts + the wall-candidate bit
@@ -15,7 +15,10 @@
  *   k_wall_c    one interval per lane: end counts, corrected counts, Skellam plausibility; the
  *               reliable intervals are appended to the read's table (cpg_wall.cuh).
  *   k_rel       reliable-interval DP, forward and backward (cpg_rel.cuh), on the pooled tables.
- *   k_unrel     unreliable intervals and the class string (cpg_unrel.cuh): r bytes per read out.
+ *   k_unrel_a   one interval per lane: the pure part of the unreliable pass (neighbours, ten task
+ *               values per interval the sweeps will visit).
+ *   k_unrel_b   the two order-dependent sweeps on those values and the class string
+ *               (cpg_unrel.cuh): r bytes per read out.
  *   k_classify  the three phases in one kernel, on 4 CTAs with worst-case scratch: the retry
  *               launch for reads that outgrew the compact scratch blocks or the pool (normally
  *               none; it returns at once).  CPG_FUSED=1 runs every read through it instead.
@@ -62,7 +65,7 @@ struct BatchDev
     int32_t       *status;
     const int32_t *order;
     int32_t       *queue;        /* work counters: [0] decode, [1] classify/wall_a, [2] retry launch; [3] reads flagged
-                                    for retry; [4] reliable DP, [5] unreliable + emit, [6] wall_b, [7] wall_c */
+                                    for retry; [4] reliable DP, [5] unrel_a, [6] wall_b, [7] wall_c, [24] unrel_b */
     struct ReadRec *rec;         /* per read: where the wall kernels left its candidate records and interval tables */
     cpg_intvl     *pool;         /* interval pool of the batch: intvl[N] then rint[M] of each read */
     unsigned long long *pool_cursor;
@@ -71,15 +74,18 @@ struct BatchDev
     cpg_cbig      *big;          /* big candidate records */
     unsigned long long *hdr_cursor, *big_cursor;
     int64_t        hdr_cap, big_cap;
+    cpg_upre      *upre;         /* recorded task values of the unreliable pass, one per interval its sweeps visit */
+    unsigned long long *upre_cursor;
+    int64_t        upre_cap;
     unsigned long long *phase_cycles;   /* [4] summed per-warp cycles of the three phases (+ idle at the CTA barriers) */
   };
 
-struct ReadRec { int64_t off, hoff; int32_t N, M, ncand, mcap; };
+struct ReadRec { int64_t off, hoff, uoff; int32_t N, M, ncand, mcap, nf, pad; };
 
 /* Each kind of kernel has its own region of the scratch arena, laid out for what it uses:
    SM_WALL  k_wall_b: flag bytes, slot indices, probability slots, E-intervals, touch log
    SM_REL   k_rel:    DP working copies, back pointers, path strings
-   SM_UNREL k_unrel:  order, fixed flags, sort keys, task memo
+   SM_UNREL k_unrel_b: list of the intervals the sweeps visit, their keys and sweep order
    SM_FULL  k_classify (retry launch): all of it, worst-case capacities */
 enum { SM_WALL = 0, SM_REL = 1, SM_UNREL = 2, SM_FULL = 3 };
 #define N_OFF 18
@@ -116,9 +122,9 @@ __host__ __device__ static inline size_t scratch_layout(const ScratchDev &SC, si
   off[8]  = o; o = align_up(o+(r ? (size_t)MC : 0),16);                            /* asg_b */
   off[9]  = o; o = align_up(o+(r ? 2*(size_t)MC : 0),16);                          /* rpos (fw, bw) */
   off[10] = o; o = align_up(o+(u ? sizeof(int32_t)*(size_t)SC.capI : 0),16);       /* ord   */
-  off[11] = o; o = align_up(o+(u ? (size_t)SC.capI : 0),16);                       /* fixed */
+  off[11] = o; o = align_up(o+(u ? sizeof(int32_t)*(size_t)SC.capI : 0),16);       /* srt   */
   off[17] = o; o = align_up(o+(u ? sizeof(uint32_t)*(size_t)SC.capI : 0),16);      /* key   */
-  off[12] = o; o = align_up(o+(u ? sizeof(cpg_unmemo)*8*(size_t)CPG_MEMO_CAP : 0),16);  /* memo */
+  off[12] = o; o = align_up(o+(f ? sizeof(cpg_upre)*(size_t)SC.capI : 0),16);      /* upre  */
   return align_up(o,256);
 }
 
@@ -155,10 +161,10 @@ __device__ __forceinline__ void bind_scratch(ReadCtx &R, uint8_t *sb, const size
   R.S.asg_b = sb+off[8];
   R.S.rpos  = sb+off[9];
   R.S.ord   = reinterpret_cast<int32_t *>(sb+off[10]);
-  R.S.fixed = sb+off[11];
+  R.S.srt   = reinterpret_cast<int32_t *>(sb+off[11]);
   R.S.key   = reinterpret_cast<uint32_t *>(sb+off[17]);
   R.S.MC = SC.MC; R.S.capS = SC.capS; R.S.capE = SC.capE; R.S.capI = SC.capI; R.S.capT = SC.capT; R.S.capC = SC.capC;
-  R.S.memo = reinterpret_cast<cpg_unmemo *>(sb+off[12]);
+  R.S.upre  = reinterpret_cast<cpg_upre *>(sb+off[12]);
   R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0;
 }
 
@@ -413,7 +419,7 @@ k_wall_a(BatchDev B, cpg_dmodel M)
     { const int q = next_read(B.queue+1,lane);
       if (q >= B.n_reads) break;
       const int r = B.order[q];
-      ReadRec rc; rc.off = 0; rc.hoff = 0; rc.N = 0; rc.M = 0; rc.ncand = 0; rc.mcap = 0;
+      ReadRec rc; rc.off = 0; rc.hoff = 0; rc.uoff = 0; rc.N = 0; rc.M = 0; rc.ncand = 0; rc.mcap = 0; rc.nf = 0; rc.pad = 0;
       const int rlen = B.rlen[r], plen = rlen-M.K+1;
       if (B.status[r] != CPG_ST_OK) { if (lane == 0) B.rec[r] = rc; continue; }     /* undecodable profile: left to the host */
       const uint16_t *prof = B.cnt+B.cnt_off[r];
@@ -611,9 +617,79 @@ k_rel(BatchDev B, cpg_dmodel M, ScratchDev SC)
     }
 }
 
-/* phase 3: unreliable intervals + class string (cpg_unrel.cuh) */
+/* phase 3a: the pure step of the unreliable pass, one interval per lane (cpg_unrel.cuh, un_pre_interval):
+   a warp takes a read, queues the intervals its sweeps will visit (the ones not fixed by the DP, about a
+   third) and works them off 32 at a time: nearest reliable H / D neighbours and the ten task values. */
+#define UNRELA_QCAP 64
+__global__ void __launch_bounds__(WALLA_THREADS,WALLA_MIN_BLOCKS)
+k_unrel_a(BatchDev B, cpg_dmodel M)
+{ __shared__ cpg_dmodel s_model;
+  __shared__ int32_t s_q[WALLA_THREADS/32][UNRELA_QCAP];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_model = M;
+  __syncthreads();
+  cpg_model_fill_logs(&s_model,threadIdx.x,blockDim.x);
+  __syncthreads();
+  int32_t *pq = s_q[wib];
+  WCtx W;
+  W.lane = lane; W.M = &s_model; W.cthres = M.cthres; W.ws = 0; W.status = 0;
+  W.glane = 0; W.gsize = 1; W.gbase = lane; W.gmask = 1u << lane;
+  const unsigned lt = (1u << lane)-1u;
+  for (;;)
+    { const int q = next_read(B.queue+5,lane);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      const int st0 = B.status[r];
+      if (st0 & (CPG_ST_BAD_PROFILE|CPG_ST_RETRY|CPG_ST_EINTVL_OVF)) continue;
+      ReadRec rc = B.rec[r];
+      const int N = rc.N;
+      const cpg_intvl *v = B.pool+rc.off;
+      int nf = 0;
+      for (int i = lane; i < N; i += 32) nf += !un_is_fixed(v[i]);
+      nf = __reduce_add_sync(0xffffffffu,nf);
+      long long uoff = 0;
+      if (lane == 0) uoff = (long long)atomicAdd(B.upre_cursor,(unsigned long long)nf);
+      uoff = __shfl_sync(0xffffffffu,uoff,0);
+      if (uoff+nf > B.upre_cap)
+        { if (lane == 0) { B.status[r] = st0 | CPG_ST_RETRY; atomicAdd(B.queue+3,1); }
+          continue;
+        }
+      if (lane == 0) { B.rec[r].uoff = uoff; B.rec[r].nf = nf; }
+      cpg_upre *U = B.upre+uoff;
+      int npend = 0, done = 0;
+      for (int base = 0; base < N || npend > 0; base += 32)
+        { if (base < N)
+            { const int i = base+lane;
+              const int open = (i < N) && !un_is_fixed(v[i]);
+              const unsigned m = __ballot_sync(0xffffffffu,open);
+              if (open) pq[npend+__popc(m & lt)] = i;
+              __syncwarp();
+              npend += __popc(m);
+            }
+          const int flush = (base+32 >= N);
+          int head = 0;
+          while (npend-head >= 32 || (flush && npend-head > 0))
+            { const int nact = min(32,npend-head);
+              if (lane < nact) un_pre_interval(W,v,N,pq[head+lane],U+done+lane);
+              done += nact; head += nact;
+            }
+          const int left = npend-head;
+          if (head > 0 && left > 0)
+            { const int x = (lane < left) ? pq[head+lane] : 0;
+              __syncwarp();
+              if (lane < left) pq[lane] = x;
+            }
+          __syncwarp();
+          npend = left;
+          if (flush) break;
+        }
+    }
+}
+
+/* phase 3b: the sweeps of the unreliable pass on the recorded values, then the class string
+   (cpg_unrel.cuh: un_sweeps, emit_classes): r bytes per read out */
 __global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
-k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
+k_unrel_b(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { constexpr int G = UNREL_GROUP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PhaseShared<G,false> &sh = *reinterpret_cast<PhaseShared<G,false> *>(smem_raw);
@@ -626,7 +702,7 @@ k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
   size_t off[N_OFF];
   scratch_layout(SC,off);
   for (;;)
-    { const int q = group_next(B.queue+5,g);
+    { const int q = group_next(B.queue+24,g);
       if (q >= B.n_reads) break;
       const int r = B.order[q];
       const int st0 = B.status[r];
@@ -640,8 +716,12 @@ k_unrel(BatchDev B, cpg_dmodel M, ScratchDev SC)
       R.nslots = 0; R.N = rc.N; R.M = rc.M;
       bind_scratch(R,sb,off,SC);
       R.S.intvl = B.pool+rc.off; R.S.rint = B.pool+rc.off+rc.N;
-      int st = classify_phase3(R,W,B.cls+B.cls_off[r]);
-      st = __reduce_or_sync(g.gmask,st);
+      if (!(W.status & CPG_ST_ABORT))
+        { const int nf = un_list(R,W);                       /* == rc.nf: same rule, same order as k_unrel_a */
+          un_sweeps(R,W,nf,B.upre+rc.uoff);
+        }
+      emit_classes(R,W,B.cls+B.cls_off[r]);
+      const int st = __reduce_or_sync(g.gmask,W.status);
       if (g.glane == 0 && st != st0) B.status[r] = st;
       __syncwarp(g.gmask);
     }
@@ -676,7 +756,7 @@ struct DevBuf { void *p; size_t cap; };
 
 struct Slot
   { cudaStream_t stream;
-    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue, rec, pool, hdr, big;
+    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue, rec, pool, hdr, big, upre;
     /* small host-side (pinned) staging for arrays the library computes itself */
     int64_t *h_cnt_off; int32_t *h_order; size_t h_cap;
     int32_t *h_status; size_t h_status_cap;
@@ -698,11 +778,12 @@ struct cpg_ctx
     int        scratch_P;
     int        retry_blocks;
     int        fused;                 /* CPG_FUSED=1: the single-kernel path (k_classify) for every read */
-    int        walla_blocks, wallb_blocks, wallc_blocks, rel_blocks, unrel_blocks;
+    int        walla_blocks, wallb_blocks, wallc_blocks, rel_blocks, unrela_blocks, unrel_blocks;
     size_t     walla_smem, rel_smem, unrel_smem;
-    cudaEvent_t evp[5];               /* between the phase kernels */
+    cudaEvent_t evp[6];               /* between the phase kernels */
     uint64_t   phase_ns[4];           /* wall, reliable DP, unreliable + emit, retry launch: last timed run */
     uint64_t   wall_ns[3];            /* k_wall_a, k_wall_b, k_wall_c of that run */
+    uint64_t   unrel_ns[2];           /* k_unrel_a, k_unrel_b */
     int        n_sm, decode_blocks, classify_blocks;
     size_t     classify_smem;
     cudaEvent_t ev[3];
@@ -764,7 +845,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   for (int s = 0; s < 2; s++)
     { Slot *S = &ctx->slot[s];
       DevBuf *bufs[] = { &S->seq,&S->seq_off,&S->rlen,&S->prof,&S->prof_off,&S->cnt,&S->cnt_off,&S->cand,&S->plen,
-                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue,&S->rec,&S->pool,&S->hdr,&S->big };
+                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue,&S->rec,&S->pool,&S->hdr,&S->big,&S->upre };
       for (unsigned i = 0; i < sizeof(bufs)/sizeof(bufs[0]); i++) if (bufs[i]->p) cudaFree(bufs[i]->p);
       if (S->h_cnt_off) cudaFreeHost(S->h_cnt_off);
       if (S->h_order) cudaFreeHost(S->h_order);
@@ -777,7 +858,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   if (ctx->d_cthres) cudaFree(ctx->d_cthres);
   if (ctx->d_logfact) cudaFree(ctx->d_logfact);
   for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  for (int i = 0; i < 5; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
+  for (int i = 0; i < 6; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
   free(ctx);
 }
 
@@ -823,12 +904,12 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
       CU_C(cudaEventCreateWithFlags(&ctx->slot[s].kdone,cudaEventDisableTiming));
     }
   for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->ev[i]));
-  for (int i = 0; i < 5; i++) CU_C(cudaEventCreate(&ctx->evp[i]));
+  for (int i = 0; i < 6; i++) CU_C(cudaEventCreate(&ctx->evp[i]));
   { const char *f = getenv("CPG_FUSED"); ctx->fused = (f && atoi(f) > 0); }
   ctx->walla_smem = sizeof(WallAShared); ctx->rel_smem = sizeof(RelPhaseShared<REL_GROUP>);
   ctx->unrel_smem = sizeof(PhaseShared<UNREL_GROUP,false>);
   CU_C(cudaFuncSetAttribute(k_wall_a,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->walla_smem));
-  CU_C(cudaFuncSetAttribute(k_unrel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->unrel_smem));
+  CU_C(cudaFuncSetAttribute(k_unrel_b,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->unrel_smem));
   CU_C(cudaFuncSetAttribute(k_rel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)ctx->rel_smem));
   { int o = 0;
     CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_wall_a,WALLA_THREADS,ctx->walla_smem));
@@ -839,8 +920,10 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
     ctx->wallc_blocks = ctx->n_sm*(o < 1 ? 1 : o);
     CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_rel,PHASE_THREADS,ctx->rel_smem));
     ctx->rel_blocks = ctx->n_sm*(o < 1 ? 1 : o);
-    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_unrel,PHASE_THREADS,ctx->unrel_smem));
+    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_unrel_b,PHASE_THREADS,ctx->unrel_smem));
     ctx->unrel_blocks = ctx->n_sm*(o < 1 ? 1 : o);
+    CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o,k_unrel_a,WALLA_THREADS,0));
+    ctx->unrela_blocks = ctx->n_sm*(o < 1 ? 1 : o);
   }
 
   ctx->classify_smem = sizeof(ClassifyShared);
@@ -885,8 +968,7 @@ static int ensure_scratch(cpg_ctx *ctx, int P)
   if (rc) return rc;
   rc = reserve(ctx,&ctx->scratch_big,SB.stride*(size_t)ctx->retry_blocks*CLASSIFY_GROUPS);
   if (rc) return rc;
-  /* the flag bytes of the wall replay are zero between reads, and the memo of the unreliable pass is read
-     before it is written (entries start as "no task"): the arenas start as zeros */
+  /* the flag bytes of the wall replay are zero between reads: the arenas start as zeros */
   if (cudaMemset(ctx->scratch.p,0,ctx->scratch.cap) != cudaSuccess || cudaMemset(ctx->scratch_big.p,0,ctx->scratch_big.cap) != cudaSuccess)
     return set_err(ctx,CPG_ECUDA,"cudaMemset of the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
   /* the memsets run on the legacy default stream, which the (non-blocking) slot streams do not wait for:
@@ -982,7 +1064,13 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   { const char *f = getenv("CPG_HDR_DIV"); if (f && atoi(f) > 0) hdr_div = atoi(f); }       /* test knobs */
   { const char *f = getenv("CPG_BIG_DIV"); if (f && atoi(f) > 0) big_div = atoi(f); }
   const int64_t hdr_cap = co/hdr_div+4096, big_cap = co/big_div+4096;
-  if (!ctx->fused && ((rc = reserve(ctx,&S->hdr,sizeof(cpg_chdr)*(size_t)hdr_cap)) || (rc = reserve(ctx,&S->big,sizeof(cpg_cbig)*(size_t)big_cap))))
+  /* recorded task values of the unreliable pass: one per interval its sweeps visit (about a third of the
+     intervals, one per ~200 positions) */
+  int upre_div = 48;
+  { const char *f = getenv("CPG_UPRE_DIV"); if (f && atoi(f) > 0) upre_div = atoi(f); }
+  const int64_t upre_cap = co/upre_div+4096;
+  if (!ctx->fused && ((rc = reserve(ctx,&S->hdr,sizeof(cpg_chdr)*(size_t)hdr_cap)) || (rc = reserve(ctx,&S->big,sizeof(cpg_cbig)*(size_t)big_cap))
+                      || (rc = reserve(ctx,&S->upre,sizeof(cpg_upre)*(size_t)upre_cap))))
     return rc;
   cudaStream_t st = S->stream;
   if (n > 0)
@@ -1012,6 +1100,8 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   B.hdr_cursor = (unsigned long long *)((char *)S->queue.p+72);
   B.big_cursor = (unsigned long long *)((char *)S->queue.p+80);
   B.hdr = (cpg_chdr *)S->hdr.p; B.big = (cpg_cbig *)S->big.p; B.hdr_cap = hdr_cap; B.big_cap = big_cap;
+  B.upre_cursor = (unsigned long long *)((char *)S->queue.p+88);
+  B.upre = (cpg_upre *)S->upre.p; B.upre_cap = upre_cap;
   return CPG_OK;
 }
 
@@ -1038,7 +1128,9 @@ static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
       if (timed) CU(cudaEventRecord(ctx->evp[0],st));
       k_rel<<<ctx->rel_blocks,PHASE_THREADS,ctx->rel_smem,st>>>(S->B,ctx->dmodel,ctx->SCr);
       if (timed) CU(cudaEventRecord(ctx->evp[1],st));
-      k_unrel<<<ctx->unrel_blocks,PHASE_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SCu);
+      k_unrel_a<<<ctx->unrela_blocks,WALLA_THREADS,0,st>>>(S->B,ctx->dmodel);
+      if (timed) CU(cudaEventRecord(ctx->evp[5],st));
+      k_unrel_b<<<ctx->unrel_blocks,PHASE_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SCu);
       if (timed) CU(cudaEventRecord(ctx->evp[2],st));
     }
   k_classify<<<ctx->retry_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SCbig,1);
@@ -1152,13 +1244,16 @@ extern "C" int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float
               CU(cudaEventElapsedTime(&p1,ctx->evp[3],ctx->evp[4]));
               CU(cudaEventElapsedTime(&p2,ctx->evp[4],ctx->evp[0]));
               ctx->wall_ns[0] = (uint64_t)(p0*1e6); ctx->wall_ns[1] = (uint64_t)(p1*1e6); ctx->wall_ns[2] = (uint64_t)(p2*1e6);
+              CU(cudaEventElapsedTime(&p0,ctx->evp[1],ctx->evp[5]));
+              CU(cudaEventElapsedTime(&p1,ctx->evp[5],ctx->evp[2]));
+              ctx->unrel_ns[0] = (uint64_t)(p0*1e6); ctx->unrel_ns[1] = (uint64_t)(p1*1e6);
             }
         }
       td += a; tc += b;
     }
   if (ms_decode) *ms_decode = (float)(td/iters);
   if (ms_classify) *ms_classify = (float)(tc/iters);
-  if (launches) *launches = (ctx->fused ? 3 : 7)*iters;
+  if (launches) *launches = (ctx->fused ? 3 : 8)*iters;
   return CPG_OK;
 }
 
@@ -1176,9 +1271,10 @@ extern "C" int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4])
   return CPG_OK;
 }
 
-extern "C" int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[3])
+extern "C" int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[5])
 { if (ctx == NULL || out == NULL) return set_err(ctx,CPG_EINVAL,"cpg_wall_ns: bad argument");
   for (int i = 0; i < 3; i++) out[i] = ctx->fused ? 0 : ctx->wall_ns[i];
+  for (int i = 0; i < 2; i++) out[3+i] = ctx->fused ? 0 : ctx->unrel_ns[i];
   return CPG_OK;
 }
 

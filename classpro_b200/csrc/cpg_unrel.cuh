@@ -14,30 +14,6 @@
 #define CPG_UNREL_CUH
 #include "cpg_rel.cuh"
 
-/* src/class_unrel.c:11-25 for both states at once: nb[h][side] = nearest reliable interval
- * assigned H (h = 0) or D (h = 1) to the left (side 0) / right (side 1) of idx, or -1.  The
- * reference walks interval by interval, once per use; here the lanes of the group look at
- * consecutive intervals together and the result is shared by all the tasks of the update. */
-CPG_DEV_HELPER void un_nn_group(const WCtx &W, int idx, const cpg_intvl *v, int N, int nb[2][2])
-{ nb[0][0] = nb[0][1] = nb[1][0] = nb[1][1] = -1;
-  int need = 3;
-  CPG_LOOP for (int base = idx-1; base >= 0 && need; base -= W.gsize)
-    { const int j = base-W.glane;
-      int a = -1;
-      if (j >= 0 && v[j].is_rel) a = v[j].asgn;
-      if (need & 1) { unsigned m = cpg_gballot(W,a == ST_H); if (m) { nb[0][0] = base-(cpg_ffs(m)-1); need &= ~1; } }
-      if (need & 2) { unsigned m = cpg_gballot(W,a == ST_D); if (m) { nb[1][0] = base-(cpg_ffs(m)-1); need &= ~2; } }
-    }
-  need = 3;
-  CPG_LOOP for (int base = idx+1; base < N && need; base += W.gsize)
-    { const int j = base+W.glane;
-      int a = -1;
-      if (j < N && v[j].is_rel) a = v[j].asgn;
-      if (need & 1) { unsigned m = cpg_gballot(W,a == ST_H); if (m) { nb[0][1] = base+(cpg_ffs(m)-1); need &= ~1; } }
-      if (need & 2) { unsigned m = cpg_gballot(W,a == ST_D); if (m) { nb[1][1] = base+(cpg_ffs(m)-1); need &= ~2; } }
-    }
-}
-
 /* src/class_unrel.c:27-51 */
 CPG_DEV_HELPER uint16_t un_est_cov(WCtx &W, int x, const cpg_intvl *v, int s, const int nb[2][2])
 { int l = nb[s == ST_D][0], r = nb[s == ST_D][1];
@@ -82,13 +58,16 @@ CPG_DEV_HELPER double un_lp_r(WCtx &W, int idx, const cpg_intvl *v, const int nb
 
 /* src/class_unrel.c:115-237.  The ten independent pieces of an update -- the E and R
  * log-probabilities and, for H and D, the Skellam transition and the error-in-others tail on
- * either side -- are tasks; the arg-max (first maximum wins, order E,R,H,D) is formed uniformly
- * afterwards.
+ * either side -- are tasks; the arg-max (first maximum wins, order E,R,H,D) is formed afterwards.
  *   task 0: E     task 1: R     task 2+t, t = 4*h+2*side+kind (h: 0=H,1=D; side: 0=left,1=right;
  *   kind 0 = Skellam transition from/to the nearest fixed interval of that state,
  *   kind 1 = log binomial tail of the count against the interpolated coverage)
- * Tasks 2..9 are pure functions of a small argument triple (what, integer, double), which is how
- * they are memoised: the triple is formed by un_task_args, the value by un_task_eval. */
+ * All ten are pure functions of the interval and of its four nearest reliable H / D neighbours
+ * nb[][]: they change only when a neighbour does.  The sweeps change few states, so the tasks are
+ * evaluated BEFORE the sweeps, for every interval a sweep will visit, on the states as they are
+ * then (un_pre_interval: one interval per lane, k_unrel_a), and an update inside a sweep takes
+ * the recorded values whenever the interval's neighbours are still the recorded ones (un_update:
+ * a few loads and the arg-max); only otherwise are they evaluated again, there and then. */
 CPG_DEV_HELPER void un_task_args(WCtx &W, const cpg_intvl &I, const cpg_intvl *v, const int nb[2][2], int t,
                                  int &mkind, int &mk, double &ma)
 { const int s = (t & 4) ? ST_D : ST_H, right = (t >> 1) & 1, kind = t & 1;
@@ -118,78 +97,97 @@ CPG_DEV_HELPER double un_task_eval(const WCtx &W, int mkind, int mk, double ma, 
   return val;
 }
 
-/* Before the sweeps: the tasks of MANY intervals at once, one interval per lane, on the states
- * as they are now.  The sweeps change few states, so most of their tasks then find their triple
- * in the memo; evaluated inside un_update the same tasks run on 2-3 lanes of the group (ncu).
- * A memo entry is (triple, value) and the value depends on nothing else, so an entry left by an
- * earlier read is as good as a fresh one. */
-CPG_DEV_NOINL void un_precompute(WCtx &W, cpg_intvl *v, int N, const uint8_t *fixed, cpg_unmemo *memo)
-{ const int rcov = W.M->cov[ST_R];
-  const int n = imin(N,CPG_MEMO_CAP);
-  int bad = 0;
-  CPG_LOOP for (int idx = W.glane; idx < n; idx += W.gsize)
-    { if (fixed[idx]) continue;
-      const cpg_intvl I = v[idx];
-      if (imax(I.cb,I.ce) >= rcov) continue;
-      int nb[2][2];
-      CPG_LOOP for (int h = 0; h < 2; h++)
-        { const int s = h ? ST_D : ST_H;
-          int l = idx-1;
-          CPG_LOOP while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--;
-          int r = idx+1;
-          CPG_LOOP while (r < N && !(v[r].asgn == s && v[r].is_rel)) r++;
-          nb[h][0] = l; nb[h][1] = (r >= N) ? -1 : r;
-        }
-      cpg_unmemo *mm = memo+(size_t)idx*8;
+/* nearest reliable interval assigned H (h = 0) / D (h = 1) on either side of idx, by one lane
+   (src/class_unrel.c:11-25; most intervals are such, so the walks are short) */
+CPG_DEV_HELPER void un_nn_walk(const cpg_intvl *v, int N, int idx, int nb[2][2])
+{ CPG_LOOP for (int h = 0; h < 2; h++)
+    { const int s = h ? ST_D : ST_H;
+      int l = idx-1;
+      CPG_LOOP while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--;
+      int r = idx+1;
+      CPG_LOOP while (r < N && !(v[r].asgn == s && v[r].is_rel)) r++;
+      nb[h][0] = l; nb[h][1] = (r >= N) ? -1 : r;
+    }
+}
+
+/* the pure step for one interval, by one lane: neighbours and the ten task values as they are now */
+CPG_DEV_NOINL void un_pre_interval(WCtx &W, const cpg_intvl *v, int N, int idx, cpg_upre *out)
+{ const cpg_intvl I = v[idx];
+  cpg_upre U;
+  U.st = 0;
+  if (imax(I.cb,I.ce) >= W.M->cov[ST_R])
+    { U.nb[0] = U.nb[1] = U.nb[2] = U.nb[3] = -2;           /* forced R: never looked at */
+      CPG_LOOP for (int q = 0; q < 10; q++) U.val[q] = 0.;
+    }
+  else
+    { int nb[2][2], bad = 0;
+      const int st_in = W.status;
+      W.status = 0;
+      un_nn_walk(v,N,idx,nb);
+      U.nb[0] = nb[0][0]; U.nb[1] = nb[0][1]; U.nb[2] = nb[1][0]; U.nb[3] = nb[1][1];
+      U.val[0] = un_lp_e(W,I);
+      U.val[1] = un_lp_r(W,idx,v,nb);
       CPG_LOOP for (int t = 0; t < 8; t++)
         { int mkind, mk; double ma;
           un_task_args(W,I,v,nb,t,mkind,mk,ma);
-          if (mkind == 0 || (mm[t].kind == mkind && mm[t].k == mk && mm[t].a == ma)) continue;
-          const double val = un_task_eval(W,mkind,mk,ma,&bad);
-          mm[t].kind = mkind; mm[t].k = mk; mm[t].a = ma; mm[t].val = val;
+          U.val[2+t] = (mkind == 0) ? -CPG_INF : un_task_eval(W,mkind,mk,ma,&bad);
         }
+      if (bad) W.status |= CPG_ST_BINOM;
+      U.st = W.status;                                        /* raised only if the values are used */
+      W.status = st_in;
     }
-  if (bad) W.status |= CPG_ST_BINOM;
-  CPG_SYNCGROUP(W);
+  U.pad = 0;
+  *out = U;
 }
 
-CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *memo)
+/* src/class_unrel.c:185-237 for interval idx, whose recorded neighbours and task values are *U */
+CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, const cpg_upre *U)
 { const cpg_intvl I = v[idx];
   int ns;
   if (imax(I.cb,I.ce) >= W.M->cov[ST_R]) ns = ST_R;
   else
     { double *term = W.ws->term;
-      int bad = 0;
-      cpg_unmemo *mm = (memo != 0 && idx < CPG_MEMO_CAP) ? memo+(size_t)idx*8 : 0;
       int nb[2][2];
-      CPG_SYNCGROUP(W);
-      un_nn_group(W,idx,v,N,nb);
-      CPG_LOOP for (int q = W.glane; q < 10; q += W.gsize)
-        { double val;
-          if (q == 0) val = un_lp_e(W,I);
-          else if (q == 1) val = un_lp_r(W,idx,v,nb);
-          else
-            { const int t = q-2;
-              int mkind, mk; double ma;
-              un_task_args(W,I,v,nb,t,mkind,mk,ma);
-              if (mkind == 0) val = -CPG_INF;                      /* no task: never memoised */
-              else if (mm != 0 && mm[t].kind == mkind && mm[t].k == mk && mm[t].a == ma) val = mm[t].val;
-              else
-                { val = un_task_eval(W,mkind,mk,ma,&bad);
-                  if (mm != 0) { mm[t].kind = mkind; mm[t].k = mk; mm[t].a = ma; mm[t].val = val; }
-                }
+      /* the four walks, one per lane where there are lanes */
+      if (W.gsize >= 4)
+        { int mine = -1;
+          if (W.glane < 4)
+            { const int s = (W.glane & 2) ? ST_D : ST_H;
+              if (W.glane & 1) { int r = idx+1; CPG_LOOP while (r < N && !(v[r].asgn == s && v[r].is_rel)) r++; mine = (r >= N) ? -1 : r; }
+              else             { int l = idx-1; CPG_LOOP while (l >= 0 && !(v[l].asgn == s && v[l].is_rel)) l--; mine = l; }
             }
-          term[q] = val;
+          nb[0][0] = (int)cpg_gshfl(W,(unsigned)mine,0); nb[0][1] = (int)cpg_gshfl(W,(unsigned)mine,1);
+          nb[1][0] = (int)cpg_gshfl(W,(unsigned)mine,2); nb[1][1] = (int)cpg_gshfl(W,(unsigned)mine,3);
         }
-      CPG_SYNCGROUP(W);
-      if (bad) W.status |= CPG_ST_BINOM;
+      else un_nn_walk(v,N,idx,nb);
+      const int same = (U->nb[0] == nb[0][0] && U->nb[1] == nb[0][1] && U->nb[2] == nb[1][0] && U->nb[3] == nb[1][1]);
+      if (same) W.status |= U->st;
+      else
+        { /* a neighbour changed since the pure step: the tasks again, lanes in parallel */
+          int bad = 0;
+          CPG_SYNCGROUP(W);
+          CPG_LOOP for (int q = W.glane; q < 10; q += W.gsize)
+            { double val;
+              if (q == 0) val = un_lp_e(W,I);
+              else if (q == 1) val = un_lp_r(W,idx,v,nb);
+              else
+                { int mkind, mk; double ma;
+                  un_task_args(W,I,v,nb,q-2,mkind,mk,ma);
+                  val = (mkind == 0) ? -CPG_INF : un_task_eval(W,mkind,mk,ma,&bad);
+                }
+              term[q] = val;
+            }
+          CPG_SYNCGROUP(W);
+          if (bad) W.status |= CPG_ST_BINOM;
+        }
+      const double *tv = same ? U->val : term;
       double mx = -CPG_INF; int ms = -1;
       CPG_LOOP for (int s = ST_E; s <= ST_D; s++)
         { double lp;
-          if (s == ST_E) lp = term[0];
-          else if (s == ST_R) lp = term[1];
+          if (s == ST_E) lp = tv[0];
+          else if (s == ST_R) lp = tv[1];
           else
-            { const double *t = term+2+(s == ST_D ? 4 : 0);
+            { const double *t = tv+2+(s == ST_D ? 4 : 0);
               double er_l = -CPG_INF, er_r = -CPG_INF;
               if (idx-1 >= 0 && v[idx-1].asgn == s) er_l = I.peob;
               if (idx+1 < N && v[idx+1].asgn == s) er_r = I.peoe;
@@ -211,28 +209,66 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, cpg_unmemo *
   CPG_SYNCGROUP(W);
 }
 
-/* src/class_unrel.c:248-275 */
-CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
-{ cpg_intvl *v = R.S.intvl;
-  const int N = R.N;
-  int32_t *ord = R.S.ord;
-  uint8_t *fixed = R.S.fixed;
-  /* keys in a compact array first, then the ranks */
-  uint32_t *key = R.S.key;
-  CPG_LOOP for (int i = W.glane; i < N; i += W.gsize) key[i] = (uint32_t)imin(v[i].cb,v[i].ce);
+CPG_DEV int un_is_fixed(const cpg_intvl &I) { return I.is_rel && (I.asgn == ST_H || I.asgn == ST_D); }
+
+/* the intervals the sweeps visit (not fixed: src/class_unrel.c:249-251), in index order -> R.S.ord; returns how many */
+CPG_DEV_NOINL int un_list(ReadCtx &R, const WCtx &W)
+{ const cpg_intvl *v = R.S.intvl;
+  int nf = 0;
   CPG_SYNCGROUP(W);
-  CPG_LOOP for (int i = W.glane; i < N; i += W.gsize)
-    { const uint32_t ki = key[i];
-      int rank = 0;
-      for (int j = 0; j < i; j++) rank += (key[j] <= ki);
-      for (int j = i+1; j < N; j++) rank += (key[j] < ki);
-      ord[rank] = i;
-      fixed[i] = (uint8_t)(v[i].is_rel && (v[i].asgn == ST_H || v[i].asgn == ST_D));
+  CPG_LOOP for (int base = 0; base < R.N; base += W.gsize)
+    { const int i = base+W.glane;
+      const int open = (i < R.N) && !un_is_fixed(v[i]);
+      const unsigned m = cpg_gballot(W,open);
+      if (open) R.S.ord[nf+cpg_popc(m & ((1u << W.glane)-1u))] = i;
+      nf += cpg_popc(m);
     }
   CPG_SYNCGROUP(W);
-  un_precompute(W,v,N,fixed,R.S.memo);
-  CPG_LOOP for (int i = N-1; i >= 0; i--) { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo); }
-  CPG_LOOP for (int i = 0; i < N; i++)    { int x = ord[i]; if (!fixed[x]) un_update(W,x,v,N,R.S.memo); }
+  return nf;
+}
+
+/* src/class_unrel.c:248-275 on the listed intervals with their recorded values U[0..nf): the stable sort by
+   min(cb,ce) as lane-parallel ranks (ties by index = the order glibc's merge sort leaves, :244-258) -- only
+   the intervals the sweeps visit need an order --, then the two sweeps. */
+CPG_DEV_NOINL void un_sweeps(ReadCtx &R, WCtx &W, int nf, const cpg_upre *U)
+{ cpg_intvl *v = R.S.intvl;
+  const int N = R.N;
+  const int32_t *lst = R.S.ord;
+  uint32_t *key = R.S.key;
+  int32_t *srt = R.S.srt;
+  CPG_LOOP for (int p = W.glane; p < nf; p += W.gsize) { const cpg_intvl &I = v[lst[p]]; key[p] = (uint32_t)imin(I.cb,I.ce); }
+  CPG_SYNCGROUP(W);
+  CPG_LOOP for (int p = W.glane; p < nf; p += W.gsize)
+    { const uint32_t kp = key[p];
+      int rank = 0;
+      for (int q = 0; q < p; q++) rank += (key[q] <= kp);
+      for (int q = p+1; q < nf; q++) rank += (key[q] < kp);
+      srt[rank] = p;
+    }
+  CPG_SYNCGROUP(W);
+  CPG_LOOP for (int i = nf-1; i >= 0; i--) { const int p = srt[i]; un_update(W,lst[p],v,N,U+p); }
+  CPG_LOOP for (int i = 0; i < nf; i++)    { const int p = srt[i]; un_update(W,lst[p],v,N,U+p); }
+}
+
+/* one read, both steps back to back (retry launch, host tests) */
+CPG_DEV_NOINL void classify_unreliable(ReadCtx &R, WCtx &W)
+{ const int nf = un_list(R,W);
+  CPG_LOOP for (int p = W.glane; p < nf; p += W.gsize) un_pre_interval(W,R.S.intvl,R.N,R.S.ord[p],R.S.upre+p);
+  CPG_SYNCGROUP(W);
+  un_sweeps(R,W,nf,R.S.upre);
+}
+
+/* class characters of a read: 'N' x (K-1), then one character per k-mer (src/ClassPro.c:114-117,265-271) */
+CPG_DEV_NOINL void emit_classes(const ReadCtx &R, const WCtx &W, uint8_t *cls)
+{ const int K = W.M->K;
+  CPG_LOOP for (int j = W.glane; j < K-1; j += W.gsize) cls[j] = 'N';
+  const cpg_intvl *v = R.S.intvl;
+  CPG_LOOP for (int i = 0; i < R.N; i++)
+    { const int a = v[i].asgn;
+      const char c = (a == ST_E) ? 'E' : (a == ST_R) ? 'R' : (a == ST_H) ? 'H' : (a == ST_D) ? 'D' : '?';
+      const int b = v[i].b, e = v[i].e;
+      CPG_LOOP for (int j = b+W.glane; j < e; j += W.gsize) cls[K-1+j] = (uint8_t)c;
+    }
 }
 
 /* ---- the whole read: src/ClassPro.c:229-271, in three phases.
@@ -246,17 +282,8 @@ CPG_DEV_NOINL void classify_phase2(ReadCtx &R, WCtx &W, RelShared *sh)
 { if (!(W.status & CPG_ST_ABORT)) classify_reliable(R,W,sh); }
 
 CPG_DEV_NOINL int classify_phase3(ReadCtx &R, WCtx &W, uint8_t *cls)
-{ const int K = W.M->K;
-  if (!(W.status & CPG_ST_ABORT)) classify_unreliable(R,W);
-  /* emit: 'N' x (K-1), then one class character per k-mer */
-  CPG_LOOP for (int j = W.glane; j < K-1; j += W.gsize) cls[j] = 'N';
-  const cpg_intvl *v = R.S.intvl;
-  CPG_LOOP for (int i = 0; i < R.N; i++)
-    { const int a = v[i].asgn;
-      const char c = (a == ST_E) ? 'E' : (a == ST_R) ? 'R' : (a == ST_H) ? 'H' : (a == ST_D) ? 'D' : '?';
-      const int b = v[i].b, e = v[i].e;
-      CPG_LOOP for (int j = b+W.glane; j < e; j += W.gsize) cls[K-1+j] = (uint8_t)c;
-    }
+{ if (!(W.status & CPG_ST_ABORT)) classify_unreliable(R,W);
+  emit_classes(R,W,cls);
   CPG_SYNCGROUP(W);
   return W.status;
 }

@@ -105,7 +105,7 @@ static int fake_read(cpg_ctx *c, const cpg_batch *b, int i, uint8_t *cls)
   R.S.mark = Kk.mark.data(); R.S.slot = Kk.slot.data(); R.S.perr = Kk.perr.data(); R.S.eint = Kk.eint.data();
   R.S.intvl = Kk.intvl.data(); R.S.rint = Kk.rint.data(); R.S.wint = Kk.wint.data();
   R.S.bp = Kk.bp.data(); R.S.asg_f = Kk.af.data(); R.S.asg_b = Kk.ab.data();
-  R.S.rpos = Kk.rpos.data(); R.S.ord = Kk.ord.data(); R.S.fixed = Kk.fixed.data(); R.S.MC = Kk.mc; R.S.memo = Kk.memo.data();
+  R.S.rpos = Kk.rpos.data(); R.S.ord = Kk.ord.data(); R.S.srt = Kk.srt.data(); R.S.MC = Kk.mc; R.S.upre = Kk.upre.data();
   R.S.capS = Kk.capS; R.S.capE = Kk.capE; R.S.capI = Kk.capI;
   R.S.tlog = Kk.tlog.data(); R.S.capT = Kk.capT; R.S.capC = Kk.capC; R.S.hdr = Kk.hdr.data(); R.S.big = Kk.big.data();
   R.S.key = Kk.key.data();

@@ -97,7 +97,7 @@ struct HsWork
   { std::vector<uint8_t> mark; std::vector<uint16_t> slot; std::vector<uint32_t> cand, key; std::vector<double> perr; std::vector<cpg_eintvl> eint;
     std::vector<int32_t> tlog; std::vector<cpg_chdr> hdr; std::vector<cpg_cbig> big; int capT = 0, capC = 0;
     std::vector<cpg_intvl> intvl, rint, wint; std::vector<uint16_t> bp;
-    std::vector<uint8_t> af, ab, rpos, fixed; std::vector<int32_t> ord; std::vector<cpg_unmemo> memo; int mc = 0;
+    std::vector<uint8_t> af, ab, rpos; std::vector<int32_t> ord, srt; std::vector<cpg_upre> upre; int mc = 0;
     int capS = 0, capE = 0, capI = 0;
     /* the interval tables are allocated with exactly `cap` entries (heap, so that an access past a
        compact table is visible to a memory checker) */
@@ -106,14 +106,14 @@ struct HsWork
         if (small > 0) { capI = capE = small; capS = 2*small; }
         capT = 3*capS; capC = capI;
         perr.assign((size_t)capS*4,0.); eint.assign(capE,cpg_eintvl()); intvl.assign(capI,cpg_intvl());
-        fixed.assign(capI,0); ord.assign(capI,0); key.assign(capI,0);
+        srt.assign(capI,0); ord.assign(capI,0); key.assign(capI,0); upre.assign(capI,cpg_upre());
         tlog.assign(capT,0); hdr.assign(capC,cpg_chdr()); big.assign(capC,cpg_cbig());
       }
     void size(int P)
       { int MC = P/2+8;
         mark.assign(P+2+32,0); slot.assign(P+2,0xffff);        /* the flag bytes are zero between reads (checked below) */ cand.assign(P/32+2,0); perr.assign((size_t)(P+2)*4,0.); eint.resize(P+2); intvl.resize(P+2);
         rint.resize(MC); wint.resize(2*MC); bp.assign(2*MC,0); af.assign(MC,0); ab.assign(MC,0);
-        rpos.assign(2*MC,0); mc = MC; memo.assign((size_t)CPG_MEMO_CAP*8,cpg_unmemo()); fixed.assign(P+2,0); ord.assign(P+2,0);
+        rpos.assign(2*MC,0); mc = MC; srt.assign(P+2,0); ord.assign(P+2,0);
       }
   };
 
@@ -222,7 +222,7 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
       R.S.mark = K.mark.data(); R.S.slot = K.slot.data(); R.S.perr = K.perr.data(); R.S.eint = K.eint.data();
       R.S.intvl = K.intvl.data(); R.S.rint = K.rint.data(); R.S.wint = K.wint.data();
       R.S.bp = K.bp.data(); R.S.asg_f = K.af.data(); R.S.asg_b = K.ab.data();
-      R.S.rpos = K.rpos.data(); R.S.ord = K.ord.data(); R.S.fixed = K.fixed.data(); R.S.MC = K.mc; R.S.memo = K.memo.data();
+      R.S.rpos = K.rpos.data(); R.S.ord = K.ord.data(); R.S.srt = K.srt.data(); R.S.MC = K.mc; R.S.upre = K.upre.data();
       R.S.capS = K.capS; R.S.capE = K.capE; R.S.capI = K.capI;
       R.S.tlog = K.tlog.data(); R.S.capT = K.capT; R.S.capC = K.capC; R.S.hdr = K.hdr.data(); R.S.big = K.big.data();
       R.S.key = K.key.data();
