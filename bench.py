@@ -711,7 +711,8 @@ def main():
                   "note": "reliable-interval DP on the interval tables (48 B per interval): FP64 dependency chains"},
         "k_unrel": {"ms": ms_ph[2], "bytes": r, "traffic": traffic.get("k_unrel"),
                     "launches": {"k_unrel_a": ms_ph[2] * wall_ns[3] / max(1, sum(wall_ns[3:])),
-                                 "k_unrel_b": ms_ph[2] * wall_ns[4] / max(1, sum(wall_ns[3:]))},
+                                 "k_unrel_b": ms_ph[2] * wall_ns[4] / max(1, sum(wall_ns[3:])),
+                                 "k_emit": ms_ph[2] * wall_ns[5] / max(1, sum(wall_ns[3:]))},
                     "note": "unreliable intervals (pure per interval, then the sweeps per read) + class string (r bytes out)"},
         "retry_launch": {"ms": ms_ph[3]},
     }

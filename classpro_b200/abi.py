@@ -254,8 +254,8 @@ class Context:
         return list(out)
 
     def wall_ns(self):
-        """Device time of k_wall_a, k_wall_b, k_wall_c, k_unrel_a, k_unrel_b in the last timed resident run, nanoseconds."""
-        out = (C.c_uint64 * 5)()
+        """Device time of k_wall_a, k_wall_b, k_wall_c, k_unrel_a, k_unrel_b, k_emit in the last timed resident run, nanoseconds."""
+        out = (C.c_uint64 * 6)()
         rc = self.L.cpg_wall_ns(self.h, out)
         if rc:
             raise self._err("cpg_wall_ns", rc)

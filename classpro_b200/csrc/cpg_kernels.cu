@@ -1,7 +1,7 @@
 /*******************************************************************************************
  *  cpg_kernels.cu -- sm_100a kernels and the C ABI of libclasspro_b200.so.
  *
- *  Eight launches per batch, all persistent (grid = a multiple of the SM count, warps / lane groups
+ *  Nine launches per batch, all persistent (grid = a multiple of the SM count, warps / lane groups
  *  pull reads from an atomic queue in processing order):
  *
  *   k_decode    one warp per read: FastK profile bytes -> uint16 counts + the wall-candidate bit
@@ -17,8 +17,8 @@
  *   k_rel       reliable-interval DP, forward and backward (cpg_rel.cuh), on the pooled tables.
  *   k_unrel_a   one interval per lane: the pure part of the unreliable pass (neighbours, ten task
  *               values per interval the sweeps will visit).
- *   k_unrel_b   the two order-dependent sweeps on those values and the class string
- *               (cpg_unrel.cuh): r bytes per read out.
+ *   k_unrel_b   the two order-dependent sweeps on those values (cpg_unrel.cuh).
+ *   k_emit      class strings, streaming: r bytes per read out.
  *   k_classify  the three phases in one kernel, on 4 CTAs with worst-case scratch: the retry
  *               launch for reads that outgrew the compact scratch blocks or the pool (normally
  *               none; it returns at once).  CPG_FUSED=1 runs every read through it instead.
@@ -65,7 +65,7 @@ struct BatchDev
     int32_t       *status;
     const int32_t *order;
     int32_t       *queue;        /* work counters: [0] decode, [1] classify/wall_a, [2] retry launch; [3] reads flagged
-                                    for retry; [4] reliable DP, [5] unrel_a, [6] wall_b, [7] wall_c, [24] unrel_b */
+                                    for retry; [4] reliable DP, [5] unrel_a, [6] wall_b, [7] wall_c, [24] unrel_b, [25] emit */
     struct ReadRec *rec;         /* per read: where the wall kernels left its candidate records and interval tables */
     cpg_intvl     *pool;         /* interval pool of the batch: intvl[N] then rint[M] of each read */
     unsigned long long *pool_cursor;
@@ -332,7 +332,7 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
  * ------------------------------------------------------------------------------------------ */
 /* Lanes per read of each phase kernel (powers of two <= 32); profiles/README.md has the sweeps. */
 #ifndef WALLB_GROUP
-#define WALLB_GROUP 4
+#define WALLB_GROUP 2
 #endif
 #ifndef WALLC_GROUP
 #define WALLC_GROUP 8
@@ -369,11 +369,8 @@ template<int G> struct RelPhaseShared
     cpg_wshared ws[PHASE_THREADS/G];
     RelShared   rel[PHASE_THREADS/G][2];
   };
-struct WallAShared
-  { uint8_t     cthres[CPG_LROWS*256*4];
-    cpg_dmodel  model;
-    int32_t     q[WALLA_THREADS/32][WALLA_QCAP];
-  };
+struct WaTask;
+struct WallAShared;
 
 struct GroupId { int lane, gib, glane, gbase, gsize; unsigned gmask; };
 template<int G> __device__ __forceinline__ GroupId group_id()
@@ -397,8 +394,35 @@ __device__ __forceinline__ void init_wctx(WCtx &W, const GroupId &g, const cpg_d
 /* phase 1a: the pure step of wall detection, one wall candidate per lane (cpg_wall.cuh, wa_).
    A warp takes a read, streams its candidate bit map (1024 positions per step), queues the candidate
    positions in shared memory and works them off 32 at a time, so that the lanes stay full although
-   only one position in ~80 is a candidate.  Reads: 2 counts, the bases around the k-mer's end, the
-   threshold table (shared memory) per candidate; writes: a header per candidate, in position order. */
+   only one position in ~80 is a candidate.  That is stage 0 (context + count thresholds, cheap).  The
+   candidates that get past it (one in ten) need the probabilities (wa_tasks, expensive): the lanes of a
+   warp wait for each other (SIMT), so these are queued a second time -- across reads -- and evaluated
+   32 at a time as well.  Reads: 2 counts, the bases around the k-mer's end, the threshold table (shared
+   memory) per candidate; writes: a header per candidate, in position order, a record per queued one. */
+struct WaTask { int32_t r, pos; uint32_t idx, packed, cnts; };     /* packed: info | t << 8 | l << 12; cnts: cout | cin << 16 */
+#define WALLA_TCAP 64
+struct WallAShared
+  { uint8_t     cthres[CPG_LROWS*256*4];
+    cpg_dmodel  model;
+    int32_t     q[WALLA_THREADS/32][WALLA_QCAP];
+    WaTask      tq[WALLA_THREADS/32][WALLA_TCAP];
+  };
+
+__device__ __forceinline__ void wa_run_tasks(const BatchDev &B, const WCtx &W, const WaTask *tq, int n, int lane)
+{ if (lane < n)
+    { const WaTask T = tq[lane];
+      const int rlen = B.rlen[T.r], plen = rlen-W.M->K+1;
+      cpg_seq seq; seq.p = B.seq+B.seq_off[T.r]; seq.bits = B.seq_bits;
+      WaCand C;
+      const unsigned info = T.packed & 0xffu;
+      C.wtype = (info & CH_GAIN) ? WT_GAIN : WT_DROP;
+      C.t = (T.packed >> 8) & 0xf; C.l = (T.packed >> 12) & 0xff;
+      C.cout = (uint16_t)(T.cnts & 0xffffu); C.cin = (uint16_t)(T.cnts >> 16);
+      C.cng = (int)C.cout-(int)C.cin; C.erate = W.M->pe[C.t][C.l];
+      wa_tasks(B.cnt+B.cnt_off[T.r],plen,seq,rlen,W,T.pos,C,info,B.big+T.idx);
+    }
+}
+
 __global__ void __launch_bounds__(WALLA_THREADS,WALLA_MIN_BLOCKS)
 k_wall_a(BatchDev B, cpg_dmodel M)
 { extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -411,6 +435,8 @@ k_wall_a(BatchDev B, cpg_dmodel M)
   cpg_model_fill_logs(&sh.model,threadIdx.x,blockDim.x);
   __syncthreads();
   int32_t *pq = sh.q[wib];
+  WaTask *tq = sh.tq[wib];
+  int ntq = 0;
   WCtx W;
   W.lane = lane; W.M = &sh.model; W.cthres = sh.cthres; W.ws = 0; W.status = 0;
   W.glane = 0; W.gsize = 1; W.gbase = lane; W.gmask = 1u << lane;
@@ -440,15 +466,14 @@ k_wall_a(BatchDev B, cpg_dmodel M)
       cpg_chdr *hdr = B.hdr+hoff;
       int npend = 0, done = 0, overflow = 0;
       for (int wb = 0; wb < nwords || npend > 0; wb += 32)
-        { int total = 0;
-          if (wb < nwords)
+        { if (wb < nwords)
             { const int w = wb+lane;
               unsigned cw = (w < nwords) ? (cand[w] & (w == nwords-1 ? tail : 0xffffffffu)) : 0u;
               int incl = __popc(cw);
               const int mine = incl;
               #pragma unroll
               for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu,incl,d); if (lane >= d) incl += t; }
-              total = __shfl_sync(0xffffffffu,incl,31);
+              const int total = __shfl_sync(0xffffffffu,incl,31);
               int k = npend+incl-mine;
               while (cw) { const int bit = __ffs((int)cw)-1; cw &= cw-1; pq[k++] = (w << 5)+bit; }
               __syncwarp();
@@ -460,7 +485,7 @@ k_wall_a(BatchDev B, cpg_dmodel M)
             { const int nact = min(32,npend-head);
               const int active = lane < nact;
               const int pos = active ? pq[head+lane] : 0;
-              unsigned info = 0; WaCand C;
+              unsigned info = 0; WaCand C; C.t = 0; C.l = 0; C.cout = 0; C.cin = 0;
               if (active) info = wa_stage0(prof,seq,rlen,W,pos,C);
               int need = active && (info & (CH_REACH_S|CH_REACH_O));
               const unsigned m = __ballot_sync(0xffffffffu,need);
@@ -473,7 +498,26 @@ k_wall_a(BatchDev B, cpg_dmodel M)
                 { cpg_chdr H; H.pos = pos; H.info = info; H.big = (uint32_t)idx; H.pad = 0;
                   *reinterpret_cast<uint4 *>(hdr+done+lane) = *reinterpret_cast<const uint4 *>(&H);
                 }
-              if (need) wa_tasks(prof,plen,seq,rlen,W,pos,C,info,B.big+idx);
+              /* second queue: the expensive part, for full warps of candidates that need it */
+              const unsigned m2 = __ballot_sync(0xffffffffu,need);
+              if (need)
+                { WaTask T; T.r = r; T.pos = pos; T.idx = (uint32_t)idx;
+                  T.packed = info | ((unsigned)C.t << 8) | ((unsigned)C.l << 12);
+                  T.cnts = (unsigned)C.cout | ((unsigned)C.cin << 16);
+                  tq[ntq+__popc(m2 & lt)] = T;
+                }
+              __syncwarp();
+              ntq += __popc(m2);
+              if (ntq >= 32)
+                { wa_run_tasks(B,W,tq,32,lane);
+                  __syncwarp();
+                  const int left = ntq-32;
+                  WaTask T; if (lane < left) T = tq[32+lane];
+                  __syncwarp();
+                  if (lane < left) tq[lane] = T;
+                  __syncwarp();
+                  ntq = left;
+                }
               done += nact; head += nact;
             }
           /* bring the remainder to the front of the queue */
@@ -494,6 +538,7 @@ k_wall_a(BatchDev B, cpg_dmodel M)
           if (overflow) { B.status[r] = CPG_ST_RETRY; atomicAdd(B.queue+3,1); }
         }
     }
+  if (ntq > 0) wa_run_tasks(B,W,tq,ntq,lane);
 }
 
 /* phase 1b: the order-dependent replay of find_wall for one read per lane group (cpg_wall.cuh, wb_):
@@ -580,7 +625,10 @@ k_wall_c(BatchDev B, cpg_dmodel M)
     }
 }
 
-/* phase 2: forward/backward DP over the reliable intervals (cpg_rel.cuh) */
+/* phase 2: forward/backward DP over the reliable intervals (cpg_rel.cuh).  The lane groups of a warp run
+   the same code on different reads, so the warp executes them together wherever their control flow agrees
+   (SIMT): an explicit warp-wide barrier per DP step changed neither the instruction count nor the active
+   lanes per instruction (profiles/r02_rel_lockstep.md). */
 __global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
 k_rel(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { constexpr int G = REL_GROUP;
@@ -686,8 +734,7 @@ k_unrel_a(BatchDev B, cpg_dmodel M)
     }
 }
 
-/* phase 3b: the sweeps of the unreliable pass on the recorded values, then the class string
-   (cpg_unrel.cuh: un_sweeps, emit_classes): r bytes per read out */
+/* phase 3b: the sweeps of the unreliable pass on the recorded values (cpg_unrel.cuh: un_sweeps) */
 __global__ void __launch_bounds__(PHASE_THREADS,PHASE_MIN_BLOCKS)
 k_unrel_b(BatchDev B, cpg_dmodel M, ScratchDev SC)
 { constexpr int G = UNREL_GROUP;
@@ -720,10 +767,43 @@ k_unrel_b(BatchDev B, cpg_dmodel M, ScratchDev SC)
         { const int nf = un_list(R,W);                       /* == rc.nf: same rule, same order as k_unrel_a */
           un_sweeps(R,W,nf,B.upre+rc.uoff);
         }
-      emit_classes(R,W,B.cls+B.cls_off[r]);
       const int st = __reduce_or_sync(g.gmask,W.status);
       if (g.glane == 0 && st != st0) B.status[r] = st;
       __syncwarp(g.gmask);
+    }
+}
+
+/* phase 4: class strings (src/ClassPro.c:114-117,265-271), streaming: one warp per read, 32 intervals
+   loaded at a time (one per lane), their stretches written 32 consecutive bytes per instruction.
+   (12+5) N bytes in, r bytes out per read. */
+__global__ void __launch_bounds__(256)
+k_emit(BatchDev B, int K)
+{ const int lane = threadIdx.x & 31;
+  for (;;)
+    { const int q = next_read(B.queue+25,lane);
+      if (q >= B.n_reads) break;
+      const int r = B.order[q];
+      if (B.status[r] & (CPG_ST_BAD_PROFILE|CPG_ST_RETRY)) continue;       /* the host's / the retry launch's */
+      const ReadRec rc = B.rec[r];
+      uint8_t *out = B.cls+B.cls_off[r];
+      for (int j = lane; j < K-1; j += 32) out[j] = 'N';
+      out += K-1;
+      const cpg_intvl *v = B.pool+rc.off;
+      for (int base = 0; base < rc.N; base += 32)
+        { const int i = base+lane;
+          int b = 0, e = 0, c = '?';
+          if (i < rc.N)
+            { b = v[i].b; e = v[i].e;
+              const int a = v[i].asgn;
+              c = (a == ST_E) ? 'E' : (a == ST_R) ? 'R' : (a == ST_H) ? 'H' : (a == ST_D) ? 'D' : '?';
+            }
+          const int cnt = min(32,rc.N-base);
+          for (int k = 0; k < cnt; k++)
+            { const int kb = __shfl_sync(0xffffffffu,b,k), ke = __shfl_sync(0xffffffffu,e,k);
+              const uint8_t kc = (uint8_t)__shfl_sync(0xffffffffu,c,k);
+              for (int j = kb+lane; j < ke; j += 32) out[j] = kc;
+            }
+        }
     }
 }
 
@@ -780,10 +860,10 @@ struct cpg_ctx
     int        fused;                 /* CPG_FUSED=1: the single-kernel path (k_classify) for every read */
     int        walla_blocks, wallb_blocks, wallc_blocks, rel_blocks, unrela_blocks, unrel_blocks;
     size_t     walla_smem, rel_smem, unrel_smem;
-    cudaEvent_t evp[6];               /* between the phase kernels */
+    cudaEvent_t evp[7];               /* between the phase kernels */
     uint64_t   phase_ns[4];           /* wall, reliable DP, unreliable + emit, retry launch: last timed run */
     uint64_t   wall_ns[3];            /* k_wall_a, k_wall_b, k_wall_c of that run */
-    uint64_t   unrel_ns[2];           /* k_unrel_a, k_unrel_b */
+    uint64_t   unrel_ns[3];           /* k_unrel_a, k_unrel_b, k_emit */
     int        n_sm, decode_blocks, classify_blocks;
     size_t     classify_smem;
     cudaEvent_t ev[3];
@@ -858,7 +938,7 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   if (ctx->d_cthres) cudaFree(ctx->d_cthres);
   if (ctx->d_logfact) cudaFree(ctx->d_logfact);
   for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  for (int i = 0; i < 6; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
+  for (int i = 0; i < 7; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
   free(ctx);
 }
 
@@ -904,7 +984,7 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
       CU_C(cudaEventCreateWithFlags(&ctx->slot[s].kdone,cudaEventDisableTiming));
     }
   for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->ev[i]));
-  for (int i = 0; i < 6; i++) CU_C(cudaEventCreate(&ctx->evp[i]));
+  for (int i = 0; i < 7; i++) CU_C(cudaEventCreate(&ctx->evp[i]));
   { const char *f = getenv("CPG_FUSED"); ctx->fused = (f && atoi(f) > 0); }
   ctx->walla_smem = sizeof(WallAShared); ctx->rel_smem = sizeof(RelPhaseShared<REL_GROUP>);
   ctx->unrel_smem = sizeof(PhaseShared<UNREL_GROUP,false>);
@@ -1026,7 +1106,7 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
      batch (plain longest-first) 608 ms (profiles/r01_history.md).  CPG_ORDER_CHUNK overrides. */
   { int *bucket = (int *)calloc((size_t)maxR+2,sizeof(int));
     if (bucket == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
-    int chunk = ctx->fused ? ctx->classify_blocks*CLASSIFY_GROUPS : ctx->wallb_blocks*(PHASE_THREADS/WALLB_GROUP);
+    int chunk = ctx->fused ? ctx->classify_blocks*CLASSIFY_GROUPS : ctx->n_sm*256;
     { const char *f = getenv("CPG_ORDER_CHUNK"); if (f && atoi(f) > 0) chunk = atoi(f); }
     if (chunk < 1) chunk = 1;
     for (int c0 = 0; c0 < n; c0 += chunk)
@@ -1131,6 +1211,8 @@ static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
       k_unrel_a<<<ctx->unrela_blocks,WALLA_THREADS,0,st>>>(S->B,ctx->dmodel);
       if (timed) CU(cudaEventRecord(ctx->evp[5],st));
       k_unrel_b<<<ctx->unrel_blocks,PHASE_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SCu);
+      if (timed) CU(cudaEventRecord(ctx->evp[6],st));
+      k_emit<<<ctx->n_sm*8,256,0,st>>>(S->B,ctx->model.kmer);
       if (timed) CU(cudaEventRecord(ctx->evp[2],st));
     }
   k_classify<<<ctx->retry_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SCbig,1);
@@ -1245,15 +1327,16 @@ extern "C" int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float
               CU(cudaEventElapsedTime(&p2,ctx->evp[4],ctx->evp[0]));
               ctx->wall_ns[0] = (uint64_t)(p0*1e6); ctx->wall_ns[1] = (uint64_t)(p1*1e6); ctx->wall_ns[2] = (uint64_t)(p2*1e6);
               CU(cudaEventElapsedTime(&p0,ctx->evp[1],ctx->evp[5]));
-              CU(cudaEventElapsedTime(&p1,ctx->evp[5],ctx->evp[2]));
-              ctx->unrel_ns[0] = (uint64_t)(p0*1e6); ctx->unrel_ns[1] = (uint64_t)(p1*1e6);
+              CU(cudaEventElapsedTime(&p1,ctx->evp[5],ctx->evp[6]));
+              CU(cudaEventElapsedTime(&p2,ctx->evp[6],ctx->evp[2]));
+              ctx->unrel_ns[0] = (uint64_t)(p0*1e6); ctx->unrel_ns[1] = (uint64_t)(p1*1e6); ctx->unrel_ns[2] = (uint64_t)(p2*1e6);
             }
         }
       td += a; tc += b;
     }
   if (ms_decode) *ms_decode = (float)(td/iters);
   if (ms_classify) *ms_classify = (float)(tc/iters);
-  if (launches) *launches = (ctx->fused ? 3 : 8)*iters;
+  if (launches) *launches = (ctx->fused ? 3 : 9)*iters;
   return CPG_OK;
 }
 
@@ -1271,10 +1354,10 @@ extern "C" int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4])
   return CPG_OK;
 }
 
-extern "C" int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[5])
+extern "C" int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[6])
 { if (ctx == NULL || out == NULL) return set_err(ctx,CPG_EINVAL,"cpg_wall_ns: bad argument");
   for (int i = 0; i < 3; i++) out[i] = ctx->fused ? 0 : ctx->wall_ns[i];
-  for (int i = 0; i < 2; i++) out[3+i] = ctx->fused ? 0 : ctx->unrel_ns[i];
+  for (int i = 0; i < 3; i++) out[3+i] = ctx->fused ? 0 : ctx->unrel_ns[i];
   return CPG_OK;
 }
 

@@ -32,6 +32,7 @@ CPG_DEV_MATHFN double cpg_log(double x) { return log(x); }
 
 CPG_DEV int imin(int a, int b) { return a < b ? a : b; }
 CPG_DEV int imax(int a, int b) { return a > b ? a : b; }
+CPG_DEV int iabs(int a) { return a < 0 ? -a : a; }
 /* the reference's MAX macro on doubles: (x) > (y) ? (x) : (y) */
 CPG_DEV double dmax_ref(double x, double y) { return x > y ? x : y; }
 

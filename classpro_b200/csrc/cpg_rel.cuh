@@ -139,19 +139,36 @@ CPG_DEV_NOINL void rl_update(ReadCtx &R, WCtx &W, const RelRun &U, int i, RelSta
   const int ip = rl_pred(i,F);
   double *tr = U.sh->tr;
 
-  /* tasks 0..7 are the H/D targets (one Bessel recurrence each), 8..15 the E/R targets, so that a
-     group of eight lanes runs all the recurrences of a step at the same time */
-  CPG_LOOP for (int q0 = W.glane; q0 < 16; q0 += W.gsize)
-    { const int s = (q0 >> 1) & 3, t = ((q0 < 8) ? ST_H : ST_E)+(q0 & 1), q = s*4+t;
-      double v = 0.;
-      int need = 0, k = 0; double lambda = 0.;
-      if (prv[s].dp != -CPG_INF)
-        { if (t == ST_E)      v = cpg_exp(rl_lp_e(W,I,U.COV));
-          else if (t == ST_R) v = cpg_exp(rl_lp_r(W,I,prv[s].cnt[ST_R],F,U.COV));
-          else { rl_hd_args(W,t,I,prv[s],F,k,lambda); need = 1; }
+  /* The 16 transitions as tasks.  The 8 with target H or D cost one Bessel recurrence each, whose length
+     grows with the count difference |k| (2(|k|+sqrt(40|k|)) steps): about 20 for the state that fits the
+     interval, about 80 for the other one.  The lanes of a warp wait for the longest recurrence of a round
+     (SIMT), so the rounds are made homogeneous: a lane holds the H and the D transition of ONE predecessor
+     state and takes the longer of the two first.  With 4 lanes per chain: round 0 = the long recurrences of
+     all chains of the warp, round 1 = the short ones (before: every round as long as the longest).
+     Then the E / R targets (no recurrence). */
+  CPG_LOOP for (int s0 = W.glane; s0 < 4; s0 += W.gsize)
+    { int kk[2] = {0,0}; double ll[2] = {0.,0.};
+      const int live = (prv[s0].dp != -CPG_INF);
+      if (live)
+        { rl_hd_args(W,ST_H,I,prv[s0],F,kk[0],ll[0]);
+          rl_hd_args(W,ST_D,I,prv[s0],F,kk[1],ll[1]);
         }
-      if (need) v = cpg_exp(cpg_lp_skellam(k,lambda)+0.);
-      tr[q] = v;
+      const int first = (iabs(kk[1]) > iabs(kk[0]));            /* the longer recurrence first */
+      CPG_LOOP for (int rr = 0; rr < 2; rr++)
+        { const int x = rr ? !first : first;
+          double v = 0.;
+          if (live) v = cpg_exp(cpg_lp_skellam(kk[x],ll[x])+0.);
+          tr[s0*4+ST_H+x] = v;
+        }
+    }
+  CPG_LOOP for (int q0 = W.glane; q0 < 8; q0 += W.gsize)
+    { const int s = q0 >> 1, t = ST_E+(q0 & 1);
+      double v = 0.;
+      if (prv[s].dp != -CPG_INF)
+        { if (t == ST_E) v = cpg_exp(rl_lp_e(W,I,U.COV));
+          else           v = cpg_exp(rl_lp_r(W,I,prv[s].cnt[ST_R],F,U.COV));
+        }
+      tr[s*4+t] = v;
     }
   CPG_SYNCGROUP(W);
   double psum = 0.;

@@ -279,7 +279,8 @@ CPG_DEV_NOINL void classify_phase1(ReadCtx &R, WCtx &W)
 { find_walls_and_reliable(R,W); }
 
 CPG_DEV_NOINL void classify_phase2(ReadCtx &R, WCtx &W, RelShared *sh)
-{ if (!(W.status & CPG_ST_ABORT)) classify_reliable(R,W,sh); }
+{ if (!(W.status & CPG_ST_ABORT)) classify_reliable(R,W,sh);
+}
 
 CPG_DEV_NOINL int classify_phase3(ReadCtx &R, WCtx &W, uint8_t *cls)
 { if (!(W.status & CPG_ST_ABORT)) classify_unreliable(R,W);

@@ -149,8 +149,8 @@ int cpg_download(cpg_ctx *ctx, cpg_result *result);
 int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4]);
 /* ... and of the kernels inside those phases: [0] k_wall_a (pure, one candidate per lane), [1] k_wall_b
  * (order-dependent replay, one read per lane group), [2] k_wall_c (one interval per lane), [3] k_unrel_a (pure,
- * one interval per lane), [4] k_unrel_b (sweeps + class strings). */
-int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[5]);
+ * one interval per lane), [4] k_unrel_b (sweeps), [5] k_emit (class strings). */
+int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[6]);
 
 /* ---- profile producer (what FastK does before ClassPro runs) ----------------
  * FastK is not part of the reference tree; the reference only reads its files (src/libfastk.c:51-96
