@@ -26,6 +26,7 @@
   #define CPG_LDG(p)     (*(p))
   #define CPG_INF        ((double)INFINITY)
   #define CPG_LOOP
+  #define CPG_UNROLL4
   #if CPG_HOSTSIM == 32
     /* 32 host threads play the lanes of one warp; every warp primitive is a rendezvous, so a
        collective reached by only some lanes, or a missing __syncwarp, shows up as a hang or as
@@ -75,6 +76,8 @@
   #else
     #define CPG_LOOP     _Pragma("unroll 1")
   #endif
+  /* short loops of independent loads: unrolled so that the loads are in flight together */
+  #define CPG_UNROLL4    _Pragma("unroll 4")
   #define CPG_INF        (__longlong_as_double(0x7ff0000000000000LL))
 #endif
 

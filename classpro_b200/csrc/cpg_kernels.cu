@@ -335,7 +335,7 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
 #define WALLB_GROUP 2
 #endif
 #ifndef WALLC_GROUP
-#define WALLC_GROUP 8
+#define WALLC_GROUP 32
 #endif
 #ifndef REL_GROUP
 #define REL_GROUP   CPG_GROUP

@@ -141,15 +141,20 @@ CPG_DEV_NOINL void un_pre_interval(WCtx &W, const cpg_intvl *v, int N, int idx, 
 }
 
 /* src/class_unrel.c:185-237 for interval idx, whose recorded neighbours and task values are *U */
-CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, const cpg_upre *U)
+/* dirty: a reliable interval has entered or left H / D since the pure step (only then can a recorded
+   neighbour be out of date: the neighbours are reliable H / D intervals, and those that were so at the
+   start are never visited) */
+CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, const cpg_upre *U, int &dirty)
 { const cpg_intvl I = v[idx];
   int ns;
   if (imax(I.cb,I.ce) >= W.M->cov[ST_R]) ns = ST_R;
   else
     { double *term = W.ws->term;
       int nb[2][2];
+      int same = 1;
+      if (!dirty) { nb[0][0] = U->nb[0]; nb[0][1] = U->nb[1]; nb[1][0] = U->nb[2]; nb[1][1] = U->nb[3]; }
       /* the four walks, one per lane where there are lanes */
-      if (W.gsize >= 4)
+      else if (W.gsize >= 4)
         { int mine = -1;
           if (W.glane < 4)
             { const int s = (W.glane & 2) ? ST_D : ST_H;
@@ -160,7 +165,7 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, const cpg_up
           nb[1][0] = (int)cpg_gshfl(W,(unsigned)mine,2); nb[1][1] = (int)cpg_gshfl(W,(unsigned)mine,3);
         }
       else un_nn_walk(v,N,idx,nb);
-      const int same = (U->nb[0] == nb[0][0] && U->nb[1] == nb[0][1] && U->nb[2] == nb[1][0] && U->nb[3] == nb[1][1]);
+      if (dirty) same = (U->nb[0] == nb[0][0] && U->nb[1] == nb[0][1] && U->nb[2] == nb[1][0] && U->nb[3] == nb[1][1]);
       if (same) W.status |= U->st;
       else
         { /* a neighbour changed since the pure step: the tasks again, lanes in parallel */
@@ -205,7 +210,10 @@ CPG_DEV_NOINL void un_update(WCtx &W, int idx, cpg_intvl *v, int N, const cpg_up
       ns = ms;
     }
   CPG_SYNCGROUP(W);
-  if (W.glane == 0 && I.asgn != ns) v[idx].asgn = (int8_t)ns;
+  if (I.asgn != ns)
+    { if (W.glane == 0) v[idx].asgn = (int8_t)ns;
+      if (I.is_rel && (I.asgn == ST_H || I.asgn == ST_D || ns == ST_H || ns == ST_D)) dirty = 1;
+    }
   CPG_SYNCGROUP(W);
 }
 
@@ -246,8 +254,9 @@ CPG_DEV_NOINL void un_sweeps(ReadCtx &R, WCtx &W, int nf, const cpg_upre *U)
       srt[rank] = p;
     }
   CPG_SYNCGROUP(W);
-  CPG_LOOP for (int i = nf-1; i >= 0; i--) { const int p = srt[i]; un_update(W,lst[p],v,N,U+p); }
-  CPG_LOOP for (int i = 0; i < nf; i++)    { const int p = srt[i]; un_update(W,lst[p],v,N,U+p); }
+  int dirty = 0;
+  CPG_LOOP for (int i = nf-1; i >= 0; i--) { const int p = srt[i]; un_update(W,lst[p],v,N,U+p,dirty); }
+  CPG_LOOP for (int i = 0; i < nf; i++)    { const int p = srt[i]; un_update(W,lst[p],v,N,U+p,dirty); }
 }
 
 /* one read, both steps back to back (retry launch, host tests) */

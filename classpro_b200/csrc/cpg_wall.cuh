@@ -132,6 +132,13 @@ CPG_DEV_HELPER double perr_get(const ReadCtx &R, int pos, int e, int w)
   return R.S.perr[(size_t)R.S.slot[pos]*4+e*2+w];
 }
 
+/* max of the two OTHERS probabilities of a position (src/wall.c:941-944), -inf where it has no slot */
+CPG_DEV_HELPER double perr_max_o(const ReadCtx &R, int pos)
+{ if (!(R.S.mark[pos] & MK_SLOT)) return -CPG_INF;
+  const double *q = R.S.perr+(size_t)R.S.slot[pos]*4+ET_OTHERS*2;
+  return dmax_ref(q[WT_DROP],q[WT_GAIN]);
+}
+
 /* src/wall.c:317-322 */
 CPG_DEV_HELPER double lp_diff_pair(const uint16_t *p, const WCtx &W, int i, int j)
 { int n_drop = (int)p[i-1]-p[i], n_gain = (int)p[j]-p[j-1];
@@ -455,6 +462,23 @@ CPG_DEV_HELPER int hdr_after(const ReadCtx &R, int p)
   return lo;
 }
 
+/* Down the header list from c: the first candidate whose flag byte has all of `want` and none of `not`,
+   or the first at a position >= lim; R.ncand if neither.  Four headers, then their four flag bytes, are
+   loaded together (the list is walked for every cut: one dependent pair of loads per candidate otherwise). */
+CPG_DEV_HELPER int hdr_scan(const ReadCtx &R, int c, int lim, unsigned want, unsigned nots)
+{ CPG_LOOP while (c < R.ncand)
+    { int p[4]; unsigned m[4];
+      CPG_UNROLL4 for (int k = 0; k < 4; k++) p[k] = (c+k < R.ncand) ? R.hdr[c+k].pos : 0x7fffffff;
+      CPG_UNROLL4 for (int k = 0; k < 4; k++) m[k] = (p[k] < lim) ? R.S.mark[p[k]] : 0u;
+      CPG_UNROLL4 for (int k = 0; k < 4; k++)
+        { if (p[k] >= lim) return (c+k < R.ncand) ? c+k : R.ncand;
+          if ((m[k] & want) == want && !(m[k] & nots)) return c+k;
+        }
+      c += 4;
+    }
+  return R.ncand;
+}
+
 /* O-walls strictly inside an E-interval stop being walls (src/wall.c:727-735,865-873).  An O-wall can
    only stand at a candidate, so the open range (b,e) is walked down the header list. */
 CPG_DEV_HELPER void clear_o_range(ReadCtx &R, const WCtx &W, int b, int e)
@@ -588,11 +612,8 @@ CPG_DEV_NOINL int wb_walls(ReadCtx &R, WCtx &W)
 
   /* pass C: lone O-walls (by OTHERS, not by SELF), positions 1..plen-1; they stand at candidates */
   int midx = NS;
-  CPG_LOOP for (int c = 0; c < R.ncand; c++)
-    { const int i = R.hdr[c].pos;
-      const unsigned m = R.S.mark[i];
-      if (!(m & MK_BY_O) || (m & (MK_BY_S|MK_PAIR_MULT))) continue;
-      midx = wall_multi(R,W,i,NS,midx);
+  CPG_LOOP for (int c = hdr_scan(R,0,plen,MK_BY_O,MK_BY_S|MK_PAIR_MULT); c < R.ncand; c = hdr_scan(R,c+1,plen,MK_BY_O,MK_BY_S|MK_PAIR_MULT))
+    { midx = wall_multi(R,W,R.hdr[c].pos,NS,midx);
       if (W.status & CPG_ST_ABORT) return 0;
     }
   CPG_LOOP for (int k = NS; k < midx; k++) clear_o_range(R,W,eint[k].b,eint[k].e);
@@ -622,6 +643,23 @@ CPG_DEV_NOINL int wb_walls(ReadCtx &R, WCtx &W)
   return NS;
 }
 
+/* a fresh interval (counts are filled in by wc_interval), as three 16-byte stores */
+CPG_DEV void intvl_put(cpg_intvl *dst, int b, int e, double pe, double peob, double peoe)
+{
+#ifdef CPG_HOSTSIM
+  cpg_intvl I; memset(&I,0,sizeof(I));
+  I.b = b; I.e = e; I.asgn = ST_N; I.pe = pe; I.peob = peob; I.peoe = peoe;
+  *dst = I;
+#else
+  uint4 *q = reinterpret_cast<uint4 *>(dst);
+  q[0] = make_uint4((unsigned)b,(unsigned)e,0u,0u);                               /* b, e, cb, ce, ccb, cce */
+  const unsigned long long upe = (unsigned long long)__double_as_longlong(pe);
+  q[1] = make_uint4((unsigned)ST_N << 8,0u,(unsigned)upe,(unsigned)(upe >> 32));  /* is_rel, asgn, pad, pe */
+  const unsigned long long u1 = (unsigned long long)__double_as_longlong(peob), u2 = (unsigned long long)__double_as_longlong(peoe);
+  q[2] = make_uint4((unsigned)u1,(unsigned)(u1 >> 32),(unsigned)u2,(unsigned)(u2 >> 32));
+#endif
+}
+
 /* Pass E (src/wall.c:911-948).  The reference flags every position covered by an E-interval and cuts
    where the flag toggles, or at an O-wall outside the flagged stretches, or at plen.  Here the flagged
    stretches are the runs of the sorted E-interval list (intervals that touch or overlap merge) and the
@@ -633,7 +671,7 @@ CPG_DEV_NOINL int wb_cuts(ReadCtx &R, WCtx &W, int NS, cpg_intvl *dst, int cap, 
   const cpg_eintvl *eint = R.S.eint;
   int N = 0, b = 0, c = 0, k = 0, nlong = 0;
   double lpob = -CPG_INF;                 /* log of the OTHERS probability at the current interval start */
-  { double pob = dmax_ref(perr_get(R,0,ET_OTHERS,WT_DROP),perr_get(R,0,ET_OTHERS,WT_GAIN));
+  { const double pob = perr_max_o(R,0);
     if (dst && pob != -CPG_INF) lpob = cpg_log(pob);
   }
   CPG_LOOP for (;;)
@@ -648,8 +686,9 @@ CPG_DEV_NOINL int wb_cuts(ReadCtx &R, WCtx &W, int NS, cpg_intvl *dst, int cap, 
         { int e, in_run = 0;
           if (step == 0)
             { /* next O-wall in front of the run */
-              CPG_LOOP while (c < R.ncand && R.hdr[c].pos < rb && !(R.S.mark[R.hdr[c].pos] & MK_BY_O)) c++;
-              if (c < R.ncand && R.hdr[c].pos < rb) { e = R.hdr[c].pos; c++; }
+              c = hdr_scan(R,c,rb,MK_BY_O,0u);
+              const int pc = (c < R.ncand) ? R.hdr[c].pos : rb;
+              if (pc < rb) { e = pc; c++; }
               else { step = 1; continue; }
             }
           else if (step == 1)
@@ -670,15 +709,9 @@ CPG_DEV_NOINL int wb_cuts(ReadCtx &R, WCtx &W, int NS, cpg_intvl *dst, int cap, 
                 { const int q = ei_find(eint,0,NS-1,b,e);
                   if (q != -1) pe = cpg_log(eint[q].pe);
                 }
-              const double poe = dmax_ref(perr_get(R,e,ET_OTHERS,WT_DROP),perr_get(R,e,ET_OTHERS,WT_GAIN));
+              const double poe = perr_max_o(R,e);
               const double lpoe = (poe != -CPG_INF) ? cpg_log(poe) : -CPG_INF;
-              if (W.glane == 0 && N < cap)
-                { cpg_intvl *I = dst+N;
-                  I->b = b; I->e = e; I->cb = 0; I->ce = 0;
-                  I->ccb = 0; I->cce = 0; I->is_rel = 0; I->asgn = ST_N;
-                  CPG_LOOP for (int z = 0; z < 6; z++) I->pad[z] = 0;
-                  I->pe = pe; I->peob = lpob; I->peoe = lpoe;
-                }
+              if (W.glane == 0 && N < cap) intvl_put(dst+N,b,e,pe,lpob,lpoe);
               lpob = lpoe;
             }
           N++;
@@ -718,9 +751,9 @@ CPG_DEV_NOINL void wc_correct(const uint16_t *prof, int plen, const cpg_seq seq,
   { const int e1 = imin(I.b+K-1,I.e-1);              /* gains:  p in [I.b,e1)  */
     const int b3 = imax(I.e-K+1,I.b);                /* drops:  q in [b3,I.e-1) */
     int prev = prof[I.b];
-    CPG_LOOP for (int p = I.b; p < e1; p++) { const int nx = prof[p+1]; n_gain += imax(nx-prev,0); prev = nx; }
+    CPG_UNROLL4 for (int p = I.b; p < e1; p++) { const int nx = prof[p+1]; n_gain += imax(nx-prev,0); prev = nx; }
     prev = (b3 < I.e-1) ? prof[b3] : 0;
-    CPG_LOOP for (int q = b3; q < I.e-1; q++) { const int nx = prof[q+1]; n_drop += imax(prev-nx,0); prev = nx; }
+    CPG_UNROLL4 for (int q = b3; q < I.e-1; q++) { const int nx = prof[q+1]; n_drop += imax(prev-nx,0); prev = nx; }
   }
   /* minus the part explained by the low-complexity run at that end */
   { int e2 = I.b, b4 = I.e-1;                        /* empty ranges unless the interval is longer than K-1 */
