@@ -511,7 +511,7 @@ def main():
     ap.add_argument("--cov", type=float, default=0.)
     ap.add_argument("--chunk-mb", type=float, default=5.)
     ap.add_argument("--gen-threads", type=int, default=0)
-    ap.add_argument("--batches", type=int, default=4)
+    ap.add_argument("--batches", type=int, default=2)
     ap.add_argument("--cpu-sample-mbases", type=float, default=360.)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -638,29 +638,57 @@ def main():
     total_kmers = sum_over_ranks(float(data.kmers))
     value = total_kmers / (step_ms * 1e-3)
 
-    # ---- end to end: pinned host buffers in, class strings out, double buffered
-    def e2e_pass():
+    # ---- end to end: pinned host buffers in, results out, double buffered.  The result of a batch is its
+    # interval tables (CPG_RESULT_INTERVALS: 4 bytes per interval instead of 1 byte per base; the class
+    # strings are a host-side expansion, cpg_expand_intervals, done where the characters are written --
+    # in ClassPro's output formatter).  The class-string form of the same pass is timed beside it.
+    def e2e_pass(intervals, ivres):
         inflight = []
+
+        def fin(s, i, b, o):
+            if intervals:
+                if ivres[i] is None:
+                    ivres[i] = abi.IntervalResult(b.n, ctx.intervals_bound(s), pinned=True)
+                ctx.collect_intervals(s, ivres[i])
+            else:
+                ctx.collect(s, b, o)
+
         for i, (bt, out) in enumerate(data.batches):
             slot = i & 1
             if len(inflight) == 2:
-                s, b, o = inflight.pop(0)
-                ctx.collect(s, b, o)
+                fin(*inflight.pop(0))
             ctx.submit(slot, bt)
-            inflight.append((slot, bt, out))
-        for s, b, o in inflight:
-            ctx.collect(s, b, o)
+            inflight.append((slot, i, bt, out))
+        for x in inflight:
+            fin(*x)
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_pass()
-    barrier()
-    t0 = time.time()
-    for _ in range(args.steps):
-        e2e_pass()
-    barrier()
-    e2e_s = max_over_ranks((time.time() - t0) / args.steps)
+    def e2e_time(intervals, ivres):
+        ctx.set_result_mode(intervals)
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_pass(intervals, ivres)
+        barrier()
+        t0 = time.time()
+        for _ in range(args.steps):
+            e2e_pass(intervals, ivres)
+        barrier()
+        return max_over_ranks((time.time() - t0) / args.steps)
+
+    e2e_cls_s = e2e_time(False, None)
+    same_cls = bool(np.array_equal(data.pin_cls.u8[:data.bases], cls_res[:data.bases]))
+    ivres = [None] * len(data.batches)
+    e2e_s = e2e_time(True, ivres)
+    ctx.set_result_mode(False)
     e2e_value = total_kmers / e2e_s
-    same = bool(np.array_equal(data.pin_cls.u8[:data.bases], cls_res[:data.bases]))
+    d2h_ivl = 0
+    same = same_cls
+    at = 0
+    for (bt, out), rv in zip(data.batches, ivres):       # outside the timed region: expand and compare with the resident result
+        d2h_ivl += 4 * rv.used + 16 * bt.n
+        ex = rv.expand(K, bt.rlen)
+        nb = int(bt.cls_off[-1])
+        same = same and bool(np.array_equal(ex[:nb], cls_res[at:at + nb]))
+        at += nb
+        rv.free()
 
     # ---- parity: a seeded sample of this shard's reads through the oracle
     par = parity_sample(data, cls_res, args.parity_kmers / world, max(16, args.parity_reads // world), 4242 + rank,
@@ -769,8 +797,14 @@ def main():
                         "rank_time_imbalance": (step_ms / step_ms_min) if step_ms_min > 0 else None, "shards": shard_info},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": data.h2d_bytes,
-                        "d2h_bytes_per_step": data.d2h_bytes, "ms_per_step": e2e_s * 1e3,
+                        "d2h_bytes_per_step": int(sum_over_ranks(float(d2h_ivl)) / world) if world > 1 else d2h_ivl,
+                        "ms_per_step": e2e_s * 1e3,
                         "matches_resident_result": same,
+                        "result": "interval tables, 4 B per interval (cpg_collect_intervals); expanded to the class strings on "
+                                  "the host (cpg_expand_intervals) outside the timed region and compared with the resident result",
+                        "class_strings": {"value": total_kmers / e2e_cls_s, "ms_per_step": e2e_cls_s * 1e3,
+                                          "d2h_bytes_per_step": data.d2h_bytes,
+                                          "what": "the same pass returning 1 byte per base (cpg_collect)"},
                         "starts_from": "parsed, 2-bit packed reads and fetched profile bytes in pinned host memory "
                                        "(file parsing and output formatting are in `cli`)"},
                 "cli": cli,

@@ -64,6 +64,12 @@ def lib():
         L.cpg_download.argtypes = [C.c_void_p, C.POINTER(CResult)]
         L.cpg_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.cpg_wall_ns.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.cpg_set_result_mode.argtypes = [C.c_void_p, C.c_int]
+        L.cpg_intervals_bound.argtypes = [C.c_void_p, C.c_int]
+        L.cpg_intervals_bound.restype = C.c_int64
+        L.cpg_collect_intervals.argtypes = [C.c_void_p, C.c_int, C.POINTER(CResultIvl)]
+        L.cpg_expand_intervals.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.cpg_expand_intervals.restype = None
         L.cpg_host_alloc.argtypes = [C.c_size_t]
         L.cpg_host_alloc.restype = C.c_void_p
         L.cpg_host_free.argtypes = [C.c_void_p]
@@ -118,6 +124,51 @@ class Model:
     @property
     def cov(self):
         return list(self.c.cov)
+
+
+class CResultIvl(C.Structure):
+    _fields_ = [("ivl", C.c_void_p), ("ivl_cap", C.c_int64), ("ivl_at", C.c_void_p), ("ivl_n", C.c_void_p),
+                ("status", C.c_void_p), ("ivl_used", C.c_int64)]
+
+
+class IntervalResult:
+    """Host buffers of a compact result (cpg_result_ivl); pinned=True takes them from cpg_host_alloc."""
+
+    def __init__(self, n_reads, cap, pinned=False):
+        self.n = int(n_reads)
+        self.cap = int(cap)
+        if pinned:
+            self._pin = [PinnedArray(4 * max(self.cap, 1)), PinnedArray(8 * (self.n + 1)), PinnedArray(4 * (self.n + 1)),
+                         PinnedArray(4 * (self.n + 1))]
+            self.ivl = self._pin[0].view(np.uint32)
+            self.at = self._pin[1].view(np.int64)
+            self.cnt = self._pin[2].view(np.int32)
+            self.status = self._pin[3].view(np.int32)
+        else:
+            self.ivl = np.zeros(max(self.cap, 1), np.uint32)
+            self.at = np.zeros(self.n + 1, np.int64)
+            self.cnt = np.zeros(self.n + 1, np.int32)
+            self.status = np.zeros(self.n + 1, np.int32)
+        self.used = 0
+        self.c = CResultIvl(self.ivl.ctypes.data, self.cap, self.at.ctypes.data, self.cnt.ctypes.data,
+                            self.status.ctypes.data, 0)
+
+    def expand(self, K, rlen, out=None):
+        """Class strings of all reads, read after read (cpg_expand_intervals: host code)."""
+        L = lib()
+        rlen = np.asarray(rlen, np.int64)
+        off = np.zeros(self.n + 1, np.int64)
+        np.cumsum(rlen[:self.n], out=off[1:])
+        if out is None:
+            out = np.zeros(int(off[-1]) + 1, np.uint8)
+        for r in range(self.n):
+            L.cpg_expand_intervals(K, int(rlen[r]), self.ivl.ctypes.data + 4 * int(self.at[r]), int(self.cnt[r]),
+                                   out.ctypes.data + int(off[r]))
+        return out
+
+    def free(self):
+        for p in getattr(self, "_pin", []):
+            p.free()
 
 
 class PinnedArray:
@@ -231,6 +282,23 @@ class Context:
         if rc and not (rc == 5 and allow_read_errors):
             raise self._err("cpg_collect", rc)
         return cls, status[:batch.n]
+
+    def set_result_mode(self, intervals):
+        """False: class strings (cpg_collect); True: packed interval tables (collect_intervals)."""
+        rc = self.L.cpg_set_result_mode(self.h, 1 if intervals else 0)
+        if rc:
+            raise self._err("cpg_set_result_mode", rc)
+
+    def intervals_bound(self, slot):
+        return int(self.L.cpg_intervals_bound(self.h, slot))
+
+    def collect_intervals(self, slot, res, allow_read_errors=True):
+        """res: IntervalResult with room for intervals_bound(slot) entries."""
+        rc = self.L.cpg_collect_intervals(self.h, slot, C.byref(res.c))
+        if rc and not (rc == 5 and allow_read_errors):
+            raise self._err("cpg_collect_intervals", rc)
+        res.used = int(res.c.ivl_used)
+        return res
 
     def upload(self, batch):
         rc = self.L.cpg_upload(self.h, C.byref(batch.c))

@@ -74,6 +74,9 @@ struct BatchDev
     cpg_cbig      *big;          /* big candidate records */
     unsigned long long *hdr_cursor, *big_cursor;
     int64_t        hdr_cap, big_cap;
+    uint32_t      *ivl;          /* compact result (CPG_RESULT_INTERVALS): packed interval of pool entry i at ivl[i]; NULL = class strings */
+    int64_t       *ivl_at;       /* per read: its first entry */
+    int32_t       *ivl_n;        /* per read: its number of intervals */
     cpg_upre      *upre;         /* recorded task values of the unreliable pass, one per interval its sweeps visit */
     unsigned long long *upre_cursor;
     int64_t        upre_cap;
@@ -305,6 +308,19 @@ k_classify(BatchDev B, cpg_dmodel M, ScratchDev SC, int retry)
       if (active)
         { int st = classify_phase3(R,W,B.cls+B.cls_off[r]);
           st = __reduce_or_sync(gmask,st);
+          if (B.ivl != 0 && !(st & CPG_ST_RETRY))
+            { /* compact results: this read's table goes into the pool, where k_pack looks for it */
+              long long at = 0;
+              if (glane == 0) at = (long long)atomicAdd(B.pool_cursor,(unsigned long long)R.N);
+              at = __shfl_sync(gmask,at,gbase);
+              if (at+R.N > B.pool_cap) st |= CPG_ST_RETRY;            /* reported as an internal error */
+              else
+                { uint4 *dst = reinterpret_cast<uint4 *>(B.pool+at);
+                  const uint4 *src = reinterpret_cast<const uint4 *>(R.S.intvl);
+                  for (int i = glane; i < 3*R.N; i += CPG_GROUP) dst[i] = src[i];
+                  if (glane == 0) { ReadRec rc = B.rec[r]; rc.off = at; rc.N = R.N; B.rec[r] = rc; }
+                }
+            }
           if (glane == 0)
             { B.status[r] = st;
               if (st & CPG_ST_RETRY) atomicAdd(B.queue+3,1);
@@ -807,6 +823,22 @@ k_emit(BatchDev B, int K)
     }
 }
 
+/* compact results: (end << 3 | class) of every interval, 4 bytes instead of the 48 of the table; 12 N bytes
+   in, 4 N out per read */
+__global__ void __launch_bounds__(256)
+k_pack(BatchDev B)
+{ const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x*blockDim.x) >> 5;
+  for (int r = (blockIdx.x*blockDim.x+threadIdx.x) >> 5; r < B.n_reads; r += warps)
+    { const int st = B.status[r];
+      ReadRec rc = B.rec[r];
+      if (st & (CPG_ST_BAD_PROFILE|CPG_ST_ABORT)) { rc.N = 0; rc.off = 0; }
+      const cpg_intvl *v = B.pool+rc.off;
+      for (int i = lane; i < rc.N; i += 32) B.ivl[rc.off+i] = ((uint32_t)v[i].e << 3) | ((uint32_t)v[i].asgn & 7u);
+      if (lane == 0) { B.ivl_at[r] = rc.off; B.ivl_n[r] = rc.N; }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  *  prof2class (src/prof2class.c:236-258): a RELATIVE profile -- counts of the read's k-mers in a
  *  genome or haplotype table -- mapped to ground-truth classes, 0 -> E, 1 -> H, 2 -> D, more -> R,
@@ -836,10 +868,12 @@ struct DevBuf { void *p; size_t cap; };
 
 struct Slot
   { cudaStream_t stream;
-    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue, rec, pool, hdr, big, upre;
+    DevBuf seq, seq_off, rlen, prof, prof_off, cnt, cnt_off, cand, plen, cls, cls_off, status, order, queue, rec, pool, hdr, big, upre, ivl, ivl_at, ivl_n;
     /* small host-side (pinned) staging for arrays the library computes itself */
     int64_t *h_cnt_off; int32_t *h_order; size_t h_cap;
     int32_t *h_status; size_t h_status_cap;
+    unsigned long long *h_cursor;        /* pinned: the pool cursor after the kernels (compact results) */
+    int64_t  pool_cap;
     int32_t  n_reads; int64_t cls_bytes; int32_t maxP;
     int      busy;
     cudaEvent_t kdone;           /* recorded after this slot's kernels */
@@ -853,11 +887,15 @@ struct cpg_ctx
     cpg_dmodel dmodel;
     void      *d_cthres, *d_logfact;
     Slot       slot[2];
-    DevBuf     scratch, scratch_big; ScratchDev SC, SCbig;      /* SC: k_classify as the main launch (CPG_FUSED) */
-    ScratchDev SCw, SCr, SCu;                                   /* regions of `scratch` for k_wall_b, k_rel, k_unrel */
+    /* scratch arenas, one set per slot: the kernels of the two slots run at the same time (the CTAs of a
+       slot's next kernel move in as those of the other slot's persistent kernels run out of reads) */
+    DevBuf     scratch[2], scratch_big[2];
+    ScratchDev SC[2], SCbig[2];                                 /* SC: k_classify as the main launch (CPG_FUSED) */
+    ScratchDev SCw[2], SCr[2], SCu[2];                          /* regions of `scratch` for k_wall_b, k_rel, k_unrel */
     int        scratch_P;
     int        retry_blocks;
     int        fused;                 /* CPG_FUSED=1: the single-kernel path (k_classify) for every read */
+    int        result_mode;           /* CPG_RESULT_CLASSES / CPG_RESULT_INTERVALS */
     int        walla_blocks, wallb_blocks, wallc_blocks, rel_blocks, unrela_blocks, unrel_blocks;
     size_t     walla_smem, rel_smem, unrel_smem;
     cudaEvent_t evp[7];               /* between the phase kernels */
@@ -925,16 +963,19 @@ extern "C" void cpg_destroy(cpg_ctx *ctx)
   for (int s = 0; s < 2; s++)
     { Slot *S = &ctx->slot[s];
       DevBuf *bufs[] = { &S->seq,&S->seq_off,&S->rlen,&S->prof,&S->prof_off,&S->cnt,&S->cnt_off,&S->cand,&S->plen,
-                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue,&S->rec,&S->pool,&S->hdr,&S->big,&S->upre };
+                         &S->cls,&S->cls_off,&S->status,&S->order,&S->queue,&S->rec,&S->pool,&S->hdr,&S->big,&S->upre,&S->ivl,&S->ivl_at,&S->ivl_n };
       for (unsigned i = 0; i < sizeof(bufs)/sizeof(bufs[0]); i++) if (bufs[i]->p) cudaFree(bufs[i]->p);
       if (S->h_cnt_off) cudaFreeHost(S->h_cnt_off);
       if (S->h_order) cudaFreeHost(S->h_order);
       if (S->h_status) cudaFreeHost(S->h_status);
+      if (S->h_cursor) cudaFreeHost(S->h_cursor);
       if (S->kdone) cudaEventDestroy(S->kdone);
       if (S->stream) cudaStreamDestroy(S->stream);
     }
-  if (ctx->scratch.p) cudaFree(ctx->scratch.p);
-  if (ctx->scratch_big.p) cudaFree(ctx->scratch_big.p);
+  for (int s = 0; s < 2; s++)
+    { if (ctx->scratch[s].p) cudaFree(ctx->scratch[s].p);
+      if (ctx->scratch_big[s].p) cudaFree(ctx->scratch_big[s].p);
+    }
   if (ctx->d_cthres) cudaFree(ctx->d_cthres);
   if (ctx->d_logfact) cudaFree(ctx->d_logfact);
   for (int i = 0; i < 3; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -980,7 +1021,8 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
   d.cthres = (const uint8_t *)ctx->d_cthres;
   d.logfact = (const double *)ctx->d_logfact;
   for (int s = 0; s < 2; s++)
-    { CU_C(cudaStreamCreateWithFlags(&ctx->slot[s].stream,cudaStreamNonBlocking));
+    { CU_C(cudaHostAlloc((void **)&ctx->slot[s].h_cursor,64,cudaHostAllocDefault));
+      CU_C(cudaStreamCreateWithFlags(&ctx->slot[s].stream,cudaStreamNonBlocking));
       CU_C(cudaEventCreateWithFlags(&ctx->slot[s].kdone,cudaEventDisableTiming));
     }
   for (int i = 0; i < 3; i++) CU_C(cudaEventCreate(&ctx->ev[i]));
@@ -1012,7 +1054,7 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
   CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,k_classify,CLASSIFY_THREADS,ctx->classify_smem));
   if (occ < 1) occ = 1;
   ctx->classify_blocks = ctx->n_sm*occ;
-  ctx->retry_blocks = 4;
+  ctx->retry_blocks = 2;
   CU_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,k_decode,DECODE_THREADS,0));
   if (occ < 1) occ = 1;
   ctx->decode_blocks = ctx->n_sm*occ;
@@ -1024,10 +1066,10 @@ extern "C" int cpg_create(cpg_ctx **out, int device, const cpg_model *model,
 /* scratch arenas: compact blocks for every resident lane group of the main launch, full-size
    blocks for the few groups of the retry launch */
 static int ensure_scratch(cpg_ctx *ctx, int P)
-{ if (ctx->scratch.p && P <= ctx->scratch_P) return CPG_OK;
+{ if (ctx->scratch[0].p && P <= ctx->scratch_P) return CPG_OK;
   size_t off[N_OFF];
   const int K = ctx->model.kmer;
-  ScratchDev SC = ctx->SC, SB = ctx->SCbig, Sw = ctx->SCw, Sr = ctx->SCr, Su = ctx->SCu;
+  ScratchDev SC = ctx->SC[0], SB = ctx->SCbig[0], Sw = ctx->SCw[0], Sr = ctx->SCr[0], Su = ctx->SCu[0];
   scratch_caps(&SB,P,K,SM_FULL); SB.stride = scratch_layout(SB,off);
   size_t total = 0, o_r = 0, o_u = 0;
   if (ctx->fused)
@@ -1044,20 +1086,24 @@ static int ensure_scratch(cpg_ctx *ctx, int P)
       total = o_u+Su.stride*(size_t)ctx->unrel_blocks*(PHASE_THREADS/UNREL_GROUP);
     }
   for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->slot[s].stream);
-  int rc = reserve(ctx,&ctx->scratch,total);
-  if (rc) return rc;
-  rc = reserve(ctx,&ctx->scratch_big,SB.stride*(size_t)ctx->retry_blocks*CLASSIFY_GROUPS);
-  if (rc) return rc;
-  /* the flag bytes of the wall replay are zero between reads: the arenas start as zeros */
-  if (cudaMemset(ctx->scratch.p,0,ctx->scratch.cap) != cudaSuccess || cudaMemset(ctx->scratch_big.p,0,ctx->scratch_big.cap) != cudaSuccess)
-    return set_err(ctx,CPG_ECUDA,"cudaMemset of the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
+  for (int s = 0; s < 2; s++)
+    { int rc = reserve(ctx,&ctx->scratch[s],total);
+      if (rc) return rc;
+      rc = reserve(ctx,&ctx->scratch_big[s],SB.stride*(size_t)ctx->retry_blocks*CLASSIFY_GROUPS);
+      if (rc) return rc;
+      /* the flag bytes of the wall replay are zero between reads: the arenas start as zeros */
+      if (cudaMemset(ctx->scratch[s].p,0,ctx->scratch[s].cap) != cudaSuccess || cudaMemset(ctx->scratch_big[s].p,0,ctx->scratch_big[s].cap) != cudaSuccess)
+        return set_err(ctx,CPG_ECUDA,"cudaMemset of the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
+    }
   /* the memsets run on the legacy default stream, which the (non-blocking) slot streams do not wait for:
      nothing may be launched on them before the arenas are really zero */
   if (cudaDeviceSynchronize() != cudaSuccess)
     return set_err(ctx,CPG_ECUDA,"zeroing the scratch arenas failed: %s",cudaGetErrorString(cudaGetLastError()));
-  uint8_t *base = (uint8_t *)ctx->scratch.p;
-  SC.base = base; Sw.base = base; Sr.base = base+o_r; Su.base = base+o_u; SB.base = (uint8_t *)ctx->scratch_big.p;
-  ctx->SC = SC; ctx->SCbig = SB; ctx->SCw = Sw; ctx->SCr = Sr; ctx->SCu = Su;
+  for (int s = 0; s < 2; s++)
+    { uint8_t *base = (uint8_t *)ctx->scratch[s].p;
+      SC.base = base; Sw.base = base; Sr.base = base+o_r; Su.base = base+o_u; SB.base = (uint8_t *)ctx->scratch_big[s].p;
+      ctx->SC[s] = SC; ctx->SCbig[s] = SB; ctx->SCw[s] = Sw; ctx->SCr[s] = Sr; ctx->SCu[s] = Su;
+    }
   ctx->scratch_P = P;
   return CPG_OK;
 }
@@ -1138,6 +1184,11 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   { const char *f = getenv("CPG_POOL_DIV"); if (f && atoi(f) > 0) pool_div = atoi(f); }     /* test knob */
   const int64_t pool_cap = co/pool_div+4096;
   if ((rc = reserve(ctx,&S->pool,sizeof(cpg_intvl)*(size_t)pool_cap))) return rc;
+  S->pool_cap = pool_cap;
+  if (ctx->result_mode == CPG_RESULT_INTERVALS
+      && ((rc = reserve(ctx,&S->ivl,sizeof(uint32_t)*(size_t)pool_cap)) || (rc = reserve(ctx,&S->ivl_at,sizeof(int64_t)*(size_t)(n+1)))
+          || (rc = reserve(ctx,&S->ivl_n,sizeof(int32_t)*(size_t)(n+1)))))
+    return rc;
   /* candidate records: a header for one position in HDR_DIV (HiFi profiles have a candidate per 65-100
      positions), a big record for one in BIG_DIV (they need one per ~700); same fallback */
   int hdr_div = 24, big_div = 160;
@@ -1180,6 +1231,8 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
   B.hdr_cursor = (unsigned long long *)((char *)S->queue.p+72);
   B.big_cursor = (unsigned long long *)((char *)S->queue.p+80);
   B.hdr = (cpg_chdr *)S->hdr.p; B.big = (cpg_cbig *)S->big.p; B.hdr_cap = hdr_cap; B.big_cap = big_cap;
+  B.ivl = (ctx->result_mode == CPG_RESULT_INTERVALS) ? (uint32_t *)S->ivl.p : (uint32_t *)0;
+  B.ivl_at = (int64_t *)S->ivl_at.p; B.ivl_n = (int32_t *)S->ivl_n.p;
   B.upre_cursor = (unsigned long long *)((char *)S->queue.p+88);
   B.upre = (cpg_upre *)S->upre.p; B.upre_cap = upre_cap;
   return CPG_OK;
@@ -1188,34 +1241,37 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
 static int launch_kernels(cpg_ctx *ctx, Slot *S, int timed)
 { cudaStream_t st = S->stream;
   if (S->n_reads == 0) return CPG_OK;
-  /* The two slots overlap their copies with each other's kernels, but the kernels themselves are
-     serialised: k_classify is a persistent grid that fills the GPU, and both slots share the
-     per-warp scratch arena. */
-  Slot *other = &ctx->slot[S == &ctx->slot[0] ? 1 : 0];
-  if (other->kdone_valid) CU(cudaStreamWaitEvent(st,other->kdone,0));
+  /* The two slots overlap their copies with each other's kernels AND their kernels with each other: every
+     slot has its own scratch arenas, and as the CTAs of one slot's persistent kernel run out of reads the
+     CTAs of the other slot's kernel take their place (the tail of a batch would leave SMs idle otherwise). */
+  const int si = (S == &ctx->slot[0]) ? 0 : 1;
   CU(cudaMemsetAsync(S->queue.p,0,128,st));
   if (timed) CU(cudaEventRecord(ctx->ev[0],st));
   k_decode<<<ctx->decode_blocks,DECODE_THREADS,0,st>>>(S->B,ctx->model.kmer,(int)ctx->model.cov[1]);
   if (timed) CU(cudaEventRecord(ctx->ev[1],st));
   if (ctx->fused)
-    k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC,0);
+    k_classify<<<ctx->classify_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SC[si],0);
   else
     { k_wall_a<<<ctx->walla_blocks,WALLA_THREADS,ctx->walla_smem,st>>>(S->B,ctx->dmodel);
       if (timed) CU(cudaEventRecord(ctx->evp[3],st));
-      k_wall_b<<<ctx->wallb_blocks,PHASE_THREADS,0,st>>>(S->B,ctx->dmodel,ctx->SCw);
+      k_wall_b<<<ctx->wallb_blocks,PHASE_THREADS,0,st>>>(S->B,ctx->dmodel,ctx->SCw[si]);
       if (timed) CU(cudaEventRecord(ctx->evp[4],st));
       k_wall_c<<<ctx->wallc_blocks,PHASE_THREADS,0,st>>>(S->B,ctx->dmodel);
       if (timed) CU(cudaEventRecord(ctx->evp[0],st));
-      k_rel<<<ctx->rel_blocks,PHASE_THREADS,ctx->rel_smem,st>>>(S->B,ctx->dmodel,ctx->SCr);
+      k_rel<<<ctx->rel_blocks,PHASE_THREADS,ctx->rel_smem,st>>>(S->B,ctx->dmodel,ctx->SCr[si]);
       if (timed) CU(cudaEventRecord(ctx->evp[1],st));
       k_unrel_a<<<ctx->unrela_blocks,WALLA_THREADS,0,st>>>(S->B,ctx->dmodel);
       if (timed) CU(cudaEventRecord(ctx->evp[5],st));
-      k_unrel_b<<<ctx->unrel_blocks,PHASE_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SCu);
+      k_unrel_b<<<ctx->unrel_blocks,PHASE_THREADS,ctx->unrel_smem,st>>>(S->B,ctx->dmodel,ctx->SCu[si]);
       if (timed) CU(cudaEventRecord(ctx->evp[6],st));
-      k_emit<<<ctx->n_sm*8,256,0,st>>>(S->B,ctx->model.kmer);
+      if (S->B.ivl == 0) k_emit<<<ctx->n_sm*8,256,0,st>>>(S->B,ctx->model.kmer);
       if (timed) CU(cudaEventRecord(ctx->evp[2],st));
     }
-  k_classify<<<ctx->retry_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SCbig,1);
+  k_classify<<<ctx->retry_blocks,CLASSIFY_THREADS,ctx->classify_smem,st>>>(S->B,ctx->dmodel,ctx->SCbig[si],1);
+  if (S->B.ivl != 0)
+    { k_pack<<<ctx->n_sm*8,256,0,st>>>(S->B);
+      CU(cudaMemcpyAsync(S->h_cursor,S->B.pool_cursor,sizeof(unsigned long long),cudaMemcpyDeviceToHost,st));
+    }
   if (timed) CU(cudaEventRecord(ctx->ev[2],st));
   CU(cudaEventRecord(S->kdone,st));
   S->kdone_valid = 1;
@@ -1272,12 +1328,57 @@ extern "C" int cpg_collect(cpg_ctx *ctx, int slot, cpg_result *res)
   CU(cudaSetDevice(ctx->device));
   Slot *S = &ctx->slot[slot];
   if (!S->busy) return set_err(ctx,CPG_EINVAL,"cpg_collect: slot %d has no batch in flight",slot);
+  if (ctx->result_mode != CPG_RESULT_CLASSES) return set_err(ctx,CPG_EINVAL,"cpg_collect: the context returns intervals (cpg_collect_intervals)");
   /* a rejected result leaves the batch in flight (the slot stays busy): call again with a valid one */
   if (res->cls == NULL && S->cls_bytes > 0) return set_err(ctx,CPG_EINVAL,"cpg_result.cls is NULL");
   if (res->cls_off && (res->cls_off[0] != 0 || res->cls_off[S->n_reads] != S->cls_bytes))
     return set_err(ctx,CPG_EINVAL,"cpg_result.cls_off must be the prefix sums of rlen");
   S->busy = 0;
   return fetch_result(ctx,S,res);
+}
+
+extern "C" int cpg_set_result_mode(cpg_ctx *ctx, int mode)
+{ if (ctx == NULL || (mode != CPG_RESULT_CLASSES && mode != CPG_RESULT_INTERVALS)) return set_err(ctx,CPG_EINVAL,"cpg_set_result_mode: bad argument");
+  if (ctx->slot[0].busy || ctx->slot[1].busy) return set_err(ctx,CPG_EINVAL,"cpg_set_result_mode: a batch is in flight");
+  ctx->result_mode = mode;
+  return CPG_OK;
+}
+
+extern "C" int64_t cpg_intervals_bound(cpg_ctx *ctx, int slot)
+{ if (ctx == NULL || slot < 0 || slot > 1) return 0;
+  return ctx->slot[slot].pool_cap;
+}
+
+extern "C" int cpg_collect_intervals(cpg_ctx *ctx, int slot, cpg_result_ivl *res)
+{ if (ctx == NULL || res == NULL || slot < 0 || slot > 1) return set_err(ctx,CPG_EINVAL,"cpg_collect_intervals: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  Slot *S = &ctx->slot[slot];
+  if (!S->busy) return set_err(ctx,CPG_EINVAL,"cpg_collect_intervals: slot %d has no batch in flight",slot);
+  if (ctx->result_mode != CPG_RESULT_INTERVALS) return set_err(ctx,CPG_EINVAL,"cpg_collect_intervals: the context returns class strings (cpg_set_result_mode)");
+  const int n = S->n_reads;
+  if (n > 0 && (res->ivl == NULL || res->ivl_at == NULL || res->ivl_n == NULL)) return set_err(ctx,CPG_EINVAL,"cpg_result_ivl: NULL array");
+  cudaStream_t st = S->stream;
+  CU(cudaStreamSynchronize(st));                          /* kernels done: the number of pool entries is known */
+  const int64_t used = (n > 0) ? (int64_t)*S->h_cursor : 0;
+  if (used > res->ivl_cap) return set_err(ctx,CPG_EINVAL,"cpg_result_ivl.ivl holds %lld entries, the batch needs %lld",(long long)res->ivl_cap,(long long)used);
+  S->busy = 0;
+  res->ivl_used = used;
+  if (n > 0)
+    { CU(cudaMemcpyAsync(res->ivl,S->ivl.p,sizeof(uint32_t)*(size_t)used,cudaMemcpyDeviceToHost,st));
+      CU(cudaMemcpyAsync(res->ivl_at,S->ivl_at.p,sizeof(int64_t)*(size_t)n,cudaMemcpyDeviceToHost,st));
+      CU(cudaMemcpyAsync(res->ivl_n,S->ivl_n.p,sizeof(int32_t)*(size_t)n,cudaMemcpyDeviceToHost,st));
+      CU(cudaMemcpyAsync(S->h_status,S->status.p,sizeof(int32_t)*n,cudaMemcpyDeviceToHost,st));
+    }
+  CU(cudaStreamSynchronize(st));
+  int bad = 0;
+  for (int i = 0; i < n; i++)
+    { if (res->status) res->status[i] = S->h_status[i];
+      if (S->h_status[i] & CPG_ST_FATAL)
+        { if (!bad) set_err(ctx,CPG_EREAD,"read %d of the batch: %s",i,cpg_status_string(S->h_status[i]));
+          bad = 1;
+        }
+    }
+  return bad ? CPG_EREAD : CPG_OK;
 }
 
 extern "C" int cpg_classify(cpg_ctx *ctx, const cpg_batch *batch, cpg_result *res)

@@ -94,8 +94,11 @@ typedef struct batch
     char    **patch; int npatch, patch_cap;  /* headers rebuilt with a comment carried over a chunk boundary */
     /* device-side inputs / outputs (pinned) */
     uint8_t  *pseq; int64_t *seq_off; int32_t *rlen; uint8_t *prof; int64_t *prof_off;
-    uint8_t  *cls;  int64_t *cls_off; int32_t *status;
-    size_t    pseq_cap, prof_cap, cls_cap; int rec_cap, n_cap;
+    /* result: the interval tables of the reads (cpg_result_ivl); the class strings are written straight into
+       the output by the formatter (cpg_expand_intervals) */
+    uint32_t *ivl; int64_t *ivl_at; int32_t *ivl_n; int64_t ivl_cap;
+    int64_t  *cls_off; int32_t *status;
+    size_t    pseq_cap, prof_cap; int rec_cap, n_cap;
     int       seq_bits;
     int64_t   kmers;
     struct batch *next;
@@ -176,14 +179,16 @@ static void batch_reserve(batch_t *b, int nrec, size_t pseq, size_t prof, size_t
   if (nrec > b->n_cap)
     { int cap = nrec+nrec/2+64;
       int64_t *so = pinned(sizeof(int64_t)*(size_t)(cap+1)), *po = pinned(sizeof(int64_t)*(size_t)(cap+1)),
-              *co = pinned(sizeof(int64_t)*(size_t)(cap+1));
+              *co = pinned(sizeof(int64_t)*(size_t)(cap+1)), *ia = pinned(sizeof(int64_t)*(size_t)(cap+1));
+      int32_t *in = pinned(sizeof(int32_t)*(size_t)(cap+1));
       int32_t *rl = pinned(sizeof(int32_t)*(size_t)(cap+1)), *st = pinned(sizeof(int32_t)*(size_t)(cap+1));
       if (b->n_cap)
         { memcpy(so,b->seq_off,sizeof(int64_t)*(size_t)(b->n_cap+1)); memcpy(po,b->prof_off,sizeof(int64_t)*(size_t)(b->n_cap+1));
           memcpy(co,b->cls_off,sizeof(int64_t)*(size_t)(b->n_cap+1)); memcpy(rl,b->rlen,sizeof(int32_t)*(size_t)(b->n_cap+1));
           cpg_host_free(b->seq_off); cpg_host_free(b->prof_off); cpg_host_free(b->cls_off); cpg_host_free(b->rlen); cpg_host_free(b->status);
+          cpg_host_free(b->ivl_at); cpg_host_free(b->ivl_n);
         }
-      b->seq_off = so; b->prof_off = po; b->cls_off = co; b->rlen = rl; b->status = st;
+      b->seq_off = so; b->prof_off = po; b->cls_off = co; b->rlen = rl; b->status = st; b->ivl_at = ia; b->ivl_n = in;
       b->n_cap = cap;
     }
   if (pseq > b->pseq_cap)
@@ -196,11 +201,16 @@ static void batch_reserve(batch_t *b, int nrec, size_t pseq, size_t prof, size_t
       if (b->prof_cap) { memcpy(p,b->prof,b->prof_cap); cpg_host_free(b->prof); }
       b->prof = p; b->prof_cap = cap;
     }
-  if (cls > b->cls_cap)
-    { size_t cap = cls+cls/2+4096; uint8_t *p = pinned(cap);
-      if (b->cls_cap) cpg_host_free(b->cls);
-      b->cls = p; b->cls_cap = cap;
-    }
+  (void)cls;
+}
+
+/* room for the interval tables of the batch in flight on `slot` (known once it is submitted) */
+static void batch_reserve_ivl(batch_t *b, int64_t need)
+{ if (need <= b->ivl_cap) return;
+  const int64_t cap = need+need/4+4096;
+  uint32_t *p = pinned(sizeof(uint32_t)*(size_t)cap);
+  if (b->ivl_cap) cpg_host_free(b->ivl);
+  b->ivl = p; b->ivl_cap = cap;
 }
 
 /* ---------------------------------------------------------------------------------------
@@ -604,6 +614,7 @@ static void *gpu_main(void *arg)
   const double t_c0 = now_s();
   if (cpg_create(&ctx,G->device,A->model,0,0) != CPG_OK)
     die("%s: %s",PROG,cpg_last_error(NULL));
+  if (cpg_set_result_mode(ctx,CPG_RESULT_INTERVALS) != CPG_OK) die("%s: %s",PROG,cpg_last_error(ctx));
   if (G->device == 0) { g_t_gpu_create = now_s()-t_c0; g_tl_ctx = now_s(); }
   batch_t *fly[2] = { NULL, NULL };
   int slot = 0;
@@ -621,8 +632,9 @@ static void *gpu_main(void *arg)
       if (b != NULL) fly[slot] = b;
       if (done != NULL)
         { if (done->n > 0)
-            { cpg_result out = { done->cls, done->cls_off, done->status };
-              int rc = cpg_collect(ctx,slot ^ 1,&out);
+            { batch_reserve_ivl(done,cpg_intervals_bound(ctx,slot ^ 1));
+              cpg_result_ivl out = { done->ivl, done->ivl_cap, done->ivl_at, done->ivl_n, done->status, 0 };
+              int rc = cpg_collect_intervals(ctx,slot ^ 1,&out);
               if (rc == CPG_EREAD) check_batch_status(done);
               else if (rc != CPG_OK) die("%s: %s",PROG,cpg_last_error(ctx));
             }
@@ -654,7 +666,12 @@ static void *gpu_main(void *arg)
 typedef struct
   { batch_t *b; char *dst;               /* dst + b->out_off[i] = first byte of record i */
     const char *carry; int carry_len;    /* class string of the last classified read of earlier batches */
+    int K;
   } fmtjob_t;
+
+/* class string of classified record k of the batch (its rlen characters), from its interval table */
+static void expand_class(const batch_t *b, int K, int k, char *out)
+{ cpg_expand_intervals(K,b->rlen[k],b->ivl+b->ivl_at[k],b->ivl_n[k],out); }
 
 static void format_records(void *arg, int lo, int hi)
 { fmtjob_t *J = arg; batch_t *b = J->b;
@@ -664,15 +681,15 @@ static void format_records(void *arg, int lo, int hi)
       memcpy(p,b->header[i],(size_t)hl); p += hl; *p++ = '\n';
       memcpy(p,b->seq[i],(size_t)rlen); p += rlen;
       memcpy(p,"\n+\n",3); p += 3;
-      if (k >= 0) { memcpy(p,b->cls+b->cls_off[k],(size_t)rlen); p += rlen; }
+      if (k >= 0) { expand_class(b,J->K,k,p); p += rlen; }
       else
         { /* a read shorter than K: the class string of the last classified read again, whole,
              right-aligned in at least rlen columns ("%*s" is a minimum width, src/ClassPro.c:215) */
           const int l = b->lastc[i];
-          const char *s = l >= 0 ? (const char *)b->cls+b->cls_off[b->slot_of[l]] : J->carry;
           const int sl = l >= 0 ? b->rlen_all[l] : J->carry_len;
           if (rlen > sl) { memset(p,' ',(size_t)(rlen-sl)); p += rlen-sl; }
-          memcpy(p,s,(size_t)sl); p += sl;
+          if (l >= 0) expand_class(b,J->K,b->slot_of[l],p); else memcpy(p,J->carry,(size_t)sl);
+          p += sl;
         }
       *p++ = '\n';
     }
@@ -714,7 +731,7 @@ static void *writer_main(void *arg)
           else o += b->hlen[i]+(int64_t)rlen+5+(rlen > sl ? rlen : sl);
         }
       b->out_off[b->n_all] = o;
-      fmtjob_t J = { b, NULL, rasgn, rasgn_len };
+      fmtjob_t J = { b, NULL, rasgn, rasgn_len, K };
       char *m = MAP_FAILED; int64_t mstart = cur & ~(page-1);
       if (use_map)
         { int rc = posix_fallocate(fd,cur,o);
@@ -742,7 +759,7 @@ static void *writer_main(void *arg)
       cur += o;
       if (last >= 0)
         { rasgn_len = b->rlen_all[last];
-          memcpy(rasgn,b->cls+b->cls_off[b->slot_of[last]],(size_t)rasgn_len);
+          expand_class(b,K,b->slot_of[last],rasgn);
         }
       g_t_writer += now_s()-t_w0;
       pthread_mutex_lock(&A->mu);

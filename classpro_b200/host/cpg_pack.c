@@ -32,3 +32,19 @@ int cpg_pack_seq(const char *seq, int32_t rlen, uint8_t *out)
     }
   return bad < 0 ? 1 : 0;
 }
+
+/* Class string of a read from its packed interval table (include/classpro_gpu.h, "compact results"):
+   what the reference writes into rasgn, src/ClassPro.c:114-117 ('N' x (K-1)) and :265-271. */
+void cpg_expand_intervals(int32_t K, int32_t rlen, const uint32_t *ivl, int32_t n, char *out)
+{ static const char cls_chr[8] = { 'E','R','H','D','?','?','?','?' };
+  int32_t b = 0;
+  const int32_t plen = rlen-K+1;
+  memset(out,'N',(size_t)(K-1 < rlen ? K-1 : rlen));
+  if (plen <= 0) return;
+  out += K-1;
+  for (int32_t i = 0; i < n; i++)
+    { int32_t e = (int32_t)(ivl[i] >> 3);
+      if (e > plen) e = plen;
+      if (e > b) { memset(out+b,cls_chr[ivl[i] & 7u],(size_t)(e-b)); b = e; }
+    }
+}

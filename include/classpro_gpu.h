@@ -120,6 +120,36 @@ int cpg_classify(cpg_ctx *ctx, const cpg_batch *batch, cpg_result *result);
 int cpg_submit(cpg_ctx *ctx, int slot, const cpg_batch *batch);
 int cpg_collect(cpg_ctx *ctx, int slot, cpg_result *result);
 
+/* ---- compact results ---------------------------------------------------------------------------
+ * A class string is piecewise constant: the read's interval table (about one interval per 70 k-mers on
+ * HiFi profiles) says everything it says.  In CPG_RESULT_INTERVALS mode a batch comes back as that table
+ * -- 4 bytes per interval instead of 1 byte per base, ~30 times fewer bytes over PCIe and no class-string
+ * kernel -- and the caller expands it where the characters are needed (cpg_expand_intervals: the bytes are
+ * those of CPG_RESULT_CLASSES mode, i.e. of src/ClassPro.c:114-117,265-271).  The mode is a property of the
+ * context: set it before the first cpg_submit.
+ *   ivl      : [ivl_cap] OUT packed intervals, (end position << 3) | class code (0 E, 1 R, 2 H, 3 D); the
+ *              intervals of a read are consecutive, in position order, the first one starts at 0
+ *   ivl_cap  : entries the caller provides; cpg_intervals_bound(ctx,slot) after cpg_submit is enough
+ *   ivl_at   : [n_reads] OUT first entry of read r (reads are NOT in order inside ivl)
+ *   ivl_n    : [n_reads] OUT number of intervals of read r
+ *   status   : [n_reads] OUT as in cpg_result
+ *   ivl_used : OUT entries of ivl that were filled */
+#define CPG_RESULT_CLASSES   0
+#define CPG_RESULT_INTERVALS 1
+typedef struct
+  { uint32_t *ivl;
+    int64_t   ivl_cap;
+    int64_t  *ivl_at;
+    int32_t  *ivl_n;
+    int32_t  *status;
+    int64_t   ivl_used;
+  } cpg_result_ivl;
+int     cpg_set_result_mode(cpg_ctx *ctx, int mode);
+int64_t cpg_intervals_bound(cpg_ctx *ctx, int slot);
+int     cpg_collect_intervals(cpg_ctx *ctx, int slot, cpg_result_ivl *result);
+/* rlen characters at out: 'N' x (K-1), then the class of every k-mer (host code, no device involved) */
+void    cpg_expand_intervals(int32_t K, int32_t rlen, const uint32_t *ivl, int32_t n, char *out);
+
 /* ---- stage access (tests, benchmarks) ------------------------------------------------------
  * cpg_decode_profiles: the Fetch_Profile replacement alone (src/libfastk.c:1414-1562): counts of
  * read r are written to counts[cnt_off[r] .. ) with capacity cnt_off[r+1]-cnt_off[r]; plen[r]

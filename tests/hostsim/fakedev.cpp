@@ -19,7 +19,7 @@
 
 struct cpg_ctx
   { cpg_model model; cpg_dmodel dm;
-    std::vector<uint8_t> cls[2]; std::vector<int32_t> status[2]; int n[2]; int64_t bytes[2]; int busy[2];
+    std::vector<uint8_t> cls[2]; std::vector<int32_t> status[2], rlen[2]; int n[2]; int64_t bytes[2]; int busy[2];
     char err[256];
   };
 
@@ -122,7 +122,7 @@ int cpg_submit(cpg_ctx *c, int slot, const cpg_batch *b)
     { if (b->rlen[i] < c->dm.K) { snprintf(c->err,sizeof(c->err),"read %d of the batch: rlen %d outside [K=%d,..]",i,b->rlen[i],c->dm.K); return CPG_EINVAL; }
       tot += b->rlen[i];
     }
-  c->cls[slot].assign((size_t)tot+1,0); c->status[slot].assign((size_t)n+1,0);
+  c->cls[slot].assign((size_t)tot+1,0); c->status[slot].assign((size_t)n+1,0); c->rlen[slot].assign(b->rlen,b->rlen+n);
   int64_t at = 0;
   for (int i = 0; i < n; i++) { c->status[slot][i] = fake_read(c,b,i,c->cls[slot].data()+at); at += b->rlen[i]; }
   c->n[slot] = n; c->bytes[slot] = tot; c->busy[slot] = 1;
@@ -141,6 +141,40 @@ int cpg_collect(cpg_ctx *c, int slot, cpg_result *res)
           bad = 1;
         }
     }
+  return bad ? CPG_EREAD : CPG_OK;
+}
+
+/* compact results (include/classpro_gpu.h): here simply the run-length form of the class strings the host
+   build of the device sources produced (equal neighbours merge: the expansion is the same) */
+int cpg_set_result_mode(cpg_ctx *c, int mode) { (void)mode; return c ? CPG_OK : CPG_EINVAL; }
+int64_t cpg_intervals_bound(cpg_ctx *c, int slot) { return (c && slot >= 0 && slot <= 1) ? c->bytes[slot]+16 : 0; }
+int cpg_collect_intervals(cpg_ctx *c, int slot, cpg_result_ivl *res)
+{ if (!c || !res || slot < 0 || slot > 1 || !c->busy[slot]) { if (c) snprintf(c->err,sizeof(c->err),"cpg_collect_intervals: bad argument"); return CPG_EINVAL; }
+  if (res->ivl_cap < c->bytes[slot]) { snprintf(c->err,sizeof(c->err),"cpg_result_ivl.ivl too small"); return CPG_EINVAL; }
+  c->busy[slot] = 0;
+  const int K = c->dm.K;
+  int64_t at = 0, used = 0; int bad = 0;
+  for (int i = 0; i < c->n[slot]; i++)
+    { const int rlen = c->rlen[slot][i], plen = rlen-K+1;
+      const uint8_t *s = c->cls[slot].data()+at+K-1;
+      res->ivl_at[i] = used;
+      int n = 0;
+      for (int j = 0; j < plen; )
+        { int e = j+1;
+          while (e < plen && s[e] == s[j]) e++;
+          const unsigned code = (s[j] == 'E') ? 0u : (s[j] == 'R') ? 1u : (s[j] == 'H') ? 2u : (s[j] == 'D') ? 3u : 4u;
+          res->ivl[used++] = ((unsigned)e << 3) | code; n++;
+          j = e;
+        }
+      res->ivl_n[i] = n;
+      at += rlen;
+      if (res->status) res->status[i] = c->status[slot][i];
+      if (c->status[slot][i] & (1|2|4|8|64))
+        { if (!bad) snprintf(c->err,sizeof(c->err),"read %d of the batch: %s",i,cpg_status_string(c->status[slot][i]));
+          bad = 1;
+        }
+    }
+  res->ivl_used = used;
   return bad ? CPG_EREAD : CPG_OK;
 }
 

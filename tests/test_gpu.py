@@ -89,6 +89,43 @@ def test_retry_launch_matches_oracle(kit, cp, monkeypatch, knob):
     assert flips <= max(0, int(kmers * FLIP_BUDGET)), "%d of %d k-mers differ from the oracle" % (flips, kmers)
 
 
+@pytest.mark.parametrize("knob", [None, "CPG_SCRATCH_DIV", "CPG_FUSED"])
+def test_interval_results_expand_to_the_class_strings(kit, cp, monkeypatch, knob):
+    """CPG_RESULT_INTERVALS: the packed interval tables of a batch, expanded on the host, are the class strings
+    of CPG_RESULT_CLASSES mode byte for byte -- on the main path, with most reads through the retry launch, and
+    on the single-kernel path."""
+    from classpro_b200 import abi
+    if knob:
+        monkeypatch.setenv(knob, "1" if knob == "CPG_FUSED" else "1000000")
+    name, params, cov_opt, read_len = DATASETS[1]
+    sim = kit.simulate(**params)
+    gm = cp.Model.from_hist(sim.kmer, sim.hist[1:32768], sim.hist[32768], sim.hist[32769], cov_opt=cov_opt, read_len=read_len)
+    ctx = cp.Context(gm)
+    batch, keep = make_batch(cp, sim)
+    cls, status = ctx.classify(batch)
+    ctx.set_result_mode(True)
+    with pytest.raises(abi.CpgError):
+        ctx.submit(0, batch)
+        ctx.collect(0, batch)                      # wrong call for this mode; the batch stays in flight
+    res = abi.IntervalResult(batch.n, ctx.intervals_bound(0))
+    ctx.collect_intervals(0, res)
+    assert (res.status[:batch.n] == status).all()
+    assert 0 < res.used <= res.cap and int(res.cnt[:batch.n].sum()) <= res.used
+    ex = res.expand(sim.kmer, batch.rlen)
+    nb = int(batch.cls_off[-1])
+    assert np.array_equal(ex[:nb], cls[:nb])
+    small = abi.IntervalResult(batch.n, 8)
+    ctx.submit(1, batch)
+    with pytest.raises(abi.CpgError):
+        ctx.collect_intervals(1, small)            # too small: rejected, still in flight
+    ctx.collect_intervals(1, res)
+    assert np.array_equal(res.expand(sim.kmer, batch.rlen)[:nb], cls[:nb])
+    ctx.set_result_mode(False)
+    cls2, _ = ctx.classify(batch)
+    assert np.array_equal(cls2[:nb], cls[:nb])
+    ctx.close()
+
+
 @pytest.mark.parametrize("name,params,cov_opt,read_len", DATASETS, ids=[d[0] for d in DATASETS])
 def test_classify_matches_oracle(kit, cp, name, params, cov_opt, read_len):
     sim = kit.simulate(**params)
