@@ -4,9 +4,10 @@
  *  The reference materialises six run-length bytes per base with a serial sweep and back-fill
  *  (src/context.c:8-108) but reads them only at wall candidates and interval ends (~1-2 % of the
  *  positions).  Here each value is evaluated where it is needed, from the packed sequence, with a
- *  closed form that equals the reference's arrays at every base as long as no run reaches the
- *  127 cap (tests/test_context.py proves this exhaustively for all short sequences and on random
- *  low-complexity sequences; beyond the cap the reference reads cells it never wrote):
+ *  closed form that equals the reference's arrays at every base (tests/test_device_logic_hostsim.py:
+ *  exhaustively for all short sequences, on random low-complexity sequences, and against the
+ *  reference sweep on runs longer than the 127 cap, where the homopolymer right context has a
+ *  back-fill quirk of its own, cpg_rctx_hp_ref below):
  *
  *    L_HP(p) = length of the homopolymer run ending at p                       (lctx[p][HP])
  *    L_DS(p) = 0 if p == 0 or s[p] == s[p-1], else number of consecutive copies of the
@@ -27,6 +28,23 @@ CPG_DEV int cpg_base(const cpg_seq S, int i)
 { return (S.bits == 8) ? (int)S.p[i] : (int)((S.p[i >> 2] >> ((i & 3)*2)) & 3); }
 
 CPG_DEV int cpg_cap127(int x) { return x > 127 ? 127 : x; }
+
+/* rctx[p][HP] as the reference's back-fill leaves it in a homopolymer run LONGER than the cap
+ * (src/context.c:24-26,60-61).  When a run [s,t] of L bases ends, the fill starts lctx[t] = min(L,127)
+ * positions before its end and copies the mirrored -- and capped -- left run lengths:
+ *     rctx[j] = lctx[2t+1-min(L,127)-j]        for j = t+1-min(L,127) .. t
+ * For L <= 127 that is the right run length t-j+1.  For L > 127 it is min(L-126+(t-j),127) over the last
+ * 127 bases of the run (e.g. 127, not 1, at the last base of a run of 253 or more), and the bases before
+ * them are never written: the reference then reads whatever an earlier read left there.  The first is part
+ * of the contract and is reproduced; the second is undefined there and is DEFINED here as the cap.
+ * (Dinucleotide and trinucleotide runs are filled over their whole length by a walk, src/context.c:36-41,
+ * 55-60: their capped closed form is what the reference computes, whatever their length.)
+ *   r128: min(right run length at p, 128), p included;  l254: min(left run length at p, 254), p included */
+CPG_DEV int cpg_rctx_hp_ref(int r128, int l254)
+{ if (r128 >= 128) return 127;
+  if (l254+r128-1 <= 127) return r128;
+  return cpg_cap127(l254+2*r128-128);
+}
 
 CPG_DEV_HELPER int cpg_lctx_raw(const cpg_seq S, int rlen, int p, int t)
 { (void)rlen;
@@ -54,9 +72,10 @@ CPG_DEV_HELPER int cpg_lctx_raw(const cpg_seq S, int rlen, int p, int t)
 
 CPG_DEV_HELPER int cpg_rctx_raw(const cpg_seq S, int rlen, int p, int t)
 { if (t == CT_HP)
-    { int c = cpg_base(S,p), n = 1;
-      CPG_LOOP while (n < 127 && p+n < rlen && cpg_base(S,p+n) == c) n++;
-      return n;
+    { int c = cpg_base(S,p), n = 1, l = 1;
+      CPG_LOOP while (n < 128 && p+n < rlen && cpg_base(S,p+n) == c) n++;
+      CPG_LOOP while (l < 254 && p-l >= 0 && cpg_base(S,p-l) == c) l++;
+      return cpg_rctx_hp_ref(n,l);
     }
   if (t == CT_DS)
     { if (p >= rlen-1) return 0;
@@ -152,7 +171,11 @@ CPG_DEV_HELPER int cpg_lctx(const cpg_seq S, int rlen, int p, int t)
 
 CPG_DEV_HELPER int cpg_rctx(const cpg_seq S, int rlen, int p, int t)
 { if (S.bits == 8) return cpg_rctx_raw(S,rlen,p,t);
-  if (t == CT_HP) return 1+cpg_zf(S.p,rlen,p,1,126);
+  if (t == CT_HP)
+    { const int r = 1+cpg_zf(S.p,rlen,p,1,127);
+      if (p == 0 || cpg_base(S,p-1) != cpg_base(S,p)) return cpg_rctx_hp_ref(r,1);
+      return cpg_rctx_hp_ref(r,1+cpg_zb(S.p,p,1,253));
+    }
   if (t == CT_DS)
     { if (p >= rlen-1 || cpg_base(S,p) == cpg_base(S,p+1)) return 0;
       return 1+(cpg_zf(S.p,rlen,p,2,252) >> 1);
@@ -204,7 +227,8 @@ CPG_DEV_HELPER void cpg_rctx3(const cpg_seq S, int rlen, int p, int out[3])
       else if (c > lim) c = lim > 0 ? lim : 0;
       zf[d-1] = c;
     }
-  if (zf[0] < 0) out[0] = cpg_rctx(S,rlen,p,CT_HP); else out[0] = cpg_cap127(1+zf[0]);
+  if (zf[0] < 0 || (p > 0 && cpg_base(S,p-1) == b0)) out[0] = cpg_rctx(S,rlen,p,CT_HP);      /* inside a run: it may be a long one */
+  else out[0] = 1+zf[0];
   if (p >= rlen-1 || b0 == b1) out[1] = 0;
   else if (zf[1] < 0) out[1] = cpg_rctx(S,rlen,p,CT_DS);
   else out[1] = 1+(zf[1] >> 1);

@@ -1189,15 +1189,18 @@ static int stage_batch(cpg_ctx *ctx, Slot *S, const cpg_batch *b, const int64_t 
       && ((rc = reserve(ctx,&S->ivl,sizeof(uint32_t)*(size_t)pool_cap)) || (rc = reserve(ctx,&S->ivl_at,sizeof(int64_t)*(size_t)(n+1)))
           || (rc = reserve(ctx,&S->ivl_n,sizeof(int32_t)*(size_t)(n+1)))))
     return rc;
-  /* candidate records: a header for one position in HDR_DIV (HiFi profiles have a candidate per 65-100
-     positions), a big record for one in BIG_DIV (they need one per ~700); same fallback */
-  int hdr_div = 24, big_div = 160;
+  /* candidate records: a header for one position in HDR_DIV and a big record for one in BIG_DIV.  Measured
+     needs per position (host build of the device code): plain HiFi profiles 1.5 % / 0.26 %, repeat-rich
+     0.43 compressed bytes per k-mer 1.6 % / 1.0 %, noisy low-complexity 2.4 % / 2.1 %; same fallback.  (With
+     one big record per 160 positions nearly every read of the repeat-rich workload went to the retry
+     launch: 17 s instead of 0.2 s, profiles/r02_c4_caps.log.) */
+  int hdr_div = 24, big_div = 32;
   { const char *f = getenv("CPG_HDR_DIV"); if (f && atoi(f) > 0) hdr_div = atoi(f); }       /* test knobs */
   { const char *f = getenv("CPG_BIG_DIV"); if (f && atoi(f) > 0) big_div = atoi(f); }
   const int64_t hdr_cap = co/hdr_div+4096, big_cap = co/big_div+4096;
   /* recorded task values of the unreliable pass: one per interval its sweeps visit (about a third of the
      intervals, one per ~200 positions) */
-  int upre_div = 48;
+  int upre_div = 32;
   { const char *f = getenv("CPG_UPRE_DIV"); if (f && atoi(f) > 0) upre_div = atoi(f); }
   const int64_t upre_cap = co/upre_div+4096;
   if (!ctx->fused && ((rc = reserve(ctx,&S->hdr,sizeof(cpg_chdr)*(size_t)hdr_cap)) || (rc = reserve(ctx,&S->big,sizeof(cpg_cbig)*(size_t)big_cap))

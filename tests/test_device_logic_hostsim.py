@@ -187,6 +187,37 @@ def test_context_packed_long_runs(kit, hostsim):
                             (unit, copies, p, t, right)
 
 
+def test_context_long_runs_match_the_reference_sweep(kit, hostsim):
+    """Runs LONGER than the 127 cap against the reference sweep itself (the oracle's restatement of
+    src/context.c on dense arrays), not only packed against raw.  Left contexts and the di-/trinucleotide right
+    contexts are the capped closed form at any length.  The homopolymer right context is back-filled by the
+    reference over the last min(L,127) bases of a run with mirrored CAPPED left lengths (src/context.c:24-26): in a
+    run of 253+ bases the last base gets 127, not 1 -- reproduced; the bases before that stretch are never written
+    there (cells keep the 0xEE the test put in): the device defines them as 127 (and flags the read when it uses
+    one).  This is what made 49 of 100 k reads of the repeat-rich 50 Mb dataset differ from the reference binary
+    (profiles/r02_file_parity_c4_50mb_first.json)."""
+    L = kit.oracle_lib()
+    rng = np.random.default_rng(5)
+    for unit in (b"A", b"AC", b"ACG", b"T", b"GT", b"TTC"):
+        for copies in (100, 127, 128, 129, 200, 253, 254, 300, 400):
+            pre = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(1, 9))).tolist())
+            post = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 9))).tolist())
+            seq = pre + unit * copies + post
+            n = len(seq)
+            lc = np.zeros((n + 4, 3), dtype=np.uint8)
+            rc = np.full((n + 4, 3), 0xEE, dtype=np.uint8)
+            lc[0] = (1, 0, 0)
+            L.cpo_seq_context(lc.ctypes.data, rc.ctypes.data, seq, n)
+            step = 1 if copies in (128, 254) else 3
+            for p in list(range(0, n, step)) + [n - 1]:
+                for t in range(3):
+                    want_r = 127 if rc[p, t] == 0xEE else rc[p, t]
+                    assert hostsim.hs_ctx(seq, n, p, 0, t) == lc[p, t], (unit, copies, p, t, "left")
+                    assert hostsim.hs_ctx2(seq, n, p, 0, t, p & 3) == lc[p, t], (unit, copies, p, t, "left, packed")
+                    assert hostsim.hs_ctx(seq, n, p, 1, t) == want_r, (unit, copies, p, t, "right")
+                    assert hostsim.hs_ctx2(seq, n, p, 1, t, n & 3) == want_r, (unit, copies, p, t, "right, packed")
+
+
 def random_stream(rng, n_tokens, adversarial):
     """A FastK token stream; adversarial = arbitrary bytes (wrap-around and mask corner cases)."""
     first = int(rng.integers(0, 32768))
