@@ -168,7 +168,7 @@ __device__ __forceinline__ void bind_scratch(ReadCtx &R, uint8_t *sb, const size
   R.S.key   = reinterpret_cast<uint32_t *>(sb+off[17]);
   R.S.MC = SC.MC; R.S.capS = SC.capS; R.S.capE = SC.capE; R.S.capI = SC.capI; R.S.capT = SC.capT; R.S.capC = SC.capC;
   R.S.upre  = reinterpret_cast<cpg_upre *>(sb+off[12]);
-  R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0;
+  R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0; R.prune = 0;
 }
 
 __device__ __forceinline__ int next_read(int32_t *counter, int lane)
@@ -417,6 +417,9 @@ __device__ __forceinline__ void init_wctx(WCtx &W, const GroupId &g, const cpg_d
    memory) per candidate; writes: a header per candidate, in position order, a record per queued one. */
 struct WaTask { int32_t r, pos; uint32_t idx, packed, cnts; };     /* packed: info | t << 8 | l << 12; cnts: cout | cin << 16 */
 #define WALLA_TCAP 64
+#ifndef WALLA_PRUNE
+#define WALLA_PRUNE 1            /* wa_tasks: no partner values for an error type whose own probability is below the threshold */
+#endif
 struct WallAShared
   { uint8_t     cthres[CPG_LROWS*256*4];
     cpg_dmodel  model;
@@ -435,7 +438,7 @@ __device__ __forceinline__ void wa_run_tasks(const BatchDev &B, const WCtx &W, c
       C.t = (T.packed >> 8) & 0xf; C.l = (T.packed >> 12) & 0xff;
       C.cout = (uint16_t)(T.cnts & 0xffffu); C.cin = (uint16_t)(T.cnts >> 16);
       C.cng = (int)C.cout-(int)C.cin; C.erate = W.M->pe[C.t][C.l];
-      wa_tasks(B.cnt+B.cnt_off[T.r],plen,seq,rlen,W,T.pos,C,info,B.big+T.idx);
+      wa_tasks(B.cnt+B.cnt_off[T.r],plen,seq,rlen,W,T.pos,C,info,B.big+T.idx,WALLA_PRUNE);
     }
 }
 

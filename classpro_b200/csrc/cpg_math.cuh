@@ -164,6 +164,24 @@ CPG_DEV double cpg_lp_trans(const WCtx &W, int b, int e, int cb, int ce, uint16_
   return cpg_lp_skellam(ce-cb,(double)cov*d/W.M->read_len);
 }
 
+/* cpg_lp_trans where only "is it >= thres" is asked (src/wall.c:366,390 THRES_DIFF_EO; :1028 THRES_DIFF_REL).
+ * The Bessel recurrence takes 2(n+sqrt(40n)) steps, n = |ce-cb|: tens of thousands where the counts are in the
+ * thousands (repeat-rich profiles: one lane of a warp in such a loop, the other 31 waiting).  There the answer is
+ * known without it: I_n(x) < cosh(x) (x/2)^n / n!  (x > 0) and n! >= (n/e)^n give
+ *     logp_skellam(k,lambda) = -2 lambda + log I_n(2 lambda)  <  n (log(lambda/n) + 1),
+ * and when that bound is below the threshold by more than 2 -- far more than any rounding of the recurrence --
+ * the exact value is below it too.  Returned then: -inf (every use is the comparison).  Otherwise the exact value. */
+CPG_DEV_HELPER double cpg_lp_trans_thr(const WCtx &W, int b, int e, int cb, int ce, uint16_t cov, double thres)
+{ int d = e-b; if (d < 0) d = -d;
+  const int k = ce-cb, n = k < 0 ? -k : k;
+  const double lambda = (double)cov*d/W.M->read_len;
+  if (n >= 32)
+    { if (!(lambda > 0.)) return -CPG_INF;
+      if ((double)n*(cpg_log(lambda/(double)n)+1.) < thres-2.) return -CPG_INF;
+    }
+  return cpg_lp_skellam(k,lambda);
+}
+
 /* src/prob.c:59-65 with p = 1-PE_MEAN, the only value the path uses (src/class_rel.c:186,
    src/class_unrel.c:98-99) */
 CPG_DEV_HELPER double cpg_lp_binom99(WCtx &W, uint16_t k16, uint16_t n16)
@@ -184,19 +202,25 @@ CPG_DEV_NOINL double cpg_binom_tail_lane(const double *lf, int k, int n, const c
   const double lfn = CPG_LDG(lf+n);
   double p, p_first, t;
 #define CPG_LBP(x) (lfn-CPG_LDG(lf+(x))-CPG_LDG(lf+(n-(x)))+(x)*lpe+(n-(x))*l1mpe)
+  /* A first term that underflows to 0 can never stop the loop (10*t < 0 is false): the reference then adds
+     n-k (or k-1) further terms, each farther out in the tail than the first and so 0 as well -- up to 32 767 exps
+     for a sum that stays 0 (counts in the thousands, repeat-rich profiles: one lane of a warp in that loop, 31
+     waiting).  Same result without them. */
   if ((double)k >= mean)
     { p = p_first = cpg_exp(CPG_LBP(k));
-      CPG_LOOP for (int x = k+1; x <= n; x++)
-        { p += t = cpg_exp(CPG_LBP(x));
-          if (10*t < p_first) break;
-        }
+      if (p_first != 0.)
+        CPG_LOOP for (int x = k+1; x <= n; x++)
+          { p += t = cpg_exp(CPG_LBP(x));
+            if (10*t < p_first) break;
+          }
     }
   else
     { p = p_first = (k == 0) ? 0. : cpg_exp(CPG_LBP(k-1));
-      CPG_LOOP for (int x = k-2; x >= 0; x--)
-        { p += t = cpg_exp(CPG_LBP(x));
-          if (10*t < p_first) break;
-        }
+      if (p_first != 0.)
+        CPG_LOOP for (int x = k-2; x >= 0; x--)
+          { p += t = cpg_exp(CPG_LBP(x));
+            if (10*t < p_first) break;
+          }
       p = 1-p;
     }
 #undef CPG_LBP

@@ -96,6 +96,7 @@ struct ReadCtx
     const cpg_cbig *big;      /* base of the big records cpg_chdr.big indexes */
     int             ncand;
     int             ntlog;    /* entries of S.tlog; > S.capT: the log overflowed, clean the whole flag array */
+    int             prune;    /* single-read path: record partner values as k_wall_a does (wa_tasks; host tests) */
   };
 
 CPG_DEV uint16_t rc_prof(const ReadCtx &R, WCtx &W, int p)
@@ -143,7 +144,7 @@ CPG_DEV_HELPER double perr_max_o(const ReadCtx &R, int pos)
 CPG_DEV_HELPER double lp_diff_pair(const uint16_t *p, const WCtx &W, int i, int j)
 { int n_drop = (int)p[i-1]-p[i], n_gain = (int)p[j]-p[j-1];
   uint16_t cov = (uint16_t)imax(p[i-1],p[j]);
-  return cpg_lp_trans(W,i,j,n_drop,n_gain,cov);
+  return cpg_lp_trans_thr(W,i,j,n_drop,n_gain,cov,CPG_THRES_DIFF_EO);       /* only ever compared with that threshold */
 }
 
 CPG_DEV int cthres_at(const WCtx &W, int t, int l, int cout, int s, int e)
@@ -271,9 +272,14 @@ CPG_DEV_NOINL unsigned wa_stage0(const uint16_t *prof, const cpg_seq seq, int rl
 
 /* Everything pass A can ask for about a candidate that got past stage 0 (src/wall.c:331-507,651-690):
    the reference evaluates these one after the other and only as far as the order-dependent state lets
-   it get; here all of them are evaluated (they are pure), and the replay picks what it needs. */
+   it get; here all of them are evaluated (they are pure), and the replay picks what it needs.
+   prune: an error type whose own probability is already below the threshold gets no partner values (pass A
+   stops there too, src/wall.c:653,676 -- unless the probability it finds in the cache is another one, stored
+   by an earlier candidate under its error rate: the replay notices that case and sends the read to the retry
+   launch, which records everything).  It is what keeps the high-count candidates of repeat-rich profiles
+   cheap: above CMAX there is no count threshold, every candidate gets here, and almost none is an error. */
 CPG_DEV_NOINL void wa_tasks(const uint16_t *prof, int plen, const cpg_seq seq, int rlen, const WCtx &W, int i,
-                            const WaCand &C, unsigned info, cpg_cbig *B)
+                            const WaCand &C, unsigned info, cpg_cbig *B, int prune)
 { const cpg_dmodel *M = W.M;
   const double *lf = M->logfact;
   const int K = M->K;
@@ -282,12 +288,19 @@ CPG_DEV_NOINL void wa_tasks(const uint16_t *prof, int plen, const cpg_seq seq, i
   double term[23];
   CPG_LOOP for (int q = 0; q < 23; q++) term[q] = 0.;
   B->own[0] = B->own[1] = 0.;
+  int want[2];
+  unsigned ok = 0;
   CPG_LOOP for (int e = 0; e < 2; e++)
-    if (reach[e]) B->own[e] = cpg_p_errorin_lane(lf,e,cpg_rate_pe(M,C.t,C.l),C.cout,C.cin,&bad);
+    { if (reach[e]) B->own[e] = cpg_p_errorin_lane(lf,e,cpg_rate_pe(M,C.t,C.l),C.cout,C.cin,&bad);
+      want[e] = reach[e] && !(prune && B->own[e] < CPG_PE_FINAL);
+      if (reach[e] && !want[e]) ok |= 0x4000u << e;                         /* no partner values for this type */
+    }
 
   /* partner geometry (src/wall.c:344-357,432-450), shared by both error types */
   PairGeom G;
   G.fwd = (C.wtype == WT_DROP); G.i = i; G.t = C.t; G.l = C.l; G.cout = C.cout; G.cin = C.cin; G.erate = C.erate;
+  G.lc_kind = 0; G.lc_j = 0;
+  if (want[0] || want[1])
   { const int ulen = C.t+1, m = ulen*C.l;
     int n = 0;
     CPG_LOOP for (;;)
@@ -304,11 +317,11 @@ CPG_DEV_NOINL void wa_tasks(const uint16_t *prof, int plen, const cpg_seq seq, i
     else if (G.fwd ? (j >= plen) : (j <= 0)) { G.lc_kind = 1; G.lc_j = G.fwd ? plen : 0; }
     else { G.lc_kind = 2; G.lc_j = j; }
   }
-  unsigned ok = 0; int nhc = 0;
-  if (G.lc_kind != 0)
+  int nhc = 0;
+  if (G.lc_kind != 0 && (want[0] || want[1]))
     { CPG_LOOP for (int n = 0; n <= CPG_MAX_N_HC; n++) { if (!pg_in_range(G,plen,pg_hc_j(G,K,n))) break; nhc++; }
       CPG_LOOP for (int e = 0; e < 2; e++)
-        { if (!reach[e]) continue;
+        { if (!want[e]) continue;
           term[e*8+7] = cpg_p_errorin_lane(lf,e,cpg_rate_hc(M),C.cout,C.cin,&bad);
           if (G.lc_kind == 2 && pg_lc_ok(G,W,prof,e))
             { uint16_t cin_j, cout_j;
@@ -337,11 +350,11 @@ CPG_DEV_NOINL void wa_tasks(const uint16_t *prof, int plen, const cpg_seq seq, i
 /* one candidate: header, and the big record at big_base[big_idx] if it needs one (the caller has a
    place ready: it is simply left unused otherwise) */
 CPG_DEV void wa_candidate(const uint16_t *prof, int plen, const cpg_seq seq, int rlen, const WCtx &W, int i,
-                          cpg_chdr *H, cpg_cbig *big_base, uint32_t big_idx)
+                          cpg_chdr *H, cpg_cbig *big_base, uint32_t big_idx, int prune)
 { WaCand C;
   const unsigned info = wa_stage0(prof,seq,rlen,W,i,C);
   H->pos = i; H->info = info; H->big = big_idx; H->pad = 0;
-  if (info & (CH_REACH_S|CH_REACH_O)) wa_tasks(prof,plen,seq,rlen,W,i,C,info,big_base+big_idx);
+  if (info & (CH_REACH_S|CH_REACH_O)) wa_tasks(prof,plen,seq,rlen,W,i,C,info,big_base+big_idx,prune);
 }
 
 /* ==========================================================================================
@@ -516,6 +529,8 @@ CPG_DEV_NOINL void wb_candidate(ReadCtx &R, WCtx &W, const cpg_chdr H, int &eidx
   if (B->bad) W.status |= CPG_ST_BINOM;
 
   cpg_eintvl I;
+  if ((go[0] && (B->ok & 0x4000u)) || (go[1] && (B->ok & 0x8000u)))
+    { W.status |= CPG_ST_RETRY; return; }                 /* values not recorded (see wa_tasks, prune) */
   if (go[0] || go[1])
     { const int fwd = (wtype == WT_DROP);
       if (B->lr_walk) W.status |= CPG_ST_LONG_RUN;
@@ -798,7 +813,7 @@ CPG_DEV_NOINL int wc_interval(const uint16_t *prof, int plen, const cpg_seq seq,
   if (I.e-I.b >= M->K && imax(I.cb,I.ce) < M->cov[ST_R] && !(I.pe >= cpg_log(CPG_PE_FINAL)))
     { wc_correct(prof,plen,seq,rlen,W,I,idx);
       const int ccb = I.ccb, cce = I.cce;
-      rel = !(cpg_lp_trans(W,I.b,I.e,ccb,cce,(uint16_t)((ccb+cce)/2)) < CPG_THRES_DIFF_REL);
+      rel = !(cpg_lp_trans_thr(W,I.b,I.e,ccb,cce,(uint16_t)((ccb+cce)/2),CPG_THRES_DIFF_REL) < CPG_THRES_DIFF_REL);
       if (imax(ccb,cce) == CPG_MAX_CNT) rel = 0;
     }
   I.is_rel = (uint8_t)rel;
@@ -827,7 +842,7 @@ CPG_DEV_NOINL int wc_read(const uint16_t *prof, int plen, const cpg_seq seq, int
 CPG_DEV_HELPER int wa_flush(ReadCtx &R, WCtx &W, int ncand, int npend, int mypos)
 { if (ncand+npend > R.S.capC) { W.status |= CPG_ST_RETRY; return 1; }
   if (W.glane < npend)
-    wa_candidate(R.prof,R.plen,R.seq,R.rlen,W,mypos,R.S.hdr+ncand+W.glane,R.S.big,(uint32_t)(ncand+W.glane));
+    wa_candidate(R.prof,R.plen,R.seq,R.rlen,W,mypos,R.S.hdr+ncand+W.glane,R.S.big,(uint32_t)(ncand+W.glane),R.prune);
   return 0;
 }
 

@@ -109,7 +109,7 @@ static int fake_read(cpg_ctx *c, const cpg_batch *b, int i, uint8_t *cls)
   R.S.capS = Kk.capS; R.S.capE = Kk.capE; R.S.capI = Kk.capI;
   R.S.tlog = Kk.tlog.data(); R.S.capT = Kk.capT; R.S.capC = Kk.capC; R.S.hdr = Kk.hdr.data(); R.S.big = Kk.big.data();
   R.S.key = Kk.key.data();
-  R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0;
+  R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0; R.prune = 0;
   return classify_read(R,W,sh,cls);
 #endif
 }

@@ -197,7 +197,7 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
   std::vector<std::vector<char> > cls_g(NG);
   LaneJob jobs[CPG_WARP];
   int st = 0;
-  for (int attempt = (g_small_caps > 0 ? 0 : 1); attempt < 2; attempt++)
+  for (int attempt = 0; attempt < 2; attempt++)      /* 0: as the phase kernels (compact tables if asked for, pruned records); 1: as the retry launch */
   {
   for (int l = 0; l < CPG_WARP; l++)
     { LaneJob &J = jobs[l];
@@ -226,7 +226,7 @@ int hs_classify_read(const cpg_model *m, const char *seq, int rlen, int seq_bits
       R.S.capS = K.capS; R.S.capE = K.capE; R.S.capI = K.capI;
       R.S.tlog = K.tlog.data(); R.S.capT = K.capT; R.S.capC = K.capC; R.S.hdr = K.hdr.data(); R.S.big = K.big.data();
       R.S.key = K.key.data();
-      R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0;
+      R.hdr = 0; R.big = 0; R.ncand = 0; R.ntlog = 0; R.prune = (attempt == 0);   /* first attempt as k_wall_a records, second as the retry launch */
     }
   run_lanes(lane_classify,jobs);
   st = 0;
