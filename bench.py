@@ -630,6 +630,7 @@ def main():
     clocks = sampler.stop(t0, t1)
     phase = ctx.phase_cycles()
     wall_ns = ctx.wall_ns()
+    n_cand, n_ivl, n_rel, n_vis = ctx.batch_stats()
     cls_res, status = ctx.download(data.whole)
     n_bad = int(sum_over_ranks(float((status & cp.ST_FATAL != 0).sum())))
     my_ms = ms_dec + ms_cls
@@ -715,43 +716,63 @@ def main():
     # kernels read the counts, the bit map and the 2-bit bases and write one class byte per base.
     bytes_dec = c + 2 * n + n // 8
     bytes_cls = 2 * n + n // 8 + (r + 3) // 4 + r
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    except Exception:
-        pass
-    traffic = (traffic or {}) if args.workload == "c2" and world == 1 and abs(args.genome_mb - 100.) < 1e-9 else {}
     tot_ns = max(1, sum(phase))
     ms_ph = [ms_cls * x / tot_ns for x in phase]
-    bytes_wall = 2 * n + n // 8 + (r + 3) // 4          # counts + candidate bits + 2-bit bases
+    traffic_file = "traffic_r02.json" if args.workload == "c2" else "traffic_r02_c4.json"
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
+    except Exception:
+        traffic = {}
+    if not (world == 1 and args.genome_mb == 0.):
+        traffic = {}                                    # measured on the default size of the workload only
+
+    def sub(total_ms, parts, i):
+        return total_ms * parts[i] / max(1, sum(parts))
+
+    def K_(ms, nbytes, traf, note):
+        d = {"ms": ms, "bytes": int(nbytes), "GBps": nbytes / (max(ms, 1e-6) * 1e-3) / 1e9,
+             "frac": nbytes / (max(ms, 1e-6) * 1e-3) / 1e9 / peak, "traffic": traf, "note": note}
+        return d
+
+    # algorithmic bytes per launch: what a kernel must read and write, from the units
+    # it works on -- counts n, bases r, compressed bytes c, candidates, intervals, reliable / visited intervals
+    w3, u3 = wall_ns[:3], wall_ns[3:]
     kern = {
-        "k_decode": {"ms": ms_dec, "bytes": bytes_dec, "GBps": bytes_dec / (ms_dec * 1e-3) / 1e9,
-                     "frac": bytes_dec / (ms_dec * 1e-3) / 1e9 / peak, "traffic": traffic.get("k_decode"),
-                     "note": "profile decode + wall-candidate scan fused: c + 2n + n/8 bytes; issue bound"},
-        "k_wall": {"ms": ms_ph[0], "bytes": bytes_wall, "GBps": bytes_wall / (max(ms_ph[0], 1e-6) * 1e-3) / 1e9,
-                   "frac": bytes_wall / (max(ms_ph[0], 1e-6) * 1e-3) / 1e9 / peak, "traffic": traffic.get("k_wall"),
-                   "launches": {"k_wall_a": ms_ph[0] * wall_ns[0] / max(1, sum(wall_ns[:3])),
-                                "k_wall_b": ms_ph[0] * wall_ns[1] / max(1, sum(wall_ns[:3])),
-                                "k_wall_c": ms_ph[0] * wall_ns[2] / max(1, sum(wall_ns[:3]))},
-                   "note": "wall detection + reliable intervals as three launches (pure per candidate / replay per read / "
-                           "pure per interval): 2n + n/8 + r/4 bytes in, interval tables out"},
-        "k_rel": {"ms": ms_ph[1], "bytes": None, "traffic": traffic.get("k_rel"),
-                  "note": "reliable-interval DP on the interval tables (48 B per interval): FP64 dependency chains"},
-        "k_unrel": {"ms": ms_ph[2], "bytes": r, "traffic": traffic.get("k_unrel"),
-                    "launches": {"k_unrel_a": ms_ph[2] * wall_ns[3] / max(1, sum(wall_ns[3:])),
-                                 "k_unrel_b": ms_ph[2] * wall_ns[4] / max(1, sum(wall_ns[3:])),
-                                 "k_emit": ms_ph[2] * wall_ns[5] / max(1, sum(wall_ns[3:]))},
-                    "note": "unreliable intervals (pure per interval, then the sweeps per read) + class string (r bytes out)"},
+        "k_decode": K_(ms_dec, bytes_dec, traffic.get("k_decode"),
+                       "profile decode + wall-candidate scan fused: c + 2n + n/8 bytes; issue bound"),
+        "k_wall_a": K_(sub(ms_ph[0], w3, 0), n // 8 + n_cand * (4 + 8 + 16) + (n_cand // 5) * 216, traffic.get("k_wall_a"),
+                       "pure, one wall candidate per lane: candidate bit map n/8, per candidate 2 counts + a 64-bit window of "
+                       "bases in, a 16-byte header out, a 216-byte record for ~1 in 5 (estimate)"),
+        "k_wall_b": K_(sub(ms_ph[0], w3, 1), n_cand * 16 + (n_cand // 5) * 216 + n_ivl * 48, traffic.get("k_wall_b"),
+                       "order-dependent replay per read: candidate records in, 48-byte intervals out; DRAM-latency bound"),
+        "k_wall_c": K_(sub(ms_ph[0], w3, 2), n_ivl * (96 + 8 * (K - 1)) + n_rel * 48, traffic.get("k_wall_c"),
+                       "pure, one interval per lane: interval in and out, 4(K-1) counts, reliable ones copied"),
+        "k_rel": K_(ms_ph[1], n_rel * (48 + 48 + 1) + n_ivl, traffic.get("k_rel"),
+                    "reliable-interval DP: reliable intervals in, working copies, class codes out; FP64-issue bound "
+                    "(44 % of its instructions are Bessel recurrences at 10 active lanes, FP64 pipe 46 %, profiles/r02_ncu_full.md)"),
+        "k_unrel_a": K_(sub(ms_ph[2], u3, 0), n_ivl * 48 + n_vis * 104, traffic.get("k_unrel_a"),
+                        "pure, one visited interval per lane: intervals in, 104-byte task records out"),
+        "k_unrel_b": K_(sub(ms_ph[2], u3, 1), n_ivl * 48 + n_vis * 104, traffic.get("k_unrel_b"),
+                        "the two sweeps per read on the recorded values; DRAM-latency bound"),
+        "k_emit": K_(sub(ms_ph[2], u3, 2), n_ivl * 17 + r, traffic.get("k_emit"),
+                     "class strings, streaming: 17 bytes per interval in, r bytes out (skipped when results are interval tables)"),
         "retry_launch": {"ms": ms_ph[3]},
     }
-    dom = max(("k_decode", "k_wall", "k_rel", "k_unrel"), key=lambda k: kern[k]["ms"])
-    dom_bytes = kern[dom]["bytes"] if kern[dom]["bytes"] is not None else bytes_cls
-    dom_ms = kern[dom]["ms"]
-    roof = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-            "traffic": traffic.get(dom),
-            "algorithmic_bytes_per_launch": dom_bytes,
-            "classification_ms": ms_cls, "classification_bytes": bytes_cls,
+    phases = {"wall": ms_ph[0], "rel": ms_ph[1], "unrel_emit": ms_ph[2]}
+    dom = max((k for k in kern if k != "retry_launch"), key=lambda k: kern[k]["ms"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": kern[dom]["frac"], "peak_source": peak_src,
+            "traffic": kern[dom]["traffic"],
+            "algorithmic_bytes_per_launch": kern[dom]["bytes"],
+            "note": "the dominant kernel is not a streaming kernel: its bytes are the interval tables it works on; what bounds it "
+                    "is in its note.  `pipeline` is the whole step against the bytes each read touches (SURVEY 8d, unfused: "
+                    "c + 4n + n/4 + r/4 + r), `k_decode` the streaming kernel the north star's 50 % is about",
+            "pipeline": {"ms": ms_dec + ms_cls, "bytes": int(bytes_dec + bytes_cls),
+                         "GBps": (bytes_dec + bytes_cls) / ((ms_dec + ms_cls) * 1e-3) / 1e9,
+                         "frac": (bytes_dec + bytes_cls) / ((ms_dec + ms_cls) * 1e-3) / 1e9 / peak},
+            "units": {"kmers": n, "bases": r, "compressed_profile_bytes": c, "wall_candidates": n_cand, "intervals": n_ivl,
+                      "reliable_intervals": n_rel, "intervals_visited_by_unreliable_sweeps": n_vis},
+            "classification_ms": ms_cls, "classification_bytes": bytes_cls, "phases_ms": phases,
             "kernels": kern}
 
     ctx.close()

@@ -64,6 +64,7 @@ def lib():
         L.cpg_download.argtypes = [C.c_void_p, C.POINTER(CResult)]
         L.cpg_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.cpg_wall_ns.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.cpg_batch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.cpg_set_result_mode.argtypes = [C.c_void_p, C.c_int]
         L.cpg_intervals_bound.argtypes = [C.c_void_p, C.c_int]
         L.cpg_intervals_bound.restype = C.c_int64
@@ -327,6 +328,14 @@ class Context:
         rc = self.L.cpg_wall_ns(self.h, out)
         if rc:
             raise self._err("cpg_wall_ns", rc)
+        return list(out)
+
+    def batch_stats(self):
+        """(wall candidates, intervals, reliable intervals, intervals visited by the unreliable sweeps) of the resident batch."""
+        out = (C.c_int64 * 4)()
+        rc = self.L.cpg_batch_stats(self.h, out)
+        if rc:
+            raise self._err("cpg_batch_stats", rc)
         return list(out)
 
     def download(self, batch, allow_read_errors=True):

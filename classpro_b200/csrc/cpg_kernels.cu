@@ -1468,6 +1468,25 @@ extern "C" int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[6])
   return CPG_OK;
 }
 
+/* sums over the reads of the batch on slot 0 (after cpg_run_resident): wall candidates, intervals, reliable
+   intervals, intervals the unreliable sweeps visit -- the units the per-kernel algorithmic bytes are made of */
+extern "C" int cpg_batch_stats(cpg_ctx *ctx, int64_t out[4])
+{ if (ctx == NULL || out == NULL) return set_err(ctx,CPG_EINVAL,"cpg_batch_stats: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  Slot *S = &ctx->slot[0];
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (S->n_reads == 0 || S->rec.p == NULL || ctx->fused) return CPG_OK;
+  CU(cudaStreamSynchronize(S->stream));
+  ReadRec *h = (ReadRec *)malloc(sizeof(ReadRec)*(size_t)S->n_reads);
+  if (h == NULL) return set_err(ctx,CPG_ENOMEM,"out of host memory");
+  cudaError_t e = cudaMemcpy(h,S->rec.p,sizeof(ReadRec)*(size_t)S->n_reads,cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess)
+    for (int i = 0; i < S->n_reads; i++) { out[0] += h[i].ncand; out[1] += h[i].N; out[2] += h[i].M; out[3] += h[i].nf; }
+  free(h);
+  if (e != cudaSuccess) return set_err(ctx,CPG_ECUDA,"cpg_batch_stats: %s",cudaGetErrorString(e));
+  return CPG_OK;
+}
+
 extern "C" int cpg_download(cpg_ctx *ctx, cpg_result *res)
 { if (ctx == NULL || res == NULL) return set_err(ctx,CPG_EINVAL,"cpg_download: bad argument");
   CU(cudaSetDevice(ctx->device));

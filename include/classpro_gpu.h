@@ -181,6 +181,9 @@ int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4]);
  * (order-dependent replay, one read per lane group), [2] k_wall_c (one interval per lane), [3] k_unrel_a (pure,
  * one interval per lane), [4] k_unrel_b (sweeps), [5] k_emit (class strings). */
 int cpg_wall_ns(cpg_ctx *ctx, uint64_t out[6]);
+/* Sums over the reads of the resident batch after cpg_run_resident: [0] wall candidates, [1] intervals,
+ * [2] reliable intervals, [3] intervals the unreliable sweeps visit (the units of the per-kernel byte counts). */
+int cpg_batch_stats(cpg_ctx *ctx, int64_t out[4]);
 
 /* ---- profile producer (what FastK does before ClassPro runs) ----------------
  * FastK is not part of the reference tree; the reference only reads its files (src/libfastk.c:51-96
