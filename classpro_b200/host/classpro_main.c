@@ -887,10 +887,18 @@ int main(int argc, char **argv)
   if (A->verbose) fprintf(stderr,"Error model not specified. Using the default error model.\n");
   g_tl_model = now_s();
 
-  int ndev = cpg_device_count();
-  if (ndev <= 0) die("%s: no CUDA device found: this program has no CPU fallback",PROG);
   const char *env = getenv("CLASSPRO_GPUS");
   if (A->ngpus == 0 && env && atoi(env) > 0) A->ngpus = atoi(env);
+  /* The CUDA runtime initialises every VISIBLE device when it starts (about 0.2 s each on an 8-GPU box),
+     and nothing can be allocated before that: a run that was asked for fewer GPUs hides the others from it
+     (before the first CUDA call; an explicit CUDA_VISIBLE_DEVICES of the caller is left alone). */
+  if (A->ngpus > 0 && A->ngpus <= MAX_GPUS && getenv("CUDA_VISIBLE_DEVICES") == NULL)
+    { char vis[8*MAX_GPUS+8]; int o = 0;
+      for (int g = 0; g < A->ngpus; g++) o += snprintf(vis+o,sizeof(vis)-(size_t)o,g ? ",%d" : "%d",g);
+      setenv("CUDA_VISIBLE_DEVICES",vis,1);
+    }
+  int ndev = cpg_device_count();
+  if (ndev <= 0) die("%s: no CUDA device found: this program has no CPU fallback",PROG);
   if (A->ngpus == 0 || A->ngpus > ndev) A->ngpus = ndev;
   if (A->ngpus > MAX_GPUS) A->ngpus = MAX_GPUS;
   if (A->verbose)
