@@ -690,6 +690,10 @@ def main():
         same = same and bool(np.array_equal(ex[:nb], cls_res[at:at + nb]))
         at += nb
         rv.free()
+    # every collective is called by EVERY rank, outside the rank-0 block that prints the line (an all-reduce
+    # inside it once cost a 10-minute NCCL timeout at N = 8)
+    d2h_ivl_all = int(sum_over_ranks(float(d2h_ivl)))
+    same = bool(min_over_ranks(1.0 if same else 0.0) > 0.5)
 
     # ---- parity: a seeded sample of this shard's reads through the oracle
     par = parity_sample(data, cls_res, args.parity_kmers / world, max(16, args.parity_reads // world), 4242 + rank,
@@ -818,7 +822,7 @@ def main():
                         "rank_time_imbalance": (step_ms / step_ms_min) if step_ms_min > 0 else None, "shards": shard_info},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": data.h2d_bytes,
-                        "d2h_bytes_per_step": int(sum_over_ranks(float(d2h_ivl)) / world) if world > 1 else d2h_ivl,
+                        "d2h_bytes_per_step": d2h_ivl_all,
                         "ms_per_step": e2e_s * 1e3,
                         "matches_resident_result": same,
                         "result": "interval tables, 4 B per interval (cpg_collect_intervals); expanded to the class strings on "

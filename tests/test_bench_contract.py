@@ -45,3 +45,42 @@ def test_product_arm_needs_a_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--genome-mb", "1"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
     assert p.returncode != 0 and "no CPU path" in (p.stderr + p.stdout)
+
+
+def test_no_collective_inside_a_rank_guard():
+    """Every collective of bench.py must be reached by EVERY rank: an all-reduce inside the `if rank == 0:` block
+    that prints the JSON line once hung an 8-GPU run until NCCL's 10-minute watchdog (round 2).  Static check: no call
+    of the collective helpers / torch.distributed collectives lexically inside an `if` whose test mentions `rank`."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    collectives = {"sum_over_ranks", "max_over_ranks", "min_over_ranks", "reduce_ranks", "barrier", "all_reduce",
+                   "all_gather_object", "all_gather", "broadcast", "broadcast_object_list"}
+    bad = []
+
+    class V(ast.NodeVisitor):
+        def __init__(self):
+            self.guard = 0
+
+        def visit_If(self, node):
+            names = {n.id for n in ast.walk(node.test) if isinstance(n, ast.Name)}
+            g = "rank" in names or "local" in names
+            self.visit(node.test)
+            self.guard += g
+            for b in node.body:
+                self.visit(b)
+            self.guard -= g
+            for b in node.orelse:          # `else` of a rank test is a rank guard too
+                self.guard += g
+                self.visit(b)
+                self.guard -= g
+
+        def visit_Call(self, node):
+            f = node.func
+            name = f.id if isinstance(f, ast.Name) else (f.attr if isinstance(f, ast.Attribute) else "")
+            if self.guard and name in collectives:
+                bad.append((name, node.lineno))
+            self.generic_visit(node)
+
+    V().visit(tree)
+    assert not bad, "collectives under a rank guard: %s" % bad
