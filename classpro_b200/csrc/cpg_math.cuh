@@ -170,12 +170,15 @@ CPG_DEV double cpg_lp_trans(const WCtx &W, int b, int e, int cb, int ce, uint16_
  * known without it: I_n(x) < cosh(x) (x/2)^n / n!  (x > 0) and n! >= (n/e)^n give
  *     logp_skellam(k,lambda) = -2 lambda + log I_n(2 lambda)  <  n (log(lambda/n) + 1),
  * and when that bound is below the threshold by more than 2 -- far more than any rounding of the recurrence --
- * the exact value is below it too.  Returned then: -inf (every use is the comparison).  Otherwise the exact value. */
+ * the exact value is below it too.  Returned then: -inf (every use is the comparison).  Otherwise the exact value.
+ * Only for 2 lambda < 700: beyond that exp(2 lambda) overflows inside the reference's bessi0 (src/bessel.c:401) and
+ * its result is +inf, or NaN where the recurrence underflowed to 0 -- and NaN passes the reference's `< threshold`
+ * tests (src/wall.c:390,1028).  That behaviour is kept by evaluating those (rare: coverage x distance > 7e6) as it does. */
 CPG_DEV_HELPER double cpg_lp_trans_thr(const WCtx &W, int b, int e, int cb, int ce, uint16_t cov, double thres)
 { int d = e-b; if (d < 0) d = -d;
   const int k = ce-cb, n = k < 0 ? -k : k;
   const double lambda = (double)cov*d/W.M->read_len;
-  if (n >= 32)
+  if (n >= 32 && 2.*lambda < 700.)
     { if (!(lambda > 0.)) return -CPG_INF;
       if ((double)n*(cpg_log(lambda/(double)n)+1.) < thres-2.) return -CPG_INF;
     }

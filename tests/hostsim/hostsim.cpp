@@ -297,4 +297,16 @@ int hs_ctx2(const char *seq, int rlen, int p, int right, int t, int pad)
 
 int hs_sizeof_intvl(void) { return (int)sizeof(cpg_intvl); }
 
+/* the two shortcuts of cpg_math.cuh against the oracle's plain loops (tests/test_device_logic_hostsim.py) */
+double hs_binom_tail(const cpg_model *m, int k, int n, double p, int *bad)
+{ cpg_rate r; r.p = p; r.lp = log(p); r.l1mp = log(1-p);
+  *bad = 0;
+  return cpg_binom_tail_lane(m->logfact,k,n,r,bad);
+}
+double hs_lp_trans_thr(int read_len, int b, int e, int cb, int ce, int cov, double thres, int use_bound)
+{ cpg_dmodel dm; memset(&dm,0,sizeof(dm)); dm.read_len = read_len;
+  WCtx W; memset(&W,0,sizeof(W)); W.M = &dm; W.gsize = 1;
+  return use_bound ? cpg_lp_trans_thr(W,b,e,cb,ce,(uint16_t)cov,thres) : cpg_lp_trans(W,b,e,cb,ce,(uint16_t)cov);
+}
+
 }

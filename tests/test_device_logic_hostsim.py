@@ -218,6 +218,76 @@ def test_context_long_runs_match_the_reference_sweep(kit, hostsim):
                     assert hostsim.hs_ctx2(seq, n, p, 1, t, n & 3) == want_r, (unit, copies, p, t, "right, packed")
 
 
+def test_math_shortcuts_are_bit_identical(kit, hostsim):
+    """cpg_math.cuh answers two loops without running them; both must leave every bit / every decision as the
+    reference's loops do (oracle: src/prob.c:76-112 restated, src/bessel.c:482-521 restated).
+    (1) a binomial tail whose first term underflows to 0: the reference adds up to 32 767 further terms, all 0;
+    (2) cpg_lp_trans_thr: a Skellam log-probability that is only compared with a threshold is -inf when the bound
+        n(log(lambda/n)+1) < threshold-2 decides the comparison -- then the exact value must be below the threshold;
+        otherwise it is the exact value, bit for bit."""
+    import ctypes as C
+    import math
+    L = kit.oracle_lib()
+    sim = kit.simulate(seed=5, genome_len=60000, cov=25., het=0.01, len_mean=8000)
+    om = kit.oracle_model(sim)
+    gm = kit.gpu_model_from_sim(hostsim, sim)
+    L.cpo_binom_test_g.restype = C.c_double
+    L.cpo_binom_test_g.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]
+    L.cpo_bessi.restype = C.c_double
+    L.cpo_bessi.argtypes = [C.c_int, C.c_double]
+    hostsim.hs_binom_tail.restype = C.c_double
+    hostsim.hs_binom_tail.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int)]
+    hostsim.hs_lp_trans_thr.restype = C.c_double
+    hostsim.hs_lp_trans_thr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+    rng = np.random.default_rng(3)
+    bad = C.c_int()
+    n_under = 0
+    cases = [(0, 32767, 0.004), (32767, 32767, 0.004), (20000, 32767, 0.004), (5, 32767, 0.802), (100, 30000, 0.5),
+             (1, 2, 0.004), (0, 0, 0.1), (3000, 3000, 0.05), (2, 20000, 0.3)]
+    for _ in range(4000):
+        n = int(rng.choice([rng.integers(1, 80), rng.integers(80, 3000), rng.integers(3000, 32768)]))
+        k = int(rng.integers(0, n + 1))
+        p = float(rng.choice([0.004, 0.01, 0.1, 0.2, 0.802, rng.uniform(0.002, 0.9)]))
+        cases.append((k, n, p))
+    for k, n, p in cases:
+        a = L.cpo_binom_test_g(C.byref(om), k, n, p, 0)
+        b = hostsim.hs_binom_tail(C.byref(gm), k, n, p, C.byref(bad))
+        assert np.float64(a).tobytes() == np.float64(b).tobytes(), (k, n, p, a, b)
+        n_under += (a == 0.0 or a == 1.0)
+    assert n_under > 100                     # the underflow branch is really exercised
+
+    def exact(read_len, b, e, cb, ce, cov):
+        lam = float(cov) * abs(e - b) / read_len
+        with np.errstate(all="ignore"):
+            return float(np.float64(-2. * lam) + np.log(np.float64(L.cpo_bessi(abs(ce - cb), 2. * lam))))
+
+    def same_bits(x, y):
+        return np.float64(x).tobytes() == np.float64(y).tobytes() or (math.isnan(x) and math.isnan(y))
+
+    n_skip = n_odd = 0
+    for thres in (-23.025851, -9.210340):
+        for _ in range(3000):
+            cov = int(rng.choice([rng.integers(1, 60), rng.integers(60, 5000), rng.integers(5000, 32768)]))
+            d = int(rng.integers(1, 450))
+            cb = int(rng.integers(0, cov + 1))
+            ce = int(rng.choice([cb + rng.integers(-3, 4), rng.integers(0, 32768)]))
+            ce = max(0, min(32767, ce))
+            b0 = int(rng.integers(0, 20000))
+            got = hostsim.hs_lp_trans_thr(20000, b0, b0 + d, cb, ce, cov, thres, 1)
+            plain = hostsim.hs_lp_trans_thr(20000, b0, b0 + d, cb, ce, cov, thres, 0)
+            ex = exact(20000, b0, b0 + d, cb, ce, cov)
+            assert same_bits(plain, ex), (cov, d, cb, ce, plain, ex)
+            if got == -math.inf and not same_bits(plain, got):
+                n_skip += 1
+                assert plain < thres - 1.0, (cov, d, cb, ce, plain)          # decided, with room to spare
+            else:
+                assert same_bits(got, plain)
+            # both forms the reference uses (src/wall.c:366 `>=`, :390 and :1028 `<`): NaN and +inf included
+            assert (got >= thres) == (plain >= thres) and (got < thres) == (plain < thres)
+            n_odd += (math.isnan(plain) or plain == math.inf)
+    assert n_skip > 20 and n_odd > 20            # exp overflow inside bessi0 (2 lambda > 709): kept as the reference has it
+
+
 def random_stream(rng, n_tokens, adversarial):
     """A FastK token stream; adversarial = arbitrary bytes (wrap-around and mask corner cases)."""
     first = int(rng.integers(0, 32768))
@@ -321,3 +391,30 @@ def test_warp32_emulation_decode(kit):
         n1, o1 = kit.oracle_decode(np.frombuffer(s, dtype=np.uint8), 100000)
         n2, o2 = kit.hostsim_decode(np.frombuffer(s, dtype=np.uint8), 100000, lib=L32)
         assert n2 == n1 and np.array_equal(o2, o1)
+
+
+def test_reads_that_differed_from_the_reference_binary(kit, hostsim):
+    """Six of the 49 reads of the repeat-rich 50 Mb file-level run of round 2 whose class line differed from the
+    unmodified reference binary's (tests/golden/long_hp_runs.npz: sequence, exact counts, the REFERENCE's class
+    line, the histogram of the run; written by tools/trace_file_flips.py on the GPU box).  All of them have a
+    homopolymer run longer than 127 bases next to a wall.  The oracle and the host build of the device code must
+    both give the reference's line."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "long_hp_runs.npz"))
+
+    class S:
+        pass
+    sim = S()
+    sim.kmer = 40
+    sim.hist = d["hist"]
+    om = kit.oracle_model(sim, 0, 20000)
+    gm = kit.gpu_model_from_sim(hostsim, sim, 0, 20000)
+    ow = kit.OracleWork(clean=True)
+    reads = sorted(int(k[4:]) for k in d.files if k.startswith("seq_"))
+    assert len(reads) == 6
+    for r in reads:
+        seq, cnt, ref = d["seq_%d" % r].tobytes(), d["cnt_%d" % r], d["ref_%d" % r].tobytes()
+        assert ow.classify(om, seq, cnt) == ref, r
+        st, cls = kit.hostsim_classify(gm, seq, cnt, lib=hostsim)
+        assert cls == ref, r
+        assert not (st & ~32), (r, st)
