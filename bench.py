@@ -693,6 +693,8 @@ def main():
     # every collective is called by EVERY rank, outside the rank-0 block that prints the line (an all-reduce
     # inside it once cost a 10-minute NCCL timeout at N = 8)
     d2h_ivl_all = int(sum_over_ranks(float(d2h_ivl)))
+    h2d_all = int(sum_over_ranks(float(data.h2d_bytes)))
+    d2h_cls_all = int(sum_over_ranks(float(data.d2h_bytes)))
     same = bool(min_over_ranks(1.0 if same else 0.0) > 0.5)
 
     # ---- parity: a seeded sample of this shard's reads through the oracle
@@ -821,14 +823,14 @@ def main():
                         "ms_per_step_min_over_ranks": step_ms_min,
                         "rank_time_imbalance": (step_ms / step_ms_min) if step_ms_min > 0 else None, "shards": shard_info},
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": data.h2d_bytes,
+                "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": h2d_all,
                         "d2h_bytes_per_step": d2h_ivl_all,
                         "ms_per_step": e2e_s * 1e3,
                         "matches_resident_result": same,
                         "result": "interval tables, 4 B per interval (cpg_collect_intervals); expanded to the class strings on "
                                   "the host (cpg_expand_intervals) outside the timed region and compared with the resident result",
                         "class_strings": {"value": total_kmers / e2e_cls_s, "ms_per_step": e2e_cls_s * 1e3,
-                                          "d2h_bytes_per_step": data.d2h_bytes,
+                                          "d2h_bytes_per_step": d2h_cls_all,
                                           "what": "the same pass returning 1 byte per base (cpg_collect)"},
                         "starts_from": "parsed, 2-bit packed reads and fetched profile bytes in pinned host memory "
                                        "(file parsing and output formatting are in `cli`)"},

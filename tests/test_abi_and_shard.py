@@ -89,6 +89,37 @@ def test_pack_seq():
         assert np.array_equal(ref, pk[po[r]:po[r + 1]])
 
 
+def test_expand_intervals():
+    """cpg_expand_intervals (host code of the library): 'N' x (K-1), then every interval's class over its stretch
+    -- the class string of CPG_RESULT_CLASSES mode (src/ClassPro.c:114-117,265-271).  Also: a table that stops short
+    of the profile leaves the rest untouched, entries past the profile are clipped, reads shorter than K are all N."""
+    import classpro_b200 as cp
+    L = cp.lib()
+    rng = np.random.default_rng(9)
+    K = 40
+    for _ in range(200):
+        rlen = int(rng.integers(K, 3000))
+        plen = rlen - K + 1
+        ncut = int(rng.integers(0, min(plen, 60)))
+        ends = np.unique(np.concatenate([rng.integers(1, plen + 1, size=ncut), [plen]])).astype(np.int64)
+        codes = rng.integers(0, 4, size=len(ends))
+        ivl = ((ends << 3) | codes).astype(np.uint32)
+        out = np.full(rlen + 8, ord("#"), dtype=np.uint8)
+        L.cpg_expand_intervals(K, rlen, ivl.ctypes.data, len(ivl), out.ctypes.data)
+        want = bytearray(b"N" * (K - 1))
+        b = 0
+        for e, c in zip(ends, codes):
+            want += bytes([b"ERHD"[c]]) * int(e - b)
+            b = int(e)
+        assert out[:rlen].tobytes() == bytes(want) and (out[rlen:] == ord("#")).all()
+    out = np.full(64, ord("#"), dtype=np.uint8)
+    L.cpg_expand_intervals(K, 30, None, 0, out.ctypes.data)                  # shorter than K: rlen 'N's
+    assert out[:30].tobytes() == b"N" * 30 and out[30] == ord("#")
+    ivl = np.array([(5 << 3) | 2, (500 << 3) | 3], dtype=np.uint32)          # second entry past the profile: clipped
+    L.cpg_expand_intervals(K, 50, ivl.ctypes.data, 2, out.ctypes.data)
+    assert out[:50].tobytes() == b"N" * 39 + b"HHHHH" + b"DDDDDD" and out[50] == ord("#")
+
+
 def test_shard_ranges_properties():
     from classpro_b200.shard import shard_ranges, reference_thread_ranges
     rng = np.random.default_rng(5)
