@@ -19,7 +19,7 @@
  *               values per interval the sweeps will visit).
  *   k_unrel_b   the two order-dependent sweeps on those values (cpg_unrel.cuh).
  *   k_emit      class strings, streaming: r bytes per read out.
- *   k_classify  the three phases in one kernel, on 4 CTAs with worst-case scratch: the retry
+ *   k_classify  the three phases in one kernel, on 2 CTAs with worst-case scratch: the retry
  *               launch for reads that outgrew the compact scratch blocks or the pool (normally
  *               none; it returns at once).  CPG_FUSED=1 runs every read through it instead.
  *  The classification kernels are bound by FP64 dependency chains (Bessel recurrences), DRAM
@@ -591,7 +591,7 @@ k_wall_b(BatchDev B, cpg_dmodel M, ScratchDev SC)
       long long at = 0;
       if (!(W.status & CPG_ST_ABORT))
         { N = wb_cuts(R,W,NS,0,0,&mcap);
-          /* the per-interval arrays of k_unrel's scratch blocks hold capI entries */
+          /* the per-interval arrays of k_unrel_b's scratch blocks hold capI entries */
           if (N > SC.capI) W.status |= CPG_ST_RETRY;
           else
             { /* a place in the pool for intvl[N] and the (at most mcap) reliable ones behind them */

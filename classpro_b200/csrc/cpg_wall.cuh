@@ -99,11 +99,6 @@ struct ReadCtx
     int             prune;    /* single-read path: record partner values as k_wall_a does (wa_tasks; host tests) */
   };
 
-CPG_DEV uint16_t rc_prof(const ReadCtx &R, WCtx &W, int p)
-{ if (p >= R.plen) { W.status |= MK_STALE_PROF; p = R.plen-1; }
-  return R.prof[p];
-}
-
 CPG_DEV unsigned mk_by(int e)   { return e == ET_SELF ? MK_BY_S : MK_BY_O; }
 CPG_DEV unsigned mk_pair(int e) { return e == ET_SELF ? MK_PAIR_S : MK_PAIR_O; }
 

@@ -173,7 +173,7 @@ int cpg_run_resident(cpg_ctx *ctx, int iters, float *ms_decode, float *ms_classi
 int cpg_download(cpg_ctx *ctx, cpg_result *result);
 /* Device time of the classification phases in the last cpg_run_resident iteration, nanoseconds
  * (CUDA events between the kernels): [0] the three wall kernels (wall detection + reliable intervals), [1] k_rel
- * (reliable-interval DP), [2] k_unrel (unreliable intervals + class strings), [3] the retry launch.
+ * (reliable-interval DP), [2] k_unrel_a + k_unrel_b + k_emit (unreliable intervals + class strings), [3] the retry launch.
  * With CPG_FUSED=1 (single-kernel path): summed per-group clock cycles of the three phases and of
  * the waits at the CTA phase barriers. */
 int cpg_phase_cycles(cpg_ctx *ctx, uint64_t out[4]);

@@ -192,7 +192,7 @@ def test_host_side_under_sanitizers(kit, progs, tmp_path, san):
 @pytest.mark.parametrize("group", [4, 8])
 def test_warp_emulation_under_thread_sanitizer(kit, progs, tmp_path, group):
     """The device sources with 32 host threads playing the lanes of a warp (lane groups of 4 / 8, as
-    in k_wall / k_rel, k_unrel), built with -fsanitize=thread: a scratch or shared word written by one
+    in k_wall_b / k_rel / k_unrel_b), built with -fsanitize=thread: a scratch or shared word written by one
     lane and read by another without a group barrier in between is a data race it reports.  30 reads
     of the golden fixture through decode and all three phases: no report, same bytes."""
     from test_oracle import unpack_golden
