@@ -64,8 +64,38 @@ def test_class2acc_errors(kit, class_pair, tmp_path):
     short.write_text("\n".join(open(truth).read().split("\n")[:8]) + "\n")
     rc, _, err = run([exe, est, str(short)])
     assert rc == 1 and b"# seqs in" in err
-    rc, _, err = run([exe, "-w100", est, truth])
-    assert rc == 1 and b"not supported" in err
+    rc, _, err = run([exe, "-pno_such_root", est, truth])
+    assert rc == 1 and b"Cannot open" in err
+
+
+@pytest.mark.parametrize("opts", [["-e0"], ["-w500"], ["-w1000", "-e2", "-r5"], ["-w77", "-f40"]])
+def test_class2acc_with_profiles_matches_reference(kit, tmp_path, opts):
+    """-p<FastK root> (coverages of a read from the counts of its true H / D-mers) and -w<int> (one line per
+    window), src/class2acc.c:98-104,174-185,228-247,272-279, on a dataset with several profile parts: the estimate
+    is the reference's own .class, the truth the same with some class characters redrawn."""
+    ref = os.path.join(REF, "class2acc")
+    if not os.path.exists(ref) or not kit.have_reference():
+        pytest.skip("reference tools not built (no /root/reference here)")
+    kit.build_product()
+    kit.simulate(write_to=str(tmp_path), root="w", seed=31, genome_len=150000, cov=25., het=0.01, repeat_frac=0.2,
+                 len_mean=9000, len_sd=1500, nparts=3)
+    fasta = str(tmp_path / "w.fasta")
+    est = kit.run_reference(fasta, threads=2)
+    lines = open(est).read().split("\n")
+    rnd = random.Random(7)
+    out = []
+    for i, l in enumerate(lines):
+        if i % 4 == 3:
+            l = "".join((rnd.choice("EHDR") if (c != "N" and rnd.random() < 0.04) else c) for c in l)
+        out.append(l)
+    truth = tmp_path / "truth.class"
+    truth.write_text("\n".join(out))
+    root = str(tmp_path / "w")
+    a = run([ref, "-p" + root] + opts + [est, str(truth)])
+    b = run([os.path.join(BIN, "class2acc"), "-p" + root] + opts + [est, str(truth)])
+    assert a[0] == 0 and b[0] == 0, (a[2][-500:], b[2][-500:])
+    assert a[1] == b[1]
+    assert b"H1-cov=" in b[1] or opts == ["-f40"]
 
 
 @pytest.mark.gpu
